@@ -1,0 +1,147 @@
+/* ventb200 -- C ABI of the B200-native Vent_Analysis voxel hot path (N4 -> VDP -> CI).
+ *
+ * Plain C: pointers, sizes, status codes.  No torch / numpy / C++ types cross this
+ * boundary.  The reference (thomenr/Vent_Analysis) is pure Python and has no FFI of its
+ * own; each entry point below names the reference function whose arithmetic it replaces,
+ * and INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   * A batch is `n` subjects.  Subject i is a C-ordered [rows][cols][slices] volume
+ *     (exactly numpy's layout of the reference's arrays) with shape shapes[3*i .. 3*i+2];
+ *     all per-voxel arrays are the subjects' volumes concatenated in batch order.
+ *   * `_dev` entry points take DEVICE pointers and a cudaStream_t (as void*), enqueue work
+ *     and return without synchronising; `shapes` / `table_handles` are HOST arrays.
+ *   * `_host` entry points take HOST pointers, copy in, run, copy out and synchronise.
+ *   * Every function returns VB_OK or a VB_ERR_* code; vb_last_error() gives the text
+ *     (thread local).  Nothing falls back to the CPU: without a CUDA device vb_create fails.
+ */
+#ifndef VENTB200_H
+#define VENTB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_OK 0
+#define VB_ERR_CUDA 1        /* CUDA runtime / launch failure                              */
+#define VB_ERR_ARG 2         /* bad argument                                               */
+#define VB_ERR_UNSUPPORTED 3 /* size outside what the kernels were built for               */
+#define VB_ERR_CI_RMAX 4     /* a defect voxel exhausted the sphere table: the reference
+                                raises ValueError there (CI.py:101-103)                    */
+
+#define VB_DO_SNR 1u         /* Vent_Analysis.calculate_SNR        Vent_Analysis.py:337-357 */
+#define VB_DO_N4 2u          /* Vent_Analysis.N4_bias_correction   Vent_Analysis.py:316-334 */
+#define VB_DO_VDP 4u         /* Vent_Analysis.calculate_VDP body   Vent_Analysis.py:244-257 */
+#define VB_DO_CI 8u          /* CI.calculate_CI + percentile  CI.py:107-145, V_A.py:268-270 */
+#define VB_DO_MASK_BORDER 16u/* Vent_Analysis.calculateBorder(mask) Vent_Analysis.py:225-231 */
+
+#define VB_MAX_LEVELS 8
+#define VB_CI_OFF 0xFFFFu    /* ci_shell value of a voxel that is not a defect             */
+
+typedef struct vb_ctx vb_ctx;
+
+/* Parameters of sitk.N4BiasFieldCorrectionImageFilter (Vent_Analysis.py:330 uses defaults). */
+typedef struct vb_n4_params {
+    int32_t n_levels;                 /* len(MaximumNumberOfIterations)            4       */
+    int32_t max_iter[VB_MAX_LEVELS];  /* MaximumNumberOfIterations                 50 x 4  */
+    float conv_threshold;             /* ConvergenceThreshold                      0.001   */
+    float fwhm;                       /* BiasFieldFullWidthAtHalfMaximum           0.15    */
+    float wiener_noise;               /* WienerFilterNoise                         0.01    */
+    int32_t n_bins;                   /* NumberOfHistogramBins                     200     */
+    int32_t ncp[3];                   /* NumberOfControlPoints (row, col, slice)   4,4,4   */
+    int32_t mask_label;               /* MaskLabel (UseMaskLabel = true)           1       */
+    int32_t max_total_iters;          /* 0 = no cap; >0 stops after that many iterations
+                                         overall (used by the stage-level parity tests)    */
+} vb_n4_params;
+
+/* Per-subject scalars.  Counts are exact integers; the Python shim forms the reference's
+ * float64 expressions (100*sum(defect)/sum(mask), ...) from them. */
+typedef struct vb_subject_stats {
+    int32_t n4_iters[VB_MAX_LEVELS];  /* iterations run at each fitting level              */
+    float n4_last_conv;               /* last convergence measurement                      */
+    int32_t n4_n_mask;                /* #(mask == mask_label)                             */
+    int32_t n_mask;                   /* #(mask != 0)            np.sum(mask) for 0/1 masks */
+    float mean;                       /* float32 mean of N4 over the mask   V_A.py:246     */
+    float p99;                        /* sorted(N4[mask>0])[int(M*.99)]     V_A.py:255     */
+    int32_t n_defect;                 /* np.sum(defectArray)                V_A.py:251     */
+    int32_t n_lb12;                   /* #(defectArrayLB in {1,2})          V_A.py:257     */
+    int32_t n_noise;                  /* #noise voxels of calculate_SNR                    */
+    double signal_mean, noise_mean, noise_std, snr; /* V_A.py:356 (float64 accumulation)  */
+    int32_t ci_n;                     /* defect voxels given to CI                         */
+    int32_t ci_t95;                   /* shell ordinal of sort(CV)[int(.95*D)], -1 if D==0 */
+    int32_t ci_error;                 /* 1 = a voxel exhausted the table (VB_ERR_CI_RMAX)  */
+    int32_t reserved;
+} vb_subject_stats;
+
+/* Output (and in/out) arrays of the pipeline; NULL = not wanted (where optional). */
+typedef struct vb_buffers {
+    const float* image;       /* in   HPvent.astype(float32)                               */
+    const uint8_t* mask;      /* in   mask.astype(float32) -> uint8 (V_A.py:323,327)       */
+    float* n4;                /* out  N4HPvent; INPUT when VB_DO_N4 is off and VDP is on    */
+    float* logbias;           /* out  optional: log bias field (every voxel)               */
+    uint8_t* defect;          /* out  defectArray as 0/1                                   */
+    uint8_t* defect_lb;       /* out  defectArrayLB as 0..6                                */
+    uint8_t* defect_border;   /* out  defectBorder as 0/1                                  */
+    uint8_t* mask_border;     /* out  optional: mask_border as 0/1                         */
+    uint16_t* ci_shell;       /* out  shell ordinal t per voxel, VB_CI_OFF off-defect;
+                                      CIarray = radii[t] * min(vox) (vb_ci_table_radii)    */
+    vb_subject_stats* stats;  /* out  [n]                                                  */
+} vb_buffers;
+
+int vb_version(void);
+const char* vb_last_error(void);
+int vb_device_count(void);
+int vb_create(int device, vb_ctx** ctx);
+void vb_destroy(vb_ctx* ctx);
+/* kernels launched by this context so far (bench.py's gpu_launches) */
+uint64_t vb_launch_count(const vb_ctx* ctx);
+void vb_n4_default_params(vb_n4_params* p);
+
+/* Sphere-growing table (CI.getSpherePix, CI.py:33-63): `table` is the reference's N x 4
+ * float64 [radius, dx, dy, dz] array (host).  Prepares, for one volume shape, the
+ * de-duplicated flat offsets and the shell boundaries (CI.py:79-85, :93) on the device. */
+int vb_ci_table_create(vb_ctx* ctx, const double* table, int64_t nrows, int32_t n0, int32_t n1,
+                       int32_t n2, int32_t* handle);
+/* radii[t] = table[ii_t - 1][0] for every shell boundary t (CI.py:105); returns the count */
+int vb_ci_table_radii(vb_ctx* ctx, int32_t handle, double* radii, int32_t capacity, int32_t* n_bounds);
+
+/* ---- stage entry points, device buffers ------------------------------------------------ */
+/* Vent_Analysis.calculate_SNR (V_A.py:337-357): fills stats[i].snr & co. */
+int vb_snr_batch_dev(vb_ctx* ctx, const float* image, const uint8_t* mask, int32_t n,
+                     const int32_t* shapes, int32_t fov_buffer, vb_subject_stats* stats, void* stream);
+/* Vent_Analysis.N4_bias_correction (V_A.py:316-334) */
+int vb_n4_batch_dev(vb_ctx* ctx, const float* image, const uint8_t* mask, int32_t n,
+                    const int32_t* shapes, const vb_n4_params* params, float* n4, float* logbias,
+                    vb_subject_stats* stats, void* stream);
+/* Vent_Analysis.calculate_VDP after N4 (V_A.py:244-257) */
+int vb_vdp_batch_dev(vb_ctx* ctx, const float* n4, const uint8_t* mask, int32_t n,
+                     const int32_t* shapes, float thresh, uint8_t* defect, uint8_t* defect_lb,
+                     uint8_t* defect_border, vb_subject_stats* stats, void* stream);
+/* Vent_Analysis.calculateBorder (V_A.py:225-231) on any 0/1 volume */
+int vb_border_batch_dev(vb_ctx* ctx, const uint8_t* a, int32_t n, const int32_t* shapes,
+                        uint8_t* border, void* stream);
+/* CI.calculate_CI (CI.py:107-145) + the percentile of V_A.py:268-270 */
+int vb_ci_batch_dev(vb_ctx* ctx, const uint8_t* defect, int32_t n, const int32_t* shapes,
+                    const int32_t* table_handles, uint16_t* ci_shell, vb_subject_stats* stats,
+                    void* stream);
+
+/* ---- whole path --------------------------------------------------------------------------- */
+int vb_pipeline_batch_dev(vb_ctx* ctx, int32_t n, const int32_t* shapes, const int32_t* table_handles,
+                          const vb_n4_params* params, float thresh, uint32_t flags,
+                          const vb_buffers* dev, void* stream);
+/* Same with HOST buffers: H2D of image+mask, the kernels, D2H of every non-NULL output,
+ * then a stream synchronise.  Returns VB_ERR_CI_RMAX if any subject hit it. */
+int vb_pipeline_batch_host(vb_ctx* ctx, int32_t n, const int32_t* shapes, const int32_t* table_handles,
+                           const vb_n4_params* params, float thresh, uint32_t flags,
+                           const vb_buffers* host);
+
+/* debug: last Parzen histogram / E(u|v) table / lattice of subject `i` of the most recent
+ * vb_n4_batch_* call (needs ctx debug capture; see vb_set_debug). */
+int vb_set_debug(vb_ctx* ctx, int32_t on);
+int vb_n4_debug_fetch(vb_ctx* ctx, int32_t subject, float* hist, float* emap, float* lattice,
+                      int32_t lattice_capacity, int32_t* ncp, float* conv_trace, int32_t trace_capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,280 @@
+"""ctypes binding of ``libventb200.so`` (C ABI in ``include/ventb200.h``).
+
+The product only ever opens the CUDA library built by ``vent_analysis_b200/build.py``.
+There is NO CPU fallback: if the library is missing, or no CUDA device is present,
+:func:`load` / :class:`Context` raise ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libventb200.so")
+
+VB_OK, VB_ERR_CUDA, VB_ERR_ARG, VB_ERR_UNSUPPORTED, VB_ERR_CI_RMAX = 0, 1, 2, 3, 4
+DO_SNR, DO_N4, DO_VDP, DO_CI, DO_MASK_BORDER = 1, 2, 4, 8, 16
+MAX_LEVELS = 8
+CI_OFF = 0xFFFF
+
+
+class N4Params(C.Structure):
+    """``vb_n4_params`` -- SimpleITK ``N4BiasFieldCorrectionImageFilter`` settings."""
+    _fields_ = [("n_levels", C.c_int32), ("max_iter", C.c_int32 * MAX_LEVELS), ("conv_threshold", C.c_float),
+                ("fwhm", C.c_float), ("wiener_noise", C.c_float), ("n_bins", C.c_int32), ("ncp", C.c_int32 * 3),
+                ("mask_label", C.c_int32), ("max_total_iters", C.c_int32)]
+
+
+class SubjectStats(C.Structure):
+    """``vb_subject_stats``"""
+    _fields_ = [("n4_iters", C.c_int32 * MAX_LEVELS), ("n4_last_conv", C.c_float), ("n4_n_mask", C.c_int32),
+                ("n_mask", C.c_int32), ("mean", C.c_float), ("p99", C.c_float), ("n_defect", C.c_int32),
+                ("n_lb12", C.c_int32), ("n_noise", C.c_int32), ("signal_mean", C.c_double),
+                ("noise_mean", C.c_double), ("noise_std", C.c_double), ("snr", C.c_double), ("ci_n", C.c_int32),
+                ("ci_t95", C.c_int32), ("ci_error", C.c_int32), ("reserved", C.c_int32)]
+
+
+STATS_DTYPE = np.dtype([("n4_iters", np.int32, (MAX_LEVELS,)), ("n4_last_conv", np.float32), ("n4_n_mask", np.int32),
+                        ("n_mask", np.int32), ("mean", np.float32), ("p99", np.float32), ("n_defect", np.int32),
+                        ("n_lb12", np.int32), ("n_noise", np.int32), ("signal_mean", np.float64),
+                        ("noise_mean", np.float64), ("noise_std", np.float64), ("snr", np.float64),
+                        ("ci_n", np.int32), ("ci_t95", np.int32), ("ci_error", np.int32), ("reserved", np.int32)],
+                       align=True)
+assert STATS_DTYPE.itemsize == C.sizeof(SubjectStats), (STATS_DTYPE.itemsize, C.sizeof(SubjectStats))
+
+
+class Buffers(C.Structure):
+    """``vb_buffers``"""
+    _fields_ = [("image", C.c_void_p), ("mask", C.c_void_p), ("n4", C.c_void_p), ("logbias", C.c_void_p),
+                ("defect", C.c_void_p), ("defect_lb", C.c_void_p), ("defect_border", C.c_void_p),
+                ("mask_border", C.c_void_p), ("ci_shell", C.c_void_p), ("stats", C.c_void_p)]
+
+
+class VbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ventb200 error {code}: {msg}")
+        self.code = code
+
+
+EXPORTS = ["vb_version", "vb_last_error", "vb_device_count", "vb_create", "vb_destroy", "vb_launch_count",
+           "vb_n4_default_params", "vb_ci_table_create", "vb_ci_table_radii", "vb_snr_batch_dev", "vb_n4_batch_dev",
+           "vb_vdp_batch_dev", "vb_border_batch_dev", "vb_ci_batch_dev", "vb_pipeline_batch_dev",
+           "vb_pipeline_batch_host", "vb_set_debug", "vb_n4_debug_fetch"]
+
+
+def bind(path):
+    """Open a library exporting the ventb200 C ABI and declare its prototypes."""
+    lib = C.CDLL(path)
+    vp, i32, i64, u32, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float
+    lib.vb_version.restype = C.c_int
+    lib.vb_last_error.restype = C.c_char_p
+    lib.vb_device_count.restype = C.c_int
+    lib.vb_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.vb_destroy.argtypes = [vp]
+    lib.vb_destroy.restype = None
+    lib.vb_launch_count.argtypes = [vp]
+    lib.vb_launch_count.restype = C.c_uint64
+    lib.vb_n4_default_params.argtypes = [C.POINTER(N4Params)]
+    lib.vb_n4_default_params.restype = None
+    lib.vb_ci_table_create.argtypes = [vp, vp, i64, i32, i32, i32, C.POINTER(i32)]
+    lib.vb_ci_table_radii.argtypes = [vp, i32, vp, i32, C.POINTER(i32)]
+    lib.vb_snr_batch_dev.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp]
+    lib.vb_n4_batch_dev.argtypes = [vp, vp, vp, i32, vp, C.POINTER(N4Params), vp, vp, vp, vp]
+    lib.vb_vdp_batch_dev.argtypes = [vp, vp, vp, i32, vp, f32, vp, vp, vp, vp, vp]
+    lib.vb_border_batch_dev.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.vb_ci_batch_dev.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.vb_pipeline_batch_dev.argtypes = [vp, i32, vp, vp, C.POINTER(N4Params), f32, u32, C.POINTER(Buffers), vp]
+    lib.vb_pipeline_batch_host.argtypes = [vp, i32, vp, vp, C.POINTER(N4Params), f32, u32, C.POINTER(Buffers)]
+    lib.vb_set_debug.argtypes = [vp, i32]
+    lib.vb_n4_debug_fetch.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i32]
+    return lib
+
+
+_LIB = None
+
+
+def load():
+    """The CUDA library (and only that).  Raises if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m vent_analysis_b200.build` "
+                "(nvcc, sm_100a).  vent_analysis_b200 has no CPU fallback.")
+        _LIB = bind(LIB_PATH)
+    return _LIB
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One ``vb_ctx`` (one CUDA device).  ``lib`` is only overridden by the test-suite's
+    emulation harness (tests/emu)."""
+
+    def __init__(self, device=0, lib=None):
+        self.lib = lib if lib is not None else load()
+        h = C.c_void_p()
+        rc = self.lib.vb_create(int(device), C.byref(h))
+        if rc != VB_OK:
+            raise VbError(rc, self.lib.vb_last_error().decode())
+        self.h = h
+        self.device = int(device)
+        self._tables = {}
+        self._radii = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != VB_OK:
+            raise VbError(rc, self.lib.vb_last_error().decode())
+
+    def launch_count(self):
+        return int(self.lib.vb_launch_count(self.h))
+
+    def default_n4_params(self, **kw):
+        p = N4Params()
+        self.lib.vb_n4_default_params(C.byref(p))
+        if "max_iter" in kw:
+            mi = list(kw.pop("max_iter"))
+            p.n_levels = len(mi)
+            for i, v in enumerate(mi):
+                p.max_iter[i] = int(v)
+        if "ncp" in kw:
+            for i, v in enumerate(kw.pop("ncp")):
+                p.ncp[i] = int(v)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    # -- CI tables ---------------------------------------------------------------------------
+    def ci_table(self, table, shape, key=None):
+        """Handle of the sphere table prepared for volume ``shape`` (memoised by ``key``)."""
+        shape = tuple(int(s) for s in shape)
+        k = (key if key is not None else id(table), shape)
+        if k not in self._tables:
+            t = np.ascontiguousarray(table, dtype=np.float64)
+            h = C.c_int32(-1)
+            self.check(self.lib.vb_ci_table_create(self.h, _ptr(t), t.shape[0], shape[0], shape[1], shape[2],
+                                                   C.byref(h)))
+            nb = C.c_int32(0)
+            self.check(self.lib.vb_ci_table_radii(self.h, h.value, None, 0, C.byref(nb)))
+            radii = np.zeros(nb.value, dtype=np.float64)
+            self.check(self.lib.vb_ci_table_radii(self.h, h.value, _ptr(radii), nb.value, C.byref(nb)))
+            self._tables[k] = h.value
+            self._radii[h.value] = radii
+        return self._tables[k]
+
+    def ci_radii(self, handle):
+        return self._radii[handle]
+
+    # -- whole path, host buffers ----------------------------------------------------------------
+    def pipeline_host(self, shapes, flags, image=None, mask=None, n4=None, handles=None, params=None, thresh=0.6,
+                      want_logbias=False, want_mask_border=False):
+        """Run the selected stages on a batch given as HOST arrays (concatenated, C order).
+        Returns a dict of numpy outputs (compact dtypes) and the per-subject stats record array."""
+        shapes = np.ascontiguousarray(shapes, dtype=np.int32).reshape(-1, 3)
+        n = shapes.shape[0]
+        V = int(np.prod(shapes.astype(np.int64), axis=1).sum())
+        mask = np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1)
+        assert mask.size == V
+        out = {}
+        b = Buffers()
+        b.mask = mask.ctypes.data
+        if image is not None:
+            image = np.ascontiguousarray(image, dtype=np.float32).reshape(-1)
+            assert image.size == V
+            b.image = image.ctypes.data
+        if flags & (DO_N4 | DO_VDP):
+            if flags & DO_N4:
+                out["n4"] = np.empty(V, dtype=np.float32)
+            else:
+                out["n4"] = np.ascontiguousarray(n4, dtype=np.float32).reshape(-1)
+            b.n4 = out["n4"].ctypes.data
+        if want_logbias and flags & DO_N4:
+            out["logbias"] = np.empty(V, dtype=np.float32)
+            b.logbias = out["logbias"].ctypes.data
+        if flags & DO_VDP:
+            for k in ("defect", "defect_lb", "defect_border"):
+                out[k] = np.empty(V, dtype=np.uint8)
+                setattr(b, k, out[k].ctypes.data)
+        elif flags & DO_CI:
+            raise ValueError("CI without VDP: use ci_host()")
+        if want_mask_border or flags & DO_MASK_BORDER:
+            flags |= DO_MASK_BORDER
+            out["mask_border"] = np.empty(V, dtype=np.uint8)
+            b.mask_border = out["mask_border"].ctypes.data
+        if flags & DO_CI:
+            out["ci_shell"] = np.empty(V, dtype=np.uint16)
+            b.ci_shell = out["ci_shell"].ctypes.data
+        stats = np.zeros(n, dtype=STATS_DTYPE)
+        b.stats = stats.ctypes.data
+        hd = None if handles is None else np.ascontiguousarray(handles, dtype=np.int32)
+        p = params if params is not None else self.default_n4_params()
+        rc = self.lib.vb_pipeline_batch_host(self.h, n, _ptr(shapes), _ptr(hd), C.byref(p), float(thresh),
+                                             int(flags), C.byref(b))
+        out["stats"] = stats
+        out["rc"] = rc
+        if rc not in (VB_OK, VB_ERR_CI_RMAX):
+            self.check(rc)
+        return out
+
+    def ci_host(self, defect, shapes, handles):
+        """CI stage alone on host arrays: defect uint8 0/1 -> (ci_shell uint16, stats, rc)."""
+        shapes = np.ascontiguousarray(shapes, dtype=np.int32).reshape(-1, 3)
+        n = shapes.shape[0]
+        V = int(np.prod(shapes.astype(np.int64), axis=1).sum())
+        defect = np.ascontiguousarray(defect, dtype=np.uint8).reshape(-1)
+        assert defect.size == V
+        b = Buffers()
+        dummy_mask = defect
+        b.mask = dummy_mask.ctypes.data
+        b.defect = defect.ctypes.data
+        shell = np.empty(V, dtype=np.uint16)
+        b.ci_shell = shell.ctypes.data
+        stats = np.zeros(n, dtype=STATS_DTYPE)
+        b.stats = stats.ctypes.data
+        hd = np.ascontiguousarray(handles, dtype=np.int32)
+        p = self.default_n4_params()
+        rc = self.lib.vb_pipeline_batch_host(self.h, n, _ptr(shapes), _ptr(hd), C.byref(p), 0.6, DO_CI, C.byref(b))
+        if rc not in (VB_OK, VB_ERR_CI_RMAX):
+            self.check(rc)
+        return shell, stats, rc
+
+    def n4_debug(self, subject, nbins, lattice_capacity, trace_capacity=200):
+        self.check(self.lib.vb_set_debug(self.h, 1))
+        hist = np.zeros(nbins, dtype=np.float32)
+        emap = np.zeros(nbins, dtype=np.float32)
+        lat = np.zeros(lattice_capacity, dtype=np.float32)
+        ncp = np.zeros(3, dtype=np.int32)
+        trace = np.zeros(trace_capacity, dtype=np.float32)
+        self.check(self.lib.vb_n4_debug_fetch(self.h, int(subject), _ptr(hist), _ptr(emap), _ptr(lat),
+                                              lattice_capacity, _ptr(ncp), _ptr(trace), trace_capacity))
+        L = int(np.prod(ncp))
+        return dict(hist=hist, emap=emap, lattice=lat[:L].reshape(tuple(int(x) for x in ncp)).copy(), ncp=ncp,
+                    conv=trace[trace >= 0])
+
+    def set_debug(self, on=True):
+        self.check(self.lib.vb_set_debug(self.h, 1 if on else 0))
+
+
+_CTX = {}
+
+
+def context(device=0):
+    """Process-wide context per device (created on first use)."""
+    if device not in _CTX:
+        _CTX[device] = Context(device)
+    return _CTX[device]

@@ -1,0 +1,284 @@
+// Device-code portability layer.
+//
+// Product build (nvcc, sm_100a): everything maps 1:1 onto CUDA.
+//
+// Emulation build (g++ -DVB_EMULATE, TEST INFRASTRUCTURE ONLY -- see tests/emu/): the same
+// kernel sources are compiled for the host and every CUDA thread of a block becomes one OS
+// thread, __syncthreads() a std::barrier, warp collectives a 32-thread barrier plus a scratch
+// row.  Blocks run one after another.  It exists so that the kernel *logic* can be checked
+// against the oracle in the GPU-less build container (pytest -m "not gpu"); it is never
+// loaded by the product (vent_analysis_b200/_lib.py only opens the CUDA library and raises
+// if it is missing).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if !defined(VB_EMULATE)
+// ------------------------------------------------------------------------------------ CUDA
+#include <cuda_runtime.h>
+#define VB_SHARED __shared__
+#define VB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define VB_KERNEL __global__
+#define VB_DEV __device__ __forceinline__
+#define VB_DEV_MEMBER __device__ __forceinline__
+#define VB_DEV_NOINLINE __device__ __noinline__
+#define VB_RESTRICT __restrict__
+#define VB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define VB_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+VB_DEV void vb_sincospi(double x, double* s, double* c) { sincospi(x, s, c); }
+VB_DEV float vb_ldg(const float* p) { return __ldg(p); }
+VB_DEV uint32_t vb_ldg(const uint32_t* p) { return __ldg(p); }
+VB_DEV uint8_t vb_ldg(const uint8_t* p) { return __ldg(p); }
+VB_DEV int vb_ldg(const int* p) { return __ldg(p); }
+VB_DEV int2 vb_ldg(const int2* p) { return __ldg(p); }
+VB_DEV float4 vb_ldg(const float4* p) { return __ldg(p); }
+// streaming (read-once) loads: keep them out of L1
+VB_DEV float vb_ld_stream(const float* p) { return __ldcs(p); }
+VB_DEV uint8_t vb_ld_stream(const uint8_t* p) { return __ldcs(p); }
+VB_DEV void vb_st_stream(float* p, float v) { __stcs(p, v); }
+#else
+// ------------------------------------------------------------------------------- emulation
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <barrier>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define VB_SHARED static
+#define VB_DYN_SMEM(name) unsigned char* name = vbemu::g_block->dyn_smem
+#define VB_KERNEL static
+#define VB_DEV static inline
+#define VB_DEV_MEMBER inline
+#define VB_DEV_NOINLINE static
+#define VB_RESTRICT __restrict__
+#define VB_LAUNCH_BOUNDS(t, b)
+#define __forceinline__ inline
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct double2 { double x, y; };
+struct int2 { int x, y; };
+struct uint2 { unsigned x, y; };
+static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+static inline double2 make_double2(double a, double b) { return double2{a, b}; }
+static inline int2 make_int2(int a, int b) { return int2{a, b}; }
+
+namespace vbemu {
+struct Idx { unsigned x, y, z; };
+struct Warp {
+    std::barrier<> bar;
+    uint64_t scratch[32];
+    explicit Warp(int n) : bar(n) {}
+};
+struct Block {
+    std::barrier<> bar;
+    std::vector<std::unique_ptr<Warp>> warps;
+    unsigned char* dyn_smem;
+    Block(int nthreads, size_t smem) : bar(nthreads) {
+        for (int w = 0; w < (nthreads + 31) / 32; ++w)
+            warps.emplace_back(new Warp(std::min(32, nthreads - 32 * w)));
+        dyn_smem = (unsigned char*)aligned_alloc(128, (smem + 127) / 128 * 128 + 128);
+        memset(dyn_smem, 0xCD, smem);   // poison: smem is NOT zero-initialised on a GPU
+    }
+    ~Block() { free(dyn_smem); }
+};
+inline thread_local Idx t_threadIdx, t_blockIdx;
+inline Idx g_blockDim, g_gridDim;
+inline Block* g_block = nullptr;
+inline uint64_t g_launches = 0;
+
+inline Warp& warp() { return *g_block->warps[t_threadIdx.x >> 5]; }
+inline int lane() { return (int)(t_threadIdx.x & 31); }
+
+template <class T> inline uint64_t pack(T v) { uint64_t u = 0; memcpy(&u, &v, sizeof(T)); return u; }
+template <class T> inline T unpack(uint64_t u) { T v; memcpy(&v, &u, sizeof(T)); return v; }
+
+// every lane publishes a value, then reads whatever it needs
+template <class T, class F> inline auto collective(T v, F reader) {
+    Warp& W = warp();
+    W.scratch[lane()] = pack(v);
+    W.bar.arrive_and_wait();
+    auto r = reader(W.scratch);
+    W.bar.arrive_and_wait();
+    return r;
+}
+
+template <class Body> void launch(dim3 grid, dim3 block, size_t smem, Body body) {
+    ++g_launches;
+    g_gridDim = Idx{grid.x, grid.y, grid.z};
+    g_blockDim = Idx{block.x, block.y, block.z};
+    const int nthreads = (int)(block.x * block.y * block.z);
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                Block blk(nthreads, smem);
+                g_block = &blk;
+                std::vector<std::thread> th;
+                th.reserve(nthreads);
+                for (int t = 0; t < nthreads; ++t)
+                    th.emplace_back([&, t] {
+                        t_threadIdx = Idx{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y,
+                                          (unsigned)t / (block.x * block.y)};
+                        t_blockIdx = Idx{bx, by, bz};
+                        body();
+                    });
+                for (auto& x : th) x.join();
+                g_block = nullptr;
+            }
+}
+}  // namespace vbemu
+
+#define threadIdx vbemu::t_threadIdx
+#define blockIdx vbemu::t_blockIdx
+#define blockDim vbemu::g_blockDim
+#define gridDim vbemu::g_gridDim
+#define VB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    vbemu::launch((grid), (block), (smem), [=] { kernel(__VA_ARGS__); })
+
+static inline void __syncthreads() { vbemu::g_block->bar.arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) {
+    vbemu::warp().bar.arrive_and_wait();
+}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    return vbemu::collective<uint32_t>(pred ? 1u : 0u, [](uint64_t* s) {
+        unsigned r = 0;
+        const int n = std::min(32u, blockDim.x - (threadIdx.x & ~31u));
+        for (int l = 0; l < n; ++l) if (s[l]) r |= 1u << l;
+        return r;
+    });
+}
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+static inline int __all_sync(unsigned m, int pred) {
+    const int n = std::min(32u, blockDim.x - (threadIdx.x & ~31u));
+    return __ballot_sync(m, pred) == (n == 32 ? 0xffffffffu : ((1u << n) - 1));
+}
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
+    return vbemu::collective<T>(v, [src](uint64_t* s) { return vbemu::unpack<T>(s[src & 31]); });
+}
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
+    const int me = vbemu::lane();
+    return vbemu::collective<T>(v, [me, m](uint64_t* s) { return vbemu::unpack<T>(s[(me ^ m) & 31]); });
+}
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) {
+    const int me = vbemu::lane();
+    return vbemu::collective<T>(v, [me, d](uint64_t* s) { return vbemu::unpack<T>(s[me + d < 32 ? me + d : me]); });
+}
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) {
+    const int me = vbemu::lane();
+    return vbemu::collective<T>(v, [me, d](uint64_t* s) { return vbemu::unpack<T>(s[me - d >= 0 ? me - d : me]); });
+}
+static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+    return vbemu::collective<uint32_t>(v, [](uint64_t* s) {
+        unsigned r = 0;
+        const int n = std::min(32u, blockDim.x - (threadIdx.x & ~31u));
+        for (int l = 0; l < n; ++l) r |= (unsigned)s[l];
+        return r;
+    });
+}
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+    return vbemu::collective<uint32_t>(v, [](uint64_t* s) {
+        unsigned r = 0;
+        const int n = std::min(32u, blockDim.x - (threadIdx.x & ~31u));
+        for (int l = 0; l < n; ++l) r += (unsigned)s[l];
+        return r;
+    });
+}
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+    return vbemu::collective<uint32_t>(v, [](uint64_t* s) {
+        unsigned r = 0xffffffffu;
+        const int n = std::min(32u, blockDim.x - (threadIdx.x & ~31u));
+        for (int l = 0; l < n; ++l) r = std::min(r, (unsigned)s[l]);
+        return r;
+    });
+}
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+    return vbemu::collective<uint32_t>(v, [](uint64_t* s) {
+        unsigned r = 0;
+        const int n = std::min(32u, blockDim.x - (threadIdx.x & ~31u));
+        for (int l = 0; l < n; ++l) r = std::max(r, (unsigned)s[l]);
+        return r;
+    });
+}
+
+// atomics
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+    return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
+}
+static inline float atomicAdd(float* p, float v) {
+    uint32_t* u = (uint32_t*)p;
+    uint32_t old = __atomic_load_n(u, __ATOMIC_SEQ_CST), nw;
+    do {
+        float f; memcpy(&f, &old, 4); f += v; memcpy(&nw, &f, 4);
+    } while (!__atomic_compare_exchange_n(u, &old, nw, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+    float r; memcpy(&r, &old, 4); return r;
+}
+static inline double atomicAdd(double* p, double v) {
+    uint64_t* u = (uint64_t*)p;
+    uint64_t old = __atomic_load_n(u, __ATOMIC_SEQ_CST), nw;
+    do {
+        double f; memcpy(&f, &old, 8); f += v; memcpy(&nw, &f, 8);
+    } while (!__atomic_compare_exchange_n(u, &old, nw, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+    double r; memcpy(&r, &old, 8); return r;
+}
+static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicMax(int* p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+static inline int atomicMin(int* p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+static inline unsigned atomicMax(unsigned* p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+static inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+
+// bit / math intrinsics
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline unsigned __brev(unsigned v) {
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i);
+    return r;
+}
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
+static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline void vb_sincospi(double x, double* s, double* c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }
+template <class T> static inline T vb_ldg(const T* p) { return *p; }
+template <class T> static inline T vb_ld_stream(const T* p) { return *p; }
+static inline void vb_st_stream(float* p, float v) { *p = v; }
+using std::max;
+using std::min;
+#endif

@@ -1,0 +1,68 @@
+// Host-side runtime shim: the handful of CUDA runtime calls the library makes, with a
+// host-memory stand-in for the emulation build (tests/emu, TEST INFRASTRUCTURE ONLY).
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include "vb_platform.h"
+
+namespace vbrt {
+
+inline thread_local std::string g_err;
+inline void set_error(const std::string& s) { g_err = s; }
+
+#if !defined(VB_EMULATE)
+typedef cudaStream_t stream_t;
+
+inline bool ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return false;
+}
+inline bool dev_malloc(void** p, size_t n) { return ok(cudaMalloc(p, n ? n : 1), "cudaMalloc"); }
+inline void dev_free(void* p) { if (p) cudaFree(p); }
+inline bool host_malloc(void** p, size_t n) { return ok(cudaMallocHost(p, n ? n : 1), "cudaMallocHost"); }
+inline void host_free(void* p) { if (p) cudaFreeHost(p); }
+inline bool h2d(void* d, const void* h, size_t n, stream_t s) {
+    return ok(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync(H2D)");
+}
+inline bool d2h(void* h, const void* d, size_t n, stream_t s) {
+    return ok(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(D2H)");
+}
+inline bool dev_memset(void* d, int v, size_t n, stream_t s) { return ok(cudaMemsetAsync(d, v, n, s), "cudaMemsetAsync"); }
+inline bool stream_sync(stream_t s) { return ok(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
+inline bool device_sync() { return ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize"); }
+inline bool last_launch_ok(const char* what) { return ok(cudaGetLastError(), what); }
+inline bool set_device(int d) { return ok(cudaSetDevice(d), "cudaSetDevice"); }
+inline int device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+inline int sm_count(int dev) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
+inline int max_smem_optin(int dev) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); return n; }
+template <class K> inline bool allow_smem(K kernel, int bytes) {
+    return ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute(smem)");
+}
+inline bool stream_create(stream_t* s) { return ok(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking), "cudaStreamCreate"); }
+inline void stream_destroy(stream_t s) { if (s) cudaStreamDestroy(s); }
+#else
+typedef void* stream_t;
+inline bool dev_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); memset(*p, 0xAB, n); return *p != nullptr; }
+inline void dev_free(void* p) { free(p); }
+inline bool host_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p != nullptr; }
+inline void host_free(void* p) { free(p); }
+inline bool h2d(void* d, const void* h, size_t n, stream_t) { memcpy(d, h, n); return true; }
+inline bool d2h(void* h, const void* d, size_t n, stream_t) { memcpy(h, d, n); return true; }
+inline bool dev_memset(void* d, int v, size_t n, stream_t) { memset(d, v, n); return true; }
+inline bool stream_sync(stream_t) { return true; }
+inline bool device_sync() { return true; }
+inline bool last_launch_ok(const char*) { return true; }
+inline bool set_device(int) { return true; }
+inline int device_count() { return 1; }
+inline int sm_count(int) { const char* e = getenv("VB_EMU_SMS"); return e ? atoi(e) : 2; }
+inline int max_smem_optin(int) { return 232448; }
+template <class K> inline bool allow_smem(K, int) { return true; }
+inline bool stream_create(stream_t* s) { *s = nullptr; return true; }
+inline void stream_destroy(stream_t) {}
+#endif
+
+}  // namespace vbrt

@@ -1,0 +1,236 @@
+// SNR, VDP (mean-anchored threshold + 3x3 median), linear binning and border maps.
+//
+// Replaces, with integer-exact outputs:
+//   Vent_Analysis.calculate_SNR      Vent_Analysis.py:337-357
+//   Vent_Analysis.calculate_VDP body Vent_Analysis.py:244-257
+//   Vent_Analysis.calculateBorder    Vent_Analysis.py:225-231
+// (CPU restatement: oracle/vdp_oracle.py.)
+#pragma once
+#include <float.h>
+#include "vb_common.cuh"
+
+#define VB_VDP_THREADS 256
+#define VB_SNR_MAX_AXIS 8192   // n0 + n1 + n2 must not exceed this (projection flags in smem)
+
+// ---------------------------------------------------------------------------------------------
+// calculate_SNR: one CTA per subject.  Signal = mask > 0.  Noise = voxels outside
+// {rows with mask, plus row 0} x {cols [first masked col > 0, last masked col)} x
+// {slices with mask, plus slice 0}, minus the first / last `fov` rows.  Population std.
+VB_KERNEL void VB_LAUNCH_BOUNDS(VB_VDP_THREADS, 1)
+snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, int n,
+           int fov, vb_subject_stats* stats) {
+    VB_SHARED int flags[VB_SNR_MAX_AXIS];
+    VB_SHARED double red[64];
+    VB_SHARED int s_cmin, s_cmax;
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    for (int si = (int)blockIdx.x; si < n; si += (int)gridDim.x) {
+        const VbSubject S = subj[si];
+        const float* img = image + S.off;
+        const uint8_t* msk = mask + S.off;
+        const int n0 = S.n0, n1 = S.n1, n2 = S.n2, ncols = n1 * n2;
+        int* rowf = flags; int* colf = flags + n0; int* slcf = flags + n0 + n1;
+        __syncthreads();
+        for (int i = tid; i < n0 + n1 + n2; i += nt) flags[i] = 0;
+        __syncthreads();
+        for (int v = tid; v < S.V; v += nt)
+            if (msk[v]) {
+                const int i = v / ncols, rem = v - i * ncols, j = rem / n2, k = rem - j * n2;
+                rowf[i] = 1; colf[j] = 1; slcf[k] = 1;
+            }
+        __syncthreads();
+        if (tid == 0) {
+            int cmin = -1, cmax = 0;
+            for (int j = 1; j < n1; ++j) if (colf[j]) { if (cmin < 0) cmin = j; }
+            for (int j = 0; j < n1; ++j) if (colf[j]) cmax = j;
+            s_cmin = cmin; s_cmax = cmax;          // arange(cmin, cmax): cmax excluded
+            rowf[0] = 1; slcf[0] = 1;              // "(…>0)*range" keeps index 0
+        }
+        __syncthreads();
+        const int cmin = s_cmin, cmax = s_cmax;
+        const int lo = fov < n0 ? fov : n0;        // noisemask[:fov] = 0
+        int hi = n0 - fov;                         // noisemask[n0-fov:] = 0 (python slice rules)
+        if (hi < 0) { hi += n0; if (hi < 0) hi = 0; }
+        double ssum = 0.0, nsum = 0.0;
+        long long scnt = 0, ncnt = 0;
+        for (int v = tid; v < S.V; v += nt) {
+            const int i = v / ncols, rem = v - i * ncols, j = rem / n2, k = rem - j * n2;
+            const float x = img[v];
+            if (msk[v]) { ssum += (double)x; ++scnt; }
+            const bool inbox = rowf[i] && (j >= cmin && j < cmax && cmin >= 0) && slcf[k];
+            if (!inbox && i >= lo && i < hi) { nsum += (double)x; ++ncnt; }
+        }
+        ssum = vb_block_reduce(ssum, VbAddD(), 0.0, red);
+        nsum = vb_block_reduce(nsum, VbAddD(), 0.0, red);
+        scnt = vb_block_reduce(scnt, VbAddLL(), 0LL, (long long*)red);
+        ncnt = vb_block_reduce(ncnt, VbAddLL(), 0LL, (long long*)red);
+        const double nmean = nsum / (double)ncnt;
+        double ss = 0.0;
+        for (int v = tid; v < S.V; v += nt) {
+            const int i = v / ncols, rem = v - i * ncols, j = rem / n2, k = rem - j * n2;
+            const bool inbox = rowf[i] && (j >= cmin && j < cmax && cmin >= 0) && slcf[k];
+            if (!inbox && i >= lo && i < hi) { const double d = (double)img[v] - nmean; ss += d * d; }
+        }
+        ss = vb_block_reduce(ss, VbAddD(), 0.0, red);
+        if (tid == 0) {
+            vb_subject_stats* st = stats + si;
+            const double smean = ssum / (double)scnt, nstd = sqrt(ss / (double)ncnt);
+            st->signal_mean = smean; st->noise_mean = nmean; st->noise_std = nstd;
+            st->snr = (smean - nmean) / nstd;
+            st->n_noise = (cmin < 0) ? -1 : (int)ncnt;   // -1: reference raises (np.min of empty)
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// VDP statistics, one CTA per subject: M = #mask, mean (float32 of the float64 sum), and the
+// exact order statistic sorted(N4[mask>0])[int(M*.99)] by a 3-pass (11+11+10 bit) radix select
+// on the order-preserving key of the float bits.  Also zeroes the defect / LB counters.
+VB_DEV int vdp_find_bin(unsigned* hist, int nb, long long& k, int* s_bin, long long* s_k) {
+    // thread 0 scans (<= 2048 bins); result broadcast through shared memory
+    if (threadIdx.x == 0) {
+        long long cum = 0;
+        int b = 0;
+        for (; b < nb - 1; ++b) {
+            if (cum + (long long)hist[b] > k) break;
+            cum += hist[b];
+        }
+        *s_bin = b; *s_k = k - cum;
+    }
+    __syncthreads();
+    k = *s_k;
+    return *s_bin;
+}
+
+VB_KERNEL void VB_LAUNCH_BOUNDS(VB_VDP_THREADS, 1)
+vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, int n,
+                 vb_subject_stats* stats) {
+    VB_SHARED unsigned hist[2048];
+    VB_SHARED double red[64];
+    VB_SHARED int s_bin;
+    VB_SHARED long long s_k;
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    for (int si = (int)blockIdx.x; si < n; si += (int)gridDim.x) {
+        const VbSubject S = subj[si];
+        const float* x = n4 + S.off;
+        const uint8_t* msk = mask + S.off;
+        __syncthreads();
+        for (int i = tid; i < 2048; i += nt) hist[i] = 0;
+        __syncthreads();
+        double sum = 0.0;
+        long long cnt = 0;
+        for (int v = tid; v < S.V; v += nt)
+            if (msk[v]) {
+                const float f = x[v];
+                sum += (double)f; ++cnt;
+                atomicAdd(&hist[vb_float_key(f) >> 21], 1u);
+            }
+        sum = vb_block_reduce(sum, VbAddD(), 0.0, red);
+        cnt = vb_block_reduce(cnt, VbAddLL(), 0LL, (long long*)red);
+        float p99 = 0.0f;
+        if (cnt > 0) {
+            long long k = (long long)((double)cnt * .99);            // int(len(signal_list)*.99)
+            if (k >= cnt) k = cnt - 1;
+            const unsigned b1 = (unsigned)vdp_find_bin(hist, 2048, k, &s_bin, &s_k);
+            __syncthreads();
+            for (int i = tid; i < 2048; i += nt) hist[i] = 0;
+            __syncthreads();
+            for (int v = tid; v < S.V; v += nt)
+                if (msk[v]) {
+                    const unsigned key = vb_float_key(x[v]);
+                    if ((key >> 21) == b1) atomicAdd(&hist[(key >> 10) & 0x7FFu], 1u);
+                }
+            __syncthreads();
+            const unsigned b2 = (unsigned)vdp_find_bin(hist, 2048, k, &s_bin, &s_k);
+            __syncthreads();
+            for (int i = tid; i < 1024; i += nt) hist[i] = 0;
+            __syncthreads();
+            const unsigned pre = (b1 << 11) | b2;
+            for (int v = tid; v < S.V; v += nt)
+                if (msk[v]) {
+                    const unsigned key = vb_float_key(x[v]);
+                    if ((key >> 10) == pre) atomicAdd(&hist[key & 0x3FFu], 1u);
+                }
+            __syncthreads();
+            const unsigned b3 = (unsigned)vdp_find_bin(hist, 1024, k, &s_bin, &s_k);
+            p99 = vb_key_float((pre << 10) | b3);
+        }
+        if (tid == 0) {
+            vb_subject_stats* st = stats + si;
+            st->n_mask = (int)cnt;
+            st->mean = (cnt > 0) ? (float)(sum / (double)cnt) : 0.0f;
+            st->p99 = p99;
+            st->n_defect = 0;
+            st->n_lb12 = 0;
+        }
+    }
+}
+
+// d0 = (N4/mean < thresh) * mask  (float32 compare, V_A.py:246-249) and the linear-binning code
+// (V_A.py:255-256).  grid = (chunks, subjects).
+VB_KERNEL void vdp_threshold_kernel(const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask,
+                                    const VbSubject* subj, float thresh, uint8_t* d0, uint8_t* lb,
+                                    vb_subject_stats* stats) {
+    VB_SHARED int red[64];
+    const int si = (int)blockIdx.y;
+    const VbSubject S = subj[si];
+    const float mean = stats[si].mean, p99 = stats[si].p99;
+    int c12 = 0;
+    for (int v = (int)(blockIdx.x * blockDim.x + threadIdx.x); v < S.V; v += (int)(gridDim.x * blockDim.x)) {
+        const float x = n4[S.off + v];
+        const bool m = mask[S.off + v] != 0;
+        const float a = __fdiv_rn(x, mean);
+        d0[S.off + v] = (uint8_t)((a < thresh) && m);
+        const float b = __fdiv_rn(x, p99);
+        int code = (b <= 0.16f) ? 1 : (b <= 0.34f) ? 2 : (b <= 0.52f) ? 3 : (b <= 0.7f) ? 4 : (b <= 0.88f) ? 5
+                 : (b > 0.88f) ? 6 : 0;      // NaN compares false everywhere -> 0, as in numpy
+        code = m ? code : 0;
+        lb[S.off + v] = (uint8_t)code;
+        c12 += (code == 1 || code == 2);
+    }
+    c12 = vb_block_reduce(c12, VbAddI(), 0, red);
+    if (threadIdx.x == 0 && c12) atomicAdd(&stats[si].n_lb12, c12);
+}
+
+// defect = medfilt2d(d0[:, :, k]) per slice: zero padded 3x3 neighbour count >= 5 (V_A.py:249)
+VB_KERNEL void vdp_median_kernel(const uint8_t* VB_RESTRICT d0, const VbSubject* subj, uint8_t* defect,
+                                 vb_subject_stats* stats) {
+    VB_SHARED int red[64];
+    const int si = (int)blockIdx.y;
+    const VbSubject S = subj[si];
+    const int n0 = S.n0, n1 = S.n1, n2 = S.n2, ncols = n1 * n2;
+    const uint8_t* a = d0 + S.off;
+    int nd = 0;
+    for (int v = (int)(blockIdx.x * blockDim.x + threadIdx.x); v < S.V; v += (int)(gridDim.x * blockDim.x)) {
+        const int i = v / ncols, rem = v - i * ncols, j = rem / n2;
+        int cnt = 0;
+#pragma unroll
+        for (int di = -1; di <= 1; ++di)
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+                const int ii = i + di, jj = j + dj;
+                if (ii >= 0 && ii < n0 && jj >= 0 && jj < n1) cnt += a[v + di * ncols + dj * n2];
+            }
+        const int d = cnt >= 5;
+        defect[S.off + v] = (uint8_t)d;
+        nd += d;
+    }
+    nd = vb_block_reduce(nd, VbAddI(), 0, red);
+    if (threadIdx.x == 0 && nd) atomicAdd(&stats[si].n_defect, nd);
+}
+
+// calculateBorder: per slice, np.gradient != 0 along rows OR along columns (V_A.py:225-231)
+VB_KERNEL void border_kernel(const uint8_t* VB_RESTRICT a_, const VbSubject* subj, uint8_t* border) {
+    const int si = (int)blockIdx.y;
+    const VbSubject S = subj[si];
+    const int n0 = S.n0, n1 = S.n1, n2 = S.n2, ncols = n1 * n2;
+    const uint8_t* a = a_ + S.off;
+    for (int v = (int)(blockIdx.x * blockDim.x + threadIdx.x); v < S.V; v += (int)(gridDim.x * blockDim.x)) {
+        const int i = v / ncols, rem = v - i * ncols, j = rem / n2;
+        // interior: A[i+1] != A[i-1]; edges: one-sided difference
+        const int ilo = (i == 0) ? 0 : i - 1, ihi = (i == n0 - 1) ? n0 - 1 : i + 1;
+        const int jlo = (j == 0) ? 0 : j - 1, jhi = (j == n1 - 1) ? n1 - 1 : j + 1;
+        const bool gr = (a[v + (ihi - i) * ncols] != 0) != (a[v + (ilo - i) * ncols] != 0);
+        const bool gc = (a[v + (jhi - j) * n2] != 0) != (a[v + (jlo - j) * n2] != 0);
+        border[S.off + v] = (uint8_t)(gr || gc);
+    }
+}

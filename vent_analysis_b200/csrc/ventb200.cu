@@ -1,0 +1,550 @@
+// libventb200: C ABI (include/ventb200.h) + host orchestration of the sm_100a kernels.
+// Also compiled for the host with -DVB_EMULATE by tests/emu (test infrastructure only).
+#include <math.h>
+#include <algorithm>
+#include <unordered_set>
+#include <vector>
+
+#include "vb_rt.h"
+#include "vb_common.cuh"
+#include "n4_kernels.cuh"
+#include "vdp_kernels.cuh"
+#include "ci_kernels.cuh"
+
+namespace {
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct TableHost {
+    int n0, n1, n2;
+    int n_unique, n_bounds;
+    void* d_rows = nullptr;
+    void* d_ii = nullptr;
+    std::vector<double> radii;
+};
+
+}  // namespace
+
+struct vb_ctx {
+    int device = 0, sms = 0, max_smem = 0;
+    vbrt::stream_t stream = nullptr;
+    uint64_t launches = 0;
+    bool debug = false;
+    // subject descriptors
+    std::vector<VbSubject> last_subj;
+    std::vector<long long> last_wordoff;
+    Buf h_desc, d_subj, d_wordoff;
+    long long v_total = 0, words_total = 0;
+    // workspaces
+    Buf ws_logI, ws_colmask, ws_axis, ws_counter, ws_d0, ws_bits, ws_list, ws_count, dbg;
+    int dbg_stride = 0, dbg_nbins = 0, dbg_Lmax = 0, dbg_n = 0;
+    // CI tables
+    std::vector<TableHost> tables;
+    Buf d_tables;
+    bool tables_dirty = true;
+    // host-API mirrors
+    Buf m_image, m_mask, m_n4, m_logbias, m_defect, m_lb, m_dborder, m_mborder, m_shell, m_stats;
+};
+
+namespace {
+
+int fail(int code, const std::string& msg) {
+    vbrt::set_error(msg);
+    return code;
+}
+
+bool ensure(Buf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return true;
+    vbrt::dev_free(b.p);
+    b.p = nullptr; b.cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    if (!vbrt::dev_malloc(&b.p, want)) return false;
+    b.cap = want;
+    return true;
+}
+
+// Upload the batch description (cached: a repeated batch costs nothing).
+int prepare(vb_ctx* c, int n, const int32_t* shapes, const int32_t* handles, vbrt::stream_t s) {
+    if (n <= 0 || !shapes) return fail(VB_ERR_ARG, "empty batch");
+    if (n > 65535) return fail(VB_ERR_UNSUPPORTED, "more than 65535 subjects in one batch");
+    std::vector<VbSubject> subj((size_t)n);
+    std::vector<long long> woff((size_t)n + 1);
+    long long off = 0, w = 0;
+    for (int i = 0; i < n; ++i) {
+        const long long n0 = shapes[3 * i], n1 = shapes[3 * i + 1], n2 = shapes[3 * i + 2];
+        if (n0 < 1 || n1 < 1 || n2 < 1) return fail(VB_ERR_ARG, "non-positive shape");
+        const long long V = n0 * n1 * n2;
+        if (V > (1LL << 30)) return fail(VB_ERR_UNSUPPORTED, "volume larger than 2^30 voxels");
+        VbSubject S;
+        S.off = off; S.n0 = (int)n0; S.n1 = (int)n1; S.n2 = (int)n2; S.V = (int)V;
+        S.table = handles ? handles[i] : -1; S.pad = 0;
+        if (handles) {
+            if (S.table < 0 || S.table >= (int)c->tables.size()) return fail(VB_ERR_ARG, "bad CI table handle");
+            const TableHost& T = c->tables[(size_t)S.table];
+            if (T.n0 != S.n0 || T.n1 != S.n1 || T.n2 != S.n2)
+                return fail(VB_ERR_ARG, "CI table was prepared for a different volume shape");
+        }
+        subj[(size_t)i] = S;
+        woff[(size_t)i] = w;
+        off += V;
+        w += (V + 31) / 32 + 1;
+    }
+    woff[(size_t)n] = w;
+    const bool same = subj.size() == c->last_subj.size() &&
+                      memcmp(subj.data(), c->last_subj.data(), subj.size() * sizeof(VbSubject)) == 0;
+    c->v_total = off; c->words_total = w;
+    if (same) return VB_OK;
+    // a previous upload may still be in flight from the staging buffer
+    if (!vbrt::stream_sync(s)) return VB_ERR_CUDA;
+    const size_t sb = subj.size() * sizeof(VbSubject), wb = woff.size() * sizeof(long long);
+    if (c->h_desc.cap < sb + wb) {
+        vbrt::host_free(c->h_desc.p);
+        c->h_desc.p = nullptr; c->h_desc.cap = 0;
+        if (!vbrt::host_malloc(&c->h_desc.p, (sb + wb) * 2)) return VB_ERR_CUDA;
+        c->h_desc.cap = (sb + wb) * 2;
+    }
+    if (!ensure(c->d_subj, sb) || !ensure(c->d_wordoff, wb)) return VB_ERR_CUDA;
+    memcpy(c->h_desc.p, subj.data(), sb);
+    memcpy((char*)c->h_desc.p + sb, woff.data(), wb);
+    if (!vbrt::h2d(c->d_subj.p, c->h_desc.p, sb, s)) return VB_ERR_CUDA;
+    if (!vbrt::h2d(c->d_wordoff.p, (char*)c->h_desc.p + sb, wb, s)) return VB_ERR_CUDA;
+    c->last_subj.swap(subj);
+    c->last_wordoff.swap(woff);
+    return VB_OK;
+}
+
+int grid_x_for(const vb_ctx* c, int n, long long vmax, int per_block) {
+    long long want = (c->sms * 8LL + n - 1) / n;
+    const long long cap = (vmax + per_block - 1) / per_block;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    if (want > 4096) want = 4096;
+    return (int)want;
+}
+
+long long vmax_of(const vb_ctx* c) {
+    long long m = 0;
+    for (const VbSubject& S : c->last_subj) m = std::max<long long>(m, S.V);
+    return m;
+}
+
+int upload_tables(vb_ctx* c, vbrt::stream_t s) {
+    if (!c->tables_dirty) return VB_OK;
+    std::vector<CiTableDev> t(c->tables.size());
+    for (size_t i = 0; i < t.size(); ++i) {
+        t[i].rows = (const int2*)c->tables[i].d_rows;
+        t[i].ii = (const int*)c->tables[i].d_ii;
+        t[i].n_unique = c->tables[i].n_unique;
+        t[i].n_bounds = c->tables[i].n_bounds;
+    }
+    if (!vbrt::stream_sync(s)) return VB_ERR_CUDA;
+    if (!ensure(c->d_tables, t.size() * sizeof(CiTableDev))) return VB_ERR_CUDA;
+    if (!vbrt::h2d(c->d_tables.p, t.data(), t.size() * sizeof(CiTableDev), s)) return VB_ERR_CUDA;
+    if (!vbrt::stream_sync(s)) return VB_ERR_CUDA;      // `t` is a stack object
+    c->tables_dirty = false;
+    return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------- stages
+int run_snr(vb_ctx* c, const float* image, const uint8_t* mask, int n, int fov, vb_subject_stats* stats,
+            vbrt::stream_t s) {
+    for (const VbSubject& S : c->last_subj)
+        if (S.n0 + S.n1 + S.n2 > VB_SNR_MAX_AXIS) return fail(VB_ERR_UNSUPPORTED, "SNR: n0+n1+n2 too large");
+    const int grid = std::min(n, c->sms * 4);
+    VB_LAUNCH(snr_kernel, dim3(grid), dim3(VB_VDP_THREADS), 0, s, image, mask, (const VbSubject*)c->d_subj.p, n,
+              fov, stats);
+    ++c->launches;
+    return vbrt::last_launch_ok("snr_kernel") ? VB_OK : VB_ERR_CUDA;
+}
+
+int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n4_params* pp, float* out,
+           float* logbias, vb_subject_stats* stats, vbrt::stream_t s) {
+    vb_n4_params p = *pp;
+    if (p.n_levels < 1 || p.n_levels > VB_MAX_LEVELS) return fail(VB_ERR_ARG, "N4: n_levels out of range");
+    if (p.n_bins < 2) return fail(VB_ERR_ARG, "N4: n_bins < 2");
+    int ncpf[3];
+    for (int a = 0; a < 3; ++a) {
+        if (p.ncp[a] < 4) return fail(VB_ERR_ARG, "N4: cubic splines need >= 4 control points");
+        long long v = p.ncp[a];
+        for (int l = 1; l < p.n_levels; ++l) v = 2 * v - 3;
+        if (v > 4096) return fail(VB_ERR_UNSUPPORTED, "N4: lattice too large");
+        ncpf[a] = (int)v;
+    }
+    const long long Lmax = (long long)ncpf[0] * ncpf[1] * ncpf[2];
+    int e = 0;
+    while ((1 << e) < p.n_bins) ++e;
+    const int fftN = 1 << (e + 1);
+    long long vmax = 0, cmw = 0, axis = 0, n2max = 0;
+    for (const VbSubject& S : c->last_subj) {
+        vmax = std::max<long long>(vmax, S.V);
+        cmw = std::max<long long>(cmw, (long long)((S.n0 + 31) / 32) * S.n1 * S.n2);
+        axis = std::max<long long>(axis, 16LL * (S.n0 + S.n1 + S.n2));
+        n2max = std::max<long long>(n2max, S.n2);
+    }
+    const long long fixed = 4 * (2 * ((Lmax + 3) & ~3LL) + 2 * ((p.n_bins + 3) & ~3)) + 64 * 8;
+    const long long avail = (long long)c->max_smem - fixed;
+    int HT = (int)std::min<long long>(VB_N4_THREADS, avail / (4LL * p.n_bins) / 32 * 32);
+    if (HT < 32) return fail(VB_ERR_UNSUPPORTED, "N4: histogram does not fit shared memory");
+    const long long Qn = (((long long)ncpf[0] * ncpf[1] * n2max) + 3) & ~3LL;
+    long long ub = 4LL * HT * p.n_bins;
+    ub = std::max(ub, 8LL * 7 * fftN);
+    ub = std::max(ub, 4LL * (Qn + (long long)ncpf[0] * VB_N4_THREADS));
+    ub = std::max(ub, 4LL * Lmax);
+    ub = (ub + 15) & ~15LL;
+    if (ub + fixed > c->max_smem)
+        return fail(VB_ERR_UNSUPPORTED, "N4: working set does not fit the 227 KB of shared memory");
+    const int grid = std::min(n, c->sms);
+    if (!ensure(c->ws_logI, sizeof(float) * (size_t)grid * (size_t)vmax) ||
+        !ensure(c->ws_colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(c->ws_axis, 4 * (size_t)grid * (size_t)axis) ||
+        !ensure(c->ws_counter, 64))
+        return VB_ERR_CUDA;
+    int trace = 0;
+    for (int l = 0; l < p.n_levels; ++l) trace += p.max_iter[l];
+    float* dbg = nullptr;
+    int dbg_stride = 0;
+    if (c->debug) {
+        dbg_stride = VB_DBG_HDR + 2 * p.n_bins + (int)Lmax + trace;
+        if (!ensure(c->dbg, sizeof(float) * (size_t)n * dbg_stride)) return VB_ERR_CUDA;
+        dbg = (float*)c->dbg.p;
+        c->dbg_stride = dbg_stride; c->dbg_nbins = p.n_bins; c->dbg_Lmax = (int)Lmax; c->dbg_n = n;
+        if (!vbrt::dev_memset(dbg, 0, sizeof(float) * (size_t)n * dbg_stride, s)) return VB_ERR_CUDA;
+    }
+    if (!vbrt::dev_memset(c->ws_counter.p, 0, 64, s)) return VB_ERR_CUDA;
+    N4Args a;
+    a.image = image; a.mask = mask; a.out = out; a.logbias = logbias;
+    a.subj = (const VbSubject*)c->d_subj.p; a.n = n; a.p = p; a.stats = stats;
+    a.ws_logI = (float*)c->ws_logI.p; a.ws_colmask = (uint32_t*)c->ws_colmask.p; a.ws_axis = (float*)c->ws_axis.p;
+    a.work_counter = (int*)c->ws_counter.p; a.debug = dbg;
+    a.Vmax = vmax; a.cmw_max = cmw; a.axis_stride = (int)axis; a.debug_stride = dbg_stride;
+    a.hist_threads = HT; a.Lmax = (int)Lmax; a.fftN = fftN; a.union_bytes = (int)ub;
+    const int smem = (int)(ub + fixed);
+    if (!vbrt::allow_smem(n4_subject_kernel, smem)) return VB_ERR_CUDA;
+    VB_LAUNCH(n4_subject_kernel, dim3(grid), dim3(VB_N4_THREADS), (size_t)smem, s, a);
+    ++c->launches;
+    return vbrt::last_launch_ok("n4_subject_kernel") ? VB_OK : VB_ERR_CUDA;
+}
+
+int run_border(vb_ctx* c, const uint8_t* a, int n, uint8_t* border, vbrt::stream_t s) {
+    const int gx = grid_x_for(c, n, vmax_of(c), 256);
+    VB_LAUNCH(border_kernel, dim3(gx, n), dim3(256), 0, s, a, (const VbSubject*)c->d_subj.p, border);
+    ++c->launches;
+    return vbrt::last_launch_ok("border_kernel") ? VB_OK : VB_ERR_CUDA;
+}
+
+int run_vdp(vb_ctx* c, const float* n4, const uint8_t* mask, int n, float thresh, uint8_t* defect, uint8_t* lb,
+            uint8_t* dborder, vb_subject_stats* stats, vbrt::stream_t s) {
+    if (!ensure(c->ws_d0, (size_t)c->v_total)) return VB_ERR_CUDA;
+    const VbSubject* subj = (const VbSubject*)c->d_subj.p;
+    const int gx = grid_x_for(c, n, vmax_of(c), 256);
+    VB_LAUNCH(vdp_stats_kernel, dim3(std::min(n, c->sms * 4)), dim3(VB_VDP_THREADS), 0, s, n4, mask, subj, n, stats);
+    VB_LAUNCH(vdp_threshold_kernel, dim3(gx, n), dim3(256), 0, s, n4, mask, subj, thresh, (uint8_t*)c->ws_d0.p, lb,
+              stats);
+    VB_LAUNCH(vdp_median_kernel, dim3(gx, n), dim3(256), 0, s, (const uint8_t*)c->ws_d0.p, subj, defect, stats);
+    c->launches += 3;
+    if (!vbrt::last_launch_ok("vdp kernels")) return VB_ERR_CUDA;
+    return dborder ? run_border(c, defect, n, dborder, s) : VB_OK;
+}
+
+int run_ci(vb_ctx* c, const uint8_t* defect, int n, uint16_t* shell, vb_subject_stats* stats, vbrt::stream_t s) {
+    int rc = upload_tables(c, s);
+    if (rc) return rc;
+    if (!ensure(c->ws_bits, 4 * (size_t)c->words_total) || !ensure(c->ws_list, 4 * (size_t)c->v_total) ||
+        !ensure(c->ws_count, 4 * (size_t)n))
+        return VB_ERR_CUDA;
+    if (!vbrt::dev_memset(shell, 0xFF, 2 * (size_t)c->v_total, s) || !vbrt::dev_memset(c->ws_count.p, 0, 4 * (size_t)n, s))
+        return VB_ERR_CUDA;
+    CiArgs a;
+    a.defect = defect; a.subj = (const VbSubject*)c->d_subj.p; a.n = n;
+    a.tables = (const CiTableDev*)c->d_tables.p; a.bits = (uint32_t*)c->ws_bits.p;
+    a.word_off = (const long long*)c->d_wordoff.p; a.list = (int*)c->ws_list.p; a.count = (int*)c->ws_count.p;
+    a.shell = shell; a.stats = stats;
+    const long long vmax = vmax_of(c);
+    const int words = (int)((vmax + 31) / 32);
+    int nbmax = 0;
+    for (const VbSubject& S : c->last_subj) nbmax = std::max(nbmax, c->tables[(size_t)S.table].n_bounds);
+    VB_LAUNCH(ci_pack_kernel, dim3(grid_x_for(c, n, words, 256), n), dim3(256), 0, s, a);
+    const int gx = std::max(1, std::min(64, (c->sms * 8 + n - 1) / n));
+    if (words <= VB_CI_SMEM_WORDS_MAX) {
+        if (!vbrt::allow_smem(ci_grow_kernel<true>, 4 * words)) return VB_ERR_CUDA;
+        VB_LAUNCH(ci_grow_kernel<true>, dim3(gx, n), dim3(VB_CI_THREADS), (size_t)4 * words, s, a);
+    } else {
+        VB_LAUNCH(ci_grow_kernel<false>, dim3(gx, n), dim3(VB_CI_THREADS), 0, s, a);
+    }
+    if (!vbrt::allow_smem(ci_percentile_kernel, 4 * nbmax)) return VB_ERR_CUDA;
+    VB_LAUNCH(ci_percentile_kernel, dim3(std::min(n, c->sms * 4)), dim3(VB_CI_THREADS), (size_t)4 * nbmax, s, a);
+    c->launches += 3;
+    return vbrt::last_launch_ok("ci kernels") ? VB_OK : VB_ERR_CUDA;
+}
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+int vb_version(void) { return 100; }
+const char* vb_last_error(void) { return vbrt::g_err.c_str(); }
+int vb_device_count(void) { return vbrt::device_count(); }
+
+int vb_create(int device, vb_ctx** out) {
+    if (!out) return fail(VB_ERR_ARG, "null ctx pointer");
+    *out = nullptr;
+    const int nd = vbrt::device_count();
+    if (nd <= 0) return fail(VB_ERR_CUDA, "no CUDA device: ventb200 has no CPU fallback");
+    if (device < 0 || device >= nd) return fail(VB_ERR_ARG, "bad device index");
+    if (!vbrt::set_device(device)) return VB_ERR_CUDA;
+    vb_ctx* c = new vb_ctx();
+    c->device = device;
+    c->sms = vbrt::sm_count(device);
+    c->max_smem = vbrt::max_smem_optin(device);
+    if (!vbrt::stream_create(&c->stream)) { delete c; return VB_ERR_CUDA; }
+    *out = c;
+    return VB_OK;
+}
+
+void vb_destroy(vb_ctx* c) {
+    if (!c) return;
+    vbrt::set_device(c->device);
+    vbrt::stream_sync(c->stream);
+    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_logI, &c->ws_colmask, &c->ws_axis, &c->ws_counter, &c->ws_d0,
+                   &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
+                   &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats};
+    for (Buf* b : bufs) vbrt::dev_free(b->p);
+    for (TableHost& t : c->tables) { vbrt::dev_free(t.d_rows); vbrt::dev_free(t.d_ii); }
+    vbrt::host_free(c->h_desc.p);
+    vbrt::stream_destroy(c->stream);
+    delete c;
+}
+
+uint64_t vb_launch_count(const vb_ctx* c) { return c ? c->launches : 0; }
+
+void vb_n4_default_params(vb_n4_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->n_levels = 4;
+    for (int i = 0; i < 4; ++i) p->max_iter[i] = 50;
+    p->conv_threshold = 0.001f; p->fwhm = 0.15f; p->wiener_noise = 0.01f; p->n_bins = 200;
+    p->ncp[0] = p->ncp[1] = p->ncp[2] = 4;
+    p->mask_label = 1; p->max_total_iters = 0;
+}
+
+int vb_ci_table_create(vb_ctx* c, const double* table, int64_t nrows, int32_t n0, int32_t n1, int32_t n2,
+                       int32_t* handle) {
+    if (!c || !table || nrows < 2 || !handle || n0 < 1 || n1 < 1 || n2 < 1) return fail(VB_ERR_ARG, "ci_table_create");
+    vbrt::set_device(c->device);
+    // shell boundaries: getRadiiIndices (CI.py:79-85) == where(diff(radius) > 0) + 1
+    std::vector<int> bnd;
+    for (int64_t r = 0; r + 1 < nrows; ++r)
+        if (table[4 * (r + 1)] - table[4 * r] > 0) bnd.push_back((int)(r + 1));
+    if (bnd.empty()) return fail(VB_ERR_ARG, "sphere table has no shell boundary");
+    if (bnd.size() >= 0xFFFE) return fail(VB_ERR_UNSUPPORTED, "more than 65533 shells");
+    const int last = bnd.back();                 // rows >= last are never looked at (CI.py:94)
+    std::vector<int2> rows;
+    rows.reserve((size_t)last);
+    std::unordered_set<long long> seen;
+    seen.reserve((size_t)last * 2);
+    std::vector<int> ucount(bnd.size());
+    size_t bi = 0;
+    for (int r = 0; r < last; ++r) {
+        while (bi < bnd.size() && bnd[bi] == r) ucount[bi++] = (int)rows.size();
+        const long long off = (long long)table[4 * r + 1] + (long long)table[4 * r + 2] * n0 +
+                              (long long)table[4 * r + 3] * n0 * (long long)n1;
+        if (off > 0x3fffffffLL || off < -0x3fffffffLL) continue;   // can never land inside a <=2^30 volume
+        if (seen.insert(off).second) { int2 e; e.x = (int)off; e.y = 0; rows.push_back(e); }
+    }
+    while (bi < bnd.size()) ucount[bi++] = (int)rows.size();
+    for (size_t t = 0; t < bnd.size(); ++t) {
+        const int u = ucount[t] - 1;             // >= 0: row 0 (the centre) is always unique
+        if (u < 0) return fail(VB_ERR_ARG, "sphere table must start with the centre voxel");
+        const int cnt = rows[(size_t)u].y & 0xFFFF;
+        if (cnt == 0) rows[(size_t)u].y = (int)(((unsigned)t << 16) | 1u);
+        else rows[(size_t)u].y = (int)(((unsigned)rows[(size_t)u].y & 0xFFFF0000u) | (unsigned)(cnt + 1));
+    }
+    TableHost T;
+    T.n0 = n0; T.n1 = n1; T.n2 = n2;
+    T.n_unique = (int)rows.size(); T.n_bounds = (int)bnd.size();
+    T.radii.resize(bnd.size());
+    for (size_t t = 0; t < bnd.size(); ++t) T.radii[t] = table[4 * (size_t)(bnd[t] - 1)];   // CI.py:105
+    if (!vbrt::dev_malloc(&T.d_rows, rows.size() * sizeof(int2)) || !vbrt::dev_malloc(&T.d_ii, bnd.size() * sizeof(int)))
+        return VB_ERR_CUDA;
+    if (!vbrt::h2d(T.d_rows, rows.data(), rows.size() * sizeof(int2), c->stream) ||
+        !vbrt::h2d(T.d_ii, bnd.data(), bnd.size() * sizeof(int), c->stream) || !vbrt::stream_sync(c->stream))
+        return VB_ERR_CUDA;
+    c->tables.push_back(T);
+    c->tables_dirty = true;
+    *handle = (int32_t)c->tables.size() - 1;
+    return VB_OK;
+}
+
+int vb_ci_table_radii(vb_ctx* c, int32_t handle, double* radii, int32_t capacity, int32_t* n_bounds) {
+    if (!c || handle < 0 || handle >= (int)c->tables.size()) return fail(VB_ERR_ARG, "bad CI table handle");
+    const TableHost& T = c->tables[(size_t)handle];
+    if (n_bounds) *n_bounds = T.n_bounds;
+    if (radii)
+        for (int t = 0; t < T.n_bounds && t < capacity; ++t) radii[t] = T.radii[(size_t)t];
+    return VB_OK;
+}
+
+int vb_snr_batch_dev(vb_ctx* c, const float* image, const uint8_t* mask, int32_t n, const int32_t* shapes,
+                     int32_t fov, vb_subject_stats* stats, void* stream) {
+    if (!c || !image || !mask || !stats) return fail(VB_ERR_ARG, "snr: null argument");
+    vbrt::set_device(c->device);
+    int rc = prepare(c, n, shapes, nullptr, (vbrt::stream_t)stream);
+    return rc ? rc : run_snr(c, image, mask, n, fov, stats, (vbrt::stream_t)stream);
+}
+
+int vb_n4_batch_dev(vb_ctx* c, const float* image, const uint8_t* mask, int32_t n, const int32_t* shapes,
+                    const vb_n4_params* params, float* n4, float* logbias, vb_subject_stats* stats, void* stream) {
+    if (!c || !image || !mask || !n4 || !params) return fail(VB_ERR_ARG, "n4: null argument");
+    vbrt::set_device(c->device);
+    int rc = prepare(c, n, shapes, nullptr, (vbrt::stream_t)stream);
+    return rc ? rc : run_n4(c, image, mask, n, params, n4, logbias, stats, (vbrt::stream_t)stream);
+}
+
+int vb_vdp_batch_dev(vb_ctx* c, const float* n4, const uint8_t* mask, int32_t n, const int32_t* shapes, float thresh,
+                     uint8_t* defect, uint8_t* lb, uint8_t* dborder, vb_subject_stats* stats, void* stream) {
+    if (!c || !n4 || !mask || !defect || !lb || !stats) return fail(VB_ERR_ARG, "vdp: null argument");
+    vbrt::set_device(c->device);
+    int rc = prepare(c, n, shapes, nullptr, (vbrt::stream_t)stream);
+    return rc ? rc : run_vdp(c, n4, mask, n, thresh, defect, lb, dborder, stats, (vbrt::stream_t)stream);
+}
+
+int vb_border_batch_dev(vb_ctx* c, const uint8_t* a, int32_t n, const int32_t* shapes, uint8_t* border, void* stream) {
+    if (!c || !a || !border) return fail(VB_ERR_ARG, "border: null argument");
+    vbrt::set_device(c->device);
+    int rc = prepare(c, n, shapes, nullptr, (vbrt::stream_t)stream);
+    return rc ? rc : run_border(c, a, n, border, (vbrt::stream_t)stream);
+}
+
+int vb_ci_batch_dev(vb_ctx* c, const uint8_t* defect, int32_t n, const int32_t* shapes, const int32_t* handles,
+                    uint16_t* shell, vb_subject_stats* stats, void* stream) {
+    if (!c || !defect || !handles || !shell || !stats) return fail(VB_ERR_ARG, "ci: null argument");
+    vbrt::set_device(c->device);
+    int rc = prepare(c, n, shapes, handles, (vbrt::stream_t)stream);
+    return rc ? rc : run_ci(c, defect, n, shell, stats, (vbrt::stream_t)stream);
+}
+
+int vb_pipeline_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const int32_t* handles,
+                          const vb_n4_params* params, float thresh, uint32_t flags, const vb_buffers* d, void* stream) {
+    if (!c || !d || !d->mask || !d->stats) return fail(VB_ERR_ARG, "pipeline: null argument");
+    vbrt::stream_t s = (vbrt::stream_t)stream;
+    vbrt::set_device(c->device);
+    if ((flags & VB_DO_CI) && !handles) return fail(VB_ERR_ARG, "pipeline: CI needs table handles");
+    int rc = prepare(c, n, shapes, (flags & VB_DO_CI) ? handles : nullptr, s);
+    if (rc) return rc;
+    if (!vbrt::dev_memset(d->stats, 0, sizeof(vb_subject_stats) * (size_t)n, s)) return VB_ERR_CUDA;
+    if (flags & VB_DO_SNR) {
+        if (!d->image) return fail(VB_ERR_ARG, "pipeline: SNR needs image");
+        if ((rc = run_snr(c, d->image, d->mask, n, 20, d->stats, s))) return rc;
+    }
+    if (flags & VB_DO_N4) {
+        if (!d->image || !d->n4 || !params) return fail(VB_ERR_ARG, "pipeline: N4 needs image, n4, params");
+        if ((rc = run_n4(c, d->image, d->mask, n, params, d->n4, d->logbias, d->stats, s))) return rc;
+    }
+    if (flags & VB_DO_VDP) {
+        if (!d->n4 || !d->defect || !d->defect_lb) return fail(VB_ERR_ARG, "pipeline: VDP needs n4, defect, defect_lb");
+        if ((rc = run_vdp(c, d->n4, d->mask, n, thresh, d->defect, d->defect_lb, d->defect_border, d->stats, s))) return rc;
+    }
+    if ((flags & VB_DO_MASK_BORDER) && d->mask_border)
+        if ((rc = run_border(c, d->mask, n, d->mask_border, s))) return rc;
+    if (flags & VB_DO_CI) {
+        if (!d->defect || !d->ci_shell) return fail(VB_ERR_ARG, "pipeline: CI needs defect, ci_shell");
+        if ((rc = run_ci(c, d->defect, n, d->ci_shell, d->stats, s))) return rc;
+    }
+    return VB_OK;
+}
+
+int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const int32_t* handles,
+                           const vb_n4_params* params, float thresh, uint32_t flags, const vb_buffers* h) {
+    if (!c || !h || !h->mask || !h->stats || !shapes || n <= 0) return fail(VB_ERR_ARG, "pipeline_host: null argument");
+    vbrt::set_device(c->device);
+    vbrt::stream_t s = c->stream;
+    size_t V = 0;
+    for (int i = 0; i < n; ++i) V += (size_t)shapes[3 * i] * shapes[3 * i + 1] * shapes[3 * i + 2];
+    const bool need_n4 = (flags & (VB_DO_N4 | VB_DO_VDP)) != 0;
+    const bool need_def = (flags & (VB_DO_VDP | VB_DO_CI)) != 0;
+    vb_buffers d;
+    memset(&d, 0, sizeof(d));
+    if (!ensure(c->m_mask, V) || !ensure(c->m_stats, sizeof(vb_subject_stats) * (size_t)n)) return VB_ERR_CUDA;
+    d.mask = (const uint8_t*)c->m_mask.p; d.stats = (vb_subject_stats*)c->m_stats.p;
+    if (!vbrt::h2d(c->m_mask.p, h->mask, V, s)) return VB_ERR_CUDA;
+    if (h->image) {
+        if (!ensure(c->m_image, 4 * V) || !vbrt::h2d(c->m_image.p, h->image, 4 * V, s)) return VB_ERR_CUDA;
+        d.image = (const float*)c->m_image.p;
+    }
+    if (need_n4) {
+        if (!h->n4) return fail(VB_ERR_ARG, "pipeline_host: n4 buffer required");
+        if (!ensure(c->m_n4, 4 * V)) return VB_ERR_CUDA;
+        d.n4 = (float*)c->m_n4.p;
+        if (!(flags & VB_DO_N4) && !vbrt::h2d(c->m_n4.p, h->n4, 4 * V, s)) return VB_ERR_CUDA;
+    }
+    if (h->logbias && (flags & VB_DO_N4)) { if (!ensure(c->m_logbias, 4 * V)) return VB_ERR_CUDA; d.logbias = (float*)c->m_logbias.p; }
+    if (need_def) {
+        if (!h->defect) return fail(VB_ERR_ARG, "pipeline_host: defect buffer required");
+        if (!ensure(c->m_defect, V)) return VB_ERR_CUDA;
+        d.defect = (uint8_t*)c->m_defect.p;
+        if (!(flags & VB_DO_VDP) && !vbrt::h2d(c->m_defect.p, h->defect, V, s)) return VB_ERR_CUDA;
+    }
+    if (flags & VB_DO_VDP) {
+        if (!h->defect_lb) return fail(VB_ERR_ARG, "pipeline_host: defect_lb buffer required");
+        if (!ensure(c->m_lb, V)) return VB_ERR_CUDA;
+        d.defect_lb = (uint8_t*)c->m_lb.p;
+        if (h->defect_border) { if (!ensure(c->m_dborder, V)) return VB_ERR_CUDA; d.defect_border = (uint8_t*)c->m_dborder.p; }
+    }
+    if ((flags & VB_DO_MASK_BORDER) && h->mask_border) { if (!ensure(c->m_mborder, V)) return VB_ERR_CUDA; d.mask_border = (uint8_t*)c->m_mborder.p; }
+    if (flags & VB_DO_CI) {
+        if (!h->ci_shell) return fail(VB_ERR_ARG, "pipeline_host: ci_shell buffer required");
+        if (!ensure(c->m_shell, 2 * V)) return VB_ERR_CUDA;
+        d.ci_shell = (uint16_t*)c->m_shell.p;
+    }
+    int rc = vb_pipeline_batch_dev(c, n, shapes, handles, params, thresh, flags, &d, (void*)s);
+    if (rc) return rc;
+    bool ok = true;
+    if (flags & VB_DO_N4) ok = ok && vbrt::d2h(h->n4, d.n4, 4 * V, s);
+    if (d.logbias) ok = ok && vbrt::d2h(h->logbias, d.logbias, 4 * V, s);
+    if (flags & VB_DO_VDP) {
+        ok = ok && vbrt::d2h(h->defect, d.defect, V, s) && vbrt::d2h(h->defect_lb, d.defect_lb, V, s);
+        if (d.defect_border) ok = ok && vbrt::d2h(h->defect_border, d.defect_border, V, s);
+    }
+    if (d.mask_border) ok = ok && vbrt::d2h(h->mask_border, d.mask_border, V, s);
+    if (flags & VB_DO_CI) ok = ok && vbrt::d2h(h->ci_shell, d.ci_shell, 2 * V, s);
+    ok = ok && vbrt::d2h(h->stats, d.stats, sizeof(vb_subject_stats) * (size_t)n, s);
+    if (!ok || !vbrt::stream_sync(s)) return VB_ERR_CUDA;
+    if (flags & VB_DO_CI)
+        for (int i = 0; i < n; ++i)
+            if (h->stats[i].ci_error) return fail(VB_ERR_CI_RMAX, "CI: maximum sphere radius reached (table exhausted)");
+    return VB_OK;
+}
+
+int vb_set_debug(vb_ctx* c, int32_t on) {
+    if (!c) return fail(VB_ERR_ARG, "null ctx");
+    c->debug = on != 0;
+    return VB_OK;
+}
+
+int vb_n4_debug_fetch(vb_ctx* c, int32_t subject, float* hist, float* emap, float* lattice, int32_t lattice_capacity,
+                      int32_t* ncp, float* conv_trace, int32_t trace_capacity) {
+    if (!c || !c->dbg.p || subject < 0 || subject >= c->dbg_n) return fail(VB_ERR_ARG, "no debug capture");
+    vbrt::set_device(c->device);
+    std::vector<float> rec((size_t)c->dbg_stride);
+    if (!vbrt::device_sync()) return VB_ERR_CUDA;
+    if (!vbrt::d2h(rec.data(), (const float*)c->dbg.p + (size_t)subject * c->dbg_stride, sizeof(float) * rec.size(), c->stream) ||
+        !vbrt::stream_sync(c->stream))
+        return VB_ERR_CUDA;
+    const int nb = c->dbg_nbins;
+    if (hist) memcpy(hist, rec.data() + VB_DBG_HDR, sizeof(float) * (size_t)nb);
+    if (emap) memcpy(emap, rec.data() + VB_DBG_HDR + nb, sizeof(float) * (size_t)nb);
+    const int n0 = (int)rec[2], n1 = (int)rec[3], n2 = (int)rec[4];
+    if (ncp) { ncp[0] = n0; ncp[1] = n1; ncp[2] = n2; }
+    if (lattice) memcpy(lattice, rec.data() + VB_DBG_HDR + 2 * nb, sizeof(float) * (size_t)std::min(lattice_capacity, n0 * n1 * n2));
+    const int nt = (int)rec[5];
+    if (conv_trace) {
+        for (int i = 0; i < trace_capacity; ++i) conv_trace[i] = -1.0f;
+        memcpy(conv_trace, rec.data() + VB_DBG_HDR + 2 * nb + c->dbg_Lmax, sizeof(float) * (size_t)std::min(trace_capacity, nt));
+    }
+    return VB_OK;
+}
+
+}  // extern "C"
