@@ -18,7 +18,7 @@ def build(force=False):
         return SO
     os.makedirs(os.path.dirname(SO), exist_ok=True)
     cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-DVB_EMULATE", "-ffp-contract=off",
-           "-Wall", "-Wno-unused-function", "-Wno-unused-variable", "-x", "c++", os.path.join(CSRC, "ventb200.cu"),
+           "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable", "-x", "c++", os.path.join(CSRC, "ventb200.cu"),
            "-o", SO]
     subprocess.check_call(cmd)
     return SO

@@ -1,0 +1,120 @@
+"""CPU suite: the product's KERNEL SOURCES (vent_analysis_b200/csrc), compiled for the host
+by tests/emu (one OS thread per CUDA thread), checked against the golden fixtures and the
+oracle through the same C ABI.  This pins the kernel logic in the GPU-less build container;
+tests/test_gpu_parity.py repeats it on the real sm_100a build."""
+import numpy as np
+import pytest
+
+import helpers
+from emu.harness import emu_context
+from oracle import n4_oracle
+from vent_analysis_b200 import _lib
+from vent_analysis_b200.phantom import phantom
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return emu_context()
+
+
+@pytest.mark.parametrize("name,with_ci", [("small_a", True), ("small_b", True), ("ragged_c", False)])
+def test_vdp_snr_border_ci_bit_exact(ctx, name, with_ci):
+    helpers.check_vdp_ci_against_golden(ctx, name, with_ci)
+
+
+@pytest.mark.parametrize("name", ["corner_blob", "edge_slab", "iso_regen"])
+def test_ci_edge_cases_bit_exact(ctx, name):
+    helpers.check_ci_case(ctx, name)
+
+
+def test_ci_table_exhaustion_is_reported(ctx):
+    from vent_analysis_b200.sphere_table import generate
+    d = np.ones((12, 12, 3), dtype=np.uint8)
+    h = ctx.ci_table(generate([1.0, 1.0, 1.0], 2), d.shape, key="exhaust")
+    _, stats, rc = ctx.ci_host(d, [d.shape], [h])
+    assert rc == _lib.VB_ERR_CI_RMAX and stats["ci_error"][0] == 1
+
+
+def test_n4_matches_restatement_single_iteration_stages(ctx):
+    """One iteration at one level: histogram, E(u|v) map, fitted lattice and convergence value
+    against the oracle's stage functions."""
+    shape = (40, 36, 6)
+    img, mask = phantom(shape, [1.5, 1.5, 10.0], 5)
+    ctx.set_debug(True)
+    out, ref, _ = helpers.check_n4(ctx, img, mask, max_iter=(1,))
+    dbg = ctx.n4_debug(0, 200, 11 ** 3)
+    ctx.set_debug(False)
+    m = mask > 0
+    U = np.where(m, np.log(np.maximum(img, 1e-30)), img).astype(np.float32)
+    s = n4_oracle.sharpen(U, m.astype(np.uint8))
+    assert abs(dbg["hist"].sum() - m.sum()) < 1e-2
+    assert np.abs(dbg["hist"] - s["H"]).max() < 2e-3
+    assert np.abs(dbg["emap"] - s["E"]).max() < 1e-5
+    assert np.abs(dbg["lattice"] - ref["lattice"]).max() < 1e-6
+    assert abs(dbg["conv"][0] - ref["conv"][0][0]) < 1e-6
+
+
+def test_n4_full_run_matches_restatement(ctx):
+    shape = (40, 36, 6)
+    img, mask = phantom(shape, [1.5, 1.5, 10.0], 5)
+    _, _, rel = helpers.check_n4(ctx, img, mask)
+    assert rel < 1e-4
+
+
+def test_n4_ragged_batch_and_label_semantics(ctx):
+    """Two subjects of different shapes in one launch; mask label 2 is ignored (MaskLabel=1)."""
+    a_img, a_m = phantom((24, 20, 5), [1.5, 1.5, 10.0], 21)
+    b_img, b_m = phantom((18, 30, 4), [2.0, 2.0, 11.5], 22)
+    b_m = b_m.copy()
+    b_m[:2, :, :] = np.where(b_m[:2, :, :] > 0, 2, 0)
+    shapes = [a_img.shape, b_img.shape]
+    p = ctx.default_n4_params(max_iter=(4, 3))
+    out = ctx.pipeline_host(shapes, _lib.DO_N4, image=np.concatenate([a_img.ravel(), b_img.ravel()]),
+                            mask=np.concatenate([a_m.ravel(), b_m.ravel()]), params=p, want_logbias=True)
+    off = 0
+    for img, m in ((a_img, a_m), (b_img, b_m)):
+        ref = n4_oracle.n4(img, m, max_iter=(4, 3))
+        lb = out["logbias"][off:off + img.size].reshape(img.shape)
+        assert np.abs(np.expm1(lb - ref["logbias"])).max() < 1e-4
+        off += img.size
+    assert list(out["stats"]["n4_iters"][0][:2]) == [4, 3]
+
+
+def test_class_surface_end_to_end(ctx, monkeypatch):
+    """The Vent_Analysis mirror (constructor, calculate_VDP, calculate_CI, metadata, dtypes)
+    against the reference's outputs -- N4 here is OUR kernel, so VDP is held to the
+    north_star tolerance (+-0.05 pp) and everything downstream of the defect mask to
+    bit-exactness given that mask."""
+    from vent_analysis_b200 import CI, Vent_Analysis
+    from oracle import ci_oracle, vdp_oracle
+    from vent_analysis_b200.sphere_table import generate
+    monkeypatch.setitem(_lib._CTX, 0, ctx)
+    g, shape, vox, img, mask, n4 = helpers.golden_inputs("small_a")
+    v = helpers.quiet(Vent_Analysis, xenon_array=img, mask_array=mask.astype(np.float64), vox=vox)
+    helpers.quiet(v.calculate_VDP)
+    helpers.quiet(v.calculate_CI)
+    assert abs(v.metadata["VDP"] - float(g["VDP"])) <= helpers.VDP_PP_TOL
+    assert abs(v.metadata["VDP_lb"] - float(g["VDP_lb"])) <= helpers.VDP_PP_TOL
+    assert v.metadata["LungVolume"] == float(g["LungVolume"])
+    assert np.isclose(v.metadata["SNR"], g["SNR"], rtol=2e-6) and v.metadata["SNR"].dtype == np.float32
+    for attr, key in (("defectArray", "defect_dtype"), ("defectArrayLB", "lb_dtype"), ("defectBorder", "border_dtype"),
+                      ("mask_border", "mask_border_dtype"), ("N4HPvent", "n4_dtype"), ("CIarray", "ci_dtype")):
+        assert getattr(v, attr).dtype == np.dtype(str(g[key])) and getattr(v, attr).shape == shape
+    # downstream of OUR defect mask everything is exact vs the oracle
+    ref = vdp_oracle.vdp(v.N4HPvent, mask.astype(np.float64), vox)
+    assert np.array_equal(v.defectArray, ref["defectArray"])
+    assert np.array_equal(v.defectArrayLB, ref["defectArrayLB"])
+    assert np.array_equal(v.defectBorder, ref["defectBorder"])
+    assert v.metadata["VDP"] == ref["VDP"] and v.metadata["VDP_lb"] == ref["VDP_lb"]
+    ci_ref, _ = ci_oracle.calculate_ci(v.defectArray, vox, generate(vox, 50))
+    assert np.array_equal(v.CIarray, ci_ref)
+    assert v.metadata["CI"] == vdp_oracle.ci_percentile(ci_ref, v.defectArray)
+    assert np.array_equal(CI.calculate_CI(v.defectArray, vox), ci_ref)
+    # pickling round trip keeps plain numpy state (Vent_Analysis.py:542-559)
+    import pickle
+    d = {k: val for k, val in vars(v).items()}
+    v2 = helpers.quiet(Vent_Analysis, pickle_dict=pickle.loads(pickle.dumps(d)))
+    assert np.array_equal(v2.defectArray, v.defectArray) and v2.metadata["CI"] == v.metadata["CI"]
+    # reference quirk: the array constructor without vox raises (Vent_Analysis.py:166)
+    with pytest.raises(Exception):
+        helpers.quiet(Vent_Analysis, xenon_array=img, mask_array=mask.astype(np.float64))

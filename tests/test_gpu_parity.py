@@ -1,0 +1,163 @@
+"""GPU suite (B200): the sm_100a library through its C ABI against the golden fixtures
+(outputs of the unmodified reference), the oracle, and size-independent properties at
+BASELINE.json's full sizes.  `/root/reference` is not read here."""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import ci_oracle, n4_oracle, vdp_oracle
+from vent_analysis_b200 import _lib
+from vent_analysis_b200.phantom import CONFIGS, cohort_member, phantom
+from vent_analysis_b200.sphere_table import generate
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return _lib.context(0)
+
+
+@pytest.mark.parametrize("name,with_ci", [("small_a", True), ("small_b", True), ("ragged_c", False),
+                                          ("C1", True), ("C2", True)])
+def test_vdp_snr_border_ci_bit_exact_vs_reference(ctx, name, with_ci):
+    helpers.check_vdp_ci_against_golden(ctx, name, with_ci)
+
+
+@pytest.mark.parametrize("name", ["corner_blob", "edge_slab", "iso_regen"])
+def test_ci_edge_cases_bit_exact_vs_reference(ctx, name):
+    helpers.check_ci_case(ctx, name)
+
+
+def test_ci_exhaustion_raises_like_reference(ctx):
+    from vent_analysis_b200 import CI
+    d = np.ones((12, 12, 3), dtype=np.uint8)
+    h = ctx.ci_table(generate([1.0, 1.0, 1.0], 2), d.shape, key="exhaust")
+    _, stats, rc = ctx.ci_host(d, [d.shape], [h])
+    assert rc == _lib.VB_ERR_CI_RMAX and stats["ci_error"][0] == 1
+    with pytest.raises(ValueError):
+        CI.calculate_CI(np.ones((12, 12, 3)), [1.0, 1.0, 1.0], Rmax=2)
+    with pytest.raises(IndexError):
+        CI.calculate_CI(np.zeros((12, 12, 3)), [1.0, 1.0, 1.0], Rmax=2)
+
+
+@pytest.mark.parametrize("shape,vox,seed", [((40, 36, 6), [1.5, 1.5, 10.0], 5), ((64, 64, 8), [1.5, 1.5, 10.0], 11),
+                                            (CONFIGS["C1"][0], CONFIGS["C1"][1], 0),
+                                            (CONFIGS["C2"][0], CONFIGS["C2"][1], 1)])
+def test_n4_bias_field_within_1e3_of_restatement(ctx, shape, vox, seed):
+    img, mask = phantom(shape, vox, seed)
+    _, _, rel = helpers.check_n4(ctx, img, mask)
+    assert rel < helpers.N4_BIAS_RTOL
+
+
+def test_n4_stage_level_parity(ctx):
+    shape = (40, 36, 6)
+    img, mask = phantom(shape, [1.5, 1.5, 10.0], 5)
+    ctx.set_debug(True)
+    out, ref, _ = helpers.check_n4(ctx, img, mask, max_iter=(1,))
+    dbg = ctx.n4_debug(0, 200, 11 ** 3)
+    ctx.set_debug(False)
+    m = mask > 0
+    U = np.where(m, np.log(np.maximum(img, 1e-30)), img).astype(np.float32)
+    s = n4_oracle.sharpen(U, m.astype(np.uint8))
+    assert np.abs(dbg["hist"] - s["H"]).max() < 2e-3
+    assert np.abs(dbg["emap"] - s["E"]).max() < 1e-5
+    assert np.abs(dbg["lattice"] - ref["lattice"]).max() < 1e-6
+
+
+def test_n4_c4_256x256x64_four_levels(ctx):
+    """Config 4: high-res volume, multilevel N4 (4 levels) + linear-binning VDP."""
+    shape, vox, seed = CONFIGS["C4"]
+    img, mask = phantom(shape, vox, seed)
+    out, ref, rel = helpers.check_n4(ctx, img, mask, require_same_iters=False)
+    r = vdp_oracle.vdp(out["n4"].reshape(shape), mask.astype(np.float64), vox)
+    o2 = ctx.pipeline_host([shape], _lib.DO_VDP, mask=mask, n4=out["n4"])
+    assert np.array_equal(o2["defect_lb"].reshape(shape), r["defectArrayLB"])
+    assert np.array_equal(o2["defect"].reshape(shape), r["defectArray"])
+    r_ref = vdp_oracle.vdp(ref["out"], mask.astype(np.float64), vox)
+    assert abs(100 * np.int64(o2["stats"][0]["n_lb12"]) / mask.sum() - r_ref["VDP_lb"]) <= helpers.VDP_PP_TOL
+
+
+def test_ci_c3_isotropic_large_table(ctx):
+    """Config 3: 128^3 @3.9 mm, table regenerated for that spacing (523k rows, bitset too large
+    for shared memory -> global-memory variant of the kernel).  Checked against the C oracle on
+    the full volume (bit exact)."""
+    shape, vox, seed = CONFIGS["C3"]
+    img, mask = phantom(shape, vox, seed)
+    n4 = n4_oracle.n4(img, mask, max_iter=(8, 4))["out"]
+    r = vdp_oracle.vdp(n4, mask.astype(np.float64), vox)
+    tbl = generate(vox, 50)
+    h = ctx.ci_table(tbl, shape, key=(tuple(vox), 50, tbl.shape[0]))
+    shell, stats, rc = ctx.ci_host(r["defectArray"], [shape], [h])
+    assert rc == 0
+    ci_ref, shell_ref = ci_oracle.calculate_ci(r["defectArray"], vox, tbl)
+    sel = r["defectArray"] > 0
+    assert np.array_equal(shell.reshape(shape)[sel].astype(np.int32), shell_ref[sel])
+    assert ctx.ci_radii(h)[int(stats["ci_t95"][0])] * min(vox) == vdp_oracle.ci_percentile(ci_ref, r["defectArray"])
+
+
+def test_class_surface_end_to_end_c2():
+    from vent_analysis_b200 import CI, Vent_Analysis
+    g, shape, vox, img, mask, n4 = helpers.golden_inputs("C2")
+    v = helpers.quiet(Vent_Analysis, xenon_array=img, mask_array=mask.astype(np.float64), vox=vox)
+    helpers.quiet(v.calculate_VDP)
+    helpers.quiet(v.calculate_CI)
+    # vs the reference run (whose N4 was the oracle restatement): north_star tolerances
+    assert abs(v.metadata["VDP"] - float(g["VDP"])) <= helpers.VDP_PP_TOL
+    assert abs(v.metadata["VDP_lb"] - float(g["VDP_lb"])) <= helpers.VDP_PP_TOL
+    assert v.metadata["LungVolume"] == float(g["LungVolume"])
+    assert np.isclose(v.metadata["SNR"], g["SNR"], rtol=2e-6)
+    rel = np.abs(v.N4HPvent - n4) / np.maximum(np.abs(n4), 1e-6)
+    assert rel.max() < helpers.N4_BIAS_RTOL
+    ref = vdp_oracle.vdp(v.N4HPvent, mask.astype(np.float64), vox)
+    assert np.array_equal(v.defectArray, ref["defectArray"]) and np.array_equal(v.defectArrayLB, ref["defectArrayLB"])
+    ci_ref, _ = ci_oracle.calculate_ci(v.defectArray, vox, generate(vox, 50))
+    assert np.array_equal(v.CIarray, ci_ref)
+    assert v.metadata["CI"] == vdp_oracle.ci_percentile(ci_ref, v.defectArray)
+    if np.array_equal(v.defectArray, helpers.unpack(g["defect_bits"], shape)):
+        assert v.metadata["CI"] == float(g["CI"]) and v.metadata["VDP"] == float(g["VDP"])
+    assert np.array_equal(v.calculateBorder(v.mask), helpers.unpack(g["maskBorder_bits"], shape))
+    assert v.calculate_SNR(v.HPvent).dtype == np.float32
+
+
+def test_cohort_mixed_spacings_host_and_device_paths_agree(ctx):
+    """Config 5 in miniature: 12 subjects, C1/C2 alternating, one launch sequence; per-subject
+    results equal the single-subject path bit for bit (batching / sharding changes nothing),
+    and the HBM-resident path equals the host-buffer path."""
+    from vent_analysis_b200 import cohort
+    subs = [cohort_member(i) for i in range(12)]
+    imgs, masks, voxs = zip(*subs)
+    metrics, out, stats = cohort.run_cohort_host(imgs, masks, voxs)
+    dc = cohort.DeviceCohort(imgs, masks, voxs)
+    dc.step()
+    dc.torch.cuda.synchronize()
+    m2 = dc.metrics()
+    assert np.array_equal(metrics, m2)
+    off = 0
+    for i in (0, 5, 11):
+        off = sum(im.size for im in imgs[:i])
+        one, o1, _ = cohort.run_cohort_host([imgs[i]], [masks[i]], [voxs[i]])
+        assert np.array_equal(one[0], metrics[i])
+        V = imgs[i].size
+        assert np.array_equal(o1["n4"], out["n4"][off:off + V])
+        assert np.array_equal(o1["ci_shell"], out["ci_shell"][off:off + V])
+    assert np.isfinite(metrics).all()
+    # determinism: same batch twice -> identical bits
+    metrics3, out3, _ = cohort.run_cohort_host(imgs, masks, voxs)
+    assert np.array_equal(out3["n4"], out["n4"]) and np.array_equal(metrics3, metrics)
+
+
+def test_properties_at_full_size(ctx):
+    """Size-independent properties on C1: N4 ignores a constant gain (bias field unchanged,
+    output scales), defect mask and CI invariant under that gain, CI idempotent on repeat,
+    CI >= min(vox) everywhere on defects and 0 elsewhere."""
+    from vent_analysis_b200 import cohort
+    img, mask, vox = cohort_member(0)
+    m1, o1, _ = cohort.run_cohort_host([img], [mask], [vox])
+    m2, o2, _ = cohort.run_cohort_host([img * 4.0], [mask], [vox])
+    assert np.allclose(o2["n4"], 4.0 * o1["n4"], rtol=2e-3)
+    assert abs(m1[0, 0] - m2[0, 0]) <= helpers.VDP_PP_TOL
+    sel = o1["defect"] > 0
+    assert (o1["ci_shell"][~sel] == _lib.CI_OFF).all() and (o1["ci_shell"][sel] < 5000).all()
+    m3, o3, _ = cohort.run_cohort_host([img], [mask], [vox])
+    assert np.array_equal(o3["ci_shell"], o1["ci_shell"])

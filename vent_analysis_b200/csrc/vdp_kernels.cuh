@@ -229,8 +229,8 @@ VB_KERNEL void border_kernel(const uint8_t* VB_RESTRICT a_, const VbSubject* sub
         // interior: A[i+1] != A[i-1]; edges: one-sided difference
         const int ilo = (i == 0) ? 0 : i - 1, ihi = (i == n0 - 1) ? n0 - 1 : i + 1;
         const int jlo = (j == 0) ? 0 : j - 1, jhi = (j == n1 - 1) ? n1 - 1 : j + 1;
-        const bool gr = (a[v + (ihi - i) * ncols] != 0) != (a[v + (ilo - i) * ncols] != 0);
-        const bool gc = (a[v + (jhi - j) * n2] != 0) != (a[v + (jlo - j) * n2] != 0);
+        const bool gr = a[v + (ihi - i) * ncols] != a[v + (ilo - i) * ncols];
+        const bool gc = a[v + (jhi - j) * n2] != a[v + (jlo - j) * n2];
         border[S.off + v] = (uint8_t)(gr || gc);
     }
 }
