@@ -135,6 +135,15 @@ int vb_pipeline_batch_host(vb_ctx* ctx, int32_t n, const int32_t* shapes, const 
                            const vb_n4_params* params, float thresh, uint32_t flags,
                            const vb_buffers* host);
 
+/* Per-stage device timing of vb_pipeline_batch_dev: with profiling on, every call records a
+ * CUDA event on the launching stream before the first stage and after each of the VB_N_STAGES
+ * stages (SNR, N4, VDP, mask border, CI; a skipped stage reads ~0).  vb_profile_fetch waits for
+ * the recorded calls, returns the SUM of each stage's elapsed milliseconds over them and their
+ * count, and resets the record.  (bench.py's roofline numbers come from here.) */
+#define VB_N_STAGES 5
+int vb_set_profiling(vb_ctx* ctx, int32_t on);
+int vb_profile_fetch(vb_ctx* ctx, double* stage_ms, int32_t* n_calls);
+
 /* debug: last Parzen histogram / E(u|v) table / lattice of subject `i` of the most recent
  * vb_n4_batch_* call (needs ctx debug capture; see vb_set_debug). */
 int vb_set_debug(vb_ctx* ctx, int32_t on);

@@ -61,7 +61,9 @@ class VbError(RuntimeError):
 EXPORTS = ["vb_version", "vb_last_error", "vb_device_count", "vb_create", "vb_destroy", "vb_launch_count",
            "vb_n4_default_params", "vb_ci_table_create", "vb_ci_table_radii", "vb_snr_batch_dev", "vb_n4_batch_dev",
            "vb_vdp_batch_dev", "vb_border_batch_dev", "vb_ci_batch_dev", "vb_pipeline_batch_dev",
-           "vb_pipeline_batch_host", "vb_set_debug", "vb_n4_debug_fetch"]
+           "vb_pipeline_batch_host", "vb_set_profiling", "vb_profile_fetch", "vb_set_debug", "vb_n4_debug_fetch"]
+N_STAGES = 5
+STAGE_NAMES = ("snr", "n4", "vdp", "mask_border", "ci")
 
 
 def bind(path):
@@ -87,6 +89,8 @@ def bind(path):
     lib.vb_ci_batch_dev.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     lib.vb_pipeline_batch_dev.argtypes = [vp, i32, vp, vp, C.POINTER(N4Params), f32, u32, C.POINTER(Buffers), vp]
     lib.vb_pipeline_batch_host.argtypes = [vp, i32, vp, vp, C.POINTER(N4Params), f32, u32, C.POINTER(Buffers)]
+    lib.vb_set_profiling.argtypes = [vp, i32]
+    lib.vb_profile_fetch.argtypes = [vp, vp, C.POINTER(i32)]
     lib.vb_set_debug.argtypes = [vp, i32]
     lib.vb_n4_debug_fetch.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i32]
     return lib
@@ -182,9 +186,19 @@ class Context:
 
     # -- whole path, host buffers ----------------------------------------------------------------
     def pipeline_host(self, shapes, flags, image=None, mask=None, n4=None, handles=None, params=None, thresh=0.6,
-                      want_logbias=False, want_mask_border=False):
+                      want_logbias=False, want_mask_border=False, buffers=None):
         """Run the selected stages on a batch given as HOST arrays (concatenated, C order).
-        Returns a dict of numpy outputs (compact dtypes) and the per-subject stats record array."""
+        Returns a dict of numpy outputs (compact dtypes) and the per-subject stats record array.
+        ``buffers``: optional dict of preallocated (e.g. pinned) output arrays to fill instead of
+        allocating new ones (keys as in the returned dict)."""
+        def _buf(key, dtype, size=None):
+            size = V if size is None else size
+            if buffers is not None and key in buffers:
+                a = buffers[key]
+                assert a.dtype == dtype and a.size == size and a.flags.c_contiguous, key
+                return a.reshape(-1)
+            return np.empty(size, dtype=dtype)
+
         shapes = np.ascontiguousarray(shapes, dtype=np.int32).reshape(-1, 3)
         n = shapes.shape[0]
         V = int(np.prod(shapes.astype(np.int64), axis=1).sum())
@@ -199,27 +213,27 @@ class Context:
             b.image = image.ctypes.data
         if flags & (DO_N4 | DO_VDP):
             if flags & DO_N4:
-                out["n4"] = np.empty(V, dtype=np.float32)
+                out["n4"] = _buf("n4", np.float32)
             else:
                 out["n4"] = np.ascontiguousarray(n4, dtype=np.float32).reshape(-1)
             b.n4 = out["n4"].ctypes.data
         if want_logbias and flags & DO_N4:
-            out["logbias"] = np.empty(V, dtype=np.float32)
+            out["logbias"] = _buf("logbias", np.float32)
             b.logbias = out["logbias"].ctypes.data
         if flags & DO_VDP:
             for k in ("defect", "defect_lb", "defect_border"):
-                out[k] = np.empty(V, dtype=np.uint8)
+                out[k] = _buf(k, np.uint8)
                 setattr(b, k, out[k].ctypes.data)
         elif flags & DO_CI:
             raise ValueError("CI without VDP: use ci_host()")
         if want_mask_border or flags & DO_MASK_BORDER:
             flags |= DO_MASK_BORDER
-            out["mask_border"] = np.empty(V, dtype=np.uint8)
+            out["mask_border"] = _buf("mask_border", np.uint8)
             b.mask_border = out["mask_border"].ctypes.data
         if flags & DO_CI:
-            out["ci_shell"] = np.empty(V, dtype=np.uint16)
+            out["ci_shell"] = _buf("ci_shell", np.uint16)
             b.ci_shell = out["ci_shell"].ctypes.data
-        stats = np.zeros(n, dtype=STATS_DTYPE)
+        stats = _buf("stats", STATS_DTYPE, n) if buffers is not None and "stats" in buffers else np.zeros(n, dtype=STATS_DTYPE)
         b.stats = stats.ctypes.data
         hd = None if handles is None else np.ascontiguousarray(handles, dtype=np.int32)
         p = params if params is not None else self.default_n4_params()
@@ -265,6 +279,16 @@ class Context:
         L = int(np.prod(ncp))
         return dict(hist=hist, emap=emap, lattice=lat[:L].reshape(tuple(int(x) for x in ncp)).copy(), ncp=ncp,
                     conv=trace[trace >= 0])
+
+    def set_profiling(self, on=True):
+        self.check(self.lib.vb_set_profiling(self.h, 1 if on else 0))
+
+    def profile_fetch(self):
+        """({stage: summed ms}, number of profiled pipeline calls) since the last fetch."""
+        ms = np.zeros(N_STAGES, dtype=np.float64)
+        n = C.c_int32(0)
+        self.check(self.lib.vb_profile_fetch(self.h, _ptr(ms), C.byref(n)))
+        return dict(zip(STAGE_NAMES, (float(x) for x in ms))), n.value
 
     def set_debug(self, on=True):
         self.check(self.lib.vb_set_debug(self.h, 1 if on else 0))

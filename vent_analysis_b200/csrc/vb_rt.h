@@ -44,6 +44,12 @@ template <class K> inline bool allow_smem(K kernel, int bytes) {
 }
 inline bool stream_create(stream_t* s) { return ok(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking), "cudaStreamCreate"); }
 inline void stream_destroy(stream_t s) { if (s) cudaStreamDestroy(s); }
+typedef cudaEvent_t event_t;
+inline bool event_create(event_t* e) { return ok(cudaEventCreate(e), "cudaEventCreate"); }
+inline void event_destroy(event_t e) { if (e) cudaEventDestroy(e); }
+inline bool event_record(event_t e, stream_t s) { return ok(cudaEventRecord(e, s), "cudaEventRecord"); }
+inline bool event_sync(event_t e) { return ok(cudaEventSynchronize(e), "cudaEventSynchronize"); }
+inline bool event_elapsed(float* ms, event_t a, event_t b) { return ok(cudaEventElapsedTime(ms, a, b), "cudaEventElapsedTime"); }
 #else
 typedef void* stream_t;
 inline bool dev_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); memset(*p, 0xAB, n); return *p != nullptr; }
@@ -63,6 +69,12 @@ inline int max_smem_optin(int) { return 232448; }
 template <class K> inline bool allow_smem(K, int) { return true; }
 inline bool stream_create(stream_t* s) { *s = nullptr; return true; }
 inline void stream_destroy(stream_t) {}
+typedef void* event_t;
+inline bool event_create(event_t* e) { *e = nullptr; return true; }
+inline void event_destroy(event_t) {}
+inline bool event_record(event_t, stream_t) { return true; }
+inline bool event_sync(event_t) { return true; }
+inline bool event_elapsed(float* ms, event_t, event_t) { *ms = 0.0f; return true; }
 #endif
 
 }  // namespace vbrt

@@ -45,6 +45,10 @@ struct vb_ctx {
     std::vector<TableHost> tables;
     Buf d_tables;
     bool tables_dirty = true;
+    // per-stage CUDA-event timing of vb_pipeline_batch_dev (vb_set_profiling)
+    bool prof = false;
+    std::vector<vbrt::event_t> ev;      // (VB_N_STAGES + 1) events per profiled call
+    size_t ev_used = 0;
     // host-API mirrors
     Buf m_image, m_mask, m_n4, m_logbias, m_defect, m_lb, m_dborder, m_mborder, m_shell, m_stats;
 };
@@ -314,6 +318,7 @@ void vb_destroy(vb_ctx* c) {
     for (Buf* b : bufs) vbrt::dev_free(b->p);
     for (TableHost& t : c->tables) { vbrt::dev_free(t.d_rows); vbrt::dev_free(t.d_ii); }
     vbrt::host_free(c->h_desc.p);
+    for (vbrt::event_t e : c->ev) vbrt::event_destroy(e);
     vbrt::stream_destroy(c->stream);
     delete c;
 }
@@ -435,24 +440,41 @@ int vb_pipeline_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const int
     int rc = prepare(c, n, shapes, (flags & VB_DO_CI) ? handles : nullptr, s);
     if (rc) return rc;
     if (!vbrt::dev_memset(d->stats, 0, sizeof(vb_subject_stats) * (size_t)n, s)) return VB_ERR_CUDA;
+    // stage boundaries: one event before the first stage and one after each stage
+    vbrt::event_t* ev = nullptr;
+    if (c->prof) {
+        while (c->ev.size() < c->ev_used + VB_N_STAGES + 1) {
+            vbrt::event_t e;
+            if (!vbrt::event_create(&e)) return VB_ERR_CUDA;
+            c->ev.push_back(e);
+        }
+        ev = c->ev.data() + c->ev_used;
+        c->ev_used += VB_N_STAGES + 1;
+        if (!vbrt::event_record(ev[0], s)) return VB_ERR_CUDA;
+    }
     if (flags & VB_DO_SNR) {
         if (!d->image) return fail(VB_ERR_ARG, "pipeline: SNR needs image");
         if ((rc = run_snr(c, d->image, d->mask, n, 20, d->stats, s))) return rc;
     }
+    if (ev && !vbrt::event_record(ev[1], s)) return VB_ERR_CUDA;
     if (flags & VB_DO_N4) {
         if (!d->image || !d->n4 || !params) return fail(VB_ERR_ARG, "pipeline: N4 needs image, n4, params");
         if ((rc = run_n4(c, d->image, d->mask, n, params, d->n4, d->logbias, d->stats, s))) return rc;
     }
+    if (ev && !vbrt::event_record(ev[2], s)) return VB_ERR_CUDA;
     if (flags & VB_DO_VDP) {
         if (!d->n4 || !d->defect || !d->defect_lb) return fail(VB_ERR_ARG, "pipeline: VDP needs n4, defect, defect_lb");
         if ((rc = run_vdp(c, d->n4, d->mask, n, thresh, d->defect, d->defect_lb, d->defect_border, d->stats, s))) return rc;
     }
+    if (ev && !vbrt::event_record(ev[3], s)) return VB_ERR_CUDA;
     if ((flags & VB_DO_MASK_BORDER) && d->mask_border)
         if ((rc = run_border(c, d->mask, n, d->mask_border, s))) return rc;
+    if (ev && !vbrt::event_record(ev[4], s)) return VB_ERR_CUDA;
     if (flags & VB_DO_CI) {
         if (!d->defect || !d->ci_shell) return fail(VB_ERR_ARG, "pipeline: CI needs defect, ci_shell");
         if ((rc = run_ci(c, d->defect, n, d->ci_shell, d->stats, s))) return rc;
     }
+    if (ev && !vbrt::event_record(ev[5], s)) return VB_ERR_CUDA;
     return VB_OK;
 }
 
@@ -515,6 +537,32 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
     if (flags & VB_DO_CI)
         for (int i = 0; i < n; ++i)
             if (h->stats[i].ci_error) return fail(VB_ERR_CI_RMAX, "CI: maximum sphere radius reached (table exhausted)");
+    return VB_OK;
+}
+
+int vb_set_profiling(vb_ctx* c, int32_t on) {
+    if (!c) return fail(VB_ERR_ARG, "null ctx");
+    c->prof = on != 0;
+    c->ev_used = 0;
+    return VB_OK;
+}
+
+int vb_profile_fetch(vb_ctx* c, double* stage_ms, int32_t* n_calls) {
+    if (!c || !stage_ms) return fail(VB_ERR_ARG, "profile_fetch: null argument");
+    vbrt::set_device(c->device);
+    for (int k = 0; k < VB_N_STAGES; ++k) stage_ms[k] = 0.0;
+    const size_t calls = c->ev_used / (VB_N_STAGES + 1);
+    for (size_t i = 0; i < calls; ++i) {
+        vbrt::event_t* ev = c->ev.data() + i * (VB_N_STAGES + 1);
+        if (!vbrt::event_sync(ev[VB_N_STAGES])) return VB_ERR_CUDA;
+        for (int k = 0; k < VB_N_STAGES; ++k) {
+            float ms = 0.0f;
+            if (!vbrt::event_elapsed(&ms, ev[k], ev[k + 1])) return VB_ERR_CUDA;
+            stage_ms[k] += (double)ms;
+        }
+    }
+    if (n_calls) *n_calls = (int32_t)calls;
+    c->ev_used = 0;
     return VB_OK;
 }
 
