@@ -20,6 +20,8 @@ for name in cfgs:
     it_g = [int(x) for x in out["stats"]["n4_iters"][0][:4]]
     it_r = [int(x) for x in ref["iters"]]
     print(name, libpath.split('/')[-1], "iters gpu", it_g, "ref", it_r)
+    print(" phase us:", {k: round(v, 1) for k, v in dbg["phase_us"].items()}, "per-iteration:",
+          {k: round(v / max(sum(it_g), 1), 2) for k, v in dbg["phase_us"].items()})
     g = dbg["conv"]
     pos = 0
     for lvl in range(4):

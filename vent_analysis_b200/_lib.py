@@ -267,7 +267,7 @@ class Context:
             self.check(rc)
         return shell, stats, rc
 
-    def n4_debug(self, subject, nbins, lattice_capacity, trace_capacity=200):
+    def n4_debug(self, subject, nbins, lattice_capacity, trace_capacity=208):
         self.check(self.lib.vb_set_debug(self.h, 1))
         hist = np.zeros(nbins, dtype=np.float32)
         emap = np.zeros(nbins, dtype=np.float32)
@@ -277,8 +277,11 @@ class Context:
         self.check(self.lib.vb_n4_debug_fetch(self.h, int(subject), _ptr(hist), _ptr(emap), _ptr(lat),
                                               lattice_capacity, _ptr(ncp), _ptr(trace), trace_capacity))
         L = int(np.prod(ncp))
+        phases = dict(zip(("setup", "hist", "sharpen", "fit", "update", "chain", "finalize", "other"),
+                          (float(x) for x in trace[-8:])))
+        tr = trace[:-8]
         return dict(hist=hist, emap=emap, lattice=lat[:L].reshape(tuple(int(x) for x in ncp)).copy(), ncp=ncp,
-                    conv=trace[trace >= 0])
+                    conv=tr[tr >= 0], phase_us=phases)
 
     def set_profiling(self, on=True):
         self.check(self.lib.vb_set_profiling(self.h, 1 if on else 0))

@@ -7,29 +7,41 @@
 // Design:
 //   * A CTA pulls subjects from a global work counter and runs the WHOLE filter for one
 //     subject -- 4 levels x <=50 iterations x {histogram, Wiener sharpening, B-spline fit,
-//     update/convergence} -- with block barriers only; no host round trip, subjects converge
+//     update, convergence} -- with block barriers only; no host round trip, subjects converge
 //     independently.
-//   * Volume layout is the reference's [row][col][slice] C order.  A thread owns one
-//     (col, slice) column and walks it along the row axis, so a warp touches 32 consecutive
-//     floats per row step (coalesced) and the row-axis B-spline weights are warp uniform.
-//     A per-column row bitmask (built once per subject) lets warps skip rows and whole
-//     column tiles that hold no mask voxel: only masked sectors of U are ever read.
-//   * Parzen histogram: every thread owns a private 200-bin column in shared memory
-//     ([bin][thread], conflict free, plain LDS/FADD/STS instead of atomics), reduced by a
-//     fixed warp tree => deterministic.
+//   * Only mask voxels take part in the iterations, so the log image is COMPACTED once per
+//     subject: columns (col, slice) are grouped in blocks of 32 (one warp), and within a block
+//     the masked voxels are stored row by row, lane by lane.  A warp that walks the rows of its
+//     block therefore reads one contiguous, conflict-free stream.  For the benchmark volumes
+//     (128x128x14, ~36k mask voxels = 143 KB) the compact log image lives in SHARED MEMORY for
+//     the whole filter; larger masks fall back to a compact array in global memory (L2).
+//   * Nothing else is stored per voxel: U = logI - bias is re-evaluated from the control
+//     lattice (shared memory) wherever it is needed.  The row-axis B-spline weights are warp
+//     uniform; a lane keeps a 4-tap sliding window of column coefficients in registers.
+//   * Parzen histogram: fixed-point (count-conserving) shared-memory atomics into 8 copies
+//     => deterministic, no 200 KB of private bins.
 //   * Sharpening: 4 packed 512-point complex FFTs in double in shared memory.
 //   * B-spline fit: the Lee-Wolberg-Shin scatter is separable (t = tr*tc*ts,
 //     sum t^2 = Sr*Sc*Ss), so delta = sum w^3 z / sum w^2 is three small contractions:
-//     rows (registers, sliding 4-tap window) -> cols (shared Q[a][b][s]) -> slices.
-//     omega depends only on the mask and the lattice size: once per level.
-//   * U = logI - bias is kept in the output buffer during the iterations; the corrected
-//     image overwrites it in the final dense pass (the only HBM-streaming part).
+//     rows (registers, sliding 4-tap window) -> columns -> slices.  omega depends only on the
+//     mask and the lattice size: once per level.
+//   * Convergence: ITK's CalculateConvergenceMeasurement is a SEQUENTIAL float32 Welford
+//     recurrence whose rounding (the running mean stalls once its update drops below half an
+//     ulp) decides when a level stops.  It is reproduced here in parallel: the recurrence is
+//     iterated Jacobi-style on float bit patterns in chunks (guess trajectory -> per-step
+//     increments -> prefix sum) until the trajectory reproduces itself, which proves it is the
+//     sequential one.
 #pragma once
 #include <float.h>
 #include "vb_common.cuh"
 
-#define VB_N4_THREADS 256
+#define VB_N4_THREADS 512
+#define VB_N4_WARPS (VB_N4_THREADS / 32)
 #define VB_BSPLINE_EPS 1e-3f
+#define VB_N4_EPT 8                               /* convergence chain: elements per thread   */
+#define VB_N4_CHUNK (VB_N4_THREADS * VB_N4_EPT)   /* ... per chunk                            */
+#define VB_N4_SERIAL 64                           /* first elements: one thread, sequentially */
+#define VB_N4_HCOPIES 8                           /* histogram copies (warp & 7)              */
 
 struct N4Args {
     const float* image;
@@ -41,22 +53,26 @@ struct N4Args {
     vb_n4_params p;
     vb_subject_stats* stats; // may be null
     // per-CTA workspace (slot = blockIdx.x)
-    float* ws_logI;          // [grid][Vmax]
-    uint32_t* ws_colmask;    // [grid][cmw_max]
+    float* ws_logI;          // [grid][Vmax]      compact log image when it does not fit smem
+    uint32_t* ws_colmask;    // [grid][cmw_max]   per column: row bitmask words
+    uint32_t* ws_rbb;        // [grid][rbb_max]   C-order rank of the first mask voxel of (row, block)
+    uint32_t* ws_blkbase;    // [grid][blk_max]   compact offset of every column block (+1)
     float* ws_axis;          // [grid][axis_stride]  (4-byte words)
+    float* ws_e;             // [grid][Vmax]      exp(bias_old - bias_new) over the mask, C order
+    float* ws_P;             // [grid][P_max]     row-contracted columns [ncp0][ncols]
     int* work_counter;
     float* debug;            // may be null: [n][debug_stride]
-    long long Vmax, cmw_max;
+    long long Vmax, cmw_max, rbb_max, blk_max, P_max;
     int axis_stride, debug_stride;
-    int hist_threads;        // HT: threads that own a private histogram column
     int Lmax;                // max lattice entries (after the last refinement)
     int fftN;                // padded histogram size
     int union_bytes;         // size of the shared-memory union region
+    int logI_cap;            // floats of compact log image that fit shared memory (0 = none)
 };
 
 // debug record layout (floats): [0]=bmin [1]=bmax [2..4]=ncp [5]=n_trace, then
 // hist[nbins], emap[nbins], lattice[Lmax], trace[...]
-#define VB_DBG_HDR 8
+#define VB_DBG_HDR 16   /* [8..15]: phase time in microseconds (setup, hist, sharpen, fit, update, chain, finalize, other) */
 
 VB_DEV double vb_bspline3(double u) {
     const double a = fabs(u);
@@ -76,13 +92,15 @@ VB_DEV double vb_bspline3(double u) {
     return 0.0;
 }
 
-// Per-axis tables, 16 words per sample: fit3[4] | fit2[4] | evw[4] | bfit | bev | pad[2]
+// Per-axis tables, 16 words per sample: fit3[4] | fit2[4] | evw[4] | bfit | bev | lo | hi
 struct N4Axis {
     const float4* fit3;   // B^3 / sum(B^2)   (delta numerator weights)
     const float4* fit2;   // B^2              (omega weights)
     const float4* evw;    // B                (field evaluation)
     const int* bfit;      // first supporting control point, fit parameterisation
     const int* bev;       // first supporting control point, evaluation parameterisation
+    const int* lo;        // [ncp] first sample whose fit support contains control point b
+    const int* hi;        // [ncp] one past the last such sample
 };
 VB_DEV N4Axis n4_axis(float* base, int n) {
     N4Axis a;
@@ -91,17 +109,19 @@ VB_DEV N4Axis n4_axis(float* base, int n) {
     a.evw = (const float4*)(base + 8 * (size_t)n);
     a.bfit = (const int*)(base + 12 * (size_t)n);
     a.bev = (const int*)(base + 13 * (size_t)n);
+    a.lo = (const int*)(base + 14 * (size_t)n);
+    a.hi = (const int*)(base + 15 * (size_t)n);
     return a;
 }
 
 // BSplineScatteredDataPointSetToImageFilter / BSplineControlPointImageFilter parametrisation
 // of one axis (oracle: fit_axis_table / eval_axis_table in n4_oracle.c).
-VB_DEV void n4_build_axis(float* base, int n, int ncp) {
+VB_DEV void n4_build_axis(float* base, int slot, int n, int ncp) {
     float4* fit3 = (float4*)base;
-    float4* fit2 = (float4*)(base + 4 * (size_t)n);
-    float4* evw = (float4*)(base + 8 * (size_t)n);
-    int* bfit = (int*)(base + 12 * (size_t)n);
-    int* bev = (int*)(base + 13 * (size_t)n);
+    float4* fit2 = (float4*)(base + 4 * (size_t)slot);
+    float4* evw = (float4*)(base + 8 * (size_t)slot);
+    int* bfit = (int*)(base + 12 * (size_t)slot);
+    int* bev = (int*)(base + 13 * (size_t)slot);
     const int spans = ncp - 3;
     const float fs = (float)spans;
     const float r = (n > 1) ? (float)__ddiv_rn((double)fs, (double)(float)(n - 1)) : 0.0f;
@@ -138,116 +158,337 @@ VB_DEV void n4_build_axis(float* base, int n, int ncp) {
     }
 }
 
+// support ranges of the control points along one axis (bfit is non-decreasing)
+VB_DEV void n4_build_support(float* base, int slot, int n, int ncp) {
+    const int* bfit = (const int*)(base + 12 * (size_t)slot);
+    int* lo = (int*)(base + 14 * (size_t)slot);
+    int* hi = (int*)(base + 15 * (size_t)slot);
+    for (int b = (int)threadIdx.x; b < ncp; b += (int)blockDim.x) {
+        int l = 0;
+        while (l < n && bfit[l] < b - 3) ++l;
+        int h = l;
+        while (h < n && bfit[h] <= b) ++h;
+        lo[b] = l; hi[b] = h;
+    }
+}
+
 struct N4Ctx {
     // subject
-    int n0, n1, n2, ncols, W;
+    int n0, n1, n2, ncols, W, nblk;
     long long V;
     const float* img;
     const uint8_t* msk;
-    float* U;        // aliases the output buffer
-    float* logI;
-    uint32_t* colmask;
+    float* out;
+    float* logI;          // compact log image (shared or global memory)
+    uint32_t* colmask;    // [W][ncols]
+    uint32_t* rbb;        // [n0][nblk] (+1)
+    uint32_t* blkbase;    // [nblk + 1]
     float* axis_base;
+    float* ebuf;          // [M]
+    float* P;             // [ncp0][ncols]
     // shared memory
-    float* un_f;     // union region
+    float* un_f;          // union region
     double* un_d;
-    float* L;        // lattice [ncp0][ncp1][ncp2]
-    float* Om;       // omega lattice of the current level
-    float* E;        // E(u|v) table
-    float* H;        // histogram
-    double* red;     // 64 doubles reduction scratch
+    float* L;             // lattice [ncp0][ncp1][ncp2]
+    float* Lold;          // lattice before the last update
+    float* Om;            // omega lattice of the current level
+    float* E;             // E(u|v) table
+    float* H;             // histogram
+    double* red;          // 64 doubles reduction scratch
     int ncp[3];
-    int nbins, HT, fftN;
+    int slot[3];          // per-axis table length: max(samples, final control points)
+    int nbins, fftN, hshift;
+    long long t_chain;    // debug: clock ticks spent in n4_convergence
+    int n_sweeps;         // debug: Jacobi sweeps of the convergence chain
 };
 
 VB_DEV N4Axis n4_ax(const N4Ctx& c, int a) {
-    const int n[3] = {c.n0, c.n1, c.n2};
     size_t off = 0;
-    for (int i = 0; i < a; ++i) off += 16 * (size_t)n[i];
-    return n4_axis(c.axis_base + off, n[a]);
+    for (int i = 0; i < a; ++i) off += 16 * (size_t)c.slot[i];
+    return n4_axis(c.axis_base + off, c.slot[a]);
 }
 
 // ---------------------------------------------------------------------------------------------
-// setup: per-column row bitmask, logI, U, range and count of the mask
-VB_DEV void n4_setup(N4Ctx& c, int label, float& bmin, float& bmax, int& M) {
+// block-wide exclusive scan of one int per thread; every thread gets its prefix and the total
+VB_DEV int n4_block_scan(int v, int& total, int* scratch /* >= 33 ints */) {
+    const int lane = vb_lane(), w = vb_warp(), nw = (int)(blockDim.x >> 5);
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(VB_FULL, inc, d);
+        if (lane >= d) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) scratch[w] = inc;
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int i = 0; i < nw; ++i) {
+        const int t = scratch[i];
+        if (i < w) woff += t;
+        tot += t;
+    }
+    total = tot;
+    return woff + inc - v;
+}
+
+// in-place exclusive scan of arr[0..n) (global), arr[n] = total; returns the total
+VB_DEV int n4_array_scan(uint32_t* arr, int n, int* scratch) {
     const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
-    float tmin = FLT_MAX, tmax = -FLT_MAX;
-    int cnt = 0;
-    for (int q = tid; q < c.ncols; q += nt) {
+    const int per = (n + nt - 1) / nt;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += (int)arr[i];
+    int total;
+    int run = n4_block_scan(s, total, scratch);
+    for (int i = lo; i < hi; ++i) {
+        const int t = (int)arr[i];
+        arr[i] = (uint32_t)run;
+        run += t;
+    }
+    if (tid == 0) arr[n] = (uint32_t)total;
+    __syncthreads();
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column context of one lane: evaluation weights of its (col, slice) and a 4-tap sliding window
+// of collapsed column coefficients G[a] = sum_{b,g} wc[b] ws[g] L[a][bc+b][bs+g]
+struct N4Col {
+    int bc, bs;
+    float wc0, wc1, wc2, wc3;
+    float4 ws;
+};
+VB_DEV N4Col n4_col(const N4Ctx& c, const N4Axis& ac, const N4Axis& as, int q) {
+    N4Col k;
+    const int cc = q / c.n2, ss = q - cc * c.n2;
+    k.bc = ac.bev[cc]; k.bs = as.bev[ss];
+    const float4 wc = ac.evw[cc];
+    k.wc0 = wc.x; k.wc1 = wc.y; k.wc2 = wc.z; k.wc3 = wc.w;
+    k.ws = as.evw[ss];
+    return k;
+}
+VB_DEV float n4_coef(const float* L, const N4Ctx& c, const N4Col& k, int a) {
+    const float* lp = L + ((size_t)a * c.ncp[1] + k.bc) * c.ncp[2] + k.bs;
+    const int st = c.ncp[2];
+    float g = 0.0f;
+    g += k.wc0 * (k.ws.x * lp[0] + k.ws.y * lp[1] + k.ws.z * lp[2] + k.ws.w * lp[3]);
+    lp += st;
+    g += k.wc1 * (k.ws.x * lp[0] + k.ws.y * lp[1] + k.ws.z * lp[2] + k.ws.w * lp[3]);
+    lp += st;
+    g += k.wc2 * (k.ws.x * lp[0] + k.ws.y * lp[1] + k.ws.z * lp[2] + k.ws.w * lp[3]);
+    lp += st;
+    g += k.wc3 * (k.ws.x * lp[0] + k.ws.y * lp[1] + k.ws.z * lp[2] + k.ws.w * lp[3]);
+    return g;
+}
+struct N4Win {
+    float g0, g1, g2, g3;
+    int cur;
+};
+VB_DEV void n4_win_advance(N4Win& w, const float* L, const N4Ctx& c, const N4Col& k, int base) {
+    if (base == w.cur) return;
+    if (w.cur < 0 || base - w.cur >= 4 || base < w.cur) {
+        w.g0 = n4_coef(L, c, k, base); w.g1 = n4_coef(L, c, k, base + 1);
+        w.g2 = n4_coef(L, c, k, base + 2); w.g3 = n4_coef(L, c, k, base + 3);
+        w.cur = base;
+    } else {
+        while (w.cur < base) {
+            w.g0 = w.g1; w.g1 = w.g2; w.g2 = w.g3; w.g3 = n4_coef(L, c, k, w.cur + 4);
+            ++w.cur;
+        }
+    }
+}
+VB_DEV float n4_win_eval(const N4Win& w, const float4 rw) {
+    return rw.x * w.g0 + rw.y * w.g1 + rw.z * w.g2 + rw.w * w.g3;
+}
+
+// exp(x) for the small arguments of the convergence measure: 1 + (x + x^2/2 + ...), whose final
+// addition is (almost always) the correctly rounded float, like glibc's expf in the oracle.
+VB_DEV float n4_exp_small(float x) {
+    if (fabsf(x) < 0.03125f) {
+        const float x2 = x * x;
+        float p = 1.0f / 120.0f;
+        p = fmaf(p, x, 1.0f / 24.0f);
+        p = fmaf(p, x, 1.0f / 6.0f);
+        p = fmaf(p, x, 0.5f);
+        return 1.0f + fmaf(p, x2, x);
+    }
+    return expf(x);
+}
+
+// Walk the mask voxels of one column block row by row.  BODY sees: r (row), bit (this lane's
+// voxel is in the mask), idx (compact index of this lane's voxel when bit), bal (lane mask of
+// the row).  Rows without any mask voxel in the block are skipped.
+#define VB_N4_FOR_ROWS(c, q, valid, pos0, ...)                                               \
+    {                                                                                        \
+        unsigned pos_ = (pos0);                                                              \
+        const unsigned lt_ = (1u << vb_lane()) - 1u;                                         \
+        for (int wi_ = 0; wi_ < (c).W; ++wi_) {                                              \
+            const uint32_t mw_ = (valid) ? (c).colmask[(size_t)wi_ * (c).ncols + (q)] : 0u;  \
+            uint32_t rem_ = __reduce_or_sync(VB_FULL, mw_);                                  \
+            while (rem_) {                                                                   \
+                const int b_ = __ffs((int)rem_) - 1;                                         \
+                rem_ &= rem_ - 1u;                                                           \
+                const int r = wi_ * 32 + b_;                                                 \
+                const bool bit = (mw_ >> b_) & 1u;                                           \
+                const unsigned bal = __ballot_sync(VB_FULL, bit);                            \
+                const unsigned idx = pos_ + (unsigned)__popc(bal & lt_);                     \
+                __VA_ARGS__                                                                  \
+                pos_ += (unsigned)__popc(bal);                                               \
+            }                                                                                \
+        }                                                                                    \
+    }
+
+// ---------------------------------------------------------------------------------------------
+// setup: column bitmasks, compaction tables, compact log image, range and count of the mask
+VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float& bmin, float& bmax, int& M) {
+    const int nt = (int)blockDim.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
+    for (int blk = w; blk < c.nblk; blk += nw) {
+        const int q = blk * 32 + lane;
+        const bool valid = q < c.ncols;
+        int tot = 0;
         for (int wi = 0; wi < c.W; ++wi) {
             uint32_t bits = 0;
             const int rend = min(32, c.n0 - wi * 32);
-            for (int b = 0; b < rend; ++b) {
-                const size_t v = (size_t)(wi * 32 + b) * c.ncols + q;
-                if ((int)vb_ld_stream(c.msk + v) == label) {
-                    bits |= 1u << b;
-                    const float x = vb_ld_stream(c.img + v);
-                    const float l = (x > 0.0f) ? logf(x) : x;
-                    c.logI[v] = l;
-                    c.U[v] = l;
-                    tmin = fminf(tmin, l);
-                    tmax = fmaxf(tmax, l);
-                    ++cnt;
+            for (int b0 = 0; b0 < rend; b0 += 8) {
+                uint8_t mv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    mv[j] = (valid && b0 + j < rend) ? vb_ld_stream(c.msk + (size_t)(wi * 32 + b0 + j) * c.ncols + q) : (uint8_t)0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (b0 + j >= rend) break;                       // warp uniform
+                    const bool m = valid && b0 + j < rend && (int)mv[j] == label;
+                    const unsigned bal = __ballot_sync(VB_FULL, m);
+                    if (m) bits |= 1u << (b0 + j);
+                    const int cnt = __popc(bal);
+                    if (lane == 0) c.rbb[(size_t)(wi * 32 + b0 + j) * c.nblk + blk] = (uint32_t)cnt;
+                    tot += cnt;
                 }
             }
-            c.colmask[(size_t)wi * c.ncols + q] = bits;
+            if (valid) c.colmask[(size_t)wi * c.ncols + q] = bits;
+        }
+        if (lane == 0) c.blkbase[blk] = (uint32_t)tot;
+    }
+    __syncthreads();
+    M = n4_array_scan(c.rbb, c.n0 * c.nblk, (int*)c.red);
+    n4_array_scan(c.blkbase, c.nblk, (int*)c.red);
+    // histogram fixed point: the largest number of voxels any histogram copy can receive
+    int mc = 0;
+    if ((int)threadIdx.x < VB_N4_HCOPIES)
+        for (int blk = (int)threadIdx.x; blk < c.nblk; blk += VB_N4_HCOPIES)
+            mc += (int)(c.blkbase[blk + 1] - c.blkbase[blk]);
+    mc = vb_block_reduce(mc, VbMaxI(), 0, (int*)c.red);
+    int bits = 0;
+    while ((1LL << bits) <= (long long)mc) ++bits;
+    c.hshift = min(24, 31 - bits);
+
+    if (M <= smem_cap) c.logI = smem_logI;             // the compact log image fits shared memory
+
+    float tmin = FLT_MAX, tmax = -FLT_MAX;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int blk = w; blk < c.nblk; blk += nw) {
+        unsigned pos = c.blkbase[blk];
+        if (c.blkbase[blk + 1] == pos) continue;
+        const int q = blk * 32 + lane;
+        const bool valid = q < c.ncols;
+        for (int wi = 0; wi < c.W; ++wi) {
+            const uint32_t mw = valid ? c.colmask[(size_t)wi * c.ncols + q] : 0u;
+            const uint32_t wm = __reduce_or_sync(VB_FULL, mw);
+            if (!wm) continue;
+#pragma unroll 1
+            for (int b0 = 0; b0 < 32; b0 += 8) {
+                if (((wm >> b0) & 0xFFu) == 0) continue;
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    x[j] = ((mw >> (b0 + j)) & 1u) ? vb_ld_stream(c.img + (size_t)(wi * 32 + b0 + j) * c.ncols + q) : 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool bit = (mw >> (b0 + j)) & 1u;
+                    const unsigned bal = __ballot_sync(VB_FULL, bit);
+                    if (bit) {
+                        const float l = (x[j] > 0.0f) ? logf(x[j]) : x[j];
+                        c.logI[pos + (unsigned)__popc(bal & lt)] = l;
+                        tmin = fminf(tmin, l);
+                        tmax = fmaxf(tmax, l);
+                    }
+                    pos += (unsigned)__popc(bal);
+                }
+            }
         }
     }
     bmin = vb_block_reduce(tmin, VbMinF(), FLT_MAX, (float*)c.red);
     bmax = vb_block_reduce(tmax, VbMaxF(), -FLT_MAX, (float*)c.red);
-    M = vb_block_reduce(cnt, VbAddI(), 0, (int*)c.red);
+}
+
+// range of U = logI - bias(L) over the mask (after a lattice refinement)
+VB_DEV void n4_range(N4Ctx& c, float& bmin, float& bmax) {
+    const int nt = (int)blockDim.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
+    const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
+    float tmin = FLT_MAX, tmax = -FLT_MAX;
+    for (int blk = w; blk < c.nblk; blk += nw) {
+        const unsigned p0 = c.blkbase[blk];
+        if (c.blkbase[blk + 1] == p0) continue;
+        const int q = blk * 32 + lane;
+        const bool valid = q < c.ncols;
+        const N4Col col = n4_col(c, ac, as, valid ? q : c.ncols - 1);
+        N4Win win; win.cur = -1; win.g0 = win.g1 = win.g2 = win.g3 = 0.0f;
+        VB_N4_FOR_ROWS(c, q, valid, p0, {
+            n4_win_advance(win, c.L, c, col, ar.bev[r]);
+            if (bit) {
+                const float u = c.logI[idx] - n4_win_eval(win, ar.evw[r]);
+                tmin = fminf(tmin, u);
+                tmax = fmaxf(tmax, u);
+            }
+        })
+    }
+    bmin = vb_block_reduce(tmin, VbMinF(), FLT_MAX, (float*)c.red);
+    bmax = vb_block_reduce(tmax, VbMaxF(), -FLT_MAX, (float*)c.red);
 }
 
 // ---------------------------------------------------------------------------------------------
 // P1: triangular Parzen histogram of U over the mask (SharpenImage, first half)
 VB_DEV void n4_histogram(N4Ctx& c, float bmin, float bmax) {
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, HT = c.HT;
-    float* priv = c.un_f;
-    for (int i = tid; i < c.nbins * HT; i += nt) priv[i] = 0.0f;
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
+    const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
+    uint32_t* hc = (uint32_t*)c.un_f;                    // [VB_N4_HCOPIES][nbins]
+    for (int i = tid; i < c.nbins * VB_N4_HCOPIES; i += nt) hc[i] = 0u;
     __syncthreads();
     const float slope = (bmax - bmin) / (float)(c.nbins - 1);
-    if (tid < HT) {
-        for (int q0 = 0; q0 < c.ncols; q0 += HT) {
-            const int q = q0 + tid;
-            const bool valid = q < c.ncols;
-            for (int wi = 0; wi < c.W; ++wi) {
-                const uint32_t mw = valid ? c.colmask[(size_t)wi * c.ncols + q] : 0u;
-                const uint32_t wm = __reduce_or_sync(VB_FULL, mw);
-                if (!wm) continue;
-#pragma unroll 1
-                for (int b0 = 0; b0 < 32; b0 += 8) {
-                    if (((wm >> b0) & 0xFFu) == 0) continue;
-                    float u[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        u[j] = ((mw >> (b0 + j)) & 1u) ? c.U[(size_t)(wi * 32 + b0 + j) * c.ncols + q] : 0.0f;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if ((mw >> (b0 + j)) & 1u) {
-                            const float cidx = __fdiv_rn(u[j] - bmin, slope);
-                            const float fl = floorf(cidx);
-                            const int idx = (int)fl;
-                            const float off = cidx - fl;
-                            if (off == 0.0f) {
-                                if (idx >= 0 && idx < c.nbins) priv[idx * HT + tid] += 1.0f;
-                            } else if (idx >= 0 && idx < c.nbins - 1) {
-                                priv[idx * HT + tid] += 1.0f - off;
-                                priv[(idx + 1) * HT + tid] += off;
-                            }
-                        }
+    const uint32_t one = 1u << c.hshift;
+    const float fone = (float)one;
+    uint32_t* h = hc + (size_t)(w & (VB_N4_HCOPIES - 1)) * c.nbins;
+    for (int blk = w; blk < c.nblk; blk += nw) {
+        const unsigned p0 = c.blkbase[blk];
+        if (c.blkbase[blk + 1] == p0) continue;
+        const int q = blk * 32 + lane;
+        const bool valid = q < c.ncols;
+        const N4Col col = n4_col(c, ac, as, valid ? q : c.ncols - 1);
+        N4Win win; win.cur = -1; win.g0 = win.g1 = win.g2 = win.g3 = 0.0f;
+        VB_N4_FOR_ROWS(c, q, valid, p0, {
+            n4_win_advance(win, c.L, c, col, ar.bev[r]);
+            if (bit) {
+                const float u = c.logI[idx] - n4_win_eval(win, ar.evw[r]);
+                const float cidx = __fdiv_rn(u - bmin, slope);
+                const float fl = floorf(cidx);
+                const int bi = (int)fl;
+                const float off = cidx - fl;
+                if (off == 0.0f) {
+                    if (bi >= 0 && bi < c.nbins) atomicAdd(&h[bi], one);
+                } else if (bi >= 0 && bi < c.nbins - 1) {
+                    const uint32_t o = (uint32_t)__float2uint_rn(off * fone);
+                    atomicAdd(&h[bi], one - o);
+                    atomicAdd(&h[bi + 1], o);
                 }
             }
-        }
+        })
     }
     __syncthreads();
-    // fixed-order reduction: one warp per bin
-    const int nw = nt >> 5, w = tid >> 5, lane = tid & 31;
-    for (int bin = w; bin < c.nbins; bin += nw) {
-        float s = 0.0f;
-        for (int t = lane; t < HT; t += 32) s += priv[bin * HT + t];
+    for (int bin = tid; bin < c.nbins; bin += nt) {
+        unsigned long long s = 0;
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(VB_FULL, s, m);
-        if (lane == 0) c.H[bin] = s;
+        for (int k = 0; k < VB_N4_HCOPIES; ++k) s += hc[(size_t)k * c.nbins + bin];
+        c.H[bin] = (float)((double)s / (double)one);
     }
     __syncthreads();
 }
@@ -359,126 +600,102 @@ VB_DEV void n4_sharpen(N4Ctx& c, float bmin, float bmax, float fwhm, float wiene
 // ---------------------------------------------------------------------------------------------
 // Separable B-spline contraction over the mask.
 //   OMEGA = true : value 1, weights B^2            -> c.Om
-//   OMEGA = false: value U - E(U), weights B^3/S   -> phi = delta/omega, c.L += phi
+//   OMEGA = false: value U - E(U), weights B^3/S   -> phi = delta/omega; Lold = L; L += phi
 template <bool OMEGA>
 VB_DEV void n4_contract(N4Ctx& c, float bmin, float bmax) {
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
     const int ncp0 = c.ncp[0], ncp1 = c.ncp[1], ncp2 = c.ncp[2];
     const int n2 = c.n2, ncols = c.ncols;
     const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
-    float* Q = c.un_f;                                   // [ncp0][ncp1][n2]
-    const int Qn = ncp0 * ncp1 * n2;
-    float* Pt = Q + ((Qn + 3) & ~3);                     // [ncp0][nt]
-    for (int i = tid; i < Qn; i += nt) Q[i] = 0.0f;
     const float slope = (bmax - bmin) / (float)(c.nbins - 1);
     const int nbm1 = c.nbins - 1;
+    float* P = c.P;                                      // [ncp0][ncols]
+
+    // rows: every lane reduces its column to ncp0 coefficients through a sliding 4-tap window
+    for (int blk = w; blk < c.nblk; blk += nw) {
+        const int q = blk * 32 + lane;
+        const bool valid = q < ncols;
+        const unsigned p0 = c.blkbase[blk];
+        if (c.blkbase[blk + 1] == p0) {
+            if (valid)
+                for (int a = 0; a < ncp0; ++a) P[(size_t)a * ncols + q] = 0.0f;
+            continue;
+        }
+        const N4Col col = n4_col(c, ac, as, valid ? q : ncols - 1);
+        N4Win win; win.cur = -1; win.g0 = win.g1 = win.g2 = win.g3 = 0.0f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int cur = 0;                                     // coefficients below cur are final
+        VB_N4_FOR_ROWS(c, q, valid, p0, {
+            const int base = ar.bfit[r];
+            while (cur < base) {                         // warp uniform
+                if (valid) P[(size_t)cur * ncols + q] = a0;
+                a0 = a1; a1 = a2; a2 = a3; a3 = 0.f;
+                ++cur;
+            }
+            if (!OMEGA) n4_win_advance(win, c.L, c, col, ar.bev[r]);
+            if (bit) {
+                float val;
+                float4 wt;
+                if (OMEGA) {
+                    val = 1.0f;
+                    wt = ar.fit2[r];
+                } else {
+                    const float u = c.logI[idx] - n4_win_eval(win, ar.evw[r]);
+                    const float cidx = __fdiv_rn(u - bmin, slope);
+                    const float fl = floorf(cidx);
+                    const int bi = (int)fl;
+                    float s;
+                    if (bi >= 0 && bi < nbm1) {
+                        const float e0 = c.E[bi], e1 = c.E[bi + 1];
+                        s = e0 + (e1 - e0) * (cidx - fl);
+                    } else {
+                        s = c.E[nbm1];
+                    }
+                    val = u - s;
+                    wt = ar.fit3[r];
+                }
+                a0 += wt.x * val; a1 += wt.y * val; a2 += wt.z * val; a3 += wt.w * val;
+            }
+        })
+        if (valid) {
+            for (int a = cur; a < ncp0; ++a) {
+                P[(size_t)a * ncols + q] = a0;
+                a0 = a1; a1 = a2; a2 = a3; a3 = 0.f;
+            }
+        }
+    }
     __syncthreads();
 
-    for (int q0 = 0; q0 < ncols; q0 += nt) {
-        const int q = q0 + tid;
-        const bool valid = q < ncols;
-        for (int a = 0; a < ncp0; ++a) Pt[a * nt + tid] = 0.0f;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int cur = -1;
-        for (int wi = 0; wi < c.W; ++wi) {
-            const uint32_t mw = valid ? c.colmask[(size_t)wi * ncols + q] : 0u;
-            const uint32_t wm = __reduce_or_sync(VB_FULL, mw);
-            if (!wm) continue;
-#pragma unroll 1
-            for (int b0 = 0; b0 < 32; b0 += 8) {
-                if (((wm >> b0) & 0xFFu) == 0) continue;
-                float u[8];
-                if (!OMEGA) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        u[j] = ((mw >> (b0 + j)) & 1u) ? c.U[(size_t)(wi * 32 + b0 + j) * ncols + q] : 0.0f;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (!((wm >> (b0 + j)) & 1u)) continue;       // warp uniform
-                    const int r = wi * 32 + b0 + j;
-                    const int base = ar.bfit[r];
-                    if (base != cur) {                            // warp uniform
-                        if (cur >= 0) {
-                            while (cur < base) {
-                                Pt[cur * nt + tid] = a0;
-                                a0 = a1; a1 = a2; a2 = a3; a3 = 0.f;
-                                ++cur;
-                            }
-                        } else {
-                            cur = base;
-                        }
-                    }
-                    if ((mw >> (b0 + j)) & 1u) {
-                        float val;
-                        float4 w;
-                        if (OMEGA) {
-                            val = 1.0f;
-                            w = ar.fit2[r];
-                        } else {
-                            const float cidx = __fdiv_rn(u[j] - bmin, slope);
-                            const float fl = floorf(cidx);
-                            const int idx = (int)fl;
-                            float s;
-                            if (idx >= 0 && idx < nbm1) {
-                                const float e0 = c.E[idx], e1 = c.E[idx + 1];
-                                s = e0 + (e1 - e0) * (cidx - fl);
-                            } else {
-                                s = c.E[nbm1];
-                            }
-                            val = u[j] - s;
-                            w = ar.fit3[r];
-                        }
-                        a0 += w.x * val; a1 += w.y * val; a2 += w.z * val; a3 += w.w * val;
-                    }
-                }
-            }
+    // columns: Q[a][b][s] = sum_c wc[c][b - bfit[c]] * P[a][c][s]
+    float* Q = c.un_f;                                   // [ncp0][ncp1][n2]
+    const int Qn = ncp0 * ncp1 * n2;
+    for (int e = tid; e < Qn; e += nt) {
+        const int s = e % n2, ab = e / n2, b = ab % ncp1, a = ab / ncp1;
+        const float* pp = P + (size_t)a * ncols + s;
+        float sum = 0.0f;
+        const int chi = ac.hi[b];
+#pragma unroll 4
+        for (int cc = ac.lo[b]; cc < chi; ++cc) {
+            const int k = b - ac.bfit[cc];
+            const float4 wt = OMEGA ? ac.fit2[cc] : ac.fit3[cc];
+            const float wk = (k == 0) ? wt.x : (k == 1) ? wt.y : (k == 2) ? wt.z : wt.w;
+            sum += wk * pp[(size_t)cc * n2];
         }
-        if (cur >= 0) {
-            Pt[cur * nt + tid] = a0;
-            Pt[(cur + 1) * nt + tid] = a1;
-            Pt[(cur + 2) * nt + tid] = a2;
-            Pt[(cur + 3) * nt + tid] = a3;
-        }
-        __syncthreads();
-        // columns -> Q[a][b][s]: one thread per (a, s) of this tile
-        const int tile_cols = min(nt, ncols - q0);
-        const int ns_t = min(n2, tile_cols);
-        const int s_first = q0 % n2;
-        for (int pi = tid; pi < ncp0 * ns_t; pi += nt) {
-            const int a = pi / ns_t;
-            int s = s_first + (pi - a * ns_t);
-            if (s >= n2) s -= n2;
-            int d = s - s_first;
-            if (d < 0) d += n2;
-            for (int ql = d; ql < tile_cols; ql += n2) {
-                const float val = Pt[a * nt + ql];
-                if (val != 0.0f) {
-                    const int cc = (q0 + ql) / n2;
-                    const int bc = ac.bfit[cc];
-                    const float4 w = OMEGA ? ac.fit2[cc] : ac.fit3[cc];
-                    float* qp = Q + ((size_t)a * ncp1 + bc) * n2 + s;
-                    qp[0] += w.x * val;
-                    qp[n2] += w.y * val;
-                    qp[2 * n2] += w.z * val;
-                    qp[3 * n2] += w.w * val;
-                }
-            }
-        }
-        __syncthreads();
+        Q[e] = sum;
     }
+    __syncthreads();
+
     // slices -> lattice
     const int Ln = ncp0 * ncp1 * ncp2;
     for (int e = tid; e < Ln; e += nt) {
         const int g = e % ncp2, ab = e / ncp2;
         float sum = 0.0f;
-        for (int s = 0; s < n2; ++s) {
+        const int shi = as.hi[g];
+        for (int s = as.lo[g]; s < shi; ++s) {
             const int k = g - as.bfit[s];
-            if (k >= 0 && k < 4) {
-                const float4 w = OMEGA ? as.fit2[s] : as.fit3[s];
-                const float wk = (k == 0) ? w.x : (k == 1) ? w.y : (k == 2) ? w.z : w.w;
-                sum += Q[(size_t)ab * n2 + s] * wk;
-            }
+            const float4 wt = OMEGA ? as.fit2[s] : as.fit3[s];
+            const float wk = (k == 0) ? wt.x : (k == 1) ? wt.y : (k == 2) ? wt.z : wt.w;
+            sum += Q[(size_t)ab * n2 + s] * wk;
         }
         if (OMEGA) {
             c.Om[e] = sum;
@@ -486,140 +703,204 @@ VB_DEV void n4_contract(N4Ctx& c, float bmin, float bmax) {
             const float om = c.Om[e];
             // itk::Math::NotAlmostEquals(omega, 0): |omega| > 0.1 * FLT_EPSILON
             const float phi = (fabsf(om) > 0.1f * FLT_EPSILON) ? sum / om : 0.0f;
-            c.L[e] += phi;
+            const float l = c.L[e];
+            c.Lold[e] = l;
+            c.L[e] = l + phi;
         }
     }
     __syncthreads();
 }
 
-// collapsed column coefficients G[a] = sum_{b,g} wc[b] ws[g] L[a][bc+b][bs+g]  ->  Gs[a][tid]
-VB_DEV void n4_column_coeffs(const N4Ctx& c, const N4Axis& ac, const N4Axis& as, int q, float* Gs) {
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
-    const int cc = q / c.n2, ss = q - cc * c.n2;
-    const int bc = ac.bev[cc], bs = as.bev[ss];
-    const float4 wc = ac.evw[cc], ws = as.evw[ss];
-    const float wcv[4] = {wc.x, wc.y, wc.z, wc.w};
-    for (int a = 0; a < c.ncp[0]; ++a) {
-        float g = 0.0f;
-#pragma unroll
-        for (int k1 = 0; k1 < 4; ++k1) {
-            const float* lp = c.L + ((size_t)a * c.ncp[1] + bc + k1) * c.ncp[2] + bs;
-            g += wcv[k1] * (ws.x * lp[0] + ws.y * lp[1] + ws.z * lp[2] + ws.w * lp[3]);
-        }
-        Gs[a * nt + tid] = g;
-    }
+// ---------------------------------------------------------------------------------------------
+// CalculateConvergenceMeasurement: sequential float Welford over e[0..M) (C order), reproduced
+// in parallel.  One step of the reference (n4_oracle.c: n4_convergence) is
+//     N += 1;  if (N > 1) sigma = f32(sigma + f64(f32(d*d)) * (N-1)/N),  d = f32(pixel - mu)
+//     mu = f32(f64(mu) * (1 - 1/N) + f64(f32(pixel / N)))
+// Both updates are "state + small term, rounded to float".  With 1/N = ch + cl split into two
+// floats the terms are formed in float arithmetic to ~1e-14 (absolute), so the rounded state is
+// the reference's except when the exact sum lies within that distance of a rounding boundary.
+struct N4Step {
+    float b;        // f32(pixel / N)
+    float ch, cl;   // 1/N = ch + cl
+};
+VB_DEV N4Step n4_step_consts(float pixel, int n) {
+    N4Step s;
+    const float nf = (float)n;
+    s.b = __fdiv_rn(pixel, nf);
+    s.ch = __frcp_rn(nf);
+    s.cl = __fmul_rn(fmaf(-s.ch, nf, 1.0f), s.ch);
+    return s;
+}
+VB_DEV float n4_mu_next(float mu, const N4Step& s) {
+    const float t = fmaf(-mu, s.cl, fmaf(-mu, s.ch, s.b));      // pixel/N - mu/N
+    return __fadd_rn(mu, t);
+}
+VB_DEV float n4_sigma_next(float sigma, float mu_prev, float pixel, const N4Step& s) {
+    const float d = __fsub_rn(pixel, mu_prev);
+    const float dd = __fmul_rn(d, d);
+    const float th = fmaf(-dd, s.ch, dd);                       // dd * (N-1)/N, head
+    const float tl = fmaf(-dd, s.cl, fmaf(-dd, s.ch, __fsub_rn(dd, th))); // ... and tail
+    const float r = __fadd_rn(sigma, th);                       // TwoSum: r + err == sigma + th exactly
+    const float bb = __fsub_rn(r, sigma);
+    const float err = __fadd_rn(__fsub_rn(sigma, __fsub_rn(r, bb)), __fsub_rn(th, bb));
+    return __fadd_rn(r, __fadd_rn(err, tl));
 }
 
-#define VB_N4_WINDOW_ADVANCE(base)                                                   \
-    if ((base) != cur) {                                                             \
-        if (cur < 0 || (base) - cur >= 4 || (base) < cur) {                          \
-            g0 = Gs[(base) * nt + tid]; g1 = Gs[((base) + 1) * nt + tid];            \
-            g2 = Gs[((base) + 2) * nt + tid]; g3 = Gs[((base) + 3) * nt + tid];      \
-            cur = (base);                                                            \
-        } else {                                                                     \
-            while (cur < (base)) {                                                   \
-                g0 = g1; g1 = g2; g2 = g3; g3 = Gs[(cur + 4) * nt + tid]; ++cur;     \
-            }                                                                        \
-        }                                                                            \
+VB_DEV float n4_convergence(N4Ctx& c, int M) {
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    VB_SHARED int s_state[2];                 // float bit patterns of (mu, sigma) at the chunk start
+    const float* e = c.ebuf;
+    int* scratch = (int*)c.red;
+    const int S0 = min(M, VB_N4_SERIAL);
+    if (tid == 0) {
+        float mu = 0.0f, sigma = 0.0f;
+        for (int j = 0; j < S0; ++j) {
+            const float px = e[j];
+            const N4Step s = n4_step_consts(px, j + 1);
+            if (j > 0) sigma = n4_sigma_next(sigma, mu, px, s);
+            mu = (j == 0) ? s.b : n4_mu_next(mu, s);
+        }
+        s_state[0] = __float_as_int(mu); s_state[1] = __float_as_int(sigma);
     }
+    __syncthreads();
+    int start = S0;
+    while (start < M) {
+        const int len = min(min(start, VB_N4_CHUNK), M - start);
+        const int ept = (len + nt - 1) / nt;                  // <= VB_N4_EPT
+        const int lo = start + min(len, tid * ept), hi = start + min(len, tid * ept + ept);
+        const int mu0 = s_state[0], sg0 = s_state[1];
+        float px[VB_N4_EPT];
+        N4Step st[VB_N4_EPT];
+        int kg[VB_N4_EPT];                                    // guess: bits of mu BEFORE step i
+#pragma unroll
+        for (int i = 0; i < VB_N4_EPT; ++i) {
+            const int j = lo + i;
+            px[i] = (j < hi) ? e[j] : 1.0f;
+            st[i] = n4_step_consts(px[i], j + 1);
+            kg[i] = mu0;
+        }
+        // mu: iterate until the trajectory reproduces itself
+        int total = 0;
+        for (;;) {
+            int pre[VB_N4_EPT];
+            int run = 0;
+#pragma unroll
+            for (int i = 0; i < VB_N4_EPT; ++i) {
+                pre[i] = run;
+                if (lo + i < hi) run += __float_as_int(n4_mu_next(__int_as_float(kg[i]), st[i])) - kg[i];
+            }
+            const int off = n4_block_scan(run, total, scratch);
+            ++c.n_sweeps;
+            int changed = 0;
+#pragma unroll
+            for (int i = 0; i < VB_N4_EPT; ++i) {
+                const int k = mu0 + off + pre[i];
+                changed |= (lo + i < hi) && (k != kg[i]);
+                kg[i] = k;
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+        const int mu_end = mu0 + total;
+        // sigma, given the exact mu trajectory
+        int sg[VB_N4_EPT];
+#pragma unroll
+        for (int i = 0; i < VB_N4_EPT; ++i) sg[i] = sg0;
+        for (;;) {
+            int pre[VB_N4_EPT];
+            int run = 0;
+#pragma unroll
+            for (int i = 0; i < VB_N4_EPT; ++i) {
+                pre[i] = run;
+                if (lo + i < hi)
+                    run += __float_as_int(n4_sigma_next(__int_as_float(sg[i]), __int_as_float(kg[i]), px[i], st[i])) - sg[i];
+            }
+            const int off = n4_block_scan(run, total, scratch);
+            c.n_sweeps += 1000;
+            int changed = 0;
+#pragma unroll
+            for (int i = 0; i < VB_N4_EPT; ++i) {
+                const int k = sg0 + off + pre[i];
+                changed |= (lo + i < hi) && (k != sg[i]);
+                sg[i] = k;
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+        const int sg_end = sg0 + total;
+        __syncthreads();
+        if (tid == 0) { s_state[0] = mu_end; s_state[1] = sg_end; }
+        __syncthreads();
+        start += len;
+    }
+    const float mu = __int_as_float(s_state[0]), sigma = __int_as_float(s_state[1]);
+    __syncthreads();
+    const float sd = (float)sqrt((double)sigma / ((double)(float)M - 1.0));
+    return __fdiv_rn(sd, mu);
+}
 
 // ---------------------------------------------------------------------------------------------
-// P3: evaluate the new bias on the mask, U = logI - bias, convergence statistics and new range
+// P3: evaluate the old and the new bias on the mask: e = exp(old - new) (C order, for the
+// convergence measure) and the range of the new U = logI - bias
 VB_DEV float n4_update(N4Ctx& c, int M, float& bmin, float& bmax) {
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
-    const int ncols = c.ncols;
+    const int nt = (int)blockDim.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
     const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
-    float* Gs = c.un_f;
-    double s1 = 0.0, s2 = 0.0;
     float tmin = FLT_MAX, tmax = -FLT_MAX;
-    for (int q0 = 0; q0 < ncols; q0 += nt) {
-        const int q = q0 + tid;
-        const bool valid = q < ncols;
-        uint32_t any = 0;
-        for (int wi = 0; wi < c.W; ++wi) any |= valid ? c.colmask[(size_t)wi * ncols + q] : 0u;
-        if (any) n4_column_coeffs(c, ac, as, q, Gs);
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-        int cur = -1;
-        for (int wi = 0; wi < c.W; ++wi) {
-            const uint32_t mw = valid ? c.colmask[(size_t)wi * ncols + q] : 0u;
-            const uint32_t wm = __reduce_or_sync(VB_FULL, mw);
-            if (!wm) continue;
-#pragma unroll 1
-            for (int b0 = 0; b0 < 32; b0 += 8) {
-                if (((wm >> b0) & 0xFFu) == 0) continue;
-                float lg[8], uo[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const bool p = (mw >> (b0 + j)) & 1u;
-                    const size_t v = (size_t)(wi * 32 + b0 + j) * ncols + q;
-                    lg[j] = p ? c.logI[v] : 0.0f;
-                    uo[j] = p ? c.U[v] : 0.0f;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (!((wm >> (b0 + j)) & 1u)) continue;       // warp uniform
-                    const int r = wi * 32 + b0 + j;
-                    const int base = ar.bev[r];
-                    if ((mw >> (b0 + j)) & 1u) {
-                        VB_N4_WINDOW_ADVANCE(base)
-                        const float4 w = ar.evw[r];
-                        const float bias = w.x * g0 + w.y * g1 + w.z * g2 + w.w * g3;
-                        const float un = lg[j] - bias;
-                        const float e = expf(un - uo[j]);         // exp(bias_old - bias_new)
-                        const double em = (double)e - 1.0;
-                        s1 += em;
-                        s2 += em * em;
-                        tmin = fminf(tmin, un);
-                        tmax = fmaxf(tmax, un);
-                        c.U[(size_t)r * ncols + q] = un;
-                    }
-                }
+    for (int blk = w; blk < c.nblk; blk += nw) {
+        const unsigned p0 = c.blkbase[blk];
+        if (c.blkbase[blk + 1] == p0) continue;
+        const int q = blk * 32 + lane;
+        const bool valid = q < c.ncols;
+        const N4Col col = n4_col(c, ac, as, valid ? q : c.ncols - 1);
+        N4Win wo, wn;
+        wo.cur = wn.cur = -1;
+        wo.g0 = wo.g1 = wo.g2 = wo.g3 = wn.g0 = wn.g1 = wn.g2 = wn.g3 = 0.0f;
+        const unsigned lt = (1u << lane) - 1u;
+        VB_N4_FOR_ROWS(c, q, valid, p0, {
+            const int base = ar.bev[r];
+            n4_win_advance(wo, c.Lold, c, col, base);
+            n4_win_advance(wn, c.L, c, col, base);
+            if (bit) {
+                const float4 rw = ar.evw[r];
+                const float bo = n4_win_eval(wo, rw), bn = n4_win_eval(wn, rw);
+                const float un = c.logI[idx] - bn;
+                tmin = fminf(tmin, un);
+                tmax = fmaxf(tmax, un);
+                c.ebuf[c.rbb[(size_t)r * c.nblk + blk] + (unsigned)__popc(bal & lt)] = n4_exp_small(bo - bn);
             }
-        }
+        })
     }
-    __syncthreads();     // Gs (union region) is reused by the caller next
-    s1 = vb_block_reduce(s1, VbAddD(), 0.0, c.red);
-    s2 = vb_block_reduce(s2, VbAddD(), 0.0, c.red);
     bmin = vb_block_reduce(tmin, VbMinF(), FLT_MAX, (float*)c.red);
     bmax = vb_block_reduce(tmax, VbMaxF(), -FLT_MAX, (float*)c.red);
-    // CalculateConvergenceMeasurement: sample std / mean of exp(old - new) over the mask
-    const double N = (double)M;
-    const double mean = 1.0 + s1 / N;
-    double var = (s2 - s1 * s1 / N) / (N - 1.0);
-    if (var < 0.0) var = 0.0;
-    return (float)(sqrt(var) / mean);
+    __syncthreads();
+    const long long t0 = vb_clock();
+    const float conv = n4_convergence(c, M);
+    c.t_chain += vb_clock() - t0;
+    return conv;
 }
 
 // final dense pass: bias at EVERY voxel, out = in / exp(bias)   (N4 GenerateData tail)
 VB_DEV void n4_finalize(N4Ctx& c, float* logbias) {
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    const int nt = (int)blockDim.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
     const int ncols = c.ncols;
     const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
-    float* Gs = c.un_f;
-    for (int q0 = 0; q0 < ncols; q0 += nt) {
-        const int q = q0 + tid;
-        const bool valid = q < ncols;
-        if (valid) n4_column_coeffs(c, ac, as, q, Gs);
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-        int cur = -1;
-        if (valid) {
-            for (int r0 = 0; r0 < c.n0; r0 += 8) {
-                float x[8];
+    for (int blk = w; blk < c.nblk; blk += nw) {
+        const int q = blk * 32 + lane;
+        if (q >= ncols) continue;
+        const N4Col col = n4_col(c, ac, as, q);
+        N4Win win; win.cur = -1; win.g0 = win.g1 = win.g2 = win.g3 = 0.0f;
+        for (int r0 = 0; r0 < c.n0; r0 += 8) {
+            float x[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    x[j] = (r0 + j < c.n0) ? vb_ld_stream(c.img + (size_t)(r0 + j) * ncols + q) : 0.0f;
+            for (int j = 0; j < 8; ++j)
+                x[j] = (r0 + j < c.n0) ? vb_ld_stream(c.img + (size_t)(r0 + j) * ncols + q) : 0.0f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int r = r0 + j;
-                    if (r < c.n0) {
-                        const int base = ar.bev[r];
-                        VB_N4_WINDOW_ADVANCE(base)
-                        const float4 w = ar.evw[r];
-                        const float bias = w.x * g0 + w.y * g1 + w.z * g2 + w.w * g3;
-                        const size_t v = (size_t)r * ncols + q;
-                        vb_st_stream(c.U + v, __fdiv_rn(x[j], expf(bias)));
-                        if (logbias) vb_st_stream(logbias + v, bias);
-                    }
+            for (int j = 0; j < 8; ++j) {
+                const int r = r0 + j;
+                if (r < c.n0) {
+                    n4_win_advance(win, c.L, c, col, ar.bev[r]);
+                    const float bias = n4_win_eval(win, ar.evw[r]);
+                    const size_t v = (size_t)r * ncols + q;
+                    vb_st_stream(c.out + v, __fdiv_rn(x[j], expf(bias)));
+                    if (logbias) vb_st_stream(logbias + v, bias);
                 }
             }
         }
@@ -660,8 +941,14 @@ VB_DEV void n4_build_tables(N4Ctx& c) {
     const int n[3] = {c.n0, c.n1, c.n2};
     size_t off = 0;
     for (int a = 0; a < 3; ++a) {
-        n4_build_axis(c.axis_base + off, n[a], c.ncp[a]);
-        off += 16 * (size_t)n[a];
+        n4_build_axis(c.axis_base + off, c.slot[a], n[a], c.ncp[a]);
+        off += 16 * (size_t)c.slot[a];
+    }
+    __syncthreads();
+    off = 0;
+    for (int a = 0; a < 3; ++a) {
+        n4_build_support(c.axis_base + off, c.slot[a], n[a], c.ncp[a]);
+        off += 16 * (size_t)c.slot[a];
     }
     __syncthreads();
 }
@@ -674,12 +961,15 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
     c.un_f = (float*)smem;
     c.un_d = (double*)smem;
     unsigned char* p = smem + a.union_bytes;
-    c.L = (float*)p;  p += sizeof(float) * (size_t)((a.Lmax + 3) & ~3);
-    c.Om = (float*)p; p += sizeof(float) * (size_t)((a.Lmax + 3) & ~3);
-    c.E = (float*)p;  p += sizeof(float) * (size_t)((a.p.n_bins + 3) & ~3);
-    c.H = (float*)p;  p += sizeof(float) * (size_t)((a.p.n_bins + 3) & ~3);
-    c.red = (double*)p;
-    c.nbins = a.p.n_bins; c.HT = a.hist_threads; c.fftN = a.fftN;
+    const size_t Lb = sizeof(float) * (size_t)((a.Lmax + 3) & ~3);
+    c.L = (float*)p;    p += Lb;
+    c.Lold = (float*)p; p += Lb;
+    c.Om = (float*)p;   p += Lb;
+    c.E = (float*)p;    p += sizeof(float) * (size_t)((a.p.n_bins + 3) & ~3);
+    c.H = (float*)p;    p += sizeof(float) * (size_t)((a.p.n_bins + 3) & ~3);
+    c.red = (double*)p; p += 64 * sizeof(double);
+    float* smem_logI = (float*)p;
+    c.nbins = a.p.n_bins; c.fftN = a.fftN;
 
     for (;;) {
         __syncthreads();
@@ -689,18 +979,35 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         if (si >= a.n) break;
         const VbSubject S = a.subj[si];
         c.n0 = S.n0; c.n1 = S.n1; c.n2 = S.n2; c.ncols = S.n1 * S.n2; c.W = (S.n0 + 31) >> 5;
+        c.nblk = (c.ncols + 31) >> 5;
         c.V = S.V;
-        c.img = a.image + S.off; c.msk = a.mask + S.off; c.U = a.out + S.off;
-        c.logI = a.ws_logI + (size_t)blockIdx.x * a.Vmax;
+        c.img = a.image + S.off; c.msk = a.mask + S.off; c.out = a.out + S.off;
         c.colmask = a.ws_colmask + (size_t)blockIdx.x * a.cmw_max;
+        c.rbb = a.ws_rbb + (size_t)blockIdx.x * a.rbb_max;
+        c.blkbase = a.ws_blkbase + (size_t)blockIdx.x * a.blk_max;
         c.axis_base = a.ws_axis + (size_t)blockIdx.x * a.axis_stride;
+        c.ebuf = a.ws_e + (size_t)blockIdx.x * a.Vmax;
+        c.P = a.ws_P + (size_t)blockIdx.x * a.P_max;
         c.ncp[0] = a.p.ncp[0]; c.ncp[1] = a.p.ncp[1]; c.ncp[2] = a.p.ncp[2];
+        {
+            const int nn[3] = {S.n0, S.n1, S.n2};
+            for (int ax = 0; ax < 3; ++ax) {
+                int f = a.p.ncp[ax];
+                for (int l = 1; l < a.p.n_levels; ++l) f = 2 * f - 3;
+                c.slot[ax] = max(nn[ax], f);
+            }
+        }
+        c.logI = a.ws_logI + (size_t)blockIdx.x * a.Vmax;   // n4_setup moves it to shared memory if it fits
 
         float bmin, bmax;
         int M;
-        n4_setup(c, a.p.mask_label, bmin, bmax, M);
-        for (int e = tid; e < a.Lmax; e += (int)blockDim.x) c.L[e] = 0.0f;
+        long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tq = vb_clock();
+        c.t_chain = 0; c.n_sweeps = 0;
+        n4_setup(c, a.p.mask_label, smem_logI, a.logI_cap, bmin, bmax, M);
+        for (int e = tid; e < a.Lmax; e += (int)blockDim.x) { c.L[e] = 0.0f; c.Lold[e] = 0.0f; }
         __syncthreads();
+        tph[0] = vb_clock() - tq;
 
         float conv = FLT_MAX;
         int total = 0, ntrace = 0;
@@ -713,15 +1020,21 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
             if (M >= 2 && !capped) {
                 n4_build_tables(c);
                 n4_contract<true>(c, bmin, bmax);
+                if (level > 0) n4_range(c, bmin, bmax);
                 conv = FLT_MAX;
                 while (it < a.p.max_iter[level] && conv > a.p.conv_threshold) {
                     if (a.p.max_total_iters > 0 && total >= a.p.max_total_iters) { capped = true; break; }
                     ++it; ++total;
                     if (dbg && tid == 0) { dbg[0] = bmin; dbg[1] = bmax; }
+                    tq = vb_clock();
                     n4_histogram(c, bmin, bmax);
+                    long long tn = vb_clock(); tph[1] += tn - tq; tq = tn;
                     n4_sharpen(c, bmin, bmax, a.p.fwhm, a.p.wiener_noise);
+                    tn = vb_clock(); tph[2] += tn - tq; tq = tn;
                     n4_contract<false>(c, bmin, bmax);
+                    tn = vb_clock(); tph[3] += tn - tq; tq = tn;
                     conv = n4_update(c, M, bmin, bmax);
+                    tn = vb_clock(); tph[4] += tn - tq;
                     if (dbg_trace && tid == 0 && ntrace < trace_cap) dbg_trace[ntrace] = conv;
                     ++ntrace;
                 }
@@ -729,7 +1042,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
             if (a.stats && tid == 0) a.stats[si].n4_iters[level] = it;
             if (level != a.p.n_levels - 1 && M >= 2 && !capped) n4_refine(c);
         }
-        if (M < 2) n4_build_tables(c);     // degenerate mask: zero lattice => out = in
+        if (M < 2 || capped) n4_build_tables(c);   // tables of the final lattice (M < 2: zero lattice => out = in)
         if (dbg) {
             for (int i = tid; i < c.nbins; i += (int)blockDim.x) {
                 dbg[VB_DBG_HDR + i] = c.H[i];
@@ -742,11 +1055,18 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                 dbg[5] = (float)min(ntrace, trace_cap);
             }
         }
+        tq = vb_clock();
         if (a.stats && tid == 0) {
             for (int l = a.p.n_levels; l < VB_MAX_LEVELS; ++l) a.stats[si].n4_iters[l] = 0;
             a.stats[si].n4_last_conv = conv;
             a.stats[si].n4_n_mask = M;
         }
         n4_finalize(c, a.logbias ? a.logbias + S.off : nullptr);
+        if (dbg && tid == 0) {
+            tph[6] = vb_clock() - tq;
+            tph[4] -= c.t_chain; tph[5] = c.t_chain;
+            for (int k = 0; k < 8; ++k) dbg[8 + k] = (float)((double)tph[k] * 1e-3);   // ns -> us
+            dbg[15] = (float)c.n_sweeps;
+        }
     }
 }

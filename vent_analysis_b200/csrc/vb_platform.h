@@ -37,6 +37,7 @@ VB_DEV float4 vb_ldg(const float4* p) { return __ldg(p); }
 VB_DEV float vb_ld_stream(const float* p) { return __ldcs(p); }
 VB_DEV uint8_t vb_ld_stream(const uint8_t* p) { return __ldcs(p); }
 VB_DEV void vb_st_stream(float* p, float v) { __stcs(p, v); }
+VB_DEV long long vb_clock() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return (long long)t; }
 #else
 // ------------------------------------------------------------------------------- emulation
 #include <math.h>
@@ -147,6 +148,19 @@ template <class Body> void launch(dim3 grid, dim3 block, size_t smem, Body body)
 static inline void __syncthreads() { vbemu::g_block->bar.arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {
     vbemu::warp().bar.arrive_and_wait();
+}
+static inline int __syncthreads_or(int pred) {
+    static int flag[2];
+    static int phase;
+    vbemu::g_block->bar.arrive_and_wait();
+    const int ph = phase;
+    if (pred) __atomic_store_n(&flag[ph], 1, __ATOMIC_SEQ_CST);
+    vbemu::g_block->bar.arrive_and_wait();
+    const int r = __atomic_load_n(&flag[ph], __ATOMIC_SEQ_CST);
+    vbemu::g_block->bar.arrive_and_wait();
+    if (threadIdx.x == 0) { flag[ph] = 0; phase = ph ^ 1; }
+    vbemu::g_block->bar.arrive_and_wait();
+    return r;
 }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
@@ -270,6 +284,8 @@ static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline unsigned __float2uint_rn(float a) { return (unsigned)llrintf(a); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
@@ -279,6 +295,7 @@ static inline void vb_sincospi(double x, double* s, double* c) { *s = sin(M_PI *
 template <class T> static inline T vb_ldg(const T* p) { return *p; }
 template <class T> static inline T vb_ld_stream(const T* p) { return *p; }
 static inline void vb_st_stream(float* p, float v) { *p = v; }
+static inline long long vb_clock() { return 0; }
 using std::max;
 using std::min;
 #endif

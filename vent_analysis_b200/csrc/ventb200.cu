@@ -39,7 +39,7 @@ struct vb_ctx {
     Buf h_desc, d_subj, d_wordoff;
     long long v_total = 0, words_total = 0;
     // workspaces
-    Buf ws_logI, ws_colmask, ws_axis, ws_counter, ws_d0, ws_bits, ws_list, ws_count, dbg;
+    Buf ws_logI, ws_e, ws_colmask, ws_rbb, ws_blkbase, ws_P, ws_axis, ws_counter, ws_d0, ws_bits, ws_list, ws_count, dbg;
     int dbg_stride = 0, dbg_nbins = 0, dbg_Lmax = 0, dbg_n = 0;
     // CI tables
     std::vector<TableHost> tables;
@@ -181,29 +181,35 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     int e = 0;
     while ((1 << e) < p.n_bins) ++e;
     const int fftN = 1 << (e + 1);
-    long long vmax = 0, cmw = 0, axis = 0, n2max = 0;
+    long long vmax = 0, cmw = 0, axis = 0, n2max = 0, rbb = 0, blk = 0, pmax = 0;
     for (const VbSubject& S : c->last_subj) {
+        const long long ncols = (long long)S.n1 * S.n2, nblk = (ncols + 31) / 32;
         vmax = std::max<long long>(vmax, S.V);
-        cmw = std::max<long long>(cmw, (long long)((S.n0 + 31) / 32) * S.n1 * S.n2);
-        axis = std::max<long long>(axis, 16LL * (S.n0 + S.n1 + S.n2));
+        cmw = std::max<long long>(cmw, (long long)((S.n0 + 31) / 32) * ncols);
+        axis = std::max<long long>(axis, 16LL * (std::max(S.n0, ncpf[0]) + std::max(S.n1, ncpf[1]) + std::max(S.n2, ncpf[2])));
         n2max = std::max<long long>(n2max, S.n2);
+        rbb = std::max<long long>(rbb, (long long)S.n0 * nblk + 1);
+        blk = std::max<long long>(blk, nblk + 1);
+        pmax = std::max<long long>(pmax, (long long)ncpf[0] * ncols);
     }
-    const long long fixed = 4 * (2 * ((Lmax + 3) & ~3LL) + 2 * ((p.n_bins + 3) & ~3)) + 64 * 8;
-    const long long avail = (long long)c->max_smem - fixed;
-    int HT = (int)std::min<long long>(VB_N4_THREADS, avail / (4LL * p.n_bins) / 32 * 32);
-    if (HT < 32) return fail(VB_ERR_UNSUPPORTED, "N4: histogram does not fit shared memory");
-    const long long Qn = (((long long)ncpf[0] * ncpf[1] * n2max) + 3) & ~3LL;
-    long long ub = 4LL * HT * p.n_bins;
-    ub = std::max(ub, 8LL * 7 * fftN);
-    ub = std::max(ub, 4LL * (Qn + (long long)ncpf[0] * VB_N4_THREADS));
-    ub = std::max(ub, 4LL * Lmax);
+    // shared memory: [union][L][Lold][Om][E][H][red][compact log image]
+    const long long Lb = 4 * ((Lmax + 3) & ~3LL), Hb = 4 * ((p.n_bins + 3) & ~3);
+    const long long fixed = 3 * Lb + 2 * Hb + 64 * 8;
+    long long ub = 4LL * VB_N4_HCOPIES * p.n_bins;                       // histogram copies
+    ub = std::max(ub, 8LL * 7 * fftN);                                   // FFT work arrays
+    ub = std::max(ub, 4LL * (long long)ncpf[0] * ncpf[1] * n2max);       // Q[a][b][s]
+    ub = std::max(ub, 4LL * Lmax);                                       // refinement scratch
     ub = (ub + 15) & ~15LL;
-    if (ub + fixed > c->max_smem)
+    const long long static_smem = 64;                                    // s_next, chain state
+    if (ub + fixed + static_smem > c->max_smem)
         return fail(VB_ERR_UNSUPPORTED, "N4: working set does not fit the 227 KB of shared memory");
+    const long long cap = ((long long)c->max_smem - ub - fixed - static_smem) / 4;
     const int grid = std::min(n, c->sms);
     if (!ensure(c->ws_logI, sizeof(float) * (size_t)grid * (size_t)vmax) ||
-        !ensure(c->ws_colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(c->ws_axis, 4 * (size_t)grid * (size_t)axis) ||
-        !ensure(c->ws_counter, 64))
+        !ensure(c->ws_e, sizeof(float) * (size_t)grid * (size_t)vmax) ||
+        !ensure(c->ws_colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(c->ws_rbb, 4 * (size_t)grid * (size_t)rbb) ||
+        !ensure(c->ws_blkbase, 4 * (size_t)grid * (size_t)blk) || !ensure(c->ws_P, 4 * (size_t)grid * (size_t)pmax) ||
+        !ensure(c->ws_axis, 4 * (size_t)grid * (size_t)axis) || !ensure(c->ws_counter, 64))
         return VB_ERR_CUDA;
     int trace = 0;
     for (int l = 0; l < p.n_levels; ++l) trace += p.max_iter[l];
@@ -220,11 +226,16 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     N4Args a;
     a.image = image; a.mask = mask; a.out = out; a.logbias = logbias;
     a.subj = (const VbSubject*)c->d_subj.p; a.n = n; a.p = p; a.stats = stats;
-    a.ws_logI = (float*)c->ws_logI.p; a.ws_colmask = (uint32_t*)c->ws_colmask.p; a.ws_axis = (float*)c->ws_axis.p;
+    a.ws_logI = (float*)c->ws_logI.p; a.ws_colmask = (uint32_t*)c->ws_colmask.p; a.ws_rbb = (uint32_t*)c->ws_rbb.p;
+    a.ws_blkbase = (uint32_t*)c->ws_blkbase.p; a.ws_axis = (float*)c->ws_axis.p; a.ws_e = (float*)c->ws_e.p;
+    a.ws_P = (float*)c->ws_P.p;
     a.work_counter = (int*)c->ws_counter.p; a.debug = dbg;
-    a.Vmax = vmax; a.cmw_max = cmw; a.axis_stride = (int)axis; a.debug_stride = dbg_stride;
-    a.hist_threads = HT; a.Lmax = (int)Lmax; a.fftN = fftN; a.union_bytes = (int)ub;
-    const int smem = (int)(ub + fixed);
+    a.Vmax = vmax; a.cmw_max = cmw; a.rbb_max = rbb; a.blk_max = blk; a.P_max = pmax;
+    a.axis_stride = (int)axis; a.debug_stride = dbg_stride;
+    a.Lmax = (int)Lmax; a.fftN = fftN; a.union_bytes = (int)ub;
+    // a mask that does not fit keeps its compact log image in global memory (L2)
+    a.logI_cap = (int)std::min<long long>(std::max<long long>(cap, 0), vmax);
+    const int smem = (int)(ub + fixed + 4LL * a.logI_cap);
     if (!vbrt::allow_smem(n4_subject_kernel, smem)) return VB_ERR_CUDA;
     VB_LAUNCH(n4_subject_kernel, dim3(grid), dim3(VB_N4_THREADS), (size_t)smem, s, a);
     ++c->launches;
@@ -312,7 +323,7 @@ void vb_destroy(vb_ctx* c) {
     if (!c) return;
     vbrt::set_device(c->device);
     vbrt::stream_sync(c->stream);
-    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_logI, &c->ws_colmask, &c->ws_axis, &c->ws_counter, &c->ws_d0,
+    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_logI, &c->ws_e, &c->ws_rbb, &c->ws_blkbase, &c->ws_P, &c->ws_colmask, &c->ws_axis, &c->ws_counter, &c->ws_d0,
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
                    &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats};
     for (Buf* b : bufs) vbrt::dev_free(b->p);
@@ -588,7 +599,11 @@ int vb_n4_debug_fetch(vb_ctx* c, int32_t subject, float* hist, float* emap, floa
     if (ncp) { ncp[0] = n0; ncp[1] = n1; ncp[2] = n2; }
     if (lattice) memcpy(lattice, rec.data() + VB_DBG_HDR + 2 * nb, sizeof(float) * (size_t)std::min(lattice_capacity, n0 * n1 * n2));
     const int nt = (int)rec[5];
-    if (conv_trace) {
+    if (conv_trace && trace_capacity >= 8 + nt) {          // phase microseconds ride behind the trace
+        for (int i = 0; i < trace_capacity; ++i) conv_trace[i] = -1.0f;
+        memcpy(conv_trace, rec.data() + VB_DBG_HDR + 2 * nb + c->dbg_Lmax, sizeof(float) * (size_t)nt);
+        memcpy(conv_trace + trace_capacity - 8, rec.data() + 8, sizeof(float) * 8);
+    } else if (conv_trace) {
         for (int i = 0; i < trace_capacity; ++i) conv_trace[i] = -1.0f;
         memcpy(conv_trace, rec.data() + VB_DBG_HDR + 2 * nb + c->dbg_Lmax, sizeof(float) * (size_t)std::min(trace_capacity, nt));
     }
