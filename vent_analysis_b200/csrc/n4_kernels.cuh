@@ -56,18 +56,20 @@ struct N4Args {
     float* ws_logI;          // [grid][Vmax]      compact log image when it does not fit smem
     uint32_t* ws_colmask;    // [grid][cmw_max]   per column: row bitmask words
     uint32_t* ws_rbb;        // [grid][rbb_max]   C-order rank of the first mask voxel of (row, block)
-    uint32_t* ws_blkbase;    // [grid][blk_max]   compact offset of every column block (+1)
+    uint32_t* ws_wbase;      // [grid][wb_max]    compact offset of every (block, 32-row word) (+1)
+    uint32_t* ws_acol;       // [grid][ncols_max] active (mask-carrying) columns, ascending
     float* ws_axis;          // [grid][axis_stride]  (4-byte words)
     float* ws_e;             // [grid][Vmax]      exp(bias_old - bias_new) over the mask, C order
-    float* ws_P;             // [grid][P_max]     row-contracted columns [ncp0][ncols]
+    uint32_t* ws_perm;       // [grid][Vmax]      C-order rank -> compact index of the mask voxels
     int* work_counter;
     float* debug;            // may be null: [n][debug_stride]
-    long long Vmax, cmw_max, rbb_max, blk_max, P_max;
+    long long Vmax, cmw_max, rbb_max, wb_max, ncols_max;
     int axis_stride, debug_stride;
     int Lmax;                // max lattice entries (after the last refinement)
     int fftN;                // padded histogram size
     int union_bytes;         // size of the shared-memory union region
     int logI_cap;            // floats of compact log image that fit shared memory (0 = none)
+    int rowtab_rows;         // rows whose row-axis tables fit shared memory (0 = keep them in global)
 };
 
 // debug record layout (floats): [0]=bmin [1]=bmax [2..4]=ncp [5]=n_trace, then
@@ -174,7 +176,7 @@ VB_DEV void n4_build_support(float* base, int slot, int n, int ncp) {
 
 struct N4Ctx {
     // subject
-    int n0, n1, n2, ncols, W, nblk;
+    int n0, n1, n2, ncols, W, nblk;   // nblk: blocks of 32 ACTIVE columns
     long long V;
     const float* img;
     const uint8_t* msk;
@@ -182,10 +184,18 @@ struct N4Ctx {
     float* logI;          // compact log image (shared or global memory)
     uint32_t* colmask;    // [W][ncols]
     uint32_t* rbb;        // [n0][nblk] (+1)
-    uint32_t* blkbase;    // [nblk + 1]
+    uint32_t* wbase;      // [nblk][W] (+1)
+    uint32_t* acol;       // [nact]
+    int nact, nseg, wps;  // active columns; row segments per block; 32-row words per segment
     float* axis_base;
-    float* ebuf;          // [M]
-    float* P;             // [ncp0][ncols]
+    float* ebuf;          // [M] exp(old - new), compact order
+    uint32_t* perm;       // [M] C-order rank -> compact index
+    // row-axis tables (shared memory when they fit, else inside axis_base)
+    const float4* r_evw;
+    const float4* r_fit3;
+    const int* r_bev;
+    const int* r_bfit;
+    float* rowtab;        // shared-memory home of the four arrays above (null: global)
     // shared memory
     float* un_f;          // union region
     double* un_d;
@@ -221,13 +231,14 @@ VB_DEV int n4_block_scan(int v, int& total, int* scratch /* >= 33 ints */) {
     __syncthreads();
     if (lane == 31) scratch[w] = inc;
     __syncthreads();
-    int woff = 0, tot = 0;
-    for (int i = 0; i < nw; ++i) {
-        const int t = scratch[i];
-        if (i < w) woff += t;
-        tot += t;
+    int wt = (lane < nw) ? scratch[lane] : 0;            // nw <= 32
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(VB_FULL, wt, d);
+        if (lane >= d) wt += t;
     }
-    total = tot;
+    total = __shfl_sync(VB_FULL, wt, 31);
+    const int woff = (w > 0) ? __shfl_sync(VB_FULL, wt, (w > 0) ? w - 1 : 0) : 0;
     return woff + inc - v;
 }
 
@@ -315,15 +326,34 @@ VB_DEV float n4_exp_small(float x) {
     return expf(x);
 }
 
-// Walk the mask voxels of one column block row by row.  BODY sees: r (row), bit (this lane's
-// voxel is in the mask), idx (compact index of this lane's voxel when bit), bal (lane mask of
-// the row).  Rows without any mask voxel in the block are skipped.
-#define VB_N4_FOR_ROWS(c, q, valid, pos0, ...)                                               \
+// Work item of a warp: 32 consecutive ACTIVE columns (columns that carry mask voxels) x one
+// segment of rows.  Splitting the rows gives the 16 warps enough items to balance.
+struct N4Item {
+    int blk, seg, wi0, wi1, q;
+    bool valid, empty;
+    unsigned pos;
+};
+VB_DEV N4Item n4_item(const N4Ctx& c, int it) {
+    N4Item I;
+    I.blk = it % c.nblk; I.seg = it / c.nblk;
+    I.wi0 = I.seg * c.wps; I.wi1 = min(c.W, I.wi0 + c.wps);
+    const int k = I.blk * 32 + vb_lane();
+    I.valid = k < c.nact;
+    I.q = (int)c.acol[I.valid ? k : c.nact - 1];
+    I.pos = c.wbase[(size_t)I.blk * c.W + I.wi0];
+    I.empty = c.wbase[(size_t)I.blk * c.W + I.wi1] == I.pos;
+    return I;
+}
+
+// Walk the mask voxels of one item row by row.  BODY sees: r (row), bit (this lane's voxel is
+// in the mask), idx (compact index of this lane's voxel when bit), bal (lane mask of the row).
+// Rows without any mask voxel in the block are skipped.
+#define VB_N4_FOR_ROWS(c, I, ...)                                                            \
     {                                                                                        \
-        unsigned pos_ = (pos0);                                                              \
+        unsigned pos_ = (I).pos;                                                             \
         const unsigned lt_ = (1u << vb_lane()) - 1u;                                         \
-        for (int wi_ = 0; wi_ < (c).W; ++wi_) {                                              \
-            const uint32_t mw_ = (valid) ? (c).colmask[(size_t)wi_ * (c).ncols + (q)] : 0u;  \
+        for (int wi_ = (I).wi0; wi_ < (I).wi1; ++wi_) {                                      \
+            const uint32_t mw_ = (I).valid ? (c).colmask[(size_t)wi_ * (c).ncols + (I).q] : 0u; \
             uint32_t rem_ = __reduce_or_sync(VB_FULL, mw_);                                  \
             while (rem_) {                                                                   \
                 const int b_ = __ffs((int)rem_) - 1;                                         \
@@ -341,11 +371,11 @@ VB_DEV float n4_exp_small(float x) {
 // ---------------------------------------------------------------------------------------------
 // setup: column bitmasks, compaction tables, compact log image, range and count of the mask
 VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float& bmin, float& bmax, int& M) {
-    const int nt = (int)blockDim.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
-    for (int blk = w; blk < c.nblk; blk += nw) {
-        const int q = blk * 32 + lane;
-        const bool valid = q < c.ncols;
-        int tot = 0;
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
+    // column bitmasks (coalesced over columns) and the list of active columns
+    uint32_t* flag = c.rbb;                               // scratch: [ncols + 1]
+    for (int q = tid; q < c.ncols; q += nt) {
+        uint32_t any = 0;
         for (int wi = 0; wi < c.W; ++wi) {
             uint32_t bits = 0;
             const int rend = min(32, c.n0 - wi * 32);
@@ -353,46 +383,70 @@ VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float&
                 uint8_t mv[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    mv[j] = (valid && b0 + j < rend) ? vb_ld_stream(c.msk + (size_t)(wi * 32 + b0 + j) * c.ncols + q) : (uint8_t)0;
+                    mv[j] = (b0 + j < rend) ? vb_ld_stream(c.msk + (size_t)(wi * 32 + b0 + j) * c.ncols + q) : (uint8_t)0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (b0 + j >= rend) break;                       // warp uniform
-                    const bool m = valid && b0 + j < rend && (int)mv[j] == label;
-                    const unsigned bal = __ballot_sync(VB_FULL, m);
-                    if (m) bits |= 1u << (b0 + j);
-                    const int cnt = __popc(bal);
-                    if (lane == 0) c.rbb[(size_t)(wi * 32 + b0 + j) * c.nblk + blk] = (uint32_t)cnt;
-                    tot += cnt;
-                }
+                for (int j = 0; j < 8; ++j)
+                    if (b0 + j < rend && (int)mv[j] == label) bits |= 1u << (b0 + j);
             }
-            if (valid) c.colmask[(size_t)wi * c.ncols + q] = bits;
+            c.colmask[(size_t)wi * c.ncols + q] = bits;
+            any |= bits;
         }
-        if (lane == 0) c.blkbase[blk] = (uint32_t)tot;
+        flag[q] = any ? 1u : 0u;
+    }
+    __syncthreads();
+    c.nact = n4_array_scan(flag, c.ncols, (int*)c.red);
+    for (int q = tid; q < c.ncols; q += nt)
+        if (flag[q + 1] != flag[q]) c.acol[flag[q]] = (uint32_t)q;
+    c.nblk = (c.nact + 31) >> 5;
+    // row segments: enough items to keep every warp busy (about three items per warp)
+    c.nseg = 1;
+    while (c.nseg < min(c.W, 8) && c.nblk * c.nseg < 3 * nw) c.nseg <<= 1;
+    c.wps = (c.W + c.nseg - 1) / c.nseg;
+    c.nseg = (c.W + c.wps - 1) / c.wps;
+    __syncthreads();                                      // flag (= rbb) is rewritten below
+    // per (row, block) and per (block, word) voxel counts
+    for (int blk = w; blk < c.nblk; blk += nw) {
+        const int k = blk * 32 + lane;
+        const bool valid = k < c.nact;
+        const int q = valid ? (int)c.acol[k] : 0;
+        for (int wi = 0; wi < c.W; ++wi) {
+            const uint32_t mw = valid ? c.colmask[(size_t)wi * c.ncols + q] : 0u;
+            const int rend = min(32, c.n0 - wi * 32);
+            int tot = 0, mine = 0;
+            for (int b = 0; b < rend; ++b) {
+                const int cnt = __popc(__ballot_sync(VB_FULL, (mw >> b) & 1u));
+                if (lane == b) mine = cnt;
+                tot += cnt;
+            }
+            if (lane < rend) c.rbb[(size_t)(wi * 32 + lane) * c.nblk + blk] = (uint32_t)mine;
+            if (lane == 0) c.wbase[(size_t)blk * c.W + wi] = (uint32_t)tot;
+        }
     }
     __syncthreads();
     M = n4_array_scan(c.rbb, c.n0 * c.nblk, (int*)c.red);
-    n4_array_scan(c.blkbase, c.nblk, (int*)c.red);
+    n4_array_scan(c.wbase, c.nblk * c.W, (int*)c.red);
     // histogram fixed point: the largest number of voxels any histogram copy can receive
     int mc = 0;
-    if ((int)threadIdx.x < VB_N4_HCOPIES)
-        for (int blk = (int)threadIdx.x; blk < c.nblk; blk += VB_N4_HCOPIES)
-            mc += (int)(c.blkbase[blk + 1] - c.blkbase[blk]);
+    if (tid < VB_N4_HCOPIES)
+        for (int it = 0; it < c.nblk * c.nseg; ++it)
+            if (((it % nw) & (VB_N4_HCOPIES - 1)) == tid) {
+                const int blk = it % c.nblk, wi0 = (it / c.nblk) * c.wps, wi1 = min(c.W, wi0 + c.wps);
+                mc += (int)(c.wbase[(size_t)blk * c.W + wi1] - c.wbase[(size_t)blk * c.W + wi0]);
+            }
     mc = vb_block_reduce(mc, VbMaxI(), 0, (int*)c.red);
     int bits = 0;
     while ((1LL << bits) <= (long long)mc) ++bits;
     c.hshift = min(24, 31 - bits);
-
     if (M <= smem_cap) c.logI = smem_logI;             // the compact log image fits shared memory
 
     float tmin = FLT_MAX, tmax = -FLT_MAX;
     const unsigned lt = (1u << lane) - 1u;
-    for (int blk = w; blk < c.nblk; blk += nw) {
-        unsigned pos = c.blkbase[blk];
-        if (c.blkbase[blk + 1] == pos) continue;
-        const int q = blk * 32 + lane;
-        const bool valid = q < c.ncols;
-        for (int wi = 0; wi < c.W; ++wi) {
-            const uint32_t mw = valid ? c.colmask[(size_t)wi * c.ncols + q] : 0u;
+    for (int it = w; it < c.nblk * c.nseg; it += nw) {
+        const N4Item I = n4_item(c, it);
+        if (I.empty) continue;
+        unsigned pos = I.pos;
+        for (int wi = I.wi0; wi < I.wi1; ++wi) {
+            const uint32_t mw = I.valid ? c.colmask[(size_t)wi * c.ncols + I.q] : 0u;
             const uint32_t wm = __reduce_or_sync(VB_FULL, mw);
             if (!wm) continue;
 #pragma unroll 1
@@ -401,14 +455,16 @@ VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float&
                 float x[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    x[j] = ((mw >> (b0 + j)) & 1u) ? vb_ld_stream(c.img + (size_t)(wi * 32 + b0 + j) * c.ncols + q) : 0.0f;
+                    x[j] = ((mw >> (b0 + j)) & 1u) ? vb_ld_stream(c.img + (size_t)(wi * 32 + b0 + j) * c.ncols + I.q) : 0.0f;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const bool bit = (mw >> (b0 + j)) & 1u;
                     const unsigned bal = __ballot_sync(VB_FULL, bit);
                     if (bit) {
                         const float l = (x[j] > 0.0f) ? logf(x[j]) : x[j];
-                        c.logI[pos + (unsigned)__popc(bal & lt)] = l;
+                        const unsigned below = (unsigned)__popc(bal & lt);
+                        c.logI[pos + below] = l;
+                        c.perm[c.rbb[(size_t)(wi * 32 + b0 + j) * c.nblk + I.blk] + below] = pos + below;
                         tmin = fminf(tmin, l);
                         tmax = fmaxf(tmax, l);
                     }
@@ -424,19 +480,17 @@ VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float&
 // range of U = logI - bias(L) over the mask (after a lattice refinement)
 VB_DEV void n4_range(N4Ctx& c, float& bmin, float& bmax) {
     const int nt = (int)blockDim.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
-    const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
+    const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     float tmin = FLT_MAX, tmax = -FLT_MAX;
-    for (int blk = w; blk < c.nblk; blk += nw) {
-        const unsigned p0 = c.blkbase[blk];
-        if (c.blkbase[blk + 1] == p0) continue;
-        const int q = blk * 32 + lane;
-        const bool valid = q < c.ncols;
-        const N4Col col = n4_col(c, ac, as, valid ? q : c.ncols - 1);
+    for (int it = w; it < c.nblk * c.nseg; it += nw) {
+        const N4Item I = n4_item(c, it);
+        if (I.empty) continue;
+        const N4Col col = n4_col(c, ac, as, I.q);
         N4Win win; win.cur = -1; win.g0 = win.g1 = win.g2 = win.g3 = 0.0f;
-        VB_N4_FOR_ROWS(c, q, valid, p0, {
-            n4_win_advance(win, c.L, c, col, ar.bev[r]);
+        VB_N4_FOR_ROWS(c, I, {
+            n4_win_advance(win, c.L, c, col, c.r_bev[r]);
             if (bit) {
-                const float u = c.logI[idx] - n4_win_eval(win, ar.evw[r]);
+                const float u = c.logI[idx] - n4_win_eval(win, c.r_evw[r]);
                 tmin = fminf(tmin, u);
                 tmax = fmaxf(tmax, u);
             }
@@ -450,7 +504,7 @@ VB_DEV void n4_range(N4Ctx& c, float& bmin, float& bmax) {
 // P1: triangular Parzen histogram of U over the mask (SharpenImage, first half)
 VB_DEV void n4_histogram(N4Ctx& c, float bmin, float bmax) {
     const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
-    const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
+    const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     uint32_t* hc = (uint32_t*)c.un_f;                    // [VB_N4_HCOPIES][nbins]
     for (int i = tid; i < c.nbins * VB_N4_HCOPIES; i += nt) hc[i] = 0u;
     __syncthreads();
@@ -458,17 +512,15 @@ VB_DEV void n4_histogram(N4Ctx& c, float bmin, float bmax) {
     const uint32_t one = 1u << c.hshift;
     const float fone = (float)one;
     uint32_t* h = hc + (size_t)(w & (VB_N4_HCOPIES - 1)) * c.nbins;
-    for (int blk = w; blk < c.nblk; blk += nw) {
-        const unsigned p0 = c.blkbase[blk];
-        if (c.blkbase[blk + 1] == p0) continue;
-        const int q = blk * 32 + lane;
-        const bool valid = q < c.ncols;
-        const N4Col col = n4_col(c, ac, as, valid ? q : c.ncols - 1);
+    for (int it = w; it < c.nblk * c.nseg; it += nw) {
+        const N4Item I = n4_item(c, it);
+        if (I.empty) continue;
+        const N4Col col = n4_col(c, ac, as, I.q);
         N4Win win; win.cur = -1; win.g0 = win.g1 = win.g2 = win.g3 = 0.0f;
-        VB_N4_FOR_ROWS(c, q, valid, p0, {
-            n4_win_advance(win, c.L, c, col, ar.bev[r]);
+        VB_N4_FOR_ROWS(c, I, {
+            n4_win_advance(win, c.L, c, col, c.r_bev[r]);
             if (bit) {
-                const float u = c.logI[idx] - n4_win_eval(win, ar.evw[r]);
+                const float u = c.logI[idx] - n4_win_eval(win, c.r_evw[r]);
                 const float cidx = __fdiv_rn(u - bmin, slope);
                 const float fl = floorf(cidx);
                 const int bi = (int)fl;
@@ -601,38 +653,52 @@ VB_DEV void n4_sharpen(N4Ctx& c, float bmin, float bmax, float fwhm, float wiene
 // Separable B-spline contraction over the mask.
 //   OMEGA = true : value 1, weights B^2            -> c.Om
 //   OMEGA = false: value U - E(U), weights B^3/S   -> phi = delta/omega; Lold = L; L += phi
+// Rows: a lane reduces its column (one row segment) to row coefficients through a sliding 4-tap
+// window; a coefficient that leaves the window is spread over the 4 column control points into
+// Q[a][b][s] with 64-bit FIXED-POINT shared-memory atomics (exactly associative => the result
+// does not depend on the order in which warps arrive).  Slices -> lattice afterwards.
+#define VB_N4_QSCALE 1099511627776.0f         /* 2^40: sums stay below 2^63 for |sum| < 8e6 */
+VB_DEV void n4_qflush(unsigned long long* Q, int a, int ncp1, int n2, int bc, int s, const float4 wc, float v) {
+    if (v == 0.0f) return;
+    unsigned long long* qp = Q + ((size_t)a * ncp1 + bc) * n2 + s;
+    atomicAdd(qp, (unsigned long long)__float2ll_rn(wc.x * v * VB_N4_QSCALE));
+    atomicAdd(qp + n2, (unsigned long long)__float2ll_rn(wc.y * v * VB_N4_QSCALE));
+    atomicAdd(qp + 2 * n2, (unsigned long long)__float2ll_rn(wc.z * v * VB_N4_QSCALE));
+    atomicAdd(qp + 3 * n2, (unsigned long long)__float2ll_rn(wc.w * v * VB_N4_QSCALE));
+}
+
 template <bool OMEGA>
 VB_DEV void n4_contract(N4Ctx& c, float bmin, float bmax) {
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, w = vb_warp(), nw = nt >> 5;
     const int ncp0 = c.ncp[0], ncp1 = c.ncp[1], ncp2 = c.ncp[2];
-    const int n2 = c.n2, ncols = c.ncols;
+    const int n2 = c.n2;
     const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
     const float slope = (bmax - bmin) / (float)(c.nbins - 1);
     const int nbm1 = c.nbins - 1;
-    float* P = c.P;                                      // [ncp0][ncols]
+    unsigned long long* Q = (unsigned long long*)c.un_d;             // [ncp0][ncp1][n2]
+    const int Qn = ncp0 * ncp1 * n2;
+    for (int e = tid; e < Qn; e += nt) Q[e] = 0ull;
+    __syncthreads();
 
-    // rows: every lane reduces its column to ncp0 coefficients through a sliding 4-tap window
-    for (int blk = w; blk < c.nblk; blk += nw) {
-        const int q = blk * 32 + lane;
-        const bool valid = q < ncols;
-        const unsigned p0 = c.blkbase[blk];
-        if (c.blkbase[blk + 1] == p0) {
-            if (valid)
-                for (int a = 0; a < ncp0; ++a) P[(size_t)a * ncols + q] = 0.0f;
-            continue;
-        }
-        const N4Col col = n4_col(c, ac, as, valid ? q : ncols - 1);
+    for (int it = w; it < c.nblk * c.nseg; it += nw) {
+        const N4Item I = n4_item(c, it);
+        if (I.empty) continue;
+        const N4Col col = n4_col(c, ac, as, I.q);
+        const int cc = I.q / n2, ss = I.q - cc * n2;
+        const int bc = ac.bfit[cc];
+        const float4 wc = OMEGA ? ac.fit2[cc] : ac.fit3[cc];
         N4Win win; win.cur = -1; win.g0 = win.g1 = win.g2 = win.g3 = 0.0f;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int cur = 0;                                     // coefficients below cur are final
-        VB_N4_FOR_ROWS(c, q, valid, p0, {
-            const int base = ar.bfit[r];
+        int cur = -1;                                    // window = coefficients cur .. cur+3
+        VB_N4_FOR_ROWS(c, I, {
+            const int base = c.r_bfit[r];
+            if (cur < 0) cur = base;
             while (cur < base) {                         // warp uniform
-                if (valid) P[(size_t)cur * ncols + q] = a0;
+                if (I.valid) n4_qflush(Q, cur, ncp1, n2, bc, ss, wc, a0);
                 a0 = a1; a1 = a2; a2 = a3; a3 = 0.f;
                 ++cur;
             }
-            if (!OMEGA) n4_win_advance(win, c.L, c, col, ar.bev[r]);
+            if (!OMEGA) n4_win_advance(win, c.L, c, col, c.r_bev[r]);
             if (bit) {
                 float val;
                 float4 wt;
@@ -640,7 +706,7 @@ VB_DEV void n4_contract(N4Ctx& c, float bmin, float bmax) {
                     val = 1.0f;
                     wt = ar.fit2[r];
                 } else {
-                    const float u = c.logI[idx] - n4_win_eval(win, ar.evw[r]);
+                    const float u = c.logI[idx] - n4_win_eval(win, c.r_evw[r]);
                     const float cidx = __fdiv_rn(u - bmin, slope);
                     const float fl = floorf(cidx);
                     const int bi = (int)fl;
@@ -652,36 +718,17 @@ VB_DEV void n4_contract(N4Ctx& c, float bmin, float bmax) {
                         s = c.E[nbm1];
                     }
                     val = u - s;
-                    wt = ar.fit3[r];
+                    wt = c.r_fit3[r];
                 }
                 a0 += wt.x * val; a1 += wt.y * val; a2 += wt.z * val; a3 += wt.w * val;
             }
         })
-        if (valid) {
-            for (int a = cur; a < ncp0; ++a) {
-                P[(size_t)a * ncols + q] = a0;
-                a0 = a1; a1 = a2; a2 = a3; a3 = 0.f;
-            }
+        if (I.valid && cur >= 0) {
+            n4_qflush(Q, cur, ncp1, n2, bc, ss, wc, a0);
+            n4_qflush(Q, cur + 1, ncp1, n2, bc, ss, wc, a1);
+            n4_qflush(Q, cur + 2, ncp1, n2, bc, ss, wc, a2);
+            n4_qflush(Q, cur + 3, ncp1, n2, bc, ss, wc, a3);
         }
-    }
-    __syncthreads();
-
-    // columns: Q[a][b][s] = sum_c wc[c][b - bfit[c]] * P[a][c][s]
-    float* Q = c.un_f;                                   // [ncp0][ncp1][n2]
-    const int Qn = ncp0 * ncp1 * n2;
-    for (int e = tid; e < Qn; e += nt) {
-        const int s = e % n2, ab = e / n2, b = ab % ncp1, a = ab / ncp1;
-        const float* pp = P + (size_t)a * ncols + s;
-        float sum = 0.0f;
-        const int chi = ac.hi[b];
-#pragma unroll 4
-        for (int cc = ac.lo[b]; cc < chi; ++cc) {
-            const int k = b - ac.bfit[cc];
-            const float4 wt = OMEGA ? ac.fit2[cc] : ac.fit3[cc];
-            const float wk = (k == 0) ? wt.x : (k == 1) ? wt.y : (k == 2) ? wt.z : wt.w;
-            sum += wk * pp[(size_t)cc * n2];
-        }
-        Q[e] = sum;
     }
     __syncthreads();
 
@@ -695,7 +742,8 @@ VB_DEV void n4_contract(N4Ctx& c, float bmin, float bmax) {
             const int k = g - as.bfit[s];
             const float4 wt = OMEGA ? as.fit2[s] : as.fit3[s];
             const float wk = (k == 0) ? wt.x : (k == 1) ? wt.y : (k == 2) ? wt.z : wt.w;
-            sum += Q[(size_t)ab * n2 + s] * wk;
+            const float qv = (float)((double)(long long)Q[(size_t)ab * n2 + s] * (1.0 / (double)VB_N4_QSCALE));
+            sum += qv * wk;
         }
         if (OMEGA) {
             c.Om[e] = sum;
@@ -750,12 +798,13 @@ VB_DEV float n4_convergence(N4Ctx& c, int M) {
     const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
     VB_SHARED int s_state[2];                 // float bit patterns of (mu, sigma) at the chunk start
     const float* e = c.ebuf;
+    const uint32_t* perm = c.perm;
     int* scratch = (int*)c.red;
     const int S0 = min(M, VB_N4_SERIAL);
     if (tid == 0) {
         float mu = 0.0f, sigma = 0.0f;
         for (int j = 0; j < S0; ++j) {
-            const float px = e[j];
+            const float px = e[perm[j]];
             const N4Step s = n4_step_consts(px, j + 1);
             if (j > 0) sigma = n4_sigma_next(sigma, mu, px, s);
             mu = (j == 0) ? s.b : n4_mu_next(mu, s);
@@ -767,66 +816,50 @@ VB_DEV float n4_convergence(N4Ctx& c, int M) {
     while (start < M) {
         const int len = min(min(start, VB_N4_CHUNK), M - start);
         const int ept = (len + nt - 1) / nt;                  // <= VB_N4_EPT
-        const int lo = start + min(len, tid * ept), hi = start + min(len, tid * ept + ept);
+        const int lo = start + min(len, tid * ept);
+        const int cnt = start + min(len, tid * ept + ept) - lo;   // steps of this thread
         const int mu0 = s_state[0], sg0 = s_state[1];
         float px[VB_N4_EPT];
         N4Step st[VB_N4_EPT];
-        int kg[VB_N4_EPT];                                    // guess: bits of mu BEFORE step i
 #pragma unroll
         for (int i = 0; i < VB_N4_EPT; ++i) {
-            const int j = lo + i;
-            px[i] = (j < hi) ? e[j] : 1.0f;
-            st[i] = n4_step_consts(px[i], j + 1);
-            kg[i] = mu0;
+            px[i] = (i < cnt) ? e[perm[lo + i]] : 1.0f;
+            st[i] = n4_step_consts(px[i], lo + i + 1);
         }
-        // mu: iterate until the trajectory reproduces itself
-        int total = 0;
+        // mu: a thread runs its steps sequentially (exactly) from its guessed start; the starts
+        // are re-derived from the prefix sum of the threads' increments until none moves
+        int km = mu0, total = 0;
         for (;;) {
-            int pre[VB_N4_EPT];
-            int run = 0;
+            float mu = __int_as_float(km);
 #pragma unroll
-            for (int i = 0; i < VB_N4_EPT; ++i) {
-                pre[i] = run;
-                if (lo + i < hi) run += __float_as_int(n4_mu_next(__int_as_float(kg[i]), st[i])) - kg[i];
-            }
-            const int off = n4_block_scan(run, total, scratch);
+            for (int i = 0; i < VB_N4_EPT; ++i)
+                if (i < cnt) mu = n4_mu_next(mu, st[i]);
+            const int off = n4_block_scan(__float_as_int(mu) - km, total, scratch);
+            const int k = mu0 + off;
+            const int changed = (k != km);
+            km = k;
             ++c.n_sweeps;
-            int changed = 0;
-#pragma unroll
-            for (int i = 0; i < VB_N4_EPT; ++i) {
-                const int k = mu0 + off + pre[i];
-                changed |= (lo + i < hi) && (k != kg[i]);
-                kg[i] = k;
-            }
             if (!__syncthreads_or(changed)) break;
         }
         const int mu_end = mu0 + total;
-        // sigma, given the exact mu trajectory
-        int sg[VB_N4_EPT];
-#pragma unroll
-        for (int i = 0; i < VB_N4_EPT; ++i) sg[i] = sg0;
+        // sigma, along the exact mu trajectory
+        int ks = sg0;
         for (;;) {
-            int pre[VB_N4_EPT];
-            int run = 0;
+            float mu = __int_as_float(km), sg = __int_as_float(ks);
 #pragma unroll
-            for (int i = 0; i < VB_N4_EPT; ++i) {
-                pre[i] = run;
-                if (lo + i < hi)
-                    run += __float_as_int(n4_sigma_next(__int_as_float(sg[i]), __int_as_float(kg[i]), px[i], st[i])) - sg[i];
-            }
-            const int off = n4_block_scan(run, total, scratch);
+            for (int i = 0; i < VB_N4_EPT; ++i)
+                if (i < cnt) {
+                    sg = n4_sigma_next(sg, mu, px[i], st[i]);
+                    mu = n4_mu_next(mu, st[i]);
+                }
+            const int off = n4_block_scan(__float_as_int(sg) - ks, total, scratch);
+            const int k = sg0 + off;
+            const int changed = (k != ks);
+            ks = k;
             c.n_sweeps += 1000;
-            int changed = 0;
-#pragma unroll
-            for (int i = 0; i < VB_N4_EPT; ++i) {
-                const int k = sg0 + off + pre[i];
-                changed |= (lo + i < hi) && (k != sg[i]);
-                sg[i] = k;
-            }
             if (!__syncthreads_or(changed)) break;
         }
         const int sg_end = sg0 + total;
-        __syncthreads();
         if (tid == 0) { s_state[0] = mu_end; s_state[1] = sg_end; }
         __syncthreads();
         start += len;
@@ -840,37 +873,57 @@ VB_DEV float n4_convergence(N4Ctx& c, int M) {
 // ---------------------------------------------------------------------------------------------
 // P3: evaluate the old and the new bias on the mask: e = exp(old - new) (C order, for the
 // convergence measure) and the range of the new U = logI - bias
-VB_DEV float n4_update(N4Ctx& c, int M, float& bmin, float& bmax) {
-    const int nt = (int)blockDim.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
-    const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
+// The sequential float Welford (n4_convergence) is only run when its outcome can matter.  Its
+// running mean lags the exact one by at most u*(j+1)/4 after j steps (u = 2^-23, one rounding of
+// at most u/2 per step, damped by (j-1)/j), so by Cauchy-Schwarz its value is at least
+//     (sqrt(S) - u*M^1.5/(4*sqrt(3))) / sqrt(M-1) / mean  ~  cv_exact - u*M/(4*sqrt(3))
+// (S = exact sum of squared deviations).  If that bound, with 2 % to spare for the float
+// rounding of sigma and mean, still exceeds the threshold the level certainly continues and the
+// exact double-precision cv is returned instead (`exact_needed` forces the chain: last allowed
+// iteration of a level, debug capture).
+VB_DEV float n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool exact_needed) {
+    const int nt = (int)blockDim.x, w = vb_warp(), nw = nt >> 5;
+    const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     float tmin = FLT_MAX, tmax = -FLT_MAX;
-    for (int blk = w; blk < c.nblk; blk += nw) {
-        const unsigned p0 = c.blkbase[blk];
-        if (c.blkbase[blk + 1] == p0) continue;
-        const int q = blk * 32 + lane;
-        const bool valid = q < c.ncols;
-        const N4Col col = n4_col(c, ac, as, valid ? q : c.ncols - 1);
+    double s1 = 0.0, s2 = 0.0;
+    for (int it = w; it < c.nblk * c.nseg; it += nw) {
+        const N4Item I = n4_item(c, it);
+        if (I.empty) continue;
+        const N4Col col = n4_col(c, ac, as, I.q);
         N4Win wo, wn;
         wo.cur = wn.cur = -1;
         wo.g0 = wo.g1 = wo.g2 = wo.g3 = wn.g0 = wn.g1 = wn.g2 = wn.g3 = 0.0f;
-        const unsigned lt = (1u << lane) - 1u;
-        VB_N4_FOR_ROWS(c, q, valid, p0, {
-            const int base = ar.bev[r];
+        VB_N4_FOR_ROWS(c, I, {
+            const int base = c.r_bev[r];
             n4_win_advance(wo, c.Lold, c, col, base);
             n4_win_advance(wn, c.L, c, col, base);
             if (bit) {
-                const float4 rw = ar.evw[r];
+                const float4 rw = c.r_evw[r];
                 const float bo = n4_win_eval(wo, rw), bn = n4_win_eval(wn, rw);
                 const float un = c.logI[idx] - bn;
                 tmin = fminf(tmin, un);
                 tmax = fmaxf(tmax, un);
-                c.ebuf[c.rbb[(size_t)r * c.nblk + blk] + (unsigned)__popc(bal & lt)] = n4_exp_small(bo - bn);
+                const float ev = n4_exp_small(bo - bn);
+                c.ebuf[idx] = ev;
+                const double em = (double)ev - 1.0;
+                s1 += em; s2 += em * em;
             }
         })
     }
     bmin = vb_block_reduce(tmin, VbMinF(), FLT_MAX, (float*)c.red);
     bmax = vb_block_reduce(tmax, VbMaxF(), -FLT_MAX, (float*)c.red);
+    s1 = vb_block_reduce(s1, VbAddD(), 0.0, c.red);
+    s2 = vb_block_reduce(s2, VbAddD(), 0.0, c.red);
     __syncthreads();
+    if (!exact_needed) {
+        const double N = (double)M;
+        double var = (s2 - s1 * s1 / N) / (N - 1.0);
+        if (var < 0.0) var = 0.0;
+        const double mean = 1.0 + s1 / N;
+        const double lag = 1.1920929e-7 * N / (4.0 * 1.7320508) * 1.05;
+        const double lower = (sqrt(var) - lag) / mean * 0.98;
+        if (lower > (double)thr) return (float)(sqrt(var) / mean);
+    }
     const long long t0 = vb_clock();
     const float conv = n4_convergence(c, M);
     c.t_chain += vb_clock() - t0;
@@ -881,8 +934,9 @@ VB_DEV float n4_update(N4Ctx& c, int M, float& bmin, float& bmax) {
 VB_DEV void n4_finalize(N4Ctx& c, float* logbias) {
     const int nt = (int)blockDim.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
     const int ncols = c.ncols;
-    const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
-    for (int blk = w; blk < c.nblk; blk += nw) {
+    const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
+    const int nblk_all = (ncols + 31) >> 5;              // every column, not only the active ones
+    for (int blk = w; blk < nblk_all; blk += nw) {
         const int q = blk * 32 + lane;
         if (q >= ncols) continue;
         const N4Col col = n4_col(c, ac, as, q);
@@ -896,8 +950,8 @@ VB_DEV void n4_finalize(N4Ctx& c, float* logbias) {
             for (int j = 0; j < 8; ++j) {
                 const int r = r0 + j;
                 if (r < c.n0) {
-                    n4_win_advance(win, c.L, c, col, ar.bev[r]);
-                    const float bias = n4_win_eval(win, ar.evw[r]);
+                    n4_win_advance(win, c.L, c, col, c.r_bev[r]);
+                    const float bias = n4_win_eval(win, c.r_evw[r]);
                     const size_t v = (size_t)r * ncols + q;
                     vb_st_stream(c.out + v, __fdiv_rn(x[j], expf(bias)));
                     if (logbias) vb_st_stream(logbias + v, bias);
@@ -950,6 +1004,19 @@ VB_DEV void n4_build_tables(N4Ctx& c) {
         n4_build_support(c.axis_base + off, c.slot[a], n[a], c.ncp[a]);
         off += 16 * (size_t)c.slot[a];
     }
+    const N4Axis ar = n4_ax(c, 0);
+    if (c.rowtab) {
+        float4* evw = (float4*)c.rowtab;
+        float4* fit3 = evw + c.n0;
+        int* bev = (int*)(fit3 + c.n0);
+        int* bfit = bev + c.n0;
+        for (int r = (int)threadIdx.x; r < c.n0; r += (int)blockDim.x) {
+            evw[r] = ar.evw[r]; fit3[r] = ar.fit3[r]; bev[r] = ar.bev[r]; bfit[r] = ar.bfit[r];
+        }
+        c.r_evw = evw; c.r_fit3 = fit3; c.r_bev = bev; c.r_bfit = bfit;
+    } else {
+        c.r_evw = ar.evw; c.r_fit3 = ar.fit3; c.r_bev = ar.bev; c.r_bfit = ar.bfit;
+    }
     __syncthreads();
 }
 
@@ -968,6 +1035,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
     c.E = (float*)p;    p += sizeof(float) * (size_t)((a.p.n_bins + 3) & ~3);
     c.H = (float*)p;    p += sizeof(float) * (size_t)((a.p.n_bins + 3) & ~3);
     c.red = (double*)p; p += 64 * sizeof(double);
+    float* smem_rowtab = (float*)p; p += (size_t)40 * a.rowtab_rows;
     float* smem_logI = (float*)p;
     c.nbins = a.p.n_bins; c.fftN = a.fftN;
 
@@ -979,15 +1047,16 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         if (si >= a.n) break;
         const VbSubject S = a.subj[si];
         c.n0 = S.n0; c.n1 = S.n1; c.n2 = S.n2; c.ncols = S.n1 * S.n2; c.W = (S.n0 + 31) >> 5;
-        c.nblk = (c.ncols + 31) >> 5;
+        c.nblk = 0; c.nact = 0; c.nseg = 1; c.wps = c.W;
         c.V = S.V;
         c.img = a.image + S.off; c.msk = a.mask + S.off; c.out = a.out + S.off;
         c.colmask = a.ws_colmask + (size_t)blockIdx.x * a.cmw_max;
         c.rbb = a.ws_rbb + (size_t)blockIdx.x * a.rbb_max;
-        c.blkbase = a.ws_blkbase + (size_t)blockIdx.x * a.blk_max;
+        c.wbase = a.ws_wbase + (size_t)blockIdx.x * a.wb_max;
+        c.acol = a.ws_acol + (size_t)blockIdx.x * a.ncols_max;
         c.axis_base = a.ws_axis + (size_t)blockIdx.x * a.axis_stride;
         c.ebuf = a.ws_e + (size_t)blockIdx.x * a.Vmax;
-        c.P = a.ws_P + (size_t)blockIdx.x * a.P_max;
+        c.perm = a.ws_perm + (size_t)blockIdx.x * a.Vmax;
         c.ncp[0] = a.p.ncp[0]; c.ncp[1] = a.p.ncp[1]; c.ncp[2] = a.p.ncp[2];
         {
             const int nn[3] = {S.n0, S.n1, S.n2};
@@ -998,6 +1067,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
             }
         }
         c.logI = a.ws_logI + (size_t)blockIdx.x * a.Vmax;   // n4_setup moves it to shared memory if it fits
+        c.rowtab = (a.rowtab_rows > 0 && S.n0 <= a.rowtab_rows) ? smem_rowtab : nullptr;
 
         float bmin, bmax;
         int M;
@@ -1033,7 +1103,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                     tn = vb_clock(); tph[2] += tn - tq; tq = tn;
                     n4_contract<false>(c, bmin, bmax);
                     tn = vb_clock(); tph[3] += tn - tq; tq = tn;
-                    conv = n4_update(c, M, bmin, bmax);
+                    conv = n4_update(c, M, bmin, bmax, a.p.conv_threshold, dbg != nullptr || it >= a.p.max_iter[level]);
                     tn = vb_clock(); tph[4] += tn - tq;
                     if (dbg_trace && tid == 0 && ntrace < trace_cap) dbg_trace[ntrace] = conv;
                     ++ntrace;

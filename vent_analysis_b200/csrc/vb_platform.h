@@ -286,6 +286,7 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline unsigned __float2uint_rn(float a) { return (unsigned)llrintf(a); }
+static inline long long __float2ll_rn(float a) { return llrintf(a); }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }

@@ -39,7 +39,7 @@ struct vb_ctx {
     Buf h_desc, d_subj, d_wordoff;
     long long v_total = 0, words_total = 0;
     // workspaces
-    Buf ws_logI, ws_e, ws_colmask, ws_rbb, ws_blkbase, ws_P, ws_axis, ws_counter, ws_d0, ws_bits, ws_list, ws_count, dbg;
+    Buf ws_logI, ws_e, ws_colmask, ws_rbb, ws_wbase, ws_acol, ws_perm, ws_axis, ws_counter, ws_d0, ws_bits, ws_list, ws_count, dbg;
     int dbg_stride = 0, dbg_nbins = 0, dbg_Lmax = 0, dbg_n = 0;
     // CI tables
     std::vector<TableHost> tables;
@@ -181,26 +181,29 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     int e = 0;
     while ((1 << e) < p.n_bins) ++e;
     const int fftN = 1 << (e + 1);
-    long long vmax = 0, cmw = 0, axis = 0, n2max = 0, rbb = 0, blk = 0, pmax = 0;
+    long long vmax = 0, cmw = 0, axis = 0, n2max = 0, rbb = 0, wb = 0, ncmax = 0, n0max = 0;
     for (const VbSubject& S : c->last_subj) {
         const long long ncols = (long long)S.n1 * S.n2, nblk = (ncols + 31) / 32;
         vmax = std::max<long long>(vmax, S.V);
         cmw = std::max<long long>(cmw, (long long)((S.n0 + 31) / 32) * ncols);
         axis = std::max<long long>(axis, 16LL * (std::max(S.n0, ncpf[0]) + std::max(S.n1, ncpf[1]) + std::max(S.n2, ncpf[2])));
         n2max = std::max<long long>(n2max, S.n2);
-        rbb = std::max<long long>(rbb, (long long)S.n0 * nblk + 1);
-        blk = std::max<long long>(blk, nblk + 1);
-        pmax = std::max<long long>(pmax, (long long)ncpf[0] * ncols);
+        const long long W = (S.n0 + 31) / 32;
+        rbb = std::max<long long>(rbb, std::max((long long)S.n0 * nblk + 1, ncols + 2));
+        wb = std::max<long long>(wb, nblk * W + 1);
+        ncmax = std::max<long long>(ncmax, ncols);
+        n0max = std::max<long long>(n0max, S.n0);
     }
-    // shared memory: [union][L][Lold][Om][E][H][red][compact log image]
+    // shared memory: [union][L][Lold][Om][E][H][red][row tables][compact log image]
     const long long Lb = 4 * ((Lmax + 3) & ~3LL), Hb = 4 * ((p.n_bins + 3) & ~3);
-    const long long fixed = 3 * Lb + 2 * Hb + 64 * 8;
+    const long long rowtab_rows = (40 * n0max <= 20480) ? ((n0max + 3) & ~3LL) : 0;
+    const long long fixed = 3 * Lb + 2 * Hb + 64 * 8 + 40 * rowtab_rows;
     long long ub = 4LL * VB_N4_HCOPIES * p.n_bins;                       // histogram copies
     ub = std::max(ub, 8LL * 7 * fftN);                                   // FFT work arrays
-    ub = std::max(ub, 4LL * (long long)ncpf[0] * ncpf[1] * n2max);       // Q[a][b][s]
+    ub = std::max(ub, 8LL * (long long)ncpf[0] * ncpf[1] * n2max);       // Q[a][b][s], 64-bit fixed point
     ub = std::max(ub, 4LL * Lmax);                                       // refinement scratch
     ub = (ub + 15) & ~15LL;
-    const long long static_smem = 64;                                    // s_next, chain state
+    const long long static_smem = 512;                                   // s_next, chain state
     if (ub + fixed + static_smem > c->max_smem)
         return fail(VB_ERR_UNSUPPORTED, "N4: working set does not fit the 227 KB of shared memory");
     const long long cap = ((long long)c->max_smem - ub - fixed - static_smem) / 4;
@@ -208,7 +211,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     if (!ensure(c->ws_logI, sizeof(float) * (size_t)grid * (size_t)vmax) ||
         !ensure(c->ws_e, sizeof(float) * (size_t)grid * (size_t)vmax) ||
         !ensure(c->ws_colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(c->ws_rbb, 4 * (size_t)grid * (size_t)rbb) ||
-        !ensure(c->ws_blkbase, 4 * (size_t)grid * (size_t)blk) || !ensure(c->ws_P, 4 * (size_t)grid * (size_t)pmax) ||
+        !ensure(c->ws_wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(c->ws_acol, 4 * (size_t)grid * (size_t)ncmax) || !ensure(c->ws_perm, 4 * (size_t)grid * (size_t)vmax) ||
         !ensure(c->ws_axis, 4 * (size_t)grid * (size_t)axis) || !ensure(c->ws_counter, 64))
         return VB_ERR_CUDA;
     int trace = 0;
@@ -227,10 +230,10 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     a.image = image; a.mask = mask; a.out = out; a.logbias = logbias;
     a.subj = (const VbSubject*)c->d_subj.p; a.n = n; a.p = p; a.stats = stats;
     a.ws_logI = (float*)c->ws_logI.p; a.ws_colmask = (uint32_t*)c->ws_colmask.p; a.ws_rbb = (uint32_t*)c->ws_rbb.p;
-    a.ws_blkbase = (uint32_t*)c->ws_blkbase.p; a.ws_axis = (float*)c->ws_axis.p; a.ws_e = (float*)c->ws_e.p;
-    a.ws_P = (float*)c->ws_P.p;
+    a.ws_wbase = (uint32_t*)c->ws_wbase.p; a.ws_acol = (uint32_t*)c->ws_acol.p; a.ws_axis = (float*)c->ws_axis.p; a.ws_e = (float*)c->ws_e.p;
+    a.ws_perm = (uint32_t*)c->ws_perm.p; a.rowtab_rows = (int)rowtab_rows;
     a.work_counter = (int*)c->ws_counter.p; a.debug = dbg;
-    a.Vmax = vmax; a.cmw_max = cmw; a.rbb_max = rbb; a.blk_max = blk; a.P_max = pmax;
+    a.Vmax = vmax; a.cmw_max = cmw; a.rbb_max = rbb; a.wb_max = wb; a.ncols_max = ncmax;
     a.axis_stride = (int)axis; a.debug_stride = dbg_stride;
     a.Lmax = (int)Lmax; a.fftN = fftN; a.union_bytes = (int)ub;
     // a mask that does not fit keeps its compact log image in global memory (L2)
@@ -323,7 +326,7 @@ void vb_destroy(vb_ctx* c) {
     if (!c) return;
     vbrt::set_device(c->device);
     vbrt::stream_sync(c->stream);
-    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_logI, &c->ws_e, &c->ws_rbb, &c->ws_blkbase, &c->ws_P, &c->ws_colmask, &c->ws_axis, &c->ws_counter, &c->ws_d0,
+    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_logI, &c->ws_e, &c->ws_rbb, &c->ws_wbase, &c->ws_acol, &c->ws_perm, &c->ws_colmask, &c->ws_axis, &c->ws_counter, &c->ws_d0,
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
                    &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats};
     for (Buf* b : bufs) vbrt::dev_free(b->p);
