@@ -35,7 +35,7 @@
 #include <float.h>
 #include "vb_common.cuh"
 
-#define VB_N4_THREADS 512
+#define VB_N4_THREADS 1024
 #define VB_N4_WARPS (VB_N4_THREADS / 32)
 #define VB_BSPLINE_EPS 1e-3f
 #define VB_N4_EPT 8                               /* convergence chain: elements per thread   */
@@ -658,13 +658,22 @@ VB_DEV void n4_sharpen(N4Ctx& c, float bmin, float bmax, float fwhm, float wiene
 // Q[a][b][s] with 64-bit FIXED-POINT shared-memory atomics (exactly associative => the result
 // does not depend on the order in which warps arrive).  Slices -> lattice afterwards.
 #define VB_N4_QSCALE 1099511627776.0f         /* 2^40: sums stay below 2^63 for |sum| < 8e6 */
-VB_DEV void n4_qflush(unsigned long long* Q, int a, int ncp1, int n2, int bc, int s, const float4 wc, float v) {
+// 64-bit add from two native 32-bit shared-memory atomics: every wrap of the low word is seen
+// by exactly one adder (the one whose old value + addend overflowed), which forwards the carry.
+// Once all adders are done the pair holds the exact 64-bit sum, whatever the interleaving.
+VB_DEV void n4_add64(unsigned* q, long long x) {
+    const unsigned xlo = (unsigned)(unsigned long long)x;
+    const unsigned old = atomicAdd(q, xlo);
+    const unsigned carry = (unsigned)(old + xlo < old);
+    atomicAdd(q + 1, (unsigned)((unsigned long long)x >> 32) + carry);
+}
+VB_DEV void n4_qflush(unsigned* Q, int a, int ncp1, int n2, int bc, int s, const float4 wc, float v) {
     if (v == 0.0f) return;
-    unsigned long long* qp = Q + ((size_t)a * ncp1 + bc) * n2 + s;
-    atomicAdd(qp, (unsigned long long)__float2ll_rn(wc.x * v * VB_N4_QSCALE));
-    atomicAdd(qp + n2, (unsigned long long)__float2ll_rn(wc.y * v * VB_N4_QSCALE));
-    atomicAdd(qp + 2 * n2, (unsigned long long)__float2ll_rn(wc.z * v * VB_N4_QSCALE));
-    atomicAdd(qp + 3 * n2, (unsigned long long)__float2ll_rn(wc.w * v * VB_N4_QSCALE));
+    unsigned* qp = Q + 2 * (((size_t)a * ncp1 + bc) * n2 + s);
+    n4_add64(qp, __float2ll_rn(wc.x * v * VB_N4_QSCALE));
+    n4_add64(qp + 2 * n2, __float2ll_rn(wc.y * v * VB_N4_QSCALE));
+    n4_add64(qp + 4 * n2, __float2ll_rn(wc.z * v * VB_N4_QSCALE));
+    n4_add64(qp + 6 * n2, __float2ll_rn(wc.w * v * VB_N4_QSCALE));
 }
 
 template <bool OMEGA>
@@ -675,9 +684,9 @@ VB_DEV void n4_contract(N4Ctx& c, float bmin, float bmax) {
     const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
     const float slope = (bmax - bmin) / (float)(c.nbins - 1);
     const int nbm1 = c.nbins - 1;
-    unsigned long long* Q = (unsigned long long*)c.un_d;             // [ncp0][ncp1][n2]
+    unsigned* Q = (unsigned*)c.un_d;                     // [ncp0][ncp1][n2] x {low, high} words
     const int Qn = ncp0 * ncp1 * n2;
-    for (int e = tid; e < Qn; e += nt) Q[e] = 0ull;
+    for (int e = tid; e < 2 * Qn; e += nt) Q[e] = 0u;
     __syncthreads();
 
     for (int it = w; it < c.nblk * c.nseg; it += nw) {
@@ -742,7 +751,9 @@ VB_DEV void n4_contract(N4Ctx& c, float bmin, float bmax) {
             const int k = g - as.bfit[s];
             const float4 wt = OMEGA ? as.fit2[s] : as.fit3[s];
             const float wk = (k == 0) ? wt.x : (k == 1) ? wt.y : (k == 2) ? wt.z : wt.w;
-            const float qv = (float)((double)(long long)Q[(size_t)ab * n2 + s] * (1.0 / (double)VB_N4_QSCALE));
+            const unsigned* qc = Q + 2 * ((size_t)ab * n2 + s);
+            const long long qi = (long long)(((unsigned long long)qc[1] << 32) | (unsigned long long)qc[0]);
+            const float qv = (float)((double)qi * (1.0 / (double)VB_N4_QSCALE));
             sum += qv * wk;
         }
         if (OMEGA) {
@@ -794,17 +805,44 @@ VB_DEV float n4_sigma_next(float sigma, float mu_prev, float pixel, const N4Step
     return __fadd_rn(r, __fadd_rn(err, tl));
 }
 
+// Exclusive block prefix of v with ONE barrier, which also ORs `flag` over the block (in/out).
+// `tot` is a per-sweep buffer (double buffered by the caller).
+VB_DEV int n4_chain_scan(int v, int& total, int* tot, int& flag) {
+    const int lane = vb_lane(), w = vb_warp(), nw = (int)(blockDim.x >> 5);
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(VB_FULL, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) tot[w] = inc;
+    flag = __syncthreads_or(flag);
+    int wt = (lane < nw) ? tot[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(VB_FULL, wt, d);
+        if (lane >= d) wt += t;
+    }
+    total = __shfl_sync(VB_FULL, wt, 31);
+    const int woff = __shfl_sync(VB_FULL, wt, (w > 0) ? w - 1 : 0);
+    return ((w > 0) ? woff : 0) + inc - v;
+}
+
 VB_DEV float n4_convergence(N4Ctx& c, int M) {
     const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
     VB_SHARED int s_state[2];                 // float bit patterns of (mu, sigma) at the chunk start
+    VB_SHARED int s_tot[2][32];               // warp totals, double buffered
+    int buf = 0;
     const float* e = c.ebuf;
     const uint32_t* perm = c.perm;
-    int* scratch = (int*)c.red;
     const int S0 = min(M, VB_N4_SERIAL);
+    VB_SHARED float s_px[VB_N4_SERIAL];
+    if (tid < S0) s_px[tid] = e[perm[tid]];
+    __syncthreads();
     if (tid == 0) {
         float mu = 0.0f, sigma = 0.0f;
         for (int j = 0; j < S0; ++j) {
-            const float px = e[perm[j]];
+            const float px = s_px[j];
             const N4Step s = n4_step_consts(px, j + 1);
             if (j > 0) sigma = n4_sigma_next(sigma, mu, px, s);
             mu = (j == 0) ? s.b : n4_mu_next(mu, s);
@@ -827,23 +865,27 @@ VB_DEV float n4_convergence(N4Ctx& c, int M) {
             st[i] = n4_step_consts(px[i], lo + i + 1);
         }
         // mu: a thread runs its steps sequentially (exactly) from its guessed start; the starts
-        // are re-derived from the prefix sum of the threads' increments until none moves
-        int km = mu0, total = 0;
+        // are re-derived from the prefix sum of the threads' increments until none moves.  One
+        // barrier per sweep: it publishes the warps' totals AND tells whether the previous sweep
+        // moved any start (if not, the sweep just computed has confirmed the trajectory).
+        int km = mu0, total = 0, changed = 1;
         for (;;) {
             float mu = __int_as_float(km);
 #pragma unroll
             for (int i = 0; i < VB_N4_EPT; ++i)
                 if (i < cnt) mu = n4_mu_next(mu, st[i]);
-            const int off = n4_block_scan(__float_as_int(mu) - km, total, scratch);
-            const int k = mu0 + off;
-            const int changed = (k != km);
-            km = k;
+            const int off = n4_chain_scan(__float_as_int(mu) - km, total, s_tot[buf], changed);
+            buf ^= 1;
             ++c.n_sweeps;
-            if (!__syncthreads_or(changed)) break;
+            if (!changed) break;
+            const int k = mu0 + off;
+            changed = (k != km);
+            km = k;
         }
         const int mu_end = mu0 + total;
         // sigma, along the exact mu trajectory
         int ks = sg0;
+        changed = 1;
         for (;;) {
             float mu = __int_as_float(km), sg = __int_as_float(ks);
 #pragma unroll
@@ -852,12 +894,13 @@ VB_DEV float n4_convergence(N4Ctx& c, int M) {
                     sg = n4_sigma_next(sg, mu, px[i], st[i]);
                     mu = n4_mu_next(mu, st[i]);
                 }
-            const int off = n4_block_scan(__float_as_int(sg) - ks, total, scratch);
-            const int k = sg0 + off;
-            const int changed = (k != ks);
-            ks = k;
+            const int off = n4_chain_scan(__float_as_int(sg) - ks, total, s_tot[buf], changed);
+            buf ^= 1;
             c.n_sweeps += 1000;
-            if (!__syncthreads_or(changed)) break;
+            if (!changed) break;
+            const int k = sg0 + off;
+            changed = (k != ks);
+            ks = k;
         }
         const int sg_end = sg0 + total;
         if (tid == 0) { s_state[0] = mu_end; s_state[1] = sg_end; }

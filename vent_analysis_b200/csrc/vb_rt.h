@@ -42,6 +42,11 @@ inline int max_smem_optin(int dev) { int n = 0; cudaDeviceGetAttribute(&n, cudaD
 template <class K> inline bool allow_smem(K kernel, int bytes) {
     return ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute(smem)");
 }
+template <class K> inline int static_smem(K kernel) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) { cudaGetLastError(); return 1024; }
+    return (int)fa.sharedSizeBytes;
+}
 inline bool stream_create(stream_t* s) { return ok(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking), "cudaStreamCreate"); }
 inline void stream_destroy(stream_t s) { if (s) cudaStreamDestroy(s); }
 typedef cudaEvent_t event_t;
@@ -67,6 +72,7 @@ inline int device_count() { return 1; }
 inline int sm_count(int) { const char* e = getenv("VB_EMU_SMS"); return e ? atoi(e) : 2; }
 inline int max_smem_optin(int) { return 232448; }
 template <class K> inline bool allow_smem(K, int) { return true; }
+template <class K> inline int static_smem(K) { return 0; }
 inline bool stream_create(stream_t* s) { *s = nullptr; return true; }
 inline void stream_destroy(stream_t) {}
 typedef void* event_t;

@@ -203,7 +203,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     ub = std::max(ub, 8LL * (long long)ncpf[0] * ncpf[1] * n2max);       // Q[a][b][s], 64-bit fixed point
     ub = std::max(ub, 4LL * Lmax);                                       // refinement scratch
     ub = (ub + 15) & ~15LL;
-    const long long static_smem = 512;                                   // s_next, chain state
+    const long long static_smem = vbrt::static_smem(n4_subject_kernel);    // s_next, chain state
     if (ub + fixed + static_smem > c->max_smem)
         return fail(VB_ERR_UNSUPPORTED, "N4: working set does not fit the 227 KB of shared memory");
     const long long cap = ((long long)c->max_smem - ub - fixed - static_smem) / 4;
