@@ -39,7 +39,7 @@
 #define VB_N4_WARPS (VB_N4_THREADS / 32)
 #define VB_BSPLINE_EPS 1e-3f
 #define VB_N4_EPT 8                               /* convergence chain: elements per thread   */
-#define VB_N4_CHUNK (VB_N4_THREADS * VB_N4_EPT)   /* ... per chunk                            */
+#define VB_N4_CHAIN_WARPS 16                      /* warps of the chain team while it overlaps  */
 #define VB_N4_SERIAL 64                           /* first elements: one thread, sequentially */
 #define VB_N4_HCOPIES 8                           /* histogram copies (warp & 7)              */
 
@@ -70,6 +70,7 @@ struct N4Args {
     int union_bytes;         // size of the shared-memory union region
     int logI_cap;            // floats of compact log image that fit shared memory (0 = none)
     int rowtab_rows;         // rows whose row-axis tables fit shared memory (0 = keep them in global)
+    int no_overlap;          // 1: run the convergence chain and the next iteration's phases one after the other
 };
 
 // debug record layout (floats): [0]=bmin [1]=bmax [2..4]=ncp [5]=n_trace, then
@@ -202,6 +203,7 @@ struct N4Ctx {
     float* L;             // lattice [ncp0][ncp1][ncp2]
     float* Lold;          // lattice before the last update
     float* Om;            // omega lattice of the current level
+    float* Phi;           // lattice increment of the last fit (committed by n4_commit)
     float* E;             // E(u|v) table
     float* H;             // histogram
     double* red;          // 64 doubles reduction scratch
@@ -216,6 +218,19 @@ VB_DEV N4Axis n4_ax(const N4Ctx& c, int a) {
     size_t off = 0;
     for (int i = 0; i < a; ++i) off += 16 * (size_t)c.slot[i];
     return n4_axis(c.axis_base + off, c.slot[a]);
+}
+
+// A team is a warp-aligned group of threads of the CTA with its own named barrier: the whole
+// block (barrier 0), or -- while the convergence chain of iteration i overlaps the speculative
+// histogram / sharpening / fit of iteration i+1 -- the "chain" team and the "phase" team.
+struct N4Team {
+    int tid, nt, bar;     // index inside the team, team size (multiple of 32), barrier id
+};
+VB_DEV void n4_sync(const N4Team& T) {
+    if (T.bar == 0) __syncthreads(); else vb_bar_sync(T.bar, T.nt);
+}
+VB_DEV int n4_sync_or(const N4Team& T, int pred) {
+    return (T.bar == 0) ? __syncthreads_or(pred) : vb_bar_or(T.bar, T.nt, pred);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -425,14 +440,18 @@ VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float&
     __syncthreads();
     M = n4_array_scan(c.rbb, c.n0 * c.nblk, (int*)c.red);
     n4_array_scan(c.wbase, c.nblk * c.W, (int*)c.red);
-    // histogram fixed point: the largest number of voxels any histogram copy can receive
+    // histogram fixed point: the largest number of voxels any histogram copy can receive, for
+    // the whole block and for the phase team (items are dealt round robin to the team's warps)
     int mc = 0;
-    if (tid < VB_N4_HCOPIES)
-        for (int it = 0; it < c.nblk * c.nseg; ++it)
-            if (((it % nw) & (VB_N4_HCOPIES - 1)) == tid) {
-                const int blk = it % c.nblk, wi0 = (it / c.nblk) * c.wps, wi1 = min(c.W, wi0 + c.wps);
-                mc += (int)(c.wbase[(size_t)blk * c.W + wi1] - c.wbase[(size_t)blk * c.W + wi0]);
-            }
+    if (tid < 2 * VB_N4_HCOPIES) {
+        const int tw = (tid < VB_N4_HCOPIES) ? nw : nw - VB_N4_CHAIN_WARPS, cp = tid & (VB_N4_HCOPIES - 1);
+        if (tw > 0)
+            for (int it = 0; it < c.nblk * c.nseg; ++it)
+                if (((it % tw) & (VB_N4_HCOPIES - 1)) == cp) {
+                    const int blk = it % c.nblk, wi0 = (it / c.nblk) * c.wps, wi1 = min(c.W, wi0 + c.wps);
+                    mc += (int)(c.wbase[(size_t)blk * c.W + wi1] - c.wbase[(size_t)blk * c.W + wi0]);
+                }
+    }
     mc = vb_block_reduce(mc, VbMaxI(), 0, (int*)c.red);
     int bits = 0;
     while ((1LL << bits) <= (long long)mc) ++bits;
@@ -502,12 +521,12 @@ VB_DEV void n4_range(N4Ctx& c, float& bmin, float& bmax) {
 
 // ---------------------------------------------------------------------------------------------
 // P1: triangular Parzen histogram of U over the mask (SharpenImage, first half)
-VB_DEV void n4_histogram(N4Ctx& c, float bmin, float bmax) {
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
+VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
+    const int nt = T.nt, tid = T.tid, lane = (T.tid & 31), w = (T.tid >> 5), nw = nt >> 5;
     const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     uint32_t* hc = (uint32_t*)c.un_f;                    // [VB_N4_HCOPIES][nbins]
     for (int i = tid; i < c.nbins * VB_N4_HCOPIES; i += nt) hc[i] = 0u;
-    __syncthreads();
+    n4_sync(T);
     const float slope = (bmax - bmin) / (float)(c.nbins - 1);
     const uint32_t one = 1u << c.hshift;
     const float fone = (float)one;
@@ -535,19 +554,19 @@ VB_DEV void n4_histogram(N4Ctx& c, float bmin, float bmax) {
             }
         })
     }
-    __syncthreads();
+    n4_sync(T);
     for (int bin = tid; bin < c.nbins; bin += nt) {
         unsigned long long s = 0;
 #pragma unroll
         for (int k = 0; k < VB_N4_HCOPIES; ++k) s += hc[(size_t)k * c.nbins + bin];
         c.H[bin] = (float)((double)s / (double)one);
     }
-    __syncthreads();
+    n4_sync(T);
 }
 
 // in-place radix-2 FFT on shared (re, im); tw = exp(-2 pi i k / N); sign<0 forward, >0 backward
-VB_DEV void n4_fft(double* re, double* im, int N, int logN, int sign, const double* twr, const double* twi) {
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+VB_DEV void n4_fft(const N4Team& T, double* re, double* im, int N, int logN, int sign, const double* twr, const double* twi) {
+    const int nt = T.nt, tid = T.tid;
     for (int i = tid; i < N; i += nt) {
         const int j = (int)(__brev((unsigned)i) >> (32 - logN));
         if (i < j) {
@@ -555,7 +574,7 @@ VB_DEV void n4_fft(double* re, double* im, int N, int logN, int sign, const doub
             t = im[i]; im[i] = im[j]; im[j] = t;
         }
     }
-    __syncthreads();
+    n4_sync(T);
     for (int len = 2; len <= N; len <<= 1) {
         const int half = len >> 1, step = N / len;
         for (int b = tid; b < (N >> 1); b += nt) {
@@ -566,14 +585,14 @@ VB_DEV void n4_fft(double* re, double* im, int N, int logN, int sign, const doub
             re[i1] = re[i0] - xr; im[i1] = im[i0] - xi;
             re[i0] += xr; im[i0] += xi;
         }
-        __syncthreads();
+        n4_sync(T);
     }
 }
 
 // SharpenImage, second half: Wiener-deconvolve the histogram with the Gaussian bias model and
 // build E(u|v).  Two real sequences share one complex FFT (4 FFTs instead of ITK's 7).
-VB_DEV void n4_sharpen(N4Ctx& c, float bmin, float bmax, float fwhm, float wiener) {
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+VB_DEV void n4_sharpen(N4Ctx& c, const N4Team& T, float bmin, float bmax, float fwhm, float wiener) {
+    const int nt = T.nt, tid = T.tid;
     const int N = c.fftN;
     int logN = 0;
     while ((1 << logN) < N) ++logN;
@@ -608,8 +627,8 @@ VB_DEV void n4_sharpen(N4Ctx& c, float bmin, float bmax, float fwhm, float wiene
             twr[n] = co; twi[n] = s;
         }
     }
-    __syncthreads();
-    n4_fft(Ar, Ai, N, logN, -1, twr, twi);
+    n4_sync(T);
+    n4_fft(T, Ar, Ai, N, logN, -1, twr, twi);
     const double noise = (double)wiener;
     for (int k = tid; k < N; k += nt) {
         const int kk = (N - k) & (N - 1);
@@ -620,16 +639,16 @@ VB_DEV void n4_sharpen(N4Ctx& c, float bmin, float bmax, float fwhm, float wiene
         const double g = fr / (fr * fr + fi * fi + noise);             // Re(conj(Ff)/(|Ff|^2+noise))
         Br[k] = vr * g; Bi[k] = vi * g;
     }
-    __syncthreads();
-    n4_fft(Br, Bi, N, logN, +1, twr, twi);
+    n4_sync(T);
+    n4_fft(T, Br, Bi, N, logN, +1, twr, twi);
     for (int n = tid; n < N; n += nt) {
         const double u = Br[n] > 0.0 ? Br[n] : 0.0;
         const float x = bmin + ((float)n - (float)hoff) * slope;
         Ar[n] = (double)x * u;
         Ai[n] = u;
     }
-    __syncthreads();
-    n4_fft(Ar, Ai, N, logN, -1, twr, twi);
+    n4_sync(T);
+    n4_fft(T, Ar, Ai, N, logN, -1, twr, twi);
     for (int k = tid; k < N; k += nt) {
         const int kk = (N - k) & (N - 1);
         const double ar = Ar[k], ai = Ai[k], br = Ar[kk], bi = Ai[kk];
@@ -640,13 +659,13 @@ VB_DEV void n4_sharpen(N4Ctx& c, float bmin, float bmax, float fwhm, float wiene
         const double dfr = dr * fr - di * fi, dfi = dr * fi + di * fr;
         Br[k] = nfr - dfi; Bi[k] = nfi + dfr;                          // NF + i*DF
     }
-    __syncthreads();
-    n4_fft(Br, Bi, N, logN, +1, twr, twi);
+    n4_sync(T);
+    n4_fft(T, Br, Bi, N, logN, +1, twr, twi);
     for (int n = tid; n < c.nbins; n += nt) {
         const double den = Bi[n + hoff];
         c.E[n] = (den != 0.0) ? (float)(Br[n + hoff] / den) : 0.0f;
     }
-    __syncthreads();
+    n4_sync(T);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -677,8 +696,8 @@ VB_DEV void n4_qflush(unsigned* Q, int a, int ncp1, int n2, int bc, int s, const
 }
 
 template <bool OMEGA>
-VB_DEV void n4_contract(N4Ctx& c, float bmin, float bmax) {
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, w = vb_warp(), nw = nt >> 5;
+VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
+    const int nt = T.nt, tid = T.tid, w = (T.tid >> 5), nw = nt >> 5;
     const int ncp0 = c.ncp[0], ncp1 = c.ncp[1], ncp2 = c.ncp[2];
     const int n2 = c.n2;
     const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
@@ -687,7 +706,7 @@ VB_DEV void n4_contract(N4Ctx& c, float bmin, float bmax) {
     unsigned* Q = (unsigned*)c.un_d;                     // [ncp0][ncp1][n2] x {low, high} words
     const int Qn = ncp0 * ncp1 * n2;
     for (int e = tid; e < 2 * Qn; e += nt) Q[e] = 0u;
-    __syncthreads();
+    n4_sync(T);
 
     for (int it = w; it < c.nblk * c.nseg; it += nw) {
         const N4Item I = n4_item(c, it);
@@ -739,7 +758,7 @@ VB_DEV void n4_contract(N4Ctx& c, float bmin, float bmax) {
             n4_qflush(Q, cur + 3, ncp1, n2, bc, ss, wc, a3);
         }
     }
-    __syncthreads();
+    n4_sync(T);
 
     // slices -> lattice
     const int Ln = ncp0 * ncp1 * ncp2;
@@ -762,12 +781,10 @@ VB_DEV void n4_contract(N4Ctx& c, float bmin, float bmax) {
             const float om = c.Om[e];
             // itk::Math::NotAlmostEquals(omega, 0): |omega| > 0.1 * FLT_EPSILON
             const float phi = (fabsf(om) > 0.1f * FLT_EPSILON) ? sum / om : 0.0f;
-            const float l = c.L[e];
-            c.Lold[e] = l;
-            c.L[e] = l + phi;
+            c.Phi[e] = phi;                              // committed by n4_commit (the fit may be speculative)
         }
     }
-    __syncthreads();
+    n4_sync(T);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -807,8 +824,8 @@ VB_DEV float n4_sigma_next(float sigma, float mu_prev, float pixel, const N4Step
 
 // Exclusive block prefix of v with ONE barrier, which also ORs `flag` over the block (in/out).
 // `tot` is a per-sweep buffer (double buffered by the caller).
-VB_DEV int n4_chain_scan(int v, int& total, int* tot, int& flag) {
-    const int lane = vb_lane(), w = vb_warp(), nw = (int)(blockDim.x >> 5);
+VB_DEV int n4_chain_scan(const N4Team& T, int v, int& total, int* tot, int& flag) {
+    const int lane = (T.tid & 31), w = (T.tid >> 5), nw = T.nt >> 5;
     int inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -816,7 +833,7 @@ VB_DEV int n4_chain_scan(int v, int& total, int* tot, int& flag) {
         if (lane >= d) inc += t;
     }
     if (lane == 31) tot[w] = inc;
-    flag = __syncthreads_or(flag);
+    flag = n4_sync_or(T, flag);
     int wt = (lane < nw) ? tot[lane] : 0;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -828,8 +845,8 @@ VB_DEV int n4_chain_scan(int v, int& total, int* tot, int& flag) {
     return ((w > 0) ? woff : 0) + inc - v;
 }
 
-VB_DEV float n4_convergence(N4Ctx& c, int M) {
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
+    const int nt = T.nt, tid = T.tid;
     VB_SHARED int s_state[2];                 // float bit patterns of (mu, sigma) at the chunk start
     VB_SHARED int s_tot[2][32];               // warp totals, double buffered
     int buf = 0;
@@ -838,7 +855,7 @@ VB_DEV float n4_convergence(N4Ctx& c, int M) {
     const int S0 = min(M, VB_N4_SERIAL);
     VB_SHARED float s_px[VB_N4_SERIAL];
     if (tid < S0) s_px[tid] = e[perm[tid]];
-    __syncthreads();
+    n4_sync(T);
     if (tid == 0) {
         float mu = 0.0f, sigma = 0.0f;
         for (int j = 0; j < S0; ++j) {
@@ -849,10 +866,10 @@ VB_DEV float n4_convergence(N4Ctx& c, int M) {
         }
         s_state[0] = __float_as_int(mu); s_state[1] = __float_as_int(sigma);
     }
-    __syncthreads();
+    n4_sync(T);
     int start = S0;
     while (start < M) {
-        const int len = min(min(start, VB_N4_CHUNK), M - start);
+        const int len = min(min(start, nt * VB_N4_EPT), M - start);
         const int ept = (len + nt - 1) / nt;                  // <= VB_N4_EPT
         const int lo = start + min(len, tid * ept);
         const int cnt = start + min(len, tid * ept + ept) - lo;   // steps of this thread
@@ -874,7 +891,7 @@ VB_DEV float n4_convergence(N4Ctx& c, int M) {
 #pragma unroll
             for (int i = 0; i < VB_N4_EPT; ++i)
                 if (i < cnt) mu = n4_mu_next(mu, st[i]);
-            const int off = n4_chain_scan(__float_as_int(mu) - km, total, s_tot[buf], changed);
+            const int off = n4_chain_scan(T, __float_as_int(mu) - km, total, s_tot[buf], changed);
             buf ^= 1;
             ++c.n_sweeps;
             if (!changed) break;
@@ -894,7 +911,7 @@ VB_DEV float n4_convergence(N4Ctx& c, int M) {
                     sg = n4_sigma_next(sg, mu, px[i], st[i]);
                     mu = n4_mu_next(mu, st[i]);
                 }
-            const int off = n4_chain_scan(__float_as_int(sg) - ks, total, s_tot[buf], changed);
+            const int off = n4_chain_scan(T, __float_as_int(sg) - ks, total, s_tot[buf], changed);
             buf ^= 1;
             c.n_sweeps += 1000;
             if (!changed) break;
@@ -904,11 +921,11 @@ VB_DEV float n4_convergence(N4Ctx& c, int M) {
         }
         const int sg_end = sg0 + total;
         if (tid == 0) { s_state[0] = mu_end; s_state[1] = sg_end; }
-        __syncthreads();
+        n4_sync(T);
         start += len;
     }
     const float mu = __int_as_float(s_state[0]), sigma = __int_as_float(s_state[1]);
-    __syncthreads();
+    n4_sync(T);
     const float sd = (float)sqrt((double)sigma / ((double)(float)M - 1.0));
     return __fdiv_rn(sd, mu);
 }
@@ -924,7 +941,9 @@ VB_DEV float n4_convergence(N4Ctx& c, int M) {
 // rounding of sigma and mean, still exceeds the threshold the level certainly continues and the
 // exact double-precision cv is returned instead (`exact_needed` forces the chain: last allowed
 // iteration of a level, debug capture).
-VB_DEV float n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool exact_needed) {
+// Returns true when the sequential chain has to be run on c.ebuf; otherwise `conv` holds the
+// (exact-arithmetic) value and the level certainly continues.
+VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool exact_needed, float& conv) {
     const int nt = (int)blockDim.x, w = vb_warp(), nw = nt >> 5;
     const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     float tmin = FLT_MAX, tmax = -FLT_MAX;
@@ -965,12 +984,20 @@ VB_DEV float n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, boo
         const double mean = 1.0 + s1 / N;
         const double lag = 1.1920929e-7 * N / (4.0 * 1.7320508) * 1.05;
         const double lower = (sqrt(var) - lag) / mean * 0.98;
-        if (lower > (double)thr) return (float)(sqrt(var) / mean);
+        if (lower > (double)thr) { conv = (float)(sqrt(var) / mean); return false; }
     }
-    const long long t0 = vb_clock();
-    const float conv = n4_convergence(c, M);
-    c.t_chain += vb_clock() - t0;
-    return conv;
+    return true;
+}
+
+// L <- L + Phi, keeping the previous lattice for the next update pass
+VB_DEV void n4_commit(N4Ctx& c) {
+    const int Ln = c.ncp[0] * c.ncp[1] * c.ncp[2];
+    for (int e = (int)threadIdx.x; e < Ln; e += (int)blockDim.x) {
+        const float l = c.L[e];
+        c.Lold[e] = l;
+        c.L[e] = l + c.Phi[e];
+    }
+    __syncthreads();
 }
 
 // final dense pass: bias at EVERY voxel, out = in / exp(bias)   (N4 GenerateData tail)
@@ -1066,7 +1093,12 @@ VB_DEV void n4_build_tables(N4Ctx& c) {
 VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
     VB_DYN_SMEM(smem);
     VB_SHARED int s_next;
+    VB_SHARED float s_conv;
     const int tid = (int)threadIdx.x;
+    N4Team full, TC, TP;
+    full.tid = tid; full.nt = (int)blockDim.x; full.bar = 0;
+    TC.tid = tid; TC.nt = min(VB_N4_CHAIN_WARPS * 32, (int)blockDim.x - 32); TC.bar = 1;
+    TP.tid = tid - TC.nt; TP.nt = (int)blockDim.x - TC.nt; TP.bar = 2;
     N4Ctx c;
     c.un_f = (float*)smem;
     c.un_d = (double*)smem;
@@ -1075,6 +1107,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
     c.L = (float*)p;    p += Lb;
     c.Lold = (float*)p; p += Lb;
     c.Om = (float*)p;   p += Lb;
+    c.Phi = (float*)p;  p += Lb;
     c.E = (float*)p;    p += sizeof(float) * (size_t)((a.p.n_bins + 3) & ~3);
     c.H = (float*)p;    p += sizeof(float) * (size_t)((a.p.n_bins + 3) & ~3);
     c.red = (double*)p; p += 64 * sizeof(double);
@@ -1132,23 +1165,59 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
             int it = 0;
             if (M >= 2 && !capped) {
                 n4_build_tables(c);
-                n4_contract<true>(c, bmin, bmax);
+                n4_contract<true>(c, full, bmin, bmax);
                 if (level > 0) n4_range(c, bmin, bmax);
                 conv = FLT_MAX;
-                while (it < a.p.max_iter[level] && conv > a.p.conv_threshold) {
-                    if (a.p.max_total_iters > 0 && total >= a.p.max_total_iters) { capped = true; break; }
+                // `pending`: c.ebuf holds iteration `it`'s exp(old - new) and the sequential
+                // convergence chain has not been run on it yet.  Outside debug capture the chain
+                // runs on the chain team WHILE the phase team already computes histogram,
+                // sharpening and fit of iteration it + 1; the fit is only committed if the chain
+                // says "continue", so the result is that of the sequential schedule.
+                bool pending = false;
+                const bool serial = dbg != nullptr || a.no_overlap != 0;
+                for (;;) {
+                    const bool room = it < a.p.max_iter[level];
+                    const bool cap = a.p.max_total_iters > 0 && total >= a.p.max_total_iters;
+                    bool fitted = false;
+                    if (pending) {
+                        tq = vb_clock();
+                        if (serial) {                                // no overlap: keeps the captured stages in order
+                            const float cv = n4_convergence(c, full, M);
+                            if (tid == 0) s_conv = cv;
+                        } else if (tid < TC.nt) {
+                            const float cv = n4_convergence(c, TC, M);
+                            if (tid == 0) s_conv = cv;
+                        } else if (room && !cap) {
+                            n4_histogram(c, TP, bmin, bmax);
+                            n4_sharpen(c, TP, bmin, bmax, a.p.fwhm, a.p.wiener_noise);
+                            n4_contract<false>(c, TP, bmin, bmax);
+                        }
+                        __syncthreads();
+                        conv = s_conv;
+                        __syncthreads();
+                        fitted = !serial && room && !cap;
+                        pending = false;
+                        tph[5] += vb_clock() - tq;
+                        if (dbg_trace && tid == 0 && ntrace - 1 < trace_cap && ntrace > 0) dbg_trace[ntrace - 1] = conv;
+                    }
+                    if (!(room && conv > a.p.conv_threshold)) break;
+                    if (cap) { capped = true; break; }
+                    if (!fitted) {
+                        if (dbg && tid == 0) { dbg[0] = bmin; dbg[1] = bmax; }
+                        tq = vb_clock();
+                        n4_histogram(c, full, bmin, bmax);
+                        long long tn = vb_clock(); tph[1] += tn - tq; tq = tn;
+                        n4_sharpen(c, full, bmin, bmax, a.p.fwhm, a.p.wiener_noise);
+                        tn = vb_clock(); tph[2] += tn - tq; tq = tn;
+                        n4_contract<false>(c, full, bmin, bmax);
+                        tn = vb_clock(); tph[3] += tn - tq;
+                    }
+                    n4_commit(c);
                     ++it; ++total;
-                    if (dbg && tid == 0) { dbg[0] = bmin; dbg[1] = bmax; }
                     tq = vb_clock();
-                    n4_histogram(c, bmin, bmax);
-                    long long tn = vb_clock(); tph[1] += tn - tq; tq = tn;
-                    n4_sharpen(c, bmin, bmax, a.p.fwhm, a.p.wiener_noise);
-                    tn = vb_clock(); tph[2] += tn - tq; tq = tn;
-                    n4_contract<false>(c, bmin, bmax);
-                    tn = vb_clock(); tph[3] += tn - tq; tq = tn;
-                    conv = n4_update(c, M, bmin, bmax, a.p.conv_threshold, dbg != nullptr || it >= a.p.max_iter[level]);
-                    tn = vb_clock(); tph[4] += tn - tq;
-                    if (dbg_trace && tid == 0 && ntrace < trace_cap) dbg_trace[ntrace] = conv;
+                    pending = n4_update(c, M, bmin, bmax, a.p.conv_threshold, dbg != nullptr || it >= a.p.max_iter[level], conv);
+                    tph[4] += vb_clock() - tq;
+                    if (!pending && dbg_trace && tid == 0 && ntrace < trace_cap) dbg_trace[ntrace] = conv;
                     ++ntrace;
                 }
             }
@@ -1177,7 +1246,6 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         n4_finalize(c, a.logbias ? a.logbias + S.off : nullptr);
         if (dbg && tid == 0) {
             tph[6] = vb_clock() - tq;
-            tph[4] -= c.t_chain; tph[5] = c.t_chain;
             for (int k = 0; k < 8; ++k) dbg[8 + k] = (float)((double)tph[k] * 1e-3);   // ns -> us
             dbg[15] = (float)c.n_sweeps;
         }

@@ -37,6 +37,15 @@ VB_DEV float4 vb_ldg(const float4* p) { return __ldg(p); }
 VB_DEV float vb_ld_stream(const float* p) { return __ldcs(p); }
 VB_DEV uint8_t vb_ld_stream(const uint8_t* p) { return __ldcs(p); }
 VB_DEV void vb_st_stream(float* p, float v) { __stcs(p, v); }
+// named barriers (ids 1..15) over a warp-aligned subset of the block
+VB_DEV void vb_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+VB_DEV int vb_bar_or(int id, int nthreads, int pred) {
+    int out;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %3, 0;\n\tbar.red.or.pred p, %1, %2, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+        : "=r"(out) : "r"(id), "r"(nthreads), "r"(pred) : "memory");
+    return out;
+}
 VB_DEV long long vb_clock() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return (long long)t; }
 #else
 // ------------------------------------------------------------------------------- emulation
@@ -46,6 +55,7 @@ VB_DEV long long vb_clock() { unsigned long long t; asm volatile("mov.u64 %0, %g
 #include <barrier>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -160,6 +170,32 @@ static inline int __syncthreads_or(int pred) {
     vbemu::g_block->bar.arrive_and_wait();
     if (threadIdx.x == 0) { flag[ph] = 0; phase = ph ^ 1; }
     vbemu::g_block->bar.arrive_and_wait();
+    return r;
+}
+// named barriers: one std::barrier per id, created by the first thread that needs it
+namespace vbemu {
+struct Named {
+    std::mutex mu;
+    std::unique_ptr<std::barrier<>> bar[16];
+    int flag[16][2];
+    int phase[16];
+};
+inline Named g_named;
+inline std::barrier<>& named(int id, int n) {
+    std::lock_guard<std::mutex> g(g_named.mu);
+    if (!g_named.bar[id]) g_named.bar[id].reset(new std::barrier<>(n));
+    return *g_named.bar[id];
+}
+}  // namespace vbemu
+static inline void vb_bar_sync(int id, int nthreads) { vbemu::named(id, nthreads).arrive_and_wait(); }
+static inline int vb_bar_or(int id, int nthreads, int pred) {
+    std::barrier<>& b = vbemu::named(id, nthreads);
+    b.arrive_and_wait();                                   // the flag is clear
+    if (pred) __atomic_store_n(&vbemu::g_named.flag[id][0], 1, __ATOMIC_SEQ_CST);
+    b.arrive_and_wait();
+    const int r = __atomic_load_n(&vbemu::g_named.flag[id][0], __ATOMIC_SEQ_CST);
+    b.arrive_and_wait();                                   // everybody has read it
+    __atomic_store_n(&vbemu::g_named.flag[id][0], 0, __ATOMIC_SEQ_CST);
     return r;
 }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }

@@ -9,13 +9,39 @@
 #include <float.h>
 #include "vb_common.cuh"
 
-#define VB_VDP_THREADS 256
+#define VB_VDP_THREADS 1024
 #define VB_SNR_MAX_AXIS 8192   // n0 + n1 + n2 must not exceed this (projection flags in smem)
 
 // ---------------------------------------------------------------------------------------------
 // calculate_SNR: one CTA per subject.  Signal = mask > 0.  Noise = voxels outside
 // {rows with mask, plus row 0} x {cols [first masked col > 0, last masked col)} x
 // {slices with mask, plus slice 0}, minus the first / last `fov` rows.  Population std.
+// 4 consecutive voxels per thread and step (16-byte image loads when the subject is aligned)
+struct Vb4f { float v[4]; };
+struct Vb4b { uint8_t v[4]; };
+VB_DEV Vb4f vb_load4f(const float* p, int v, int V, bool aligned) {
+    Vb4f r;
+    if (aligned && v + 3 < V) {
+        const float4 t = *(const float4*)(p + v);
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r.v[e] = (v + e < V) ? p[v + e] : 0.0f;
+    }
+    return r;
+}
+VB_DEV Vb4b vb_load4b(const uint8_t* p, int v, int V, bool aligned) {
+    Vb4b r;
+    if (aligned && v + 3 < V) {
+        const uint32_t t = *(const uint32_t*)(p + v);
+        r.v[0] = (uint8_t)t; r.v[1] = (uint8_t)(t >> 8); r.v[2] = (uint8_t)(t >> 16); r.v[3] = (uint8_t)(t >> 24);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r.v[e] = (v + e < V) ? p[v + e] : (uint8_t)0;
+    }
+    return r;
+}
+
 VB_KERNEL void VB_LAUNCH_BOUNDS(VB_VDP_THREADS, 1)
 snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, int n,
            int fov, vb_subject_stats* stats) {
@@ -27,16 +53,23 @@ snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, cons
         const VbSubject S = subj[si];
         const float* img = image + S.off;
         const uint8_t* msk = mask + S.off;
+        const bool aligned = (S.off & 3) == 0;
         const int n0 = S.n0, n1 = S.n1, n2 = S.n2, ncols = n1 * n2;
         int* rowf = flags; int* colf = flags + n0; int* slcf = flags + n0 + n1;
         __syncthreads();
         for (int i = tid; i < n0 + n1 + n2; i += nt) flags[i] = 0;
         __syncthreads();
-        for (int v = tid; v < S.V; v += nt)
-            if (msk[v]) {
-                const int i = v / ncols, rem = v - i * ncols, j = rem / n2, k = rem - j * n2;
-                rowf[i] = 1; colf[j] = 1; slcf[k] = 1;
+        for (int v = 4 * tid; v < S.V; v += 4 * nt) {
+            const Vb4b m = vb_load4b(msk, v, S.V, aligned);
+            if (m.v[0] | m.v[1] | m.v[2] | m.v[3]) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (m.v[e]) {
+                        const int vv = v + e, i = vv / ncols, rem = vv - i * ncols, j = rem / n2, k = rem - j * n2;
+                        rowf[i] = 1; colf[j] = 1; slcf[k] = 1;
+                    }
             }
+        }
         __syncthreads();
         if (tid == 0) {
             int cmin = -1, cmax = 0;
@@ -50,30 +83,41 @@ snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, cons
         const int lo = fov < n0 ? fov : n0;        // noisemask[:fov] = 0
         int hi = n0 - fov;                         // noisemask[n0-fov:] = 0 (python slice rules)
         if (hi < 0) { hi += n0; if (hi < 0) hi = 0; }
-        double ssum = 0.0, nsum = 0.0;
+        // one pass: signal sum / count, noise sum / sum of squares about a pivot / count.  The
+        // pivot (first noise candidate's neighbourhood: the image value at voxel 0... any fixed
+        // value) keeps the one-pass variance well conditioned in float64.
+        const float pivot = img[0];
+        double ssum = 0.0, nsum = 0.0, nsq = 0.0;
         long long scnt = 0, ncnt = 0;
-        for (int v = tid; v < S.V; v += nt) {
-            const int i = v / ncols, rem = v - i * ncols, j = rem / n2, k = rem - j * n2;
-            const float x = img[v];
-            if (msk[v]) { ssum += (double)x; ++scnt; }
-            const bool inbox = rowf[i] && (j >= cmin && j < cmax && cmin >= 0) && slcf[k];
-            if (!inbox && i >= lo && i < hi) { nsum += (double)x; ++ncnt; }
+        for (int v = 4 * tid; v < S.V; v += 4 * nt) {
+            const Vb4f x = vb_load4f(img, v, S.V, aligned);
+            const Vb4b m = vb_load4b(msk, v, S.V, aligned);
+            int i = v / ncols, rem = v - i * ncols;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (v + e < S.V) {
+                    const int j = rem / n2, k = rem - j * n2;
+                    if (m.v[e]) { ssum += (double)x.v[e]; ++scnt; }
+                    const bool inbox = rowf[i] && (j >= cmin && j < cmax && cmin >= 0) && slcf[k];
+                    if (!inbox && i >= lo && i < hi) {
+                        const double d = (double)x.v[e] - (double)pivot;
+                        nsum += d; nsq += d * d; ++ncnt;
+                    }
+                }
+                if (++rem == ncols) { rem = 0; ++i; }
+            }
         }
         ssum = vb_block_reduce(ssum, VbAddD(), 0.0, red);
         nsum = vb_block_reduce(nsum, VbAddD(), 0.0, red);
+        nsq = vb_block_reduce(nsq, VbAddD(), 0.0, red);
         scnt = vb_block_reduce(scnt, VbAddLL(), 0LL, (long long*)red);
         ncnt = vb_block_reduce(ncnt, VbAddLL(), 0LL, (long long*)red);
-        const double nmean = nsum / (double)ncnt;
-        double ss = 0.0;
-        for (int v = tid; v < S.V; v += nt) {
-            const int i = v / ncols, rem = v - i * ncols, j = rem / n2, k = rem - j * n2;
-            const bool inbox = rowf[i] && (j >= cmin && j < cmax && cmin >= 0) && slcf[k];
-            if (!inbox && i >= lo && i < hi) { const double d = (double)img[v] - nmean; ss += d * d; }
-        }
-        ss = vb_block_reduce(ss, VbAddD(), 0.0, red);
         if (tid == 0) {
             vb_subject_stats* st = stats + si;
-            const double smean = ssum / (double)scnt, nstd = sqrt(ss / (double)ncnt);
+            const double dm = nsum / (double)ncnt;                 // mean - pivot
+            double var = nsq / (double)ncnt - dm * dm;
+            if (var < 0.0) var = 0.0;
+            const double smean = ssum / (double)scnt, nmean = (double)pivot + dm, nstd = sqrt(var);
             st->signal_mean = smean; st->noise_mean = nmean; st->noise_std = nstd;
             st->snr = (smean - nmean) / nstd;
             st->n_noise = (cmin < 0) ? -1 : (int)ncnt;   // -1: reference raises (np.min of empty)
@@ -86,11 +130,31 @@ snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, cons
 // exact order statistic sorted(N4[mask>0])[int(M*.99)] by a 3-pass (11+11+10 bit) radix select
 // on the order-preserving key of the float bits.  Also zeroes the defect / LB counters.
 VB_DEV int vdp_find_bin(unsigned* hist, int nb, long long& k, int* s_bin, long long* s_k) {
-    // thread 0 scans (<= 2048 bins); result broadcast through shared memory
-    if (threadIdx.x == 0) {
-        long long cum = 0;
-        int b = 0;
-        for (; b < nb - 1; ++b) {
+    // block-wide exclusive prefix over the bins (each thread owns a contiguous run); the thread
+    // whose run contains the k-th element publishes (bin, rank inside the bin)
+    VB_SHARED int wsum[32];
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = tid & 31, w = tid >> 5, nw = nt >> 5;
+    const int per = (nb + nt - 1) / nt;
+    const int lo = min(nb, tid * per), hi = min(nb, lo + per);
+    int s = 0;
+    for (int b = lo; b < hi; ++b) s += (int)hist[b];
+    int inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(VB_FULL, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    if (tid == 0) { *s_bin = nb - 1; *s_k = 0; }
+    __syncthreads();
+    int woff = 0, total = 0;
+    for (int i = 0; i < nw; ++i) { const int t = wsum[i]; if (i < w) woff += t; total += t; }
+    long long cum = (long long)(woff + inc - s);
+    if (k >= (long long)total) {                       // cannot happen for k < count; keep the last bin
+        if (tid == 0) { *s_bin = nb - 1; *s_k = k - ((long long)total - (long long)hist[nb - 1]); }
+    } else if (k >= cum && k < cum + (long long)s) {
+        int b = lo;
+        for (; b < hi; ++b) {
             if (cum + (long long)hist[b] > k) break;
             cum += hist[b];
         }
@@ -113,17 +177,23 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
         const VbSubject S = subj[si];
         const float* x = n4 + S.off;
         const uint8_t* msk = mask + S.off;
+        const bool aligned = (S.off & 3) == 0;
         __syncthreads();
         for (int i = tid; i < 2048; i += nt) hist[i] = 0;
         __syncthreads();
         double sum = 0.0;
         long long cnt = 0;
-        for (int v = tid; v < S.V; v += nt)
-            if (msk[v]) {
-                const float f = x[v];
-                sum += (double)f; ++cnt;
-                atomicAdd(&hist[vb_float_key(f) >> 21], 1u);
-            }
+        for (int v = 4 * tid; v < S.V; v += 4 * nt) {
+            const Vb4b m = vb_load4b(msk, v, S.V, aligned);
+            if (!(m.v[0] | m.v[1] | m.v[2] | m.v[3])) continue;
+            const Vb4f f = vb_load4f(x, v, S.V, aligned);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (m.v[e]) {
+                    sum += (double)f.v[e]; ++cnt;
+                    atomicAdd(&hist[vb_float_key(f.v[e]) >> 21], 1u);
+                }
+        }
         sum = vb_block_reduce(sum, VbAddD(), 0.0, red);
         cnt = vb_block_reduce(cnt, VbAddLL(), 0LL, (long long*)red);
         float p99 = 0.0f;
@@ -134,22 +204,34 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
             __syncthreads();
             for (int i = tid; i < 2048; i += nt) hist[i] = 0;
             __syncthreads();
-            for (int v = tid; v < S.V; v += nt)
-                if (msk[v]) {
-                    const unsigned key = vb_float_key(x[v]);
-                    if ((key >> 21) == b1) atomicAdd(&hist[(key >> 10) & 0x7FFu], 1u);
-                }
+            for (int v = 4 * tid; v < S.V; v += 4 * nt) {
+                const Vb4b m = vb_load4b(msk, v, S.V, aligned);
+                if (!(m.v[0] | m.v[1] | m.v[2] | m.v[3])) continue;
+                const Vb4f f = vb_load4f(x, v, S.V, aligned);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (m.v[e]) {
+                        const unsigned key = vb_float_key(f.v[e]);
+                        if ((key >> 21) == b1) atomicAdd(&hist[(key >> 10) & 0x7FFu], 1u);
+                    }
+            }
             __syncthreads();
             const unsigned b2 = (unsigned)vdp_find_bin(hist, 2048, k, &s_bin, &s_k);
             __syncthreads();
             for (int i = tid; i < 1024; i += nt) hist[i] = 0;
             __syncthreads();
             const unsigned pre = (b1 << 11) | b2;
-            for (int v = tid; v < S.V; v += nt)
-                if (msk[v]) {
-                    const unsigned key = vb_float_key(x[v]);
-                    if ((key >> 10) == pre) atomicAdd(&hist[key & 0x3FFu], 1u);
-                }
+            for (int v = 4 * tid; v < S.V; v += 4 * nt) {
+                const Vb4b m = vb_load4b(msk, v, S.V, aligned);
+                if (!(m.v[0] | m.v[1] | m.v[2] | m.v[3])) continue;
+                const Vb4f f = vb_load4f(x, v, S.V, aligned);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (m.v[e]) {
+                        const unsigned key = vb_float_key(f.v[e]);
+                        if ((key >> 10) == pre) atomicAdd(&hist[key & 0x3FFu], 1u);
+                    }
+            }
             __syncthreads();
             const unsigned b3 = (unsigned)vdp_find_bin(hist, 1024, k, &s_bin, &s_k);
             p99 = vb_key_float((pre << 10) | b3);

@@ -194,10 +194,10 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
         ncmax = std::max<long long>(ncmax, ncols);
         n0max = std::max<long long>(n0max, S.n0);
     }
-    // shared memory: [union][L][Lold][Om][E][H][red][row tables][compact log image]
+    // shared memory: [union][L][Lold][Om][Phi][E][H][red][row tables][compact log image]
     const long long Lb = 4 * ((Lmax + 3) & ~3LL), Hb = 4 * ((p.n_bins + 3) & ~3);
     const long long rowtab_rows = (40 * n0max <= 20480) ? ((n0max + 3) & ~3LL) : 0;
-    const long long fixed = 3 * Lb + 2 * Hb + 64 * 8 + 40 * rowtab_rows;
+    const long long fixed = 4 * Lb + 2 * Hb + 64 * 8 + 40 * rowtab_rows;
     long long ub = 4LL * VB_N4_HCOPIES * p.n_bins;                       // histogram copies
     ub = std::max(ub, 8LL * 7 * fftN);                                   // FFT work arrays
     ub = std::max(ub, 8LL * (long long)ncpf[0] * ncpf[1] * n2max);       // Q[a][b][s], 64-bit fixed point
@@ -232,6 +232,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     a.ws_logI = (float*)c->ws_logI.p; a.ws_colmask = (uint32_t*)c->ws_colmask.p; a.ws_rbb = (uint32_t*)c->ws_rbb.p;
     a.ws_wbase = (uint32_t*)c->ws_wbase.p; a.ws_acol = (uint32_t*)c->ws_acol.p; a.ws_axis = (float*)c->ws_axis.p; a.ws_e = (float*)c->ws_e.p;
     a.ws_perm = (uint32_t*)c->ws_perm.p; a.rowtab_rows = (int)rowtab_rows;
+    { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] == '1') ? 1 : 0; }
     a.work_counter = (int*)c->ws_counter.p; a.debug = dbg;
     a.Vmax = vmax; a.cmw_max = cmw; a.rbb_max = rbb; a.wb_max = wb; a.ncols_max = ncmax;
     a.axis_stride = (int)axis; a.debug_stride = dbg_stride;
