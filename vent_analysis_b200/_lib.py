@@ -103,6 +103,10 @@ def load():
     """The CUDA library (and only that).  Raises if it has not been built."""
     global _LIB
     if _LIB is None:
+        path = os.environ.get("VENTB200_LIB", LIB_PATH)     # tuning builds only; same C ABI, same CUDA sources
+        if path != LIB_PATH:
+            _LIB = bind(path)
+            return _LIB
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -m vent_analysis_b200.build` "
@@ -267,7 +271,7 @@ class Context:
             self.check(rc)
         return shell, stats, rc
 
-    def n4_debug(self, subject, nbins, lattice_capacity, trace_capacity=208):
+    def n4_debug(self, subject, nbins, lattice_capacity, trace_capacity=212):
         self.check(self.lib.vb_set_debug(self.h, 1))
         hist = np.zeros(nbins, dtype=np.float32)
         emap = np.zeros(nbins, dtype=np.float32)
@@ -277,9 +281,9 @@ class Context:
         self.check(self.lib.vb_n4_debug_fetch(self.h, int(subject), _ptr(hist), _ptr(emap), _ptr(lat),
                                               lattice_capacity, _ptr(ncp), _ptr(trace), trace_capacity))
         L = int(np.prod(ncp))
-        phases = dict(zip(("setup", "hist", "sharpen", "fit", "update", "chain", "finalize", "other"),
-                          (float(x) for x in trace[-8:])))
-        tr = trace[:-8]
+        phases = dict(zip(("setup", "hist", "sharpen", "fit", "update", "chain", "finalize", "other",
+                           "chain_prefix", "chain_setup", "chain_mu", "chain_sigma"), (float(x) for x in trace[-12:])))
+        tr = trace[:-12]
         return dict(hist=hist, emap=emap, lattice=lat[:L].reshape(tuple(int(x) for x in ncp)).copy(), ncp=ncp,
                     conv=tr[tr >= 0], phase_us=phases)
 

@@ -39,7 +39,9 @@
 #define VB_N4_WARPS (VB_N4_THREADS / 32)
 #define VB_BSPLINE_EPS 1e-3f
 #define VB_N4_EPT 8                               /* convergence chain: elements per thread   */
+#ifndef VB_N4_CHAIN_WARPS
 #define VB_N4_CHAIN_WARPS 16                      /* warps of the chain team while it overlaps  */
+#endif
 #define VB_N4_SERIAL 64                           /* first elements: one thread, sequentially */
 #define VB_N4_HCOPIES 8                           /* histogram copies (warp & 7)              */
 
@@ -61,6 +63,8 @@ struct N4Args {
     float* ws_axis;          // [grid][axis_stride]  (4-byte words)
     float* ws_e;             // [grid][Vmax]      exp(bias_old - bias_new) over the mask, C order
     uint32_t* ws_perm;       // [grid][Vmax]      C-order rank -> compact index of the mask voxels
+    float* ws_ec;            // [grid][2*Vmax]    convergence sequence in C order: pixel[M], then pixel/N [M]
+    const float2* rcp;       // [Vmax + 1]        1/N = x + y as two floats, N = index (shared by all CTAs)
     int* work_counter;
     float* debug;            // may be null: [n][debug_stride]
     long long Vmax, cmw_max, rbb_max, wb_max, ncols_max;
@@ -71,11 +75,12 @@ struct N4Args {
     int logI_cap;            // floats of compact log image that fit shared memory (0 = none)
     int rowtab_rows;         // rows whose row-axis tables fit shared memory (0 = keep them in global)
     int no_overlap;          // 1: run the convergence chain and the next iteration's phases one after the other
+                             // (2, 3: timing diagnostics only -- WRONG results: 2 = never run the chain, 3 = chain team idles the phases)
 };
 
 // debug record layout (floats): [0]=bmin [1]=bmax [2..4]=ncp [5]=n_trace, then
 // hist[nbins], emap[nbins], lattice[Lmax], trace[...]
-#define VB_DBG_HDR 16   /* [8..15]: phase time in microseconds (setup, hist, sharpen, fit, update, chain, finalize, other) */
+#define VB_DBG_HDR 24   /* [8..15]: phase time in microseconds (setup, hist, sharpen, fit, update, chain, finalize, other) */
 
 VB_DEV double vb_bspline3(double u) {
     const double a = fabs(u);
@@ -191,6 +196,8 @@ struct N4Ctx {
     float* axis_base;
     float* ebuf;          // [M] exp(old - new), compact order
     uint32_t* perm;       // [M] C-order rank -> compact index
+    float* ec;            // [M] pixel in C order, [M] pixel / N behind it (chain input)
+    const float2* rcp;    // 1/N split in two floats
     // row-axis tables (shared memory when they fit, else inside axis_base)
     const float4* r_evw;
     const float4* r_fit3;
@@ -204,6 +211,9 @@ struct N4Ctx {
     float* Lold;          // lattice before the last update
     float* Om;            // omega lattice of the current level
     float* Phi;           // lattice increment of the last fit (committed by n4_commit)
+    float* G;             // [ncp0][gstride] column coefficients of c.L per active column (null: evaluate on the fly)
+    float* gspace;        // spare shared memory behind the compact log image
+    int gcap, gstride;    // floats available there; row stride of G (active columns rounded up to 32)
     float* E;             // E(u|v) table
     float* H;             // histogram
     double* red;          // 64 doubles reduction scratch
@@ -212,6 +222,7 @@ struct N4Ctx {
     int nbins, fftN, hshift;
     long long t_chain;    // debug: clock ticks spent in n4_convergence
     int n_sweeps;         // debug: Jacobi sweeps of the convergence chain
+    long long t_sub[4];   // debug: chain time in prefix / chunk setup / mu sweeps / sigma sweeps
 };
 
 VB_DEV N4Axis n4_ax(const N4Ctx& c, int a) {
@@ -310,21 +321,37 @@ struct N4Win {
     float g0, g1, g2, g3;
     int cur;
 };
-VB_DEV void n4_win_advance(N4Win& w, const float* L, const N4Ctx& c, const N4Col& k, int base) {
+// `G` (optional): this lane's column of a precomputed coefficient table, G[a * gs]
+VB_DEV float n4_coef_t(const float* L, const N4Ctx& c, const N4Col& k, const float* G, int gs, int a) {
+    return G ? G[(size_t)a * gs] : n4_coef(L, c, k, a);
+}
+VB_DEV void n4_win_advance(N4Win& w, const float* L, const N4Ctx& c, const N4Col& k, int base, const float* G = nullptr, int gs = 0) {
     if (base == w.cur) return;
     if (w.cur < 0 || base - w.cur >= 4 || base < w.cur) {
-        w.g0 = n4_coef(L, c, k, base); w.g1 = n4_coef(L, c, k, base + 1);
-        w.g2 = n4_coef(L, c, k, base + 2); w.g3 = n4_coef(L, c, k, base + 3);
+        w.g0 = n4_coef_t(L, c, k, G, gs, base); w.g1 = n4_coef_t(L, c, k, G, gs, base + 1);
+        w.g2 = n4_coef_t(L, c, k, G, gs, base + 2); w.g3 = n4_coef_t(L, c, k, G, gs, base + 3);
         w.cur = base;
     } else {
         while (w.cur < base) {
-            w.g0 = w.g1; w.g1 = w.g2; w.g2 = w.g3; w.g3 = n4_coef(L, c, k, w.cur + 4);
+            w.g0 = w.g1; w.g1 = w.g2; w.g2 = w.g3; w.g3 = n4_coef_t(L, c, k, G, gs, w.cur + 4);
             ++w.cur;
         }
     }
 }
 VB_DEV float n4_win_eval(const N4Win& w, const float4 rw) {
     return rw.x * w.g0 + rw.y * w.g1 + rw.z * w.g2 + rw.w * w.g3;
+}
+
+// column-coefficient table of lattice L for every active column: dst[a][k]
+VB_DEV void n4_build_G(const N4Ctx& c, const float* L, float* dst) {
+    const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
+    const int total = c.ncp[0] * c.nact;
+    for (int e = (int)threadIdx.x; e < total; e += (int)blockDim.x) {
+        const int a = e / c.nact, k = e - a * c.nact;
+        const N4Col col = n4_col(c, ac, as, (int)c.acol[k]);
+        dst[(size_t)a * c.gstride + k] = n4_coef(L, c, col, a);
+    }
+    __syncthreads();
 }
 
 // exp(x) for the small arguments of the convergence measure: 1 + (x + x^2/2 + ...), whose final
@@ -344,7 +371,7 @@ VB_DEV float n4_exp_small(float x) {
 // Work item of a warp: 32 consecutive ACTIVE columns (columns that carry mask voxels) x one
 // segment of rows.  Splitting the rows gives the 16 warps enough items to balance.
 struct N4Item {
-    int blk, seg, wi0, wi1, q;
+    int blk, seg, wi0, wi1, q, k;        // k: index of this lane's column among the active columns
     bool valid, empty;
     unsigned pos;
 };
@@ -354,7 +381,8 @@ VB_DEV N4Item n4_item(const N4Ctx& c, int it) {
     I.wi0 = I.seg * c.wps; I.wi1 = min(c.W, I.wi0 + c.wps);
     const int k = I.blk * 32 + vb_lane();
     I.valid = k < c.nact;
-    I.q = (int)c.acol[I.valid ? k : c.nact - 1];
+    I.k = I.valid ? k : c.nact - 1;
+    I.q = (int)c.acol[I.k];
     I.pos = c.wbase[(size_t)I.blk * c.W + I.wi0];
     I.empty = c.wbase[(size_t)I.blk * c.W + I.wi1] == I.pos;
     return I;
@@ -505,9 +533,10 @@ VB_DEV void n4_range(N4Ctx& c, float& bmin, float& bmax) {
         const N4Item I = n4_item(c, it);
         if (I.empty) continue;
         const N4Col col = n4_col(c, ac, as, I.q);
+        const float* Gl = c.G ? c.G + I.k : nullptr;
         N4Win win; win.cur = -1; win.g0 = win.g1 = win.g2 = win.g3 = 0.0f;
         VB_N4_FOR_ROWS(c, I, {
-            n4_win_advance(win, c.L, c, col, c.r_bev[r]);
+            n4_win_advance(win, c.L, c, col, c.r_bev[r], Gl, c.gstride);
             if (bit) {
                 const float u = c.logI[idx] - n4_win_eval(win, c.r_evw[r]);
                 tmin = fminf(tmin, u);
@@ -535,9 +564,10 @@ VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
         const N4Item I = n4_item(c, it);
         if (I.empty) continue;
         const N4Col col = n4_col(c, ac, as, I.q);
+        const float* Gl = c.G ? c.G + I.k : nullptr;
         N4Win win; win.cur = -1; win.g0 = win.g1 = win.g2 = win.g3 = 0.0f;
         VB_N4_FOR_ROWS(c, I, {
-            n4_win_advance(win, c.L, c, col, c.r_bev[r]);
+            n4_win_advance(win, c.L, c, col, c.r_bev[r], Gl, c.gstride);
             if (bit) {
                 const float u = c.logI[idx] - n4_win_eval(win, c.r_evw[r]);
                 const float cidx = __fdiv_rn(u - bmin, slope);
@@ -712,6 +742,7 @@ VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
         const N4Item I = n4_item(c, it);
         if (I.empty) continue;
         const N4Col col = n4_col(c, ac, as, I.q);
+        const float* Gl = c.G ? c.G + I.k : nullptr;
         const int cc = I.q / n2, ss = I.q - cc * n2;
         const int bc = ac.bfit[cc];
         const float4 wc = OMEGA ? ac.fit2[cc] : ac.fit3[cc];
@@ -726,7 +757,7 @@ VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
                 a0 = a1; a1 = a2; a2 = a3; a3 = 0.f;
                 ++cur;
             }
-            if (!OMEGA) n4_win_advance(win, c.L, c, col, c.r_bev[r]);
+            if (!OMEGA) n4_win_advance(win, c.L, c, col, c.r_bev[r], Gl, c.gstride);
             if (bit) {
                 float val;
                 float4 wt;
@@ -807,6 +838,14 @@ VB_DEV N4Step n4_step_consts(float pixel, int n) {
     s.cl = __fmul_rn(fmaf(-s.ch, nf, 1.0f), s.ch);
     return s;
 }
+// 1/N as two floats for every N up to nmax (one table per launch, shared by all subjects)
+VB_KERNEL void n4_rcp_table_kernel(float2* rcp, int nmax) {
+    for (int n = (int)(blockIdx.x * blockDim.x + threadIdx.x); n <= nmax; n += (int)(gridDim.x * blockDim.x)) {
+        const float nf = (float)(n > 0 ? n : 1);
+        const float ch = __frcp_rn(nf);
+        rcp[n] = make_float2(ch, __fmul_rn(fmaf(-ch, nf, 1.0f), ch));
+    }
+}
 VB_DEV float n4_mu_next(float mu, const N4Step& s) {
     const float t = fmaf(-mu, s.cl, fmaf(-mu, s.ch, s.b));      // pixel/N - mu/N
     return __fadd_rn(mu, t);
@@ -845,16 +884,26 @@ VB_DEV int n4_chain_scan(const N4Team& T, int v, int& total, int* tot, int& flag
     return ((w > 0) ? woff : 0) + inc - v;
 }
 
+// sigma + (th + tl) rounded to float (TwoSum keeps the part of th that the first add drops)
+VB_DEV float n4_sigma_add(float sigma, float th, float tl) {
+    const float r = __fadd_rn(sigma, th);
+    const float bb = __fsub_rn(r, sigma);
+    const float err = __fadd_rn(__fsub_rn(sigma, __fsub_rn(r, bb)), __fsub_rn(th, bb));
+    return __fadd_rn(r, __fadd_rn(err, tl));
+}
+VB_DEV int n4_binade(int bits) { return bits >> 23; }
+
 VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
     const int nt = T.nt, tid = T.tid;
     VB_SHARED int s_state[2];                 // float bit patterns of (mu, sigma) at the chunk start
     VB_SHARED int s_tot[2][32];               // warp totals, double buffered
     int buf = 0;
-    const float* e = c.ebuf;
-    const uint32_t* perm = c.perm;
+    const float* epx = c.ec;                  // pixel, C order
+    const float* epb = c.ec + ((M + 3) & ~3); // pixel / N
     const int S0 = min(M, VB_N4_SERIAL);
     VB_SHARED float s_px[VB_N4_SERIAL];
-    if (tid < S0) s_px[tid] = e[perm[tid]];
+    long long tq = vb_clock();
+    if (tid < S0) s_px[tid] = epx[tid];
     n4_sync(T);
     if (tid == 0) {
         float mu = 0.0f, sigma = 0.0f;
@@ -867,6 +916,7 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
         s_state[0] = __float_as_int(mu); s_state[1] = __float_as_int(sigma);
     }
     n4_sync(T);
+    { const long long tn = vb_clock(); c.t_sub[0] += tn - tq; tq = tn; }
     int start = S0;
     while (start < M) {
         const int len = min(min(start, nt * VB_N4_EPT), M - start);
@@ -876,16 +926,29 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
         const int mu0 = s_state[0], sg0 = s_state[1];
         float px[VB_N4_EPT];
         N4Step st[VB_N4_EPT];
+        if (cnt == VB_N4_EPT && VB_N4_EPT == 8) {             // lo is a multiple of 8 here: 16-byte loads
+            const float4 p0 = *(const float4*)(epx + lo), p1 = *(const float4*)(epx + lo + 4);
+            const float4 b0 = *(const float4*)(epb + lo), b1 = *(const float4*)(epb + lo + 4);
+            px[0] = p0.x; px[1] = p0.y; px[2] = p0.z; px[3] = p0.w; px[4] = p1.x; px[5] = p1.y; px[6] = p1.z; px[7] = p1.w;
+            st[0].b = b0.x; st[1].b = b0.y; st[2].b = b0.z; st[3].b = b0.w; st[4].b = b1.x; st[5].b = b1.y; st[6].b = b1.z; st[7].b = b1.w;
 #pragma unroll
-        for (int i = 0; i < VB_N4_EPT; ++i) {
-            px[i] = (i < cnt) ? e[perm[lo + i]] : 1.0f;
-            st[i] = n4_step_consts(px[i], lo + i + 1);
+            for (int i = 0; i < 8; ++i) { const float2 r = c.rcp[lo + i + 1]; st[i].ch = r.x; st[i].cl = r.y; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < VB_N4_EPT; ++i) {
+                const bool on = i < cnt;
+                px[i] = on ? epx[lo + i] : 1.0f;
+                st[i].b = on ? epb[lo + i] : 1.0f;
+                const float2 r = c.rcp[on ? lo + i + 1 : 1];
+                st[i].ch = r.x; st[i].cl = r.y;
+            }
         }
         // mu: a thread runs its steps sequentially (exactly) from its guessed start; the starts
         // are re-derived from the prefix sum of the threads' increments until none moves.  One
         // barrier per sweep: it publishes the warps' totals AND tells whether the previous sweep
         // moved any start (if not, the sweep just computed has confirmed the trajectory).
         int km = mu0, total = 0, changed = 1;
+        { const long long tn = vb_clock(); c.t_sub[1] += tn - tq; tq = tn; }
         for (;;) {
             float mu = __int_as_float(km);
 #pragma unroll
@@ -900,28 +963,55 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
             km = k;
         }
         const int mu_end = mu0 + total;
-        // sigma, along the exact mu trajectory
-        int ks = sg0;
-        changed = 1;
-        for (;;) {
-            float mu = __int_as_float(km), sg = __int_as_float(ks);
+        { const long long tn = vb_clock(); c.t_sub[2] += tn - tq; tq = tn; }
+        // sigma, along the exact mu trajectory.  The terms dd*(N-1)/N do not depend on sigma:
+        // form them once (head in px[], tail in st[].b).  A step then only depends on sigma
+        // through the binade it rounds in, so a thread re-runs its steps only when a new start
+        // lies in another binade than the one it ran from (or its span crosses a binade).
+        {
+            float mu = __int_as_float(km);
 #pragma unroll
             for (int i = 0; i < VB_N4_EPT; ++i)
                 if (i < cnt) {
-                    sg = n4_sigma_next(sg, mu, px[i], st[i]);
+                    const float d = __fsub_rn(px[i], mu);
+                    const float dd = __fmul_rn(d, d);
+                    const float th = fmaf(-dd, st[i].ch, dd);
+                    const float tl = fmaf(-dd, st[i].cl, fmaf(-dd, st[i].ch, __fsub_rn(dd, th)));
                     mu = n4_mu_next(mu, st[i]);
+                    px[i] = th; st[i].b = tl;
                 }
-            const int off = n4_chain_scan(T, __float_as_int(sg) - ks, total, s_tot[buf], changed);
+        }
+        // first guess: sigma grows about linearly with N inside the chunk
+        int ks = __float_as_int(__int_as_float(sg0) * ((float)lo / (float)start));
+        if (tid == 0 || cnt == 0) ks = sg0;
+        int inc = 0;
+        bool rerun = true;
+        changed = 1;
+        for (;;) {
+            if (rerun) {
+                float sg = __int_as_float(ks);
+#pragma unroll
+                for (int i = 0; i < VB_N4_EPT; ++i)
+                    if (i < cnt) sg = n4_sigma_add(sg, px[i], st[i].b);
+                inc = __float_as_int(sg) - ks;
+            }
+            const int off = n4_chain_scan(T, inc, total, s_tot[buf], changed);
             buf ^= 1;
             c.n_sweeps += 1000;
             if (!changed) break;
             const int k = sg0 + off;
-            changed = (k != ks);
+            // the increments computed from `ks` also hold from `k` when start and end stay in
+            // the same single binade (every add then rounds to the same grid)
+            const bool same = (k == ks) || (n4_binade(k) == n4_binade(ks) && n4_binade(k + inc) == n4_binade(k) &&
+                                            n4_binade(ks + inc) == n4_binade(ks));
+            rerun = !same;
+            changed = rerun;
             ks = k;
         }
         const int sg_end = sg0 + total;
         if (tid == 0) { s_state[0] = mu_end; s_state[1] = sg_end; }
         n4_sync(T);
+        { const long long tn = vb_clock(); c.t_sub[3] += tn - tq; tq = tn; }
         start += len;
     }
     const float mu = __int_as_float(s_state[0]), sigma = __int_as_float(s_state[1]);
@@ -948,17 +1038,21 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
     const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     float tmin = FLT_MAX, tmax = -FLT_MAX;
     double s1 = 0.0, s2 = 0.0;
+    float* Gn = c.G ? c.un_f : nullptr;                  // table of the new lattice (union region is free here)
+    if (Gn) n4_build_G(c, c.L, Gn);
     for (int it = w; it < c.nblk * c.nseg; it += nw) {
         const N4Item I = n4_item(c, it);
         if (I.empty) continue;
         const N4Col col = n4_col(c, ac, as, I.q);
+        const float* Go = c.G ? c.G + I.k : nullptr;
+        const float* Gw = Gn ? Gn + I.k : nullptr;
         N4Win wo, wn;
         wo.cur = wn.cur = -1;
         wo.g0 = wo.g1 = wo.g2 = wo.g3 = wn.g0 = wn.g1 = wn.g2 = wn.g3 = 0.0f;
         VB_N4_FOR_ROWS(c, I, {
             const int base = c.r_bev[r];
-            n4_win_advance(wo, c.Lold, c, col, base);
-            n4_win_advance(wn, c.L, c, col, base);
+            n4_win_advance(wo, c.Lold, c, col, base, Go, c.gstride);
+            n4_win_advance(wn, c.L, c, col, base, Gw, c.gstride);
             if (bit) {
                 const float4 rw = c.r_evw[r];
                 const float bo = n4_win_eval(wo, rw), bn = n4_win_eval(wn, rw);
@@ -977,6 +1071,10 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
     s1 = vb_block_reduce(s1, VbAddD(), 0.0, c.red);
     s2 = vb_block_reduce(s2, VbAddD(), 0.0, c.red);
     __syncthreads();
+    if (Gn) {                                            // the new lattice's table becomes the current one
+        for (int e = (int)threadIdx.x; e < c.ncp[0] * c.gstride; e += (int)blockDim.x) c.G[e] = Gn[e];
+        __syncthreads();
+    }
     if (!exact_needed) {
         const double N = (double)M;
         double var = (s2 - s1 * s1 / N) / (N - 1.0);
@@ -986,6 +1084,13 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
         const double lower = (sqrt(var) - lag) / mean * 0.98;
         if (lower > (double)thr) { conv = (float)(sqrt(var) / mean); return false; }
     }
+    // chain input in C order: pixel and pixel / N (float division, as the reference does)
+    for (int j = (int)threadIdx.x; j < M; j += (int)blockDim.x) {
+        const float px = c.ebuf[c.perm[j]];
+        c.ec[j] = px;
+        c.ec[((M + 3) & ~3) + j] = __fdiv_rn(px, (float)(j + 1));
+    }
+    __syncthreads();
     return true;
 }
 
@@ -1133,6 +1238,8 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         c.axis_base = a.ws_axis + (size_t)blockIdx.x * a.axis_stride;
         c.ebuf = a.ws_e + (size_t)blockIdx.x * a.Vmax;
         c.perm = a.ws_perm + (size_t)blockIdx.x * a.Vmax;
+        c.ec = a.ws_ec + (size_t)blockIdx.x * 2 * (size_t)((a.Vmax + 3) & ~3LL);
+        c.rcp = a.rcp;
         c.ncp[0] = a.p.ncp[0]; c.ncp[1] = a.p.ncp[1]; c.ncp[2] = a.p.ncp[2];
         {
             const int nn[3] = {S.n0, S.n1, S.n2};
@@ -1149,9 +1256,14 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         int M;
         long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         long long tq = vb_clock();
-        c.t_chain = 0; c.n_sweeps = 0;
+        c.t_chain = 0; c.n_sweeps = 0; c.t_sub[0] = c.t_sub[1] = c.t_sub[2] = c.t_sub[3] = 0;
         n4_setup(c, a.p.mask_label, smem_logI, a.logI_cap, bmin, bmax, M);
         for (int e = tid; e < a.Lmax; e += (int)blockDim.x) { c.L[e] = 0.0f; c.Lold[e] = 0.0f; }
+        {
+            const int used = (c.logI == smem_logI) ? ((M + 3) & ~3) : 0;
+            c.gspace = smem_logI + used; c.gcap = a.logI_cap - used;
+            c.gstride = (c.nact + 31) & ~31; c.G = nullptr;
+        }
         __syncthreads();
         tph[0] = vb_clock() - tq;
 
@@ -1165,6 +1277,11 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
             int it = 0;
             if (M >= 2 && !capped) {
                 n4_build_tables(c);
+                {
+                    const int need = c.ncp[0] * c.gstride;
+                    c.G = (need <= c.gcap && need * 4 <= a.union_bytes) ? c.gspace : nullptr;
+                    if (c.G) n4_build_G(c, c.L, c.G);
+                }
                 n4_contract<true>(c, full, bmin, bmax);
                 if (level > 0) n4_range(c, bmin, bmax);
                 conv = FLT_MAX;
@@ -1174,7 +1291,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                 // sharpening and fit of iteration it + 1; the fit is only committed if the chain
                 // says "continue", so the result is that of the sequential schedule.
                 bool pending = false;
-                const bool serial = dbg != nullptr || a.no_overlap != 0;
+                const bool serial = dbg != nullptr || a.no_overlap == 1;
                 for (;;) {
                     const bool room = it < a.p.max_iter[level];
                     const bool cap = a.p.max_total_iters > 0 && total >= a.p.max_total_iters;
@@ -1187,7 +1304,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                         } else if (tid < TC.nt) {
                             const float cv = n4_convergence(c, TC, M);
                             if (tid == 0) s_conv = cv;
-                        } else if (room && !cap) {
+                        } else if (room && !cap && a.no_overlap != 3) {
                             n4_histogram(c, TP, bmin, bmax);
                             n4_sharpen(c, TP, bmin, bmax, a.p.fwhm, a.p.wiener_noise);
                             n4_contract<false>(c, TP, bmin, bmax);
@@ -1195,7 +1312,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                         __syncthreads();
                         conv = s_conv;
                         __syncthreads();
-                        fitted = !serial && room && !cap;
+                        fitted = !serial && room && !cap && a.no_overlap != 3;
                         pending = false;
                         tph[5] += vb_clock() - tq;
                         if (dbg_trace && tid == 0 && ntrace - 1 < trace_cap && ntrace > 0) dbg_trace[ntrace - 1] = conv;
@@ -1216,6 +1333,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                     ++it; ++total;
                     tq = vb_clock();
                     pending = n4_update(c, M, bmin, bmax, a.p.conv_threshold, dbg != nullptr || it >= a.p.max_iter[level], conv);
+                    if (a.no_overlap == 2 && pending) { pending = false; conv = (it >= 12 + 20 * (level == 0)) ? 0.0f : 1.0f; }
                     tph[4] += vb_clock() - tq;
                     if (!pending && dbg_trace && tid == 0 && ntrace < trace_cap) dbg_trace[ntrace] = conv;
                     ++ntrace;
@@ -1246,8 +1364,9 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         n4_finalize(c, a.logbias ? a.logbias + S.off : nullptr);
         if (dbg && tid == 0) {
             tph[6] = vb_clock() - tq;
-            for (int k = 0; k < 8; ++k) dbg[8 + k] = (float)((double)tph[k] * 1e-3);   // ns -> us
+            for (int k = 0; k < 8; ++k) dbg[8 + k] = (float)((double)tph[k] * (1.0 / 1965.0));   // cycles -> us at 1965 MHz
             dbg[15] = (float)c.n_sweeps;
+            for (int k = 0; k < 4; ++k) dbg[16 + k] = (float)((double)c.t_sub[k] * (1.0 / 1965.0));
         }
     }
 }

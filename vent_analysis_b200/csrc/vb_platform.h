@@ -46,7 +46,7 @@ VB_DEV int vb_bar_or(int id, int nthreads, int pred) {
         : "=r"(out) : "r"(id), "r"(nthreads), "r"(pred) : "memory");
     return out;
 }
-VB_DEV long long vb_clock() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return (long long)t; }
+VB_DEV long long vb_clock() { return clock64(); }   // SM cycles
 #else
 // ------------------------------------------------------------------------------- emulation
 #include <math.h>

@@ -37,9 +37,9 @@ struct vb_ctx {
     std::vector<VbSubject> last_subj;
     std::vector<long long> last_wordoff;
     Buf h_desc, d_subj, d_wordoff;
-    long long v_total = 0, words_total = 0;
+    long long v_total = 0, words_total = 0, rcp_n = -1;
     // workspaces
-    Buf ws_logI, ws_e, ws_colmask, ws_rbb, ws_wbase, ws_acol, ws_perm, ws_axis, ws_counter, ws_d0, ws_bits, ws_list, ws_count, dbg;
+    Buf ws_logI, ws_e, ws_colmask, ws_rbb, ws_wbase, ws_acol, ws_perm, ws_ec, ws_rcp, ws_axis, ws_counter, ws_d0, ws_bits, ws_list, ws_count, dbg;
     int dbg_stride = 0, dbg_nbins = 0, dbg_Lmax = 0, dbg_n = 0;
     // CI tables
     std::vector<TableHost> tables;
@@ -211,7 +211,8 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     if (!ensure(c->ws_logI, sizeof(float) * (size_t)grid * (size_t)vmax) ||
         !ensure(c->ws_e, sizeof(float) * (size_t)grid * (size_t)vmax) ||
         !ensure(c->ws_colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(c->ws_rbb, 4 * (size_t)grid * (size_t)rbb) ||
-        !ensure(c->ws_wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(c->ws_acol, 4 * (size_t)grid * (size_t)ncmax) || !ensure(c->ws_perm, 4 * (size_t)grid * (size_t)vmax) ||
+        !ensure(c->ws_wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(c->ws_acol, 4 * (size_t)grid * (size_t)ncmax) || !ensure(c->ws_perm, 4 * (size_t)grid * (size_t)vmax) || !ensure(c->ws_ec, 8 * (size_t)grid * (size_t)((vmax + 3) & ~3LL)) ||
+        !ensure(c->ws_rcp, 8 * ((size_t)vmax + 8)) ||
         !ensure(c->ws_axis, 4 * (size_t)grid * (size_t)axis) || !ensure(c->ws_counter, 64))
         return VB_ERR_CUDA;
     int trace = 0;
@@ -231,8 +232,8 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     a.subj = (const VbSubject*)c->d_subj.p; a.n = n; a.p = p; a.stats = stats;
     a.ws_logI = (float*)c->ws_logI.p; a.ws_colmask = (uint32_t*)c->ws_colmask.p; a.ws_rbb = (uint32_t*)c->ws_rbb.p;
     a.ws_wbase = (uint32_t*)c->ws_wbase.p; a.ws_acol = (uint32_t*)c->ws_acol.p; a.ws_axis = (float*)c->ws_axis.p; a.ws_e = (float*)c->ws_e.p;
-    a.ws_perm = (uint32_t*)c->ws_perm.p; a.rowtab_rows = (int)rowtab_rows;
-    { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] == '1') ? 1 : 0; }
+    a.ws_perm = (uint32_t*)c->ws_perm.p; a.ws_ec = (float*)c->ws_ec.p; a.rcp = (const float2*)c->ws_rcp.p; a.rowtab_rows = (int)rowtab_rows;
+    { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] >= '1' && e[0] <= '9') ? e[0] - '0' : 0; }
     a.work_counter = (int*)c->ws_counter.p; a.debug = dbg;
     a.Vmax = vmax; a.cmw_max = cmw; a.rbb_max = rbb; a.wb_max = wb; a.ncols_max = ncmax;
     a.axis_stride = (int)axis; a.debug_stride = dbg_stride;
@@ -240,6 +241,11 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     // a mask that does not fit keeps its compact log image in global memory (L2)
     a.logI_cap = (int)std::min<long long>(std::max<long long>(cap, 0), vmax);
     const int smem = (int)(ub + fixed + 4LL * a.logI_cap);
+    if (c->rcp_n < vmax) {                                 // 1/N table, (re)built only when it has to grow
+        VB_LAUNCH(n4_rcp_table_kernel, dim3(c->sms), dim3(256), 0, s, (float2*)c->ws_rcp.p, (int)vmax);
+        ++c->launches;
+        c->rcp_n = vmax;
+    }
     if (!vbrt::allow_smem(n4_subject_kernel, smem)) return VB_ERR_CUDA;
     VB_LAUNCH(n4_subject_kernel, dim3(grid), dim3(VB_N4_THREADS), (size_t)smem, s, a);
     ++c->launches;
@@ -327,7 +333,7 @@ void vb_destroy(vb_ctx* c) {
     if (!c) return;
     vbrt::set_device(c->device);
     vbrt::stream_sync(c->stream);
-    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_logI, &c->ws_e, &c->ws_rbb, &c->ws_wbase, &c->ws_acol, &c->ws_perm, &c->ws_colmask, &c->ws_axis, &c->ws_counter, &c->ws_d0,
+    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_logI, &c->ws_e, &c->ws_rbb, &c->ws_wbase, &c->ws_acol, &c->ws_perm, &c->ws_ec, &c->ws_rcp, &c->ws_colmask, &c->ws_axis, &c->ws_counter, &c->ws_d0,
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
                    &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats};
     for (Buf* b : bufs) vbrt::dev_free(b->p);
@@ -603,10 +609,10 @@ int vb_n4_debug_fetch(vb_ctx* c, int32_t subject, float* hist, float* emap, floa
     if (ncp) { ncp[0] = n0; ncp[1] = n1; ncp[2] = n2; }
     if (lattice) memcpy(lattice, rec.data() + VB_DBG_HDR + 2 * nb, sizeof(float) * (size_t)std::min(lattice_capacity, n0 * n1 * n2));
     const int nt = (int)rec[5];
-    if (conv_trace && trace_capacity >= 8 + nt) {          // phase microseconds ride behind the trace
+    if (conv_trace && trace_capacity >= 12 + nt) {         // phase microseconds ride behind the trace
         for (int i = 0; i < trace_capacity; ++i) conv_trace[i] = -1.0f;
         memcpy(conv_trace, rec.data() + VB_DBG_HDR + 2 * nb + c->dbg_Lmax, sizeof(float) * (size_t)nt);
-        memcpy(conv_trace + trace_capacity - 8, rec.data() + 8, sizeof(float) * 8);
+        memcpy(conv_trace + trace_capacity - 12, rec.data() + 8, sizeof(float) * 12);
     } else if (conv_trace) {
         for (int i = 0; i < trace_capacity; ++i) conv_trace[i] = -1.0f;
         memcpy(conv_trace, rec.data() + VB_DBG_HDR + 2 * nb + c->dbg_Lmax, sizeof(float) * (size_t)std::min(trace_capacity, nt));
