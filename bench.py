@@ -159,7 +159,10 @@ def cpu_baseline_leg():
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi in loop mode; samples are kept with their time stamps so that only those that
+    fall inside the timed region are used (all samples taken under load if the region was too
+    short to catch one)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -172,11 +175,12 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", self.gpu], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20", "-i", self.gpu], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -186,25 +190,27 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for ln in open(self.path):
             p = [x.strip() for x in ln.split(",")]
-            if len(p) < 8:
+            if len(p) < 9:
                 continue
             try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
+                ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(p[2]), float(p[3]), [nm for nm, v in zip(names, p[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, p[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         try:
             os.remove(self.path)
         except OSError:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        use = inside if inside else rows
+        if use:
+            out.update(sm_mhz=float(np.median([r[1] for r in use])), sm_max_mhz=float(max(r[2] for r in use)),
+                       reasons=sorted({x for r in use for x in r[3]}), samples=len(use),
+                       window="timed region" if inside else "warm-up + timed region")
         return out
 
 
@@ -233,13 +239,14 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     # ---- value: batch resident in HBM --------------------------------------------------------
-    for _ in range(args.warmup):
-        dc.step()
-    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(args.warmup):
+        dc.step()
+    barrier()
     ctx.set_profiling(True)
+    wall0 = time.time()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -251,7 +258,7 @@ def run_ours(args, rank, local_rank, world):
     launches = ctx.launch_count() - l0
     stage_ms, ncalls = ctx.profile_fetch()
     ctx.set_profiling(False)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(wall0, time.time()) if sampler else None
     stats = dc.stats()
     metrics = dc.metrics()
 
@@ -343,7 +350,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=296, help="subjects per GPU per step (2 per SM)")
+    ap.add_argument("--batch", type=int, default=592, help="subjects per GPU per step (4 per SM)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -55,6 +55,7 @@ inline void event_destroy(event_t e) { if (e) cudaEventDestroy(e); }
 inline bool event_record(event_t e, stream_t s) { return ok(cudaEventRecord(e, s), "cudaEventRecord"); }
 inline bool event_sync(event_t e) { return ok(cudaEventSynchronize(e), "cudaEventSynchronize"); }
 inline bool event_elapsed(float* ms, event_t a, event_t b) { return ok(cudaEventElapsedTime(ms, a, b), "cudaEventElapsedTime"); }
+inline bool stream_wait(stream_t s, event_t e) { return ok(cudaStreamWaitEvent(s, e, 0), "cudaStreamWaitEvent"); }
 #else
 typedef void* stream_t;
 inline bool dev_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); memset(*p, 0xAB, n); return *p != nullptr; }
@@ -81,6 +82,7 @@ inline void event_destroy(event_t) {}
 inline bool event_record(event_t, stream_t) { return true; }
 inline bool event_sync(event_t) { return true; }
 inline bool event_elapsed(float* ms, event_t, event_t) { *ms = 0.0f; return true; }
+inline bool stream_wait(stream_t, event_t) { return true; }
 #endif
 
 }  // namespace vbrt

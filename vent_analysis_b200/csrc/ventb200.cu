@@ -30,13 +30,15 @@ struct TableHost {
 
 struct vb_ctx {
     int device = 0, sms = 0, max_smem = 0;
-    vbrt::stream_t stream = nullptr;
+    vbrt::stream_t stream = nullptr, stream_in = nullptr, stream_out = nullptr;
+    std::vector<vbrt::event_t> ev_copy;   // host pipeline: inputs-ready / outputs-ready events per chunk
+    int r0 = 0;                          // first subject of the range the stage runners work on
     uint64_t launches = 0;
     bool debug = false;
     // subject descriptors
     std::vector<VbSubject> last_subj;
     std::vector<long long> last_wordoff;
-    Buf h_desc, d_subj, d_wordoff;
+    Buf h_desc, h_stats, d_subj, d_wordoff;   // h_*: pinned host staging
     long long v_total = 0, words_total = 0, rcp_n = -1;
     // workspaces
     Buf ws_logI, ws_e, ws_colmask, ws_rbb, ws_wbase, ws_acol, ws_perm, ws_ec, ws_rcp, ws_axis, ws_counter, ws_d0, ws_bits, ws_list, ws_count, dbg;
@@ -106,6 +108,7 @@ int prepare(vb_ctx* c, int n, const int32_t* shapes, const int32_t* handles, vbr
     const size_t sb = subj.size() * sizeof(VbSubject), wb = woff.size() * sizeof(long long);
     if (c->h_desc.cap < sb + wb) {
         vbrt::host_free(c->h_desc.p);
+    vbrt::host_free(c->h_stats.p);
         c->h_desc.p = nullptr; c->h_desc.cap = 0;
         if (!vbrt::host_malloc(&c->h_desc.p, (sb + wb) * 2)) return VB_ERR_CUDA;
         c->h_desc.cap = (sb + wb) * 2;
@@ -119,6 +122,8 @@ int prepare(vb_ctx* c, int n, const int32_t* shapes, const int32_t* handles, vbr
     c->last_wordoff.swap(woff);
     return VB_OK;
 }
+
+const VbSubject* subj_ptr(const vb_ctx* c) { return (const VbSubject*)c->d_subj.p + c->r0; }
 
 int grid_x_for(const vb_ctx* c, int n, long long vmax, int per_block) {
     long long want = (c->sms * 8LL + n - 1) / n;
@@ -158,7 +163,7 @@ int run_snr(vb_ctx* c, const float* image, const uint8_t* mask, int n, int fov, 
     for (const VbSubject& S : c->last_subj)
         if (S.n0 + S.n1 + S.n2 > VB_SNR_MAX_AXIS) return fail(VB_ERR_UNSUPPORTED, "SNR: n0+n1+n2 too large");
     const int grid = std::min(n, c->sms * 4);
-    VB_LAUNCH(snr_kernel, dim3(grid), dim3(VB_VDP_THREADS), 0, s, image, mask, (const VbSubject*)c->d_subj.p, n,
+    VB_LAUNCH(snr_kernel, dim3(grid), dim3(VB_VDP_THREADS), 0, s, image, mask, subj_ptr(c), n,
               fov, stats);
     ++c->launches;
     return vbrt::last_launch_ok("snr_kernel") ? VB_OK : VB_ERR_CUDA;
@@ -229,7 +234,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     if (!vbrt::dev_memset(c->ws_counter.p, 0, 64, s)) return VB_ERR_CUDA;
     N4Args a;
     a.image = image; a.mask = mask; a.out = out; a.logbias = logbias;
-    a.subj = (const VbSubject*)c->d_subj.p; a.n = n; a.p = p; a.stats = stats;
+    a.subj = subj_ptr(c); a.n = n; a.p = p; a.stats = stats;
     a.ws_logI = (float*)c->ws_logI.p; a.ws_colmask = (uint32_t*)c->ws_colmask.p; a.ws_rbb = (uint32_t*)c->ws_rbb.p;
     a.ws_wbase = (uint32_t*)c->ws_wbase.p; a.ws_acol = (uint32_t*)c->ws_acol.p; a.ws_axis = (float*)c->ws_axis.p; a.ws_e = (float*)c->ws_e.p;
     a.ws_perm = (uint32_t*)c->ws_perm.p; a.ws_ec = (float*)c->ws_ec.p; a.rcp = (const float2*)c->ws_rcp.p; a.rowtab_rows = (int)rowtab_rows;
@@ -254,7 +259,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
 
 int run_border(vb_ctx* c, const uint8_t* a, int n, uint8_t* border, vbrt::stream_t s) {
     const int gx = grid_x_for(c, n, vmax_of(c), 256);
-    VB_LAUNCH(border_kernel, dim3(gx, n), dim3(256), 0, s, a, (const VbSubject*)c->d_subj.p, border);
+    VB_LAUNCH(border_kernel, dim3(gx, n), dim3(256), 0, s, a, subj_ptr(c), border);
     ++c->launches;
     return vbrt::last_launch_ok("border_kernel") ? VB_OK : VB_ERR_CUDA;
 }
@@ -262,7 +267,7 @@ int run_border(vb_ctx* c, const uint8_t* a, int n, uint8_t* border, vbrt::stream
 int run_vdp(vb_ctx* c, const float* n4, const uint8_t* mask, int n, float thresh, uint8_t* defect, uint8_t* lb,
             uint8_t* dborder, vb_subject_stats* stats, vbrt::stream_t s) {
     if (!ensure(c->ws_d0, (size_t)c->v_total)) return VB_ERR_CUDA;
-    const VbSubject* subj = (const VbSubject*)c->d_subj.p;
+    const VbSubject* subj = subj_ptr(c);
     const int gx = grid_x_for(c, n, vmax_of(c), 256);
     VB_LAUNCH(vdp_stats_kernel, dim3(std::min(n, c->sms * 4)), dim3(VB_VDP_THREADS), 0, s, n4, mask, subj, n, stats);
     VB_LAUNCH(vdp_threshold_kernel, dim3(gx, n), dim3(256), 0, s, n4, mask, subj, thresh, (uint8_t*)c->ws_d0.p, lb,
@@ -277,14 +282,17 @@ int run_ci(vb_ctx* c, const uint8_t* defect, int n, uint16_t* shell, vb_subject_
     int rc = upload_tables(c, s);
     if (rc) return rc;
     if (!ensure(c->ws_bits, 4 * (size_t)c->words_total) || !ensure(c->ws_list, 4 * (size_t)c->v_total) ||
-        !ensure(c->ws_count, 4 * (size_t)n))
+        !ensure(c->ws_count, 4 * c->last_subj.size()))
         return VB_ERR_CUDA;
-    if (!vbrt::dev_memset(shell, 0xFF, 2 * (size_t)c->v_total, s) || !vbrt::dev_memset(c->ws_count.p, 0, 4 * (size_t)n, s))
+    const long long voff = c->last_subj[(size_t)c->r0].off;
+    const long long vend = c->last_subj[(size_t)(c->r0 + n - 1)].off + c->last_subj[(size_t)(c->r0 + n - 1)].V;
+    if (!vbrt::dev_memset(shell + voff, 0xFF, 2 * (size_t)(vend - voff), s) ||
+        !vbrt::dev_memset((int*)c->ws_count.p + c->r0, 0, 4 * (size_t)n, s))
         return VB_ERR_CUDA;
     CiArgs a;
-    a.defect = defect; a.subj = (const VbSubject*)c->d_subj.p; a.n = n;
+    a.defect = defect; a.subj = subj_ptr(c); a.n = n;
     a.tables = (const CiTableDev*)c->d_tables.p; a.bits = (uint32_t*)c->ws_bits.p;
-    a.word_off = (const long long*)c->d_wordoff.p; a.list = (int*)c->ws_list.p; a.count = (int*)c->ws_count.p;
+    a.word_off = (const long long*)c->d_wordoff.p + c->r0; a.list = (int*)c->ws_list.p; a.count = (int*)c->ws_count.p + c->r0;
     a.shell = shell; a.stats = stats;
     const long long vmax = vmax_of(c);
     const int words = (int)((vmax + 31) / 32);
@@ -324,7 +332,10 @@ int vb_create(int device, vb_ctx** out) {
     c->device = device;
     c->sms = vbrt::sm_count(device);
     c->max_smem = vbrt::max_smem_optin(device);
-    if (!vbrt::stream_create(&c->stream)) { delete c; return VB_ERR_CUDA; }
+    if (!vbrt::stream_create(&c->stream) || !vbrt::stream_create(&c->stream_in) || !vbrt::stream_create(&c->stream_out)) {
+        delete c;
+        return VB_ERR_CUDA;
+    }
     *out = c;
     return VB_OK;
 }
@@ -339,7 +350,11 @@ void vb_destroy(vb_ctx* c) {
     for (Buf* b : bufs) vbrt::dev_free(b->p);
     for (TableHost& t : c->tables) { vbrt::dev_free(t.d_rows); vbrt::dev_free(t.d_ii); }
     vbrt::host_free(c->h_desc.p);
+    vbrt::host_free(c->h_stats.p);
     for (vbrt::event_t e : c->ev) vbrt::event_destroy(e);
+    for (vbrt::event_t e : c->ev_copy) vbrt::event_destroy(e);
+    vbrt::stream_destroy(c->stream_in);
+    vbrt::stream_destroy(c->stream_out);
     vbrt::stream_destroy(c->stream);
     delete c;
 }
@@ -452,15 +467,54 @@ int vb_ci_batch_dev(vb_ctx* c, const uint8_t* defect, int32_t n, const int32_t* 
     return rc ? rc : run_ci(c, defect, n, shell, stats, (vbrt::stream_t)stream);
 }
 
+// the selected stages on subjects [r0, r0 + cnt) of the prepared batch (buffers are whole-batch)
+static int pipeline_range(vb_ctx* c, int r0, int cnt, const vb_n4_params* params, float thresh, uint32_t flags,
+                          const vb_buffers* d, vbrt::stream_t s, vbrt::event_t* ev) {
+    int rc = VB_OK;
+    c->r0 = r0;
+    vb_subject_stats* st = d->stats + r0;
+    do {
+        if (!vbrt::dev_memset(st, 0, sizeof(vb_subject_stats) * (size_t)cnt, s)) { rc = VB_ERR_CUDA; break; }
+        if (ev && !vbrt::event_record(ev[0], s)) { rc = VB_ERR_CUDA; break; }
+        if (flags & VB_DO_SNR)
+            if ((rc = run_snr(c, d->image, d->mask, cnt, 20, st, s))) break;
+        if (ev && !vbrt::event_record(ev[1], s)) { rc = VB_ERR_CUDA; break; }
+        if (flags & VB_DO_N4)
+            if ((rc = run_n4(c, d->image, d->mask, cnt, params, d->n4, d->logbias, st, s))) break;
+        if (ev && !vbrt::event_record(ev[2], s)) { rc = VB_ERR_CUDA; break; }
+        if (flags & VB_DO_VDP)
+            if ((rc = run_vdp(c, d->n4, d->mask, cnt, thresh, d->defect, d->defect_lb, d->defect_border, st, s))) break;
+        if (ev && !vbrt::event_record(ev[3], s)) { rc = VB_ERR_CUDA; break; }
+        if ((flags & VB_DO_MASK_BORDER) && d->mask_border)
+            if ((rc = run_border(c, d->mask, cnt, d->mask_border, s))) break;
+        if (ev && !vbrt::event_record(ev[4], s)) { rc = VB_ERR_CUDA; break; }
+        if (flags & VB_DO_CI)
+            if ((rc = run_ci(c, d->defect, cnt, d->ci_shell, st, s))) break;
+        if (ev && !vbrt::event_record(ev[5], s)) { rc = VB_ERR_CUDA; break; }
+    } while (0);
+    c->r0 = 0;
+    return rc;
+}
+
+static int pipeline_check(uint32_t flags, const int32_t* handles, const vb_n4_params* params, const vb_buffers* d) {
+    if ((flags & VB_DO_CI) && !handles) return fail(VB_ERR_ARG, "pipeline: CI needs table handles");
+    if ((flags & VB_DO_SNR) && !d->image) return fail(VB_ERR_ARG, "pipeline: SNR needs image");
+    if ((flags & VB_DO_N4) && (!d->image || !d->n4 || !params)) return fail(VB_ERR_ARG, "pipeline: N4 needs image, n4, params");
+    if ((flags & VB_DO_VDP) && (!d->n4 || !d->defect || !d->defect_lb))
+        return fail(VB_ERR_ARG, "pipeline: VDP needs n4, defect, defect_lb");
+    if ((flags & VB_DO_CI) && (!d->defect || !d->ci_shell)) return fail(VB_ERR_ARG, "pipeline: CI needs defect, ci_shell");
+    return VB_OK;
+}
+
 int vb_pipeline_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const int32_t* handles,
                           const vb_n4_params* params, float thresh, uint32_t flags, const vb_buffers* d, void* stream) {
     if (!c || !d || !d->mask || !d->stats) return fail(VB_ERR_ARG, "pipeline: null argument");
     vbrt::stream_t s = (vbrt::stream_t)stream;
     vbrt::set_device(c->device);
-    if ((flags & VB_DO_CI) && !handles) return fail(VB_ERR_ARG, "pipeline: CI needs table handles");
-    int rc = prepare(c, n, shapes, (flags & VB_DO_CI) ? handles : nullptr, s);
+    int rc = pipeline_check(flags, handles, params, d);
     if (rc) return rc;
-    if (!vbrt::dev_memset(d->stats, 0, sizeof(vb_subject_stats) * (size_t)n, s)) return VB_ERR_CUDA;
+    rc = prepare(c, n, shapes, (flags & VB_DO_CI) ? handles : nullptr, s);
+    if (rc) return rc;
     // stage boundaries: one event before the first stage and one after each stage
     vbrt::event_t* ev = nullptr;
     if (c->prof) {
@@ -471,32 +525,8 @@ int vb_pipeline_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const int
         }
         ev = c->ev.data() + c->ev_used;
         c->ev_used += VB_N_STAGES + 1;
-        if (!vbrt::event_record(ev[0], s)) return VB_ERR_CUDA;
     }
-    if (flags & VB_DO_SNR) {
-        if (!d->image) return fail(VB_ERR_ARG, "pipeline: SNR needs image");
-        if ((rc = run_snr(c, d->image, d->mask, n, 20, d->stats, s))) return rc;
-    }
-    if (ev && !vbrt::event_record(ev[1], s)) return VB_ERR_CUDA;
-    if (flags & VB_DO_N4) {
-        if (!d->image || !d->n4 || !params) return fail(VB_ERR_ARG, "pipeline: N4 needs image, n4, params");
-        if ((rc = run_n4(c, d->image, d->mask, n, params, d->n4, d->logbias, d->stats, s))) return rc;
-    }
-    if (ev && !vbrt::event_record(ev[2], s)) return VB_ERR_CUDA;
-    if (flags & VB_DO_VDP) {
-        if (!d->n4 || !d->defect || !d->defect_lb) return fail(VB_ERR_ARG, "pipeline: VDP needs n4, defect, defect_lb");
-        if ((rc = run_vdp(c, d->n4, d->mask, n, thresh, d->defect, d->defect_lb, d->defect_border, d->stats, s))) return rc;
-    }
-    if (ev && !vbrt::event_record(ev[3], s)) return VB_ERR_CUDA;
-    if ((flags & VB_DO_MASK_BORDER) && d->mask_border)
-        if ((rc = run_border(c, d->mask, n, d->mask_border, s))) return rc;
-    if (ev && !vbrt::event_record(ev[4], s)) return VB_ERR_CUDA;
-    if (flags & VB_DO_CI) {
-        if (!d->defect || !d->ci_shell) return fail(VB_ERR_ARG, "pipeline: CI needs defect, ci_shell");
-        if ((rc = run_ci(c, d->defect, n, d->ci_shell, d->stats, s))) return rc;
-    }
-    if (ev && !vbrt::event_record(ev[5], s)) return VB_ERR_CUDA;
-    return VB_OK;
+    return pipeline_range(c, 0, n, params, thresh, flags, d, s, ev);
 }
 
 int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const int32_t* handles,
@@ -512,23 +542,20 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
     memset(&d, 0, sizeof(d));
     if (!ensure(c->m_mask, V) || !ensure(c->m_stats, sizeof(vb_subject_stats) * (size_t)n)) return VB_ERR_CUDA;
     d.mask = (const uint8_t*)c->m_mask.p; d.stats = (vb_subject_stats*)c->m_stats.p;
-    if (!vbrt::h2d(c->m_mask.p, h->mask, V, s)) return VB_ERR_CUDA;
     if (h->image) {
-        if (!ensure(c->m_image, 4 * V) || !vbrt::h2d(c->m_image.p, h->image, 4 * V, s)) return VB_ERR_CUDA;
+        if (!ensure(c->m_image, 4 * V)) return VB_ERR_CUDA;
         d.image = (const float*)c->m_image.p;
     }
     if (need_n4) {
         if (!h->n4) return fail(VB_ERR_ARG, "pipeline_host: n4 buffer required");
         if (!ensure(c->m_n4, 4 * V)) return VB_ERR_CUDA;
         d.n4 = (float*)c->m_n4.p;
-        if (!(flags & VB_DO_N4) && !vbrt::h2d(c->m_n4.p, h->n4, 4 * V, s)) return VB_ERR_CUDA;
     }
     if (h->logbias && (flags & VB_DO_N4)) { if (!ensure(c->m_logbias, 4 * V)) return VB_ERR_CUDA; d.logbias = (float*)c->m_logbias.p; }
     if (need_def) {
         if (!h->defect) return fail(VB_ERR_ARG, "pipeline_host: defect buffer required");
         if (!ensure(c->m_defect, V)) return VB_ERR_CUDA;
         d.defect = (uint8_t*)c->m_defect.p;
-        if (!(flags & VB_DO_VDP) && !vbrt::h2d(c->m_defect.p, h->defect, V, s)) return VB_ERR_CUDA;
     }
     if (flags & VB_DO_VDP) {
         if (!h->defect_lb) return fail(VB_ERR_ARG, "pipeline_host: defect_lb buffer required");
@@ -542,19 +569,57 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
         if (!ensure(c->m_shell, 2 * V)) return VB_ERR_CUDA;
         d.ci_shell = (uint16_t*)c->m_shell.p;
     }
-    int rc = vb_pipeline_batch_dev(c, n, shapes, handles, params, thresh, flags, &d, (void*)s);
+    int rc = pipeline_check(flags, handles, params, &d);
     if (rc) return rc;
-    bool ok = true;
-    if (flags & VB_DO_N4) ok = ok && vbrt::d2h(h->n4, d.n4, 4 * V, s);
-    if (d.logbias) ok = ok && vbrt::d2h(h->logbias, d.logbias, 4 * V, s);
-    if (flags & VB_DO_VDP) {
-        ok = ok && vbrt::d2h(h->defect, d.defect, V, s) && vbrt::d2h(h->defect_lb, d.defect_lb, V, s);
-        if (d.defect_border) ok = ok && vbrt::d2h(h->defect_border, d.defect_border, V, s);
+    rc = prepare(c, n, shapes, (flags & VB_DO_CI) ? handles : nullptr, s);
+    if (rc) return rc;
+    // Chunks of about one wave of subjects: inputs of chunk k+1 go up and outputs of chunk k-1
+    // come down (two copy streams) while chunk k computes.
+    const int per = std::max(c->sms, 1);
+    const int nchunks = std::max(1, std::min(16, n / per));
+    while (c->ev_copy.size() < 2 * (size_t)nchunks) {
+        vbrt::event_t e;
+        if (!vbrt::event_create(&e)) return VB_ERR_CUDA;
+        c->ev_copy.push_back(e);
     }
-    if (d.mask_border) ok = ok && vbrt::d2h(h->mask_border, d.mask_border, V, s);
-    if (flags & VB_DO_CI) ok = ok && vbrt::d2h(h->ci_shell, d.ci_shell, 2 * V, s);
-    ok = ok && vbrt::d2h(h->stats, d.stats, sizeof(vb_subject_stats) * (size_t)n, s);
-    if (!ok || !vbrt::stream_sync(s)) return VB_ERR_CUDA;
+    // the (small) stats records go through pinned staging: a copy into pageable user memory would
+    // block the host until the chunk has finished and serialise the pipeline
+    const size_t stb = sizeof(vb_subject_stats) * (size_t)n;
+    if (c->h_stats.cap < stb) {
+        vbrt::host_free(c->h_stats.p);
+        c->h_stats.p = nullptr; c->h_stats.cap = 0;
+        if (!vbrt::host_malloc(&c->h_stats.p, stb * 2)) return VB_ERR_CUDA;
+        c->h_stats.cap = stb * 2;
+    }
+    bool ok = true;
+    for (int k = 0; k < nchunks && ok; ++k) {
+        const int r0 = (int)((long long)n * k / nchunks), r1 = (int)((long long)n * (k + 1) / nchunks);
+        const size_t v0 = (size_t)c->last_subj[(size_t)r0].off;
+        const size_t v1 = (size_t)c->last_subj[(size_t)(r1 - 1)].off + (size_t)c->last_subj[(size_t)(r1 - 1)].V;
+        const size_t nv = v1 - v0;
+        vbrt::stream_t si = c->stream_in;
+        ok = ok && vbrt::h2d((uint8_t*)c->m_mask.p + v0, h->mask + v0, nv, si);
+        if (h->image) ok = ok && vbrt::h2d((float*)c->m_image.p + v0, h->image + v0, 4 * nv, si);
+        if (need_n4 && !(flags & VB_DO_N4)) ok = ok && vbrt::h2d((float*)c->m_n4.p + v0, h->n4 + v0, 4 * nv, si);
+        if (need_def && !(flags & VB_DO_VDP)) ok = ok && vbrt::h2d((uint8_t*)c->m_defect.p + v0, h->defect + v0, nv, si);
+        ok = ok && vbrt::event_record(c->ev_copy[2 * (size_t)k], si) && vbrt::stream_wait(s, c->ev_copy[2 * (size_t)k]);
+        if (!ok) break;
+        rc = pipeline_range(c, r0, r1 - r0, params, thresh, flags, &d, s, nullptr);
+        if (rc) return rc;
+        vbrt::stream_t so = c->stream_out;
+        ok = ok && vbrt::event_record(c->ev_copy[2 * (size_t)k + 1], s) && vbrt::stream_wait(so, c->ev_copy[2 * (size_t)k + 1]);
+        if (flags & VB_DO_N4) ok = ok && vbrt::d2h(h->n4 + v0, d.n4 + v0, 4 * nv, so);
+        if (d.logbias) ok = ok && vbrt::d2h(h->logbias + v0, d.logbias + v0, 4 * nv, so);
+        if (flags & VB_DO_VDP) {
+            ok = ok && vbrt::d2h(h->defect + v0, d.defect + v0, nv, so) && vbrt::d2h(h->defect_lb + v0, d.defect_lb + v0, nv, so);
+            if (d.defect_border) ok = ok && vbrt::d2h(h->defect_border + v0, d.defect_border + v0, nv, so);
+        }
+        if (d.mask_border) ok = ok && vbrt::d2h(h->mask_border + v0, d.mask_border + v0, nv, so);
+        if (flags & VB_DO_CI) ok = ok && vbrt::d2h(h->ci_shell + v0, d.ci_shell + v0, 2 * nv, so);
+        ok = ok && vbrt::d2h((vb_subject_stats*)c->h_stats.p + r0, d.stats + r0, sizeof(vb_subject_stats) * (size_t)(r1 - r0), so);
+    }
+    if (!ok || !vbrt::stream_sync(c->stream_out) || !vbrt::stream_sync(s) || !vbrt::stream_sync(c->stream_in)) return VB_ERR_CUDA;
+    memcpy(h->stats, c->h_stats.p, stb);
     if (flags & VB_DO_CI)
         for (int i = 0; i < n; ++i)
             if (h->stats[i].ci_error) return fail(VB_ERR_CI_RMAX, "CI: maximum sphere radius reached (table exhausted)");
