@@ -61,8 +61,6 @@ struct N4Args {
     uint32_t* ws_wbase;      // [grid][wb_max]    compact offset of every (block, 32-row word) (+1)
     uint32_t* ws_acol;       // [grid][ncols_max] active (mask-carrying) columns, ascending
     float* ws_axis;          // [grid][axis_stride]  (4-byte words)
-    float* ws_e;             // [grid][Vmax]      exp(bias_old - bias_new) over the mask, C order
-    uint32_t* ws_perm;       // [grid][Vmax]      C-order rank -> compact index of the mask voxels
     float* ws_ec;            // [grid][2*Vmax]    convergence sequence in C order: pixel[M], then pixel/N [M]
     const float2* rcp;       // [Vmax + 1]        1/N = x + y as two floats, N = index (shared by all CTAs)
     int* work_counter;
@@ -194,8 +192,6 @@ struct N4Ctx {
     uint32_t* acol;       // [nact]
     int nact, nseg, wps;  // active columns; row segments per block; 32-row words per segment
     float* axis_base;
-    float* ebuf;          // [M] exp(old - new), compact order
-    uint32_t* perm;       // [M] C-order rank -> compact index
     float* ec;            // [M] pixel in C order, [M] pixel / N behind it (chain input)
     const float2* rcp;    // 1/N split in two floats
     // row-axis tables (shared memory when they fit, else inside axis_base)
@@ -411,6 +407,34 @@ VB_DEV N4Item n4_item(const N4Ctx& c, int it) {
         }                                                                                    \
     }
 
+// Same walk; BODY additionally sees `rank`, the C-order rank of this lane's voxel among the mask
+// voxels (row-major over the whole volume): the per-(row, block) bases of a 32-row word are
+// fetched once by the lanes and broadcast by shuffle.
+#define VB_N4_FOR_ROWS_RANK(c, I, ...)                                                       \
+    {                                                                                        \
+        unsigned pos_ = (I).pos;                                                             \
+        const unsigned lt_ = (1u << vb_lane()) - 1u;                                         \
+        for (int wi_ = (I).wi0; wi_ < (I).wi1; ++wi_) {                                      \
+            const uint32_t mw_ = (I).valid ? (c).colmask[(size_t)wi_ * (c).ncols + (I).q] : 0u; \
+            uint32_t rem_ = __reduce_or_sync(VB_FULL, mw_);                                  \
+            if (!rem_) continue;                                                             \
+            const int rr_ = wi_ * 32 + vb_lane();                                            \
+            const unsigned rbw_ = (rr_ < (c).n0) ? (c).rbb[(size_t)rr_ * (c).nblk + (I).blk] : 0u; \
+            while (rem_) {                                                                   \
+                const int b_ = __ffs((int)rem_) - 1;                                         \
+                rem_ &= rem_ - 1u;                                                           \
+                const int r = wi_ * 32 + b_;                                                 \
+                const bool bit = (mw_ >> b_) & 1u;                                           \
+                const unsigned bal = __ballot_sync(VB_FULL, bit);                            \
+                const unsigned below_ = (unsigned)__popc(bal & lt_);                         \
+                const unsigned idx = pos_ + below_;                                          \
+                const unsigned rank = __shfl_sync(VB_FULL, rbw_, b_) + below_;               \
+                __VA_ARGS__                                                                  \
+                pos_ += (unsigned)__popc(bal);                                               \
+            }                                                                                \
+        }                                                                                    \
+    }
+
 // ---------------------------------------------------------------------------------------------
 // setup: column bitmasks, compaction tables, compact log image, range and count of the mask
 VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float& bmin, float& bmax, int& M) {
@@ -511,7 +535,6 @@ VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float&
                         const float l = (x[j] > 0.0f) ? logf(x[j]) : x[j];
                         const unsigned below = (unsigned)__popc(bal & lt);
                         c.logI[pos + below] = l;
-                        c.perm[c.rbb[(size_t)(wi * 32 + b0 + j) * c.nblk + I.blk] + below] = pos + below;
                         tmin = fminf(tmin, l);
                         tmax = fmaxf(tmax, l);
                     }
@@ -1031,13 +1054,14 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
 // rounding of sigma and mean, still exceeds the threshold the level certainly continues and the
 // exact double-precision cv is returned instead (`exact_needed` forces the chain: last allowed
 // iteration of a level, debug capture).
-// Returns true when the sequential chain has to be run on c.ebuf; otherwise `conv` holds the
+// Returns true when the sequential chain has to be run on c.ec; otherwise `conv` holds the
 // (exact-arithmetic) value and the level certainly continues.
 VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool exact_needed, float& conv) {
     const int nt = (int)blockDim.x, w = vb_warp(), nw = nt >> 5;
     const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     float tmin = FLT_MAX, tmax = -FLT_MAX;
     double s1 = 0.0, s2 = 0.0;
+    const unsigned Mpad = (unsigned)((M + 3) & ~3);
     float* Gn = c.G ? c.un_f : nullptr;                  // table of the new lattice (union region is free here)
     if (Gn) n4_build_G(c, c.L, Gn);
     for (int it = w; it < c.nblk * c.nseg; it += nw) {
@@ -1049,7 +1073,7 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
         N4Win wo, wn;
         wo.cur = wn.cur = -1;
         wo.g0 = wo.g1 = wo.g2 = wo.g3 = wn.g0 = wn.g1 = wn.g2 = wn.g3 = 0.0f;
-        VB_N4_FOR_ROWS(c, I, {
+        VB_N4_FOR_ROWS_RANK(c, I, {
             const int base = c.r_bev[r];
             n4_win_advance(wo, c.Lold, c, col, base, Go, c.gstride);
             n4_win_advance(wn, c.L, c, col, base, Gw, c.gstride);
@@ -1060,7 +1084,8 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
                 tmin = fminf(tmin, un);
                 tmax = fmaxf(tmax, un);
                 const float ev = n4_exp_small(bo - bn);
-                c.ebuf[idx] = ev;
+                c.ec[rank] = ev;                                       // chain input, C order:
+                c.ec[Mpad + rank] = __fdiv_rn(ev, (float)(rank + 1)); // pixel and pixel / N (float division)
                 const double em = (double)ev - 1.0;
                 s1 += em; s2 += em * em;
             }
@@ -1084,13 +1109,6 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
         const double lower = (sqrt(var) - lag) / mean * 0.98;
         if (lower > (double)thr) { conv = (float)(sqrt(var) / mean); return false; }
     }
-    // chain input in C order: pixel and pixel / N (float division, as the reference does)
-    for (int j = (int)threadIdx.x; j < M; j += (int)blockDim.x) {
-        const float px = c.ebuf[c.perm[j]];
-        c.ec[j] = px;
-        c.ec[((M + 3) & ~3) + j] = __fdiv_rn(px, (float)(j + 1));
-    }
-    __syncthreads();
     return true;
 }
 
@@ -1236,8 +1254,6 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         c.wbase = a.ws_wbase + (size_t)blockIdx.x * a.wb_max;
         c.acol = a.ws_acol + (size_t)blockIdx.x * a.ncols_max;
         c.axis_base = a.ws_axis + (size_t)blockIdx.x * a.axis_stride;
-        c.ebuf = a.ws_e + (size_t)blockIdx.x * a.Vmax;
-        c.perm = a.ws_perm + (size_t)blockIdx.x * a.Vmax;
         c.ec = a.ws_ec + (size_t)blockIdx.x * 2 * (size_t)((a.Vmax + 3) & ~3LL);
         c.rcp = a.rcp;
         c.ncp[0] = a.p.ncp[0]; c.ncp[1] = a.p.ncp[1]; c.ncp[2] = a.p.ncp[2];
@@ -1285,7 +1301,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                 n4_contract<true>(c, full, bmin, bmax);
                 if (level > 0) n4_range(c, bmin, bmax);
                 conv = FLT_MAX;
-                // `pending`: c.ebuf holds iteration `it`'s exp(old - new) and the sequential
+                // `pending`: c.ec holds iteration `it`'s exp(old - new) and the sequential
                 // convergence chain has not been run on it yet.  Outside debug capture the chain
                 // runs on the chain team WHILE the phase team already computes histogram,
                 // sharpening and fit of iteration it + 1; the fit is only committed if the chain

@@ -35,6 +35,10 @@ inline bool dev_memset(void* d, int v, size_t n, stream_t s) { return ok(cudaMem
 inline bool stream_sync(stream_t s) { return ok(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
 inline bool device_sync() { return ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize"); }
 inline bool last_launch_ok(const char* what) { return ok(cudaGetLastError(), what); }
+// Copies from pageable host memory can leave a benign `invalid argument` in the runtime's
+// last-error slot although the call itself returned success; every API call is checked through
+// its own return code, so the slot is cleared before a launch and read right after it.
+inline void clear_stale_error() { cudaGetLastError(); }
 inline bool set_device(int d) { return ok(cudaSetDevice(d), "cudaSetDevice"); }
 inline int device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 inline int sm_count(int dev) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
@@ -68,6 +72,7 @@ inline bool dev_memset(void* d, int v, size_t n, stream_t) { memset(d, v, n); re
 inline bool stream_sync(stream_t) { return true; }
 inline bool device_sync() { return true; }
 inline bool last_launch_ok(const char*) { return true; }
+inline void clear_stale_error() {}
 inline bool set_device(int) { return true; }
 inline int device_count() { return 1; }
 inline int sm_count(int) { const char* e = getenv("VB_EMU_SMS"); return e ? atoi(e) : 2; }

@@ -160,6 +160,7 @@ int upload_tables(vb_ctx* c, vbrt::stream_t s) {
 // ------------------------------------------------------------------------------------- stages
 int run_snr(vb_ctx* c, const float* image, const uint8_t* mask, int n, int fov, vb_subject_stats* stats,
             vbrt::stream_t s) {
+    vbrt::clear_stale_error();
     for (const VbSubject& S : c->last_subj)
         if (S.n0 + S.n1 + S.n2 > VB_SNR_MAX_AXIS) return fail(VB_ERR_UNSUPPORTED, "SNR: n0+n1+n2 too large");
     const int grid = std::min(n, c->sms * 4);
@@ -171,6 +172,7 @@ int run_snr(vb_ctx* c, const float* image, const uint8_t* mask, int n, int fov, 
 
 int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n4_params* pp, float* out,
            float* logbias, vb_subject_stats* stats, vbrt::stream_t s) {
+    vbrt::clear_stale_error();
     vb_n4_params p = *pp;
     if (p.n_levels < 1 || p.n_levels > VB_MAX_LEVELS) return fail(VB_ERR_ARG, "N4: n_levels out of range");
     if (p.n_bins < 2) return fail(VB_ERR_ARG, "N4: n_bins < 2");
@@ -214,9 +216,8 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     const long long cap = ((long long)c->max_smem - ub - fixed - static_smem) / 4;
     const int grid = std::min(n, c->sms);
     if (!ensure(c->ws_logI, sizeof(float) * (size_t)grid * (size_t)vmax) ||
-        !ensure(c->ws_e, sizeof(float) * (size_t)grid * (size_t)vmax) ||
         !ensure(c->ws_colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(c->ws_rbb, 4 * (size_t)grid * (size_t)rbb) ||
-        !ensure(c->ws_wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(c->ws_acol, 4 * (size_t)grid * (size_t)ncmax) || !ensure(c->ws_perm, 4 * (size_t)grid * (size_t)vmax) || !ensure(c->ws_ec, 8 * (size_t)grid * (size_t)((vmax + 3) & ~3LL)) ||
+        !ensure(c->ws_wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(c->ws_acol, 4 * (size_t)grid * (size_t)ncmax) || !ensure(c->ws_ec, 8 * (size_t)grid * (size_t)((vmax + 3) & ~3LL)) ||
         !ensure(c->ws_rcp, 8 * ((size_t)vmax + 8)) ||
         !ensure(c->ws_axis, 4 * (size_t)grid * (size_t)axis) || !ensure(c->ws_counter, 64))
         return VB_ERR_CUDA;
@@ -236,8 +237,8 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     a.image = image; a.mask = mask; a.out = out; a.logbias = logbias;
     a.subj = subj_ptr(c); a.n = n; a.p = p; a.stats = stats;
     a.ws_logI = (float*)c->ws_logI.p; a.ws_colmask = (uint32_t*)c->ws_colmask.p; a.ws_rbb = (uint32_t*)c->ws_rbb.p;
-    a.ws_wbase = (uint32_t*)c->ws_wbase.p; a.ws_acol = (uint32_t*)c->ws_acol.p; a.ws_axis = (float*)c->ws_axis.p; a.ws_e = (float*)c->ws_e.p;
-    a.ws_perm = (uint32_t*)c->ws_perm.p; a.ws_ec = (float*)c->ws_ec.p; a.rcp = (const float2*)c->ws_rcp.p; a.rowtab_rows = (int)rowtab_rows;
+    a.ws_wbase = (uint32_t*)c->ws_wbase.p; a.ws_acol = (uint32_t*)c->ws_acol.p; a.ws_axis = (float*)c->ws_axis.p; 
+    a.ws_ec = (float*)c->ws_ec.p; a.rcp = (const float2*)c->ws_rcp.p; a.rowtab_rows = (int)rowtab_rows;
     { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] >= '1' && e[0] <= '9') ? e[0] - '0' : 0; }
     a.work_counter = (int*)c->ws_counter.p; a.debug = dbg;
     a.Vmax = vmax; a.cmw_max = cmw; a.rbb_max = rbb; a.wb_max = wb; a.ncols_max = ncmax;
@@ -258,6 +259,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
 }
 
 int run_border(vb_ctx* c, const uint8_t* a, int n, uint8_t* border, vbrt::stream_t s) {
+    vbrt::clear_stale_error();
     const int gx = grid_x_for(c, n, vmax_of(c), 256);
     VB_LAUNCH(border_kernel, dim3(gx, n), dim3(256), 0, s, a, subj_ptr(c), border);
     ++c->launches;
@@ -266,6 +268,7 @@ int run_border(vb_ctx* c, const uint8_t* a, int n, uint8_t* border, vbrt::stream
 
 int run_vdp(vb_ctx* c, const float* n4, const uint8_t* mask, int n, float thresh, uint8_t* defect, uint8_t* lb,
             uint8_t* dborder, vb_subject_stats* stats, vbrt::stream_t s) {
+    vbrt::clear_stale_error();
     if (!ensure(c->ws_d0, (size_t)c->v_total)) return VB_ERR_CUDA;
     const VbSubject* subj = subj_ptr(c);
     const int gx = grid_x_for(c, n, vmax_of(c), 256);
@@ -279,6 +282,7 @@ int run_vdp(vb_ctx* c, const float* n4, const uint8_t* mask, int n, float thresh
 }
 
 int run_ci(vb_ctx* c, const uint8_t* defect, int n, uint16_t* shell, vb_subject_stats* stats, vbrt::stream_t s) {
+    vbrt::clear_stale_error();
     int rc = upload_tables(c, s);
     if (rc) return rc;
     if (!ensure(c->ws_bits, 4 * (size_t)c->words_total) || !ensure(c->ws_list, 4 * (size_t)c->v_total) ||
