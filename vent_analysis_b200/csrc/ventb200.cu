@@ -41,7 +41,7 @@ struct vb_ctx {
     Buf h_desc, h_stats, d_subj, d_wordoff;   // h_*: pinned host staging
     long long v_total = 0, words_total = 0, rcp_n = -1;
     // workspaces
-    Buf ws_logI, ws_e, ws_colmask, ws_rbb, ws_wbase, ws_acol, ws_perm, ws_ec, ws_rcp, ws_axis, ws_counter, ws_d0, ws_bits, ws_list, ws_count, dbg;
+    Buf ws_logI, ws_e, ws_colmask, ws_rbb, ws_wbase, ws_acol, ws_order, ws_perm, ws_ec, ws_rcp, ws_axis, ws_counter, ws_d0, ws_bits, ws_list, ws_count, dbg;
     int dbg_stride = 0, dbg_nbins = 0, dbg_Lmax = 0, dbg_n = 0;
     // CI tables
     std::vector<TableHost> tables;
@@ -217,7 +217,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     const int grid = std::min(n, c->sms);
     if (!ensure(c->ws_logI, sizeof(float) * (size_t)grid * (size_t)vmax) ||
         !ensure(c->ws_colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(c->ws_rbb, 4 * (size_t)grid * (size_t)rbb) ||
-        !ensure(c->ws_wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(c->ws_acol, 4 * (size_t)grid * (size_t)ncmax) || !ensure(c->ws_ec, 8 * (size_t)grid * (size_t)((vmax + 3) & ~3LL)) ||
+        !ensure(c->ws_wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(c->ws_acol, 4 * (size_t)grid * (size_t)ncmax) || !ensure(c->ws_order, 4 * (size_t)grid * (size_t)wb) || !ensure(c->ws_ec, 8 * (size_t)grid * (size_t)((vmax + 3) & ~3LL)) ||
         !ensure(c->ws_rcp, 8 * ((size_t)vmax + 8)) ||
         !ensure(c->ws_axis, 4 * (size_t)grid * (size_t)axis) || !ensure(c->ws_counter, 64))
         return VB_ERR_CUDA;
@@ -237,7 +237,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     a.image = image; a.mask = mask; a.out = out; a.logbias = logbias;
     a.subj = subj_ptr(c); a.n = n; a.p = p; a.stats = stats;
     a.ws_logI = (float*)c->ws_logI.p; a.ws_colmask = (uint32_t*)c->ws_colmask.p; a.ws_rbb = (uint32_t*)c->ws_rbb.p;
-    a.ws_wbase = (uint32_t*)c->ws_wbase.p; a.ws_acol = (uint32_t*)c->ws_acol.p; a.ws_axis = (float*)c->ws_axis.p; 
+    a.ws_wbase = (uint32_t*)c->ws_wbase.p; a.ws_acol = (uint32_t*)c->ws_acol.p; a.ws_order = (uint32_t*)c->ws_order.p; a.ws_axis = (float*)c->ws_axis.p; 
     a.ws_ec = (float*)c->ws_ec.p; a.rcp = (const float2*)c->ws_rcp.p; a.rowtab_rows = (int)rowtab_rows;
     { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] >= '1' && e[0] <= '9') ? e[0] - '0' : 0; }
     a.work_counter = (int*)c->ws_counter.p; a.debug = dbg;
@@ -348,7 +348,7 @@ void vb_destroy(vb_ctx* c) {
     if (!c) return;
     vbrt::set_device(c->device);
     vbrt::stream_sync(c->stream);
-    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_logI, &c->ws_e, &c->ws_rbb, &c->ws_wbase, &c->ws_acol, &c->ws_perm, &c->ws_ec, &c->ws_rcp, &c->ws_colmask, &c->ws_axis, &c->ws_counter, &c->ws_d0,
+    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_logI, &c->ws_e, &c->ws_rbb, &c->ws_wbase, &c->ws_acol, &c->ws_order, &c->ws_perm, &c->ws_ec, &c->ws_rcp, &c->ws_colmask, &c->ws_axis, &c->ws_counter, &c->ws_d0,
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
                    &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats};
     for (Buf* b : bufs) vbrt::dev_free(b->p);
