@@ -18,5 +18,6 @@ def emu_context():
     if _ctx is None:
         import build_emu
         from vent_analysis_b200 import _lib
-        _ctx = _lib.Context(0, lib=_lib.bind(build_emu.build()))
+        so = os.environ.get("VB_EMU_LIB") or build_emu.build()     # VB_EMU_LIB: e.g. an -fsanitize=address build
+        _ctx = _lib.Context(0, lib=_lib.bind(so))
     return _ctx

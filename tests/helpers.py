@@ -98,3 +98,49 @@ def check_n4(ctx, img, mask, max_iter=(50, 50, 50, 50), require_same_iters=True)
     assert relo.max() < N4_BIAS_RTOL, relo.max()
     assert int(st["n4_n_mask"]) == int((mask == 1).sum())
     return out, ref, float(rel.max())
+
+
+def check_edge_cases(ctx):
+    """Degenerate and ragged inputs through the whole path in ONE batch (odd voxel offsets, a
+    single-slice volume, an empty mask, a one-voxel mask, a mask with a foreign label):
+    N4 within tolerance of the restatement, everything downstream bit-exact given our N4."""
+    rng = np.random.default_rng(3)
+    cases = []
+    img, mask = phantom((33, 29, 5), [1.5, 1.5, 10.0], 41)          # odd sizes -> unaligned offsets behind it
+    cases.append((img, mask))
+    img, mask = phantom((36, 40, 1), [2.0, 2.0, 11.5], 42)          # single slice
+    cases.append((img, mask))
+    img = (100 + 10 * rng.standard_normal((21, 23, 3))).astype(np.float32)
+    cases.append((img, np.zeros((21, 23, 3), np.uint8)))            # empty mask: N4 is the identity
+    one = np.zeros((21, 23, 3), np.uint8); one[10, 11, 1] = 1
+    cases.append((img, one))                                         # one mask voxel: no fit possible
+    img, mask = phantom((40, 36, 6), [1.5, 1.5, 10.0], 43)
+    m2 = mask.copy(); m2[:6] = np.where(m2[:6] > 0, 2, 0)            # label 2 is outside N4's mask (MaskLabel = 1)
+    cases.append((img, m2))
+    shapes = [c[0].shape for c in cases]
+    p = ctx.default_n4_params(max_iter=(6, 4))
+    out = ctx.pipeline_host(shapes, _lib.DO_N4, image=np.concatenate([c[0].ravel() for c in cases]),
+                            mask=np.concatenate([c[1].ravel() for c in cases]), params=p, want_logbias=True)
+    off = 0
+    for (img, mask), shape in zip(cases, shapes):
+        V = img.size
+        n4 = out["n4"][off:off + V].reshape(shape)
+        ref = n4_oracle.n4(img, mask, max_iter=(6, 4))
+        if (mask == 1).sum() < 2:
+            assert np.array_equal(n4, img)                           # zero lattice: out = in / exp(0)
+        else:
+            lb = out["logbias"][off:off + V].reshape(shape).astype(np.float64)
+            assert np.abs(np.expm1(lb - ref["logbias"])).max() < N4_BIAS_RTOL
+        off += V
+    # VDP / borders on the first two cases (non-empty 0/1 masks), given our N4
+    off = 0
+    for (img, mask), shape in list(zip(cases, shapes))[:2]:
+        V = img.size
+        n4 = out["n4"][off:off + V].reshape(shape)
+        o = ctx.pipeline_host([shape], _lib.DO_VDP | _lib.DO_MASK_BORDER, mask=mask, n4=n4)
+        r = vdp_oracle.vdp(n4, mask.astype(np.float64), [1.5, 1.5, 10.0])
+        assert np.array_equal(o["defect"].reshape(shape), r["defectArray"])
+        assert np.array_equal(o["defect_lb"].reshape(shape), r["defectArrayLB"])
+        assert np.array_equal(o["defect_border"].reshape(shape).astype(bool), r["defectBorder"])
+        assert np.array_equal(o["mask_border"].reshape(shape), vdp_oracle.border(mask))
+        off += V

@@ -80,6 +80,10 @@ def test_n4_ragged_batch_and_label_semantics(ctx):
     assert list(out["stats"]["n4_iters"][0][:2]) == [4, 3]
 
 
+def test_edge_cases_ragged_degenerate_inputs(ctx):
+    helpers.check_edge_cases(ctx)
+
+
 def test_class_surface_end_to_end(ctx, monkeypatch):
     """The Vent_Analysis mirror (constructor, calculate_VDP, calculate_CI, metadata, dtypes)
     against the reference's outputs -- N4 here is OUR kernel, so VDP is held to the

@@ -96,6 +96,10 @@ def test_ci_c3_isotropic_large_table(ctx):
     assert ctx.ci_radii(h)[int(stats["ci_t95"][0])] * min(vox) == vdp_oracle.ci_percentile(ci_ref, r["defectArray"])
 
 
+def test_edge_cases_ragged_degenerate_inputs(ctx):
+    helpers.check_edge_cases(ctx)
+
+
 def test_class_surface_end_to_end_c2():
     from vent_analysis_b200 import CI, Vent_Analysis
     g, shape, vox, img, mask, n4 = helpers.golden_inputs("C2")

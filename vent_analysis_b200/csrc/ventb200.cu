@@ -108,7 +108,6 @@ int prepare(vb_ctx* c, int n, const int32_t* shapes, const int32_t* handles, vbr
     const size_t sb = subj.size() * sizeof(VbSubject), wb = woff.size() * sizeof(long long);
     if (c->h_desc.cap < sb + wb) {
         vbrt::host_free(c->h_desc.p);
-    vbrt::host_free(c->h_stats.p);
         c->h_desc.p = nullptr; c->h_desc.cap = 0;
         if (!vbrt::host_malloc(&c->h_desc.p, (sb + wb) * 2)) return VB_ERR_CUDA;
         c->h_desc.cap = (sb + wb) * 2;
