@@ -66,7 +66,8 @@ snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, cons
                 for (int e = 0; e < 4; ++e)
                     if (m.v[e]) {
                         const int vv = v + e, i = vv / ncols, rem = vv - i * ncols, j = rem / n2, k = rem - j * n2;
-                        rowf[i] = 1; colf[j] = 1; slcf[k] = 1;
+                        // (atomics only so that concurrent same-value writes are not a data race)
+                        atomicOr((unsigned*)&rowf[i], 1u); atomicOr((unsigned*)&colf[j], 1u); atomicOr((unsigned*)&slcf[k], 1u);
                     }
             }
         }
