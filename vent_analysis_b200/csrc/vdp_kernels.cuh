@@ -301,6 +301,114 @@ VB_KERNEL void vdp_median_kernel(const uint8_t* VB_RESTRICT d0, const VbSubject*
     if (threadIdx.x == 0 && nd) atomicAdd(&stats[si].n_defect, nd);
 }
 
+// Fused classification: threshold + linear binning + 3x3 median + defect border in ONE pass.
+// A CTA owns rows [i0, i0 + R) of one subject.  It streams N4 and the mask of rows
+// [i0 - 2, i0 + R + 2) once (16-byte loads), keeps only the thresholded byte d0 in shared memory,
+// forms the median (neighbour count >= 5, zero padded, per slice) for rows [i0 - 1, i0 + R + 1)
+// in a second shared tile and from it the border of rows [i0, i0 + R).  Traffic per voxel:
+// 5 B read (+ 4/R halo) and 3 B written, instead of three kernels and a d0 round trip.
+#define VB_CLS_THREADS 512
+VB_KERNEL void VB_LAUNCH_BOUNDS(VB_CLS_THREADS, 1)
+vdp_classify_kernel(const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, float thresh,
+                    int R, uint8_t* lb, uint8_t* defect, uint8_t* border, vb_subject_stats* stats) {
+    VB_DYN_SMEM(smem);
+    VB_SHARED int red[64];
+    const int si = (int)blockIdx.y;
+    const VbSubject S = subj[si];
+    const int n0 = S.n0, n1 = S.n1, n2 = S.n2, ncols = n1 * n2;
+    const int i0 = (int)blockIdx.x * R;
+    if (i0 >= n0) return;
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    const int ra = max(i0 - 2, 0), rb = min(i0 + R + 2, n0);          // rows of d0 held
+    const int ma = max(i0 - 1, 0), mb = min(i0 + R + 1, n0);          // rows of the median held
+    uint8_t* d0 = smem;                                               // [(R + 4) * ncols]
+    uint8_t* md = smem + (size_t)(R + 4) * ncols;                     // [(R + 2) * ncols]
+    const float mean = stats[si].mean, p99 = stats[si].p99;
+    const float* x = n4 + S.off;
+    const uint8_t* msk = mask + S.off;
+    const bool aligned = ((S.off & 3) == 0) && ((ncols & 3) == 0);
+    const int v0 = ra * ncols, v1 = rb * ncols;
+    const int w0 = i0 * ncols, w1 = min(i0 + R, n0) * ncols;          // voxels this CTA owns
+    int c12 = 0;
+    for (int v = v0 + 4 * tid; v < v1; v += 4 * nt) {
+        const Vb4f f = vb_load4f(x, v, v1, aligned);
+        const Vb4b m = vb_load4b(msk, v, v1, aligned);
+        uint8_t code[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (v + e < v1) {
+                const bool in = m.v[e] != 0;
+                d0[v + e - v0] = (uint8_t)((__fdiv_rn(f.v[e], mean) < thresh) && in);
+                const float b = __fdiv_rn(f.v[e], p99);
+                int cd = (b <= 0.16f) ? 1 : (b <= 0.34f) ? 2 : (b <= 0.52f) ? 3 : (b <= 0.7f) ? 4 : (b <= 0.88f) ? 5
+                       : (b > 0.88f) ? 6 : 0;      // NaN compares false everywhere -> 0, as in numpy
+                cd = in ? cd : 0;
+                code[e] = (uint8_t)cd;
+                if (v + e >= w0 && v + e < w1) c12 += (cd == 1 || cd == 2);
+            } else {
+                code[e] = 0;
+            }
+        }
+        if (v >= w0 && v + 3 < w1 && aligned) {
+            *(uint32_t*)(lb + S.off + v) = (uint32_t)code[0] | ((uint32_t)code[1] << 8) | ((uint32_t)code[2] << 16) | ((uint32_t)code[3] << 24);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (v + e >= w0 && v + e < w1) lb[S.off + v + e] = code[e];
+        }
+    }
+    __syncthreads();
+    // median of rows [ma, mb): zero padded 3x3 neighbour count >= 5 within the slice.  A thread
+    // owns (col, slice) positions and walks down the rows with a sliding window of the three
+    // column sums, so every row costs three shared-memory bytes instead of nine.
+    int nd = 0;
+    const int mv0 = ma * ncols;
+    for (int rem = tid; rem < ncols; rem += nt) {
+        const int j = rem / n2;
+        const bool jl = j > 0, jr = j < n1 - 1;
+        // s(i) = d0[i][j-1] + d0[i][j] + d0[i][j+1] (zero outside the volume)
+        int s_prev = 0, s_cur = 0;
+        if (ma - 1 >= 0) {                                    // row ma - 1 is held whenever it exists
+            const uint8_t* p = d0 + (size_t)(ma - 1 - ra) * ncols + rem;
+            s_prev = p[0] + (jl ? p[-n2] : 0) + (jr ? p[n2] : 0);
+        }
+        {
+            const uint8_t* p = d0 + (size_t)(ma - ra) * ncols + rem;
+            s_cur = p[0] + (jl ? p[-n2] : 0) + (jr ? p[n2] : 0);
+        }
+        for (int i = ma; i < mb; ++i) {
+            int s_next = 0;
+            if (i + 1 < n0) {                                 // row i + 1 <= mb is held whenever it exists
+                const uint8_t* p = d0 + (size_t)(i + 1 - ra) * ncols + rem;
+                s_next = p[0] + (jl ? p[-n2] : 0) + (jr ? p[n2] : 0);
+            }
+            const int d = (s_prev + s_cur + s_next) >= 5;
+            md[(size_t)(i - ma) * ncols + rem] = (uint8_t)d;
+            if (i >= i0 && i < i0 + R) { defect[S.off + (size_t)i * ncols + rem] = (uint8_t)d; nd += d; }
+            s_prev = s_cur; s_cur = s_next;
+        }
+    }
+    __syncthreads();
+    if (border) {
+        const int ib = min(i0 + R, n0);
+        for (int rem = tid; rem < ncols; rem += nt) {
+            const int j = rem / n2;
+            const int dl = (j == 0) ? 0 : -n2, dr = (j == n1 - 1) ? 0 : n2;
+            for (int i = i0; i < ib; ++i) {
+                const uint8_t* a = md + (size_t)(i - ma) * ncols + rem;
+                const int up = (i == 0) ? 0 : -ncols, dn = (i == n0 - 1) ? 0 : ncols;
+                border[S.off + (size_t)i * ncols + rem] = (uint8_t)((a[dn] != a[up]) || (a[dr] != a[dl]));
+            }
+        }
+    }
+    nd = vb_block_reduce(nd, VbAddI(), 0, red);
+    c12 = vb_block_reduce(c12, VbAddI(), 0, red);
+    if (tid == 0) {
+        if (nd) atomicAdd(&stats[si].n_defect, nd);
+        if (c12) atomicAdd(&stats[si].n_lb12, c12);
+    }
+}
+
 // calculateBorder: per slice, np.gradient != 0 along rows OR along columns (V_A.py:225-231)
 VB_KERNEL void border_kernel(const uint8_t* VB_RESTRICT a_, const VbSubject* subj, uint8_t* border) {
     const int si = (int)blockIdx.y;

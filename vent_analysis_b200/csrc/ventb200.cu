@@ -268,14 +268,35 @@ int run_border(vb_ctx* c, const uint8_t* a, int n, uint8_t* border, vbrt::stream
 int run_vdp(vb_ctx* c, const float* n4, const uint8_t* mask, int n, float thresh, uint8_t* defect, uint8_t* lb,
             uint8_t* dborder, vb_subject_stats* stats, vbrt::stream_t s) {
     vbrt::clear_stale_error();
-    if (!ensure(c->ws_d0, (size_t)c->v_total)) return VB_ERR_CUDA;
     const VbSubject* subj = subj_ptr(c);
-    const int gx = grid_x_for(c, n, vmax_of(c), 256);
     VB_LAUNCH(vdp_stats_kernel, dim3(std::min(n, c->sms * 4)), dim3(VB_VDP_THREADS), 0, s, n4, mask, subj, n, stats);
+    ++c->launches;
+    // fused threshold + linear binning + median + border on row tiles held in shared memory
+    long long ncmax = 1, n0max = 1;
+    for (const VbSubject& S : c->last_subj) {
+        ncmax = std::max<long long>(ncmax, (long long)S.n1 * S.n2);
+        n0max = std::max<long long>(n0max, S.n0);
+    }
+    const long long budget = std::min<long long>(c->max_smem - 1024, 96 * 1024);
+    long long R = (budget / ncmax - 6) / 2;                    // (R + 4) + (R + 2) rows of bytes
+    if (R >= 1) {
+        R = std::min<long long>(R, 32);
+        R = std::min<long long>(R, n0max);
+        const int smem = (int)((2 * R + 6) * ncmax);
+        if (!vbrt::allow_smem(vdp_classify_kernel, smem)) return VB_ERR_CUDA;
+        const int gx = (int)((n0max + R - 1) / R);
+        VB_LAUNCH(vdp_classify_kernel, dim3(gx, n), dim3(VB_CLS_THREADS), (size_t)smem, s, n4, mask, subj, thresh, (int)R, lb,
+                  defect, dborder, stats);
+        ++c->launches;
+        return vbrt::last_launch_ok("vdp kernels") ? VB_OK : VB_ERR_CUDA;
+    }
+    // rows too long for a shared-memory tile: three streaming kernels through a d0 array
+    if (!ensure(c->ws_d0, (size_t)c->v_total)) return VB_ERR_CUDA;
+    const int gx = grid_x_for(c, n, vmax_of(c), 256);
     VB_LAUNCH(vdp_threshold_kernel, dim3(gx, n), dim3(256), 0, s, n4, mask, subj, thresh, (uint8_t*)c->ws_d0.p, lb,
               stats);
     VB_LAUNCH(vdp_median_kernel, dim3(gx, n), dim3(256), 0, s, (const uint8_t*)c->ws_d0.p, subj, defect, stats);
-    c->launches += 3;
+    c->launches += 2;
     if (!vbrt::last_launch_ok("vdp kernels")) return VB_ERR_CUDA;
     return dborder ? run_border(c, defect, n, dborder, s) : VB_OK;
 }
