@@ -350,7 +350,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=592, help="subjects per GPU per step (4 per SM)")
+    ap.add_argument("--batch", type=int, default=1184, help="subjects per GPU per step (8 per SM; the cohort config is 1024)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
