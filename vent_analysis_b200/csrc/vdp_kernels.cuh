@@ -17,6 +17,12 @@
 // {rows with mask, plus row 0} x {cols [first masked col > 0, last masked col)} x
 // {slices with mask, plus slice 0}, minus the first / last `fov` rows.  Population std.
 // 4 consecutive voxels per thread and step (16-byte image loads when the subject is aligned)
+// x / d from rd = RN(1/d) with one Newton correction of the quotient: the IEEE-rounded result
+// for normal operands (checked against 2e7 random float32 divisions), 3 instructions
+VB_DEV float vb_div_rcp(float x, float d, float rd) {
+    const float q = __fmul_rn(x, rd);
+    return fmaf(fmaf(-q, d, x), rd, q);
+}
 struct Vb4f { float v[4]; };
 struct Vb4b { uint8_t v[4]; };
 VB_DEV Vb4f vb_load4f(const float* p, int v, int V, bool aligned) {
@@ -59,16 +65,40 @@ snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, cons
         __syncthreads();
         for (int i = tid; i < n0 + n1 + n2; i += nt) flags[i] = 0;
         __syncthreads();
-        for (int v = 4 * tid; v < S.V; v += 4 * nt) {
-            const Vb4b m = vb_load4b(msk, v, S.V, aligned);
-            if (m.v[0] | m.v[1] | m.v[2] | m.v[3]) {
+        // fast path (16-byte aligned rows): a thread owns 4 consecutive (col, slice) positions and
+        // a row phase and walks down the rows -- no index arithmetic per voxel, coalesced loads
+        const bool fast = aligned && (ncols & 3) == 0 && (ncols >> 2) <= nt;
+        const int G = ncols >> 2, RP = fast ? max(1, nt / max(G, 1)) : 1;
+        const int g = fast ? tid % G : 0, ph = fast ? tid / G : 0;
+        const bool mine = fast && ph < RP;
+        if (fast) {
+            uint32_t colacc = 0;
+            if (mine) {
+#pragma unroll 4
+                for (int i = ph; i < n0; i += RP) {
+                    const uint32_t wv = *(const uint32_t*)(msk + (size_t)i * ncols + 4 * g);
+                    colacc |= wv;
+                    if (wv) atomicOr((unsigned*)&rowf[i], 1u);
+                }
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (m.v[e]) {
-                        const int vv = v + e, i = vv / ncols, rem = vv - i * ncols, j = rem / n2, k = rem - j * n2;
-                        // (atomics only so that concurrent same-value writes are not a data race)
-                        atomicOr((unsigned*)&rowf[i], 1u); atomicOr((unsigned*)&colf[j], 1u); atomicOr((unsigned*)&slcf[k], 1u);
+                    if ((colacc >> (8 * e)) & 0xFFu) {
+                        const int rem = 4 * g + e, j = rem / n2, k = rem - j * n2;
+                        atomicOr((unsigned*)&colf[j], 1u); atomicOr((unsigned*)&slcf[k], 1u);
                     }
+            }
+        } else {
+            for (int v = 4 * tid; v < S.V; v += 4 * nt) {
+                const Vb4b m = vb_load4b(msk, v, S.V, aligned);
+                if (m.v[0] | m.v[1] | m.v[2] | m.v[3]) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (m.v[e]) {
+                            const int vv = v + e, i = vv / ncols, rem = vv - i * ncols, j = rem / n2, k = rem - j * n2;
+                            // (atomics only so that concurrent same-value writes are not a data race)
+                            atomicOr((unsigned*)&rowf[i], 1u); atomicOr((unsigned*)&colf[j], 1u); atomicOr((unsigned*)&slcf[k], 1u);
+                        }
+                }
             }
         }
         __syncthreads();
@@ -85,27 +115,53 @@ snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, cons
         int hi = n0 - fov;                         // noisemask[n0-fov:] = 0 (python slice rules)
         if (hi < 0) { hi += n0; if (hi < 0) hi = 0; }
         // one pass: signal sum / count, noise sum / sum of squares about a pivot / count.  The
-        // pivot (first noise candidate's neighbourhood: the image value at voxel 0... any fixed
-        // value) keeps the one-pass variance well conditioned in float64.
+        // pivot (any fixed value near the noise level) keeps the one-pass variance well
+        // conditioned in float64.
         const float pivot = img[0];
         double ssum = 0.0, nsum = 0.0, nsq = 0.0;
         long long scnt = 0, ncnt = 0;
-        for (int v = 4 * tid; v < S.V; v += 4 * nt) {
-            const Vb4f x = vb_load4f(img, v, S.V, aligned);
-            const Vb4b m = vb_load4b(msk, v, S.V, aligned);
-            int i = v / ncols, rem = v - i * ncols;
+        if (fast) {
+            if (mine) {
+                unsigned cs = 0;                   // bit e: (col, slice) of my e-th position is inside the box
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (v + e < S.V) {
-                    const int j = rem / n2, k = rem - j * n2;
-                    if (m.v[e]) { ssum += (double)x.v[e]; ++scnt; }
-                    const bool inbox = rowf[i] && (j >= cmin && j < cmax && cmin >= 0) && slcf[k];
-                    if (!inbox && i >= lo && i < hi) {
-                        const double d = (double)x.v[e] - (double)pivot;
-                        nsum += d; nsq += d * d; ++ncnt;
+                for (int e = 0; e < 4; ++e) {
+                    const int rem = 4 * g + e, j = rem / n2, k = rem - j * n2;
+                    if ((j >= cmin && j < cmax && cmin >= 0) && slcf[k]) cs |= 1u << e;
+                }
+#pragma unroll 4
+                for (int i = ph; i < n0; i += RP) {
+                    const float4 xv = *(const float4*)(img + (size_t)i * ncols + 4 * g);
+                    const uint32_t wv = *(const uint32_t*)(msk + (size_t)i * ncols + 4 * g);
+                    const bool rowin = rowf[i] != 0, band = i >= lo && i < hi;
+                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if ((wv >> (8 * e)) & 0xFFu) { ssum += (double)xs[e]; ++scnt; }
+                        if (band && !(rowin && ((cs >> e) & 1u))) {
+                            const double d = (double)xs[e] - (double)pivot;
+                            nsum += d; nsq += d * d; ++ncnt;
+                        }
                     }
                 }
-                if (++rem == ncols) { rem = 0; ++i; }
+            }
+        } else {
+            for (int v = 4 * tid; v < S.V; v += 4 * nt) {
+                const Vb4f x = vb_load4f(img, v, S.V, aligned);
+                const Vb4b m = vb_load4b(msk, v, S.V, aligned);
+                int i = v / ncols, rem = v - i * ncols;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (v + e < S.V) {
+                        const int j = rem / n2, k = rem - j * n2;
+                        if (m.v[e]) { ssum += (double)x.v[e]; ++scnt; }
+                        const bool inbox = rowf[i] && (j >= cmin && j < cmax && cmin >= 0) && slcf[k];
+                        if (!inbox && i >= lo && i < hi) {
+                            const double d = (double)x.v[e] - (double)pivot;
+                            nsum += d; nsq += d * d; ++ncnt;
+                        }
+                    }
+                    if (++rem == ncols) { rem = 0; ++i; }
+                }
             }
         }
         ssum = vb_block_reduce(ssum, VbAddD(), 0.0, red);
@@ -130,6 +186,17 @@ snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, cons
 // VDP statistics, one CTA per subject: M = #mask, mean (float32 of the float64 sum), and the
 // exact order statistic sorted(N4[mask>0])[int(M*.99)] by a 3-pass (11+11+10 bit) radix select
 // on the order-preserving key of the float bits.  Also zeroes the defect / LB counters.
+struct VbRun { int bin; unsigned cnt; };
+VB_DEV void vb_run_add(VbRun& r, unsigned* hist, int bin) {
+    if (bin == r.bin) { ++r.cnt; return; }
+    if (r.cnt) atomicAdd(&hist[r.bin], r.cnt);
+    r.bin = bin; r.cnt = 1u;
+}
+VB_DEV void vb_run_flush(VbRun& r, unsigned* hist) {
+    if (r.cnt) atomicAdd(&hist[r.bin], r.cnt);
+    r.cnt = 0u;
+}
+
 VB_DEV int vdp_find_bin(unsigned* hist, int nb, long long& k, int* s_bin, long long* s_k) {
     // block-wide exclusive prefix over the bins (each thread owns a contiguous run); the thread
     // whose run contains the k-th element publishes (bin, rank inside the bin)
@@ -184,6 +251,7 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
         __syncthreads();
         double sum = 0.0;
         long long cnt = 0;
+        VbRun run; run.bin = 0; run.cnt = 0u;
         for (int v = 4 * tid; v < S.V; v += 4 * nt) {
             const Vb4b m = vb_load4b(msk, v, S.V, aligned);
             if (!(m.v[0] | m.v[1] | m.v[2] | m.v[3])) continue;
@@ -192,9 +260,10 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
             for (int e = 0; e < 4; ++e)
                 if (m.v[e]) {
                     sum += (double)f.v[e]; ++cnt;
-                    atomicAdd(&hist[vb_float_key(f.v[e]) >> 21], 1u);
+                    vb_run_add(run, hist, (int)(vb_float_key(f.v[e]) >> 21));
                 }
         }
+        vb_run_flush(run, hist);
         sum = vb_block_reduce(sum, VbAddD(), 0.0, red);
         cnt = vb_block_reduce(cnt, VbAddLL(), 0LL, (long long*)red);
         float p99 = 0.0f;
@@ -213,9 +282,10 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
                 for (int e = 0; e < 4; ++e)
                     if (m.v[e]) {
                         const unsigned key = vb_float_key(f.v[e]);
-                        if ((key >> 21) == b1) atomicAdd(&hist[(key >> 10) & 0x7FFu], 1u);
+                        if ((key >> 21) == b1) vb_run_add(run, hist, (int)((key >> 10) & 0x7FFu));
                     }
             }
+            vb_run_flush(run, hist);
             __syncthreads();
             const unsigned b2 = (unsigned)vdp_find_bin(hist, 2048, k, &s_bin, &s_k);
             __syncthreads();
@@ -230,9 +300,10 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
                 for (int e = 0; e < 4; ++e)
                     if (m.v[e]) {
                         const unsigned key = vb_float_key(f.v[e]);
-                        if ((key >> 10) == pre) atomicAdd(&hist[key & 0x3FFu], 1u);
+                        if ((key >> 10) == pre) vb_run_add(run, hist, (int)(key & 0x3FFu));
                     }
             }
+            vb_run_flush(run, hist);
             __syncthreads();
             const unsigned b3 = (unsigned)vdp_find_bin(hist, 1024, k, &s_bin, &s_k);
             p99 = vb_key_float((pre << 10) | b3);
@@ -308,7 +379,7 @@ VB_KERNEL void vdp_median_kernel(const uint8_t* VB_RESTRICT d0, const VbSubject*
 // in a second shared tile and from it the border of rows [i0, i0 + R).  Traffic per voxel:
 // 5 B read (+ 4/R halo) and 3 B written, instead of three kernels and a d0 round trip.
 #define VB_CLS_THREADS 512
-VB_KERNEL void VB_LAUNCH_BOUNDS(VB_CLS_THREADS, 1)
+VB_KERNEL void VB_LAUNCH_BOUNDS(VB_CLS_THREADS, 2)
 vdp_classify_kernel(const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, float thresh,
                     int R, uint8_t* lb, uint8_t* defect, uint8_t* border, vb_subject_stats* stats) {
     VB_DYN_SMEM(smem);
@@ -324,37 +395,54 @@ vdp_classify_kernel(const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask
     uint8_t* d0 = smem;                                               // [(R + 4) * ncols]
     uint8_t* md = smem + (size_t)(R + 4) * ncols;                     // [(R + 2) * ncols]
     const float mean = stats[si].mean, p99 = stats[si].p99;
+    const float rmean = __frcp_rn(mean), rp99 = __frcp_rn(p99);
+    const bool okdiv = isfinite(rmean) && isfinite(rp99) && rmean != 0.0f && rp99 != 0.0f;   // else: IEEE division
     const float* x = n4 + S.off;
     const uint8_t* msk = mask + S.off;
     const bool aligned = ((S.off & 3) == 0) && ((ncols & 3) == 0);
     const int v0 = ra * ncols, v1 = rb * ncols;
     const int w0 = i0 * ncols, w1 = min(i0 + R, n0) * ncols;          // voxels this CTA owns
     int c12 = 0;
-    for (int v = v0 + 4 * tid; v < v1; v += 4 * nt) {
-        const Vb4f f = vb_load4f(x, v, v1, aligned);
-        const Vb4b m = vb_load4b(msk, v, v1, aligned);
-        uint8_t code[4];
+    // four independent 20-byte loads per thread in flight (the pass is latency bound otherwise)
+    for (int vb = v0 + 4 * tid; vb < v1; vb += 16 * nt) {
+        Vb4f fu[4];
+        Vb4b mu[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (v + e < v1) {
-                const bool in = m.v[e] != 0;
-                d0[v + e - v0] = (uint8_t)((__fdiv_rn(f.v[e], mean) < thresh) && in);
-                const float b = __fdiv_rn(f.v[e], p99);
-                int cd = (b <= 0.16f) ? 1 : (b <= 0.34f) ? 2 : (b <= 0.52f) ? 3 : (b <= 0.7f) ? 4 : (b <= 0.88f) ? 5
-                       : (b > 0.88f) ? 6 : 0;      // NaN compares false everywhere -> 0, as in numpy
-                cd = in ? cd : 0;
-                code[e] = (uint8_t)cd;
-                if (v + e >= w0 && v + e < w1) c12 += (cd == 1 || cd == 2);
-            } else {
-                code[e] = 0;
-            }
+        for (int u = 0; u < 4; ++u) {
+            const int v = vb + 4 * u * nt;
+            if (v < v1) { fu[u] = vb_load4f(x, v, v1, aligned); mu[u] = vb_load4b(msk, v, v1, aligned); }
         }
-        if (v >= w0 && v + 3 < w1 && aligned) {
-            *(uint32_t*)(lb + S.off + v) = (uint32_t)code[0] | ((uint32_t)code[1] << 8) | ((uint32_t)code[2] << 16) | ((uint32_t)code[3] << 24);
-        } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (v + e >= w0 && v + e < w1) lb[S.off + v + e] = code[e];
+        for (int u = 0; u < 4; ++u) {
+            const int v = vb + 4 * u * nt;
+            if (v >= v1) break;
+            const Vb4f f = fu[u];
+            const Vb4b m = mu[u];
+            uint8_t code[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (v + e < v1) {
+                    const bool in = m.v[e] != 0;
+                    const bool fin = okdiv && fabsf(f.v[e]) < 3.0e38f;      // inf / nan inputs: IEEE division
+                    const float qa = fin ? vb_div_rcp(f.v[e], mean, rmean) : __fdiv_rn(f.v[e], mean);
+                    d0[v + e - v0] = (uint8_t)((qa < thresh) && in);
+                    const float b = fin ? vb_div_rcp(f.v[e], p99, rp99) : __fdiv_rn(f.v[e], p99);
+                    int cd = (b <= 0.16f) ? 1 : (b <= 0.34f) ? 2 : (b <= 0.52f) ? 3 : (b <= 0.7f) ? 4 : (b <= 0.88f) ? 5
+                           : (b > 0.88f) ? 6 : 0;      // NaN compares false everywhere -> 0, as in numpy
+                    cd = in ? cd : 0;
+                    code[e] = (uint8_t)cd;
+                    if (v + e >= w0 && v + e < w1) c12 += (cd == 1 || cd == 2);
+                } else {
+                    code[e] = 0;
+                }
+            }
+            if (v >= w0 && v + 3 < w1 && aligned) {
+                *(uint32_t*)(lb + S.off + v) = (uint32_t)code[0] | ((uint32_t)code[1] << 8) | ((uint32_t)code[2] << 16) | ((uint32_t)code[3] << 24);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (v + e >= w0 && v + e < w1) lb[S.off + v + e] = code[e];
+            }
         }
     }
     __syncthreads();
