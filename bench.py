@@ -44,9 +44,17 @@ WORKLOAD = "C2 xenon phantoms 128x128x14 @2.0x2.0x11.5 mm, N4(4 levels, 50 it ma
 
 
 # ------------------------------------------------------------------------------------------ inputs
+MIXED = False      # --workload C5: the cohort config, C1 / C2 geometry and spacing alternating
+
+
+def _subject_vox(seed):
+    from vent_analysis_b200.phantom import CONFIGS
+    return list(CONFIGS["C1" if int(seed) % 2 == 0 else "C2"][1]) if MIXED else list(VOX)
+
+
 def _make_subject(seed):
     from vent_analysis_b200.phantom import phantom
-    return phantom(SHAPE, VOX, int(seed))
+    return phantom(SHAPE, _subject_vox(seed), int(seed))
 
 
 def make_batch(seeds, procs):
@@ -69,11 +77,12 @@ def _cpu_subject(args):
     from oracle import ci_oracle, n4_oracle, vdp_oracle
     from vent_analysis_b200.sphere_table import generate
     img, mask = _make_subject(seed)
-    table = generate(VOX, 50)
+    vox = _subject_vox(seed)
+    table = generate(vox, 50)
     t0 = time.perf_counter()
     snr = vdp_oracle.snr(img, mask)
     n4 = n4_oracle.n4(img, mask)
-    r = vdp_oracle.vdp(n4["out"], mask.astype(np.float64), VOX)
+    r = vdp_oracle.vdp(n4["out"], mask.astype(np.float64), vox)
     vdp_oracle.border(mask)
     t1 = time.perf_counter()
     d = r["defectArray"]
@@ -82,7 +91,7 @@ def _cpu_subject(args):
         sample = np.random.default_rng(seed).choice(D, ci_sample, replace=False)
     else:
         sample = None
-    ci_oracle.calculate_ci_literal(d, VOX, table, sample=sample)
+    ci_oracle.calculate_ci_literal(d, vox, table, sample=sample)
     t2 = time.perf_counter()
     n_eval = D if sample is None else len(sample)
     t_ci = (t2 - t1) * (D / max(n_eval, 1))
@@ -229,7 +238,7 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.context(local_rank)
-    voxs = [VOX] * B
+    voxs = [_subject_vox(rank * B + i) for i in range(B)]
     dc = cohort.DeviceCohort(imgs, masks, voxs, device=local_rank)
     V = dc.V
 
@@ -352,8 +361,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1184, help="subjects per GPU per step (8 per SM; the cohort config is 1024)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C2", "C5"],
+                    help="C2: BASELINE.json configs[1] (default); C5: the cohort config, C1/C2 spacings alternating")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global MIXED, WORKLOAD
+    if args.workload == "C5":
+        MIXED = True
+        WORKLOAD = ("C5 cohort: xenon phantoms 128x128x14, spacings 1.5x1.5x10 / 2.0x2.0x11.5 mm alternating, "
+                    "N4(4 levels, 50 it max)+SNR+VDP+LB+borders+CI(Rmax 50)")
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
