@@ -34,6 +34,9 @@ extern "C" {
 #define VB_DO_VDP 4u         /* Vent_Analysis.calculate_VDP body   Vent_Analysis.py:244-257 */
 #define VB_DO_CI 8u          /* CI.calculate_CI + percentile  CI.py:107-145, V_A.py:268-270 */
 #define VB_DO_MASK_BORDER 16u/* Vent_Analysis.calculateBorder(mask) Vent_Analysis.py:225-231 */
+#define VB_HOST_STATS_ONLY 32u /* vb_pipeline_batch_host: copy back only vb_subject_stats (cohort
+                                screening: VDP / VDP_lb / CI / SNR per subject); output array
+                                pointers of computed stages may then be NULL                   */
 
 #define VB_MAX_LEVELS 8
 #define VB_CI_OFF 0xFFFFu    /* ci_shell value of a voxel that is not a defect             */

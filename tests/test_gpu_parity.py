@@ -146,6 +146,9 @@ def test_cohort_mixed_spacings_host_and_device_paths_agree(ctx):
         assert np.array_equal(o1["n4"], out["n4"][off:off + V])
         assert np.array_equal(o1["ci_shell"], out["ci_shell"][off:off + V])
     assert np.isfinite(metrics).all()
+    # screening mode: only the per-subject records come back, same numbers
+    m_only, o_only, _ = cohort.run_cohort_host(imgs, masks, voxs, metrics_only=True)
+    assert np.array_equal(m_only, metrics) and set(o_only) == {"stats", "rc"}
     # determinism: same batch twice -> identical bits
     metrics3, out3, _ = cohort.run_cohort_host(imgs, masks, voxs)
     assert np.array_equal(out3["n4"], out["n4"]) and np.array_equal(metrics3, metrics)

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libventb200.so")
 
 VB_OK, VB_ERR_CUDA, VB_ERR_ARG, VB_ERR_UNSUPPORTED, VB_ERR_CI_RMAX = 0, 1, 2, 3, 4
-DO_SNR, DO_N4, DO_VDP, DO_CI, DO_MASK_BORDER = 1, 2, 4, 8, 16
+DO_SNR, DO_N4, DO_VDP, DO_CI, DO_MASK_BORDER, HOST_STATS_ONLY = 1, 2, 4, 8, 16, 32
 MAX_LEVELS = 8
 CI_OFF = 0xFFFF
 
@@ -190,7 +190,7 @@ class Context:
 
     # -- whole path, host buffers ----------------------------------------------------------------
     def pipeline_host(self, shapes, flags, image=None, mask=None, n4=None, handles=None, params=None, thresh=0.6,
-                      want_logbias=False, want_mask_border=False, buffers=None):
+                      want_logbias=False, want_mask_border=False, buffers=None, stats_only=False):
         """Run the selected stages on a batch given as HOST arrays (concatenated, C order).
         Returns a dict of numpy outputs (compact dtypes) and the per-subject stats record array.
         ``buffers``: optional dict of preallocated (e.g. pinned) output arrays to fill instead of
@@ -211,6 +211,19 @@ class Context:
         out = {}
         b = Buffers()
         b.mask = mask.ctypes.data
+        if stats_only:                                   # per-subject records only (no output arrays)
+            if image is not None:
+                image = np.ascontiguousarray(image, dtype=np.float32).reshape(-1)
+                b.image = image.ctypes.data
+            stats = np.zeros(n, dtype=STATS_DTYPE)
+            b.stats = stats.ctypes.data
+            hd = None if handles is None else np.ascontiguousarray(handles, dtype=np.int32)
+            p = params if params is not None else self.default_n4_params()
+            rc = self.lib.vb_pipeline_batch_host(self.h, n, _ptr(shapes), _ptr(hd), C.byref(p), float(thresh),
+                                                 int(flags) | HOST_STATS_ONLY, C.byref(b))
+            if rc not in (VB_OK, VB_ERR_CI_RMAX):
+                self.check(rc)
+            return {"stats": stats, "rc": rc}
         if image is not None:
             image = np.ascontiguousarray(image, dtype=np.float32).reshape(-1)
             assert image.size == V

@@ -60,15 +60,18 @@ def metrics_from_stats(ctx, stats, shapes, voxs, handles, n_mask_eq1=None):
     return out
 
 
-def run_cohort_host(images, masks, voxs, device=0, flags=ALL_STAGES, thresh=0.6, ctx=None, params=None):
+def run_cohort_host(images, masks, voxs, device=0, flags=ALL_STAGES, thresh=0.6, ctx=None, params=None,
+                    metrics_only=False):
     """Whole path on a list of subjects given as host arrays.  Returns
-    ``(metrics [n,6], outputs dict of concatenated arrays, stats)``."""
+    ``(metrics [n,6], outputs dict of concatenated arrays, stats)``.  ``metrics_only``: cohort
+    screening -- only the per-subject records come back from the GPU (no output arrays)."""
     ctx = ctx if ctx is not None else _lib.context(device)
     shapes = [tuple(int(s) for s in im.shape) for im in images]
     img = np.concatenate([np.asarray(im, dtype=np.float32).ravel() for im in images])
     msk = np.concatenate([np.asarray(m).astype(np.float32).astype(np.uint8).ravel() for m in masks])
     handles = table_handles(ctx, shapes, voxs) if flags & _lib.DO_CI else None
-    out = ctx.pipeline_host(shapes, flags, image=img, mask=msk, handles=handles, thresh=thresh, params=params)
+    out = ctx.pipeline_host(shapes, flags, image=img, mask=msk, handles=handles, thresh=thresh, params=params,
+                            stats_only=metrics_only)
     if out["rc"] == _lib.VB_ERR_CI_RMAX:
         raise ValueError("--MAX RADIUS REACHED-- for at least one subject (CI.py:101-103)")
     return metrics_from_stats(ctx, out["stats"], shapes, voxs, handles), out, out["stats"]

@@ -18,6 +18,12 @@ struct Buf {
     size_t cap = 0;
 };
 
+// per-resident-CTA workspace of the N4 kernel; two sets so that the launches of consecutive chunks
+// of the host pipeline (two compute streams) can overlap
+struct N4Ws {
+    Buf logI, colmask, rbb, wbase, acol, order, ec, axis, counter;
+};
+
 struct TableHost {
     int n0, n1, n2;
     int n_unique, n_bounds;
@@ -41,7 +47,10 @@ struct vb_ctx {
     Buf h_desc, h_stats, d_subj, d_wordoff;   // h_*: pinned host staging
     long long v_total = 0, words_total = 0, rcp_n = -1;
     // workspaces
-    Buf ws_logI, ws_e, ws_colmask, ws_rbb, ws_wbase, ws_acol, ws_order, ws_perm, ws_ec, ws_rcp, ws_axis, ws_counter, ws_d0, ws_bits, ws_list, ws_count, dbg;
+    N4Ws n4ws[2];
+    int wsi = 0;                         // workspace set the next N4 launch uses
+    vbrt::stream_t stream2 = nullptr;    // second compute stream of the host pipeline
+    Buf ws_rcp, ws_d0, ws_bits, ws_list, ws_count, dbg;
     int dbg_stride = 0, dbg_nbins = 0, dbg_Lmax = 0, dbg_n = 0;
     // CI tables
     std::vector<TableHost> tables;
@@ -157,6 +166,20 @@ int upload_tables(vb_ctx* c, vbrt::stream_t s) {
 }
 
 // ------------------------------------------------------------------------------------- stages
+// 1/N table of the N4 convergence chain, (re)built only when it has to grow
+int ensure_rcp(vb_ctx* c, long long vmax, vbrt::stream_t s, bool* launched) {
+    if (launched) *launched = false;
+    if (c->rcp_n >= vmax) return VB_OK;
+    if (!ensure(c->ws_rcp, 8 * ((size_t)vmax + 8))) return VB_ERR_CUDA;
+    vbrt::clear_stale_error();
+    VB_LAUNCH(n4_rcp_table_kernel, dim3(c->sms), dim3(256), 0, s, (float2*)c->ws_rcp.p, (int)vmax);
+    ++c->launches;
+    if (!vbrt::last_launch_ok("n4_rcp_table_kernel")) return VB_ERR_CUDA;
+    c->rcp_n = vmax;
+    if (launched) *launched = true;
+    return VB_OK;
+}
+
 int run_snr(vb_ctx* c, const float* image, const uint8_t* mask, int n, int fov, vb_subject_stats* stats,
             vbrt::stream_t s) {
     vbrt::clear_stale_error();
@@ -214,11 +237,12 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
         return fail(VB_ERR_UNSUPPORTED, "N4: working set does not fit the 227 KB of shared memory");
     const long long cap = ((long long)c->max_smem - ub - fixed - static_smem) / 4;
     const int grid = std::min(n, c->sms);
-    if (!ensure(c->ws_logI, sizeof(float) * (size_t)grid * (size_t)vmax) ||
-        !ensure(c->ws_colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(c->ws_rbb, 4 * (size_t)grid * (size_t)rbb) ||
-        !ensure(c->ws_wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(c->ws_acol, 4 * (size_t)grid * (size_t)ncmax) || !ensure(c->ws_order, 4 * (size_t)grid * (size_t)wb) || !ensure(c->ws_ec, 8 * (size_t)grid * (size_t)((vmax + 3) & ~3LL)) ||
-        !ensure(c->ws_rcp, 8 * ((size_t)vmax + 8)) ||
-        !ensure(c->ws_axis, 4 * (size_t)grid * (size_t)axis) || !ensure(c->ws_counter, 64))
+    N4Ws& W = c->n4ws[c->wsi & 1];
+    if (!ensure(W.logI, sizeof(float) * (size_t)grid * (size_t)vmax) ||
+        !ensure(W.colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(W.rbb, 4 * (size_t)grid * (size_t)rbb) ||
+        !ensure(W.wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(W.acol, 4 * (size_t)grid * (size_t)ncmax) ||
+        !ensure(W.order, 4 * (size_t)grid * (size_t)wb) || !ensure(W.ec, 8 * (size_t)grid * (size_t)((vmax + 3) & ~3LL)) ||
+        !ensure(W.axis, 4 * (size_t)grid * (size_t)axis) || !ensure(W.counter, 64))
         return VB_ERR_CUDA;
     int trace = 0;
     for (int l = 0; l < p.n_levels; ++l) trace += p.max_iter[l];
@@ -231,26 +255,23 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
         c->dbg_stride = dbg_stride; c->dbg_nbins = p.n_bins; c->dbg_Lmax = (int)Lmax; c->dbg_n = n;
         if (!vbrt::dev_memset(dbg, 0, sizeof(float) * (size_t)n * dbg_stride, s)) return VB_ERR_CUDA;
     }
-    if (!vbrt::dev_memset(c->ws_counter.p, 0, 64, s)) return VB_ERR_CUDA;
+    if (!vbrt::dev_memset(W.counter.p, 0, 64, s)) return VB_ERR_CUDA;
     N4Args a;
     a.image = image; a.mask = mask; a.out = out; a.logbias = logbias;
     a.subj = subj_ptr(c); a.n = n; a.p = p; a.stats = stats;
-    a.ws_logI = (float*)c->ws_logI.p; a.ws_colmask = (uint32_t*)c->ws_colmask.p; a.ws_rbb = (uint32_t*)c->ws_rbb.p;
-    a.ws_wbase = (uint32_t*)c->ws_wbase.p; a.ws_acol = (uint32_t*)c->ws_acol.p; a.ws_order = (uint32_t*)c->ws_order.p; a.ws_axis = (float*)c->ws_axis.p; 
-    a.ws_ec = (float*)c->ws_ec.p; a.rcp = (const float2*)c->ws_rcp.p; a.rowtab_rows = (int)rowtab_rows;
+    a.ws_logI = (float*)W.logI.p; a.ws_colmask = (uint32_t*)W.colmask.p; a.ws_rbb = (uint32_t*)W.rbb.p;
+    a.ws_wbase = (uint32_t*)W.wbase.p; a.ws_acol = (uint32_t*)W.acol.p; a.ws_order = (uint32_t*)W.order.p; a.ws_axis = (float*)W.axis.p;
+    a.ws_ec = (float*)W.ec.p; a.rowtab_rows = (int)rowtab_rows;
     { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] >= '1' && e[0] <= '9') ? e[0] - '0' : 0; }
-    a.work_counter = (int*)c->ws_counter.p; a.debug = dbg;
+    a.work_counter = (int*)W.counter.p; a.debug = dbg;
     a.Vmax = vmax; a.cmw_max = cmw; a.rbb_max = rbb; a.wb_max = wb; a.ncols_max = ncmax;
     a.axis_stride = (int)axis; a.debug_stride = dbg_stride;
     a.Lmax = (int)Lmax; a.fftN = fftN; a.union_bytes = (int)ub;
     // a mask that does not fit keeps its compact log image in global memory (L2)
     a.logI_cap = (int)std::min<long long>(std::max<long long>(cap, 0), vmax);
     const int smem = (int)(ub + fixed + 4LL * a.logI_cap);
-    if (c->rcp_n < vmax) {                                 // 1/N table, (re)built only when it has to grow
-        VB_LAUNCH(n4_rcp_table_kernel, dim3(c->sms), dim3(256), 0, s, (float2*)c->ws_rcp.p, (int)vmax);
-        ++c->launches;
-        c->rcp_n = vmax;
-    }
+    if (int rcr = ensure_rcp(c, vmax, s, nullptr)) return rcr;
+    a.rcp = (const float2*)c->ws_rcp.p;
     if (!vbrt::allow_smem(n4_subject_kernel, smem)) return VB_ERR_CUDA;
     VB_LAUNCH(n4_subject_kernel, dim3(grid), dim3(VB_N4_THREADS), (size_t)smem, s, a);
     ++c->launches;
@@ -356,7 +377,8 @@ int vb_create(int device, vb_ctx** out) {
     c->device = device;
     c->sms = vbrt::sm_count(device);
     c->max_smem = vbrt::max_smem_optin(device);
-    if (!vbrt::stream_create(&c->stream) || !vbrt::stream_create(&c->stream_in) || !vbrt::stream_create(&c->stream_out)) {
+    if (!vbrt::stream_create(&c->stream) || !vbrt::stream_create(&c->stream_in) || !vbrt::stream_create(&c->stream_out) ||
+        !vbrt::stream_create(&c->stream2)) {
         delete c;
         return VB_ERR_CUDA;
     }
@@ -368,7 +390,12 @@ void vb_destroy(vb_ctx* c) {
     if (!c) return;
     vbrt::set_device(c->device);
     vbrt::stream_sync(c->stream);
-    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_logI, &c->ws_e, &c->ws_rbb, &c->ws_wbase, &c->ws_acol, &c->ws_order, &c->ws_perm, &c->ws_ec, &c->ws_rcp, &c->ws_colmask, &c->ws_axis, &c->ws_counter, &c->ws_d0,
+    for (N4Ws& W : c->n4ws) {
+        Buf* wb[] = {&W.logI, &W.colmask, &W.rbb, &W.wbase, &W.acol, &W.order, &W.ec, &W.axis, &W.counter};
+        for (Buf* b : wb) vbrt::dev_free(b->p);
+    }
+    vbrt::stream_destroy(c->stream2);
+    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_rcp, &c->ws_d0,
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
                    &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats};
     for (Buf* b : bufs) vbrt::dev_free(b->p);
@@ -560,6 +587,7 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
     vbrt::stream_t s = c->stream;
     size_t V = 0;
     for (int i = 0; i < n; ++i) V += (size_t)shapes[3 * i] * shapes[3 * i + 1] * shapes[3 * i + 2];
+    const bool so_only = (flags & VB_HOST_STATS_ONLY) != 0;     // per-subject records only: no array comes back
     const bool need_n4 = (flags & (VB_DO_N4 | VB_DO_VDP)) != 0;
     const bool need_def = (flags & (VB_DO_VDP | VB_DO_CI)) != 0;
     vb_buffers d;
@@ -571,25 +599,25 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
         d.image = (const float*)c->m_image.p;
     }
     if (need_n4) {
-        if (!h->n4) return fail(VB_ERR_ARG, "pipeline_host: n4 buffer required");
+        if (!h->n4 && (!so_only || !(flags & VB_DO_N4))) return fail(VB_ERR_ARG, "pipeline_host: n4 buffer required");
         if (!ensure(c->m_n4, 4 * V)) return VB_ERR_CUDA;
         d.n4 = (float*)c->m_n4.p;
     }
     if (h->logbias && (flags & VB_DO_N4)) { if (!ensure(c->m_logbias, 4 * V)) return VB_ERR_CUDA; d.logbias = (float*)c->m_logbias.p; }
     if (need_def) {
-        if (!h->defect) return fail(VB_ERR_ARG, "pipeline_host: defect buffer required");
+        if (!h->defect && (!so_only || !(flags & VB_DO_VDP))) return fail(VB_ERR_ARG, "pipeline_host: defect buffer required");
         if (!ensure(c->m_defect, V)) return VB_ERR_CUDA;
         d.defect = (uint8_t*)c->m_defect.p;
     }
     if (flags & VB_DO_VDP) {
-        if (!h->defect_lb) return fail(VB_ERR_ARG, "pipeline_host: defect_lb buffer required");
+        if (!h->defect_lb && !so_only) return fail(VB_ERR_ARG, "pipeline_host: defect_lb buffer required");
         if (!ensure(c->m_lb, V)) return VB_ERR_CUDA;
         d.defect_lb = (uint8_t*)c->m_lb.p;
         if (h->defect_border) { if (!ensure(c->m_dborder, V)) return VB_ERR_CUDA; d.defect_border = (uint8_t*)c->m_dborder.p; }
     }
     if ((flags & VB_DO_MASK_BORDER) && h->mask_border) { if (!ensure(c->m_mborder, V)) return VB_ERR_CUDA; d.mask_border = (uint8_t*)c->m_mborder.p; }
     if (flags & VB_DO_CI) {
-        if (!h->ci_shell) return fail(VB_ERR_ARG, "pipeline_host: ci_shell buffer required");
+        if (!h->ci_shell && !so_only) return fail(VB_ERR_ARG, "pipeline_host: ci_shell buffer required");
         if (!ensure(c->m_shell, 2 * V)) return VB_ERR_CUDA;
         d.ci_shell = (uint16_t*)c->m_shell.p;
     }
@@ -605,6 +633,11 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
         vbrt::event_t e;
         if (!vbrt::event_create(&e)) return VB_ERR_CUDA;
         c->ev_copy.push_back(e);
+    }
+    if (flags & VB_DO_N4) {                                // shared by both compute streams: finish it first
+        bool launched = false;
+        if ((rc = ensure_rcp(c, vmax_of(c), s, &launched))) return rc;
+        if (launched && !vbrt::stream_sync(s)) return VB_ERR_CUDA;
     }
     // the (small) stats records go through pinned staging: a copy into pageable user memory would
     // block the host until the chunk has finished and serialise the pipeline
@@ -626,12 +659,18 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
         if (h->image) ok = ok && vbrt::h2d((float*)c->m_image.p + v0, h->image + v0, 4 * nv, si);
         if (need_n4 && !(flags & VB_DO_N4)) ok = ok && vbrt::h2d((float*)c->m_n4.p + v0, h->n4 + v0, 4 * nv, si);
         if (need_def && !(flags & VB_DO_VDP)) ok = ok && vbrt::h2d((uint8_t*)c->m_defect.p + v0, h->defect + v0, nv, si);
-        ok = ok && vbrt::event_record(c->ev_copy[2 * (size_t)k], si) && vbrt::stream_wait(s, c->ev_copy[2 * (size_t)k]);
+        // consecutive chunks alternate between two compute streams (and N4 workspace sets), so the
+        // stragglers of one chunk's persistent N4 kernel overlap the next chunk's CTAs
+        vbrt::stream_t cs = (k & 1) ? c->stream2 : s;
+        ok = ok && vbrt::event_record(c->ev_copy[2 * (size_t)k], si) && vbrt::stream_wait(cs, c->ev_copy[2 * (size_t)k]);
         if (!ok) break;
-        rc = pipeline_range(c, r0, r1 - r0, params, thresh, flags, &d, s, nullptr);
+        c->wsi = k & 1;
+        rc = pipeline_range(c, r0, r1 - r0, params, thresh, flags, &d, cs, nullptr);
+        c->wsi = 0;
         if (rc) return rc;
         vbrt::stream_t so = c->stream_out;
-        ok = ok && vbrt::event_record(c->ev_copy[2 * (size_t)k + 1], s) && vbrt::stream_wait(so, c->ev_copy[2 * (size_t)k + 1]);
+        ok = ok && vbrt::event_record(c->ev_copy[2 * (size_t)k + 1], cs) && vbrt::stream_wait(so, c->ev_copy[2 * (size_t)k + 1]);
+        if (!so_only) {
         if (flags & VB_DO_N4) ok = ok && vbrt::d2h(h->n4 + v0, d.n4 + v0, 4 * nv, so);
         if (d.logbias) ok = ok && vbrt::d2h(h->logbias + v0, d.logbias + v0, 4 * nv, so);
         if (flags & VB_DO_VDP) {
@@ -640,9 +679,12 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
         }
         if (d.mask_border) ok = ok && vbrt::d2h(h->mask_border + v0, d.mask_border + v0, nv, so);
         if (flags & VB_DO_CI) ok = ok && vbrt::d2h(h->ci_shell + v0, d.ci_shell + v0, 2 * nv, so);
+        }
         ok = ok && vbrt::d2h((vb_subject_stats*)c->h_stats.p + r0, d.stats + r0, sizeof(vb_subject_stats) * (size_t)(r1 - r0), so);
     }
-    if (!ok || !vbrt::stream_sync(c->stream_out) || !vbrt::stream_sync(s) || !vbrt::stream_sync(c->stream_in)) return VB_ERR_CUDA;
+    if (!ok || !vbrt::stream_sync(c->stream_out) || !vbrt::stream_sync(s) || !vbrt::stream_sync(c->stream2) ||
+        !vbrt::stream_sync(c->stream_in))
+        return VB_ERR_CUDA;
     memcpy(h->stats, c->h_stats.p, stb);
     if (flags & VB_DO_CI)
         for (int i = 0; i < n; ++i)
