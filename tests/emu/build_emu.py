@@ -10,6 +10,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "vent_analysis_b200", "csrc")
 SO = os.path.join(HERE, "_build", "libventb200_emu.so")
+# one OS thread per CUDA thread: the emulation uses smaller blocks than the product build (the
+# kernels only assume warp-multiple block sizes), which keeps the CPU suite to a few minutes
+SMALL_BLOCKS = ["-DVB_N4_THREADS=256", "-DVB_N4_CHAIN_WARPS=4", "-DVB_VDP_THREADS=256", "-DVB_CLS_THREADS=128"]
 
 
 def build(force=False):
@@ -17,7 +20,7 @@ def build(force=False):
     if not force and os.path.exists(SO) and all(os.path.getmtime(s) <= os.path.getmtime(SO) for s in srcs):
         return SO
     os.makedirs(os.path.dirname(SO), exist_ok=True)
-    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-DVB_EMULATE", "-ffp-contract=off",
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-DVB_EMULATE", *SMALL_BLOCKS, "-ffp-contract=off",
            "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable", "-x", "c++", os.path.join(CSRC, "ventb200.cu"),
            "-o", SO]
     subprocess.check_call(cmd)

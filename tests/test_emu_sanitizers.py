@@ -9,6 +9,7 @@ import sys
 import pytest
 
 from conftest import ROOT
+from emu.build_emu import SMALL_BLOCKS
 
 _SCRIPT = r'''
 import sys
@@ -57,7 +58,7 @@ def test_kernels_are_race_free_under_tsan(tmp_path):
     so = os.path.join(ROOT, "tests", "emu", "_build", "libventb200_emu_tsan.so")
     os.makedirs(os.path.dirname(so), exist_ok=True)
     src = os.path.join(ROOT, "vent_analysis_b200", "csrc", "ventb200.cu")
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-DVB_EMULATE",
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-DVB_EMULATE", *SMALL_BLOCKS,
                            "-ffp-contract=off", "-fsanitize=thread", "-fno-omit-frame-pointer",
                            "-Wno-unknown-pragmas", "-x", "c++", src, "-o", so])
     script = tmp_path / "run.py"
@@ -75,7 +76,7 @@ def test_host_layer_and_kernels_are_asan_clean(tmp_path):
     so = os.path.join(ROOT, "tests", "emu", "_build", "libventb200_emu_asan.so")
     os.makedirs(os.path.dirname(so), exist_ok=True)
     src = os.path.join(ROOT, "vent_analysis_b200", "csrc", "ventb200.cu")
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-DVB_EMULATE",
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-DVB_EMULATE", *SMALL_BLOCKS,
                            "-ffp-contract=off", "-fsanitize=address", "-fno-omit-frame-pointer",
                            "-Wno-unknown-pragmas", "-x", "c++", src, "-o", so])
     script = tmp_path / "run.py"

@@ -35,7 +35,9 @@
 #include <float.h>
 #include "vb_common.cuh"
 
+#ifndef VB_N4_THREADS
 #define VB_N4_THREADS 1024
+#endif
 #define VB_N4_WARPS (VB_N4_THREADS / 32)
 #define VB_BSPLINE_EPS 1e-3f
 #define VB_N4_EPT 8                               /* convergence chain: elements per thread   */
@@ -74,7 +76,7 @@ struct N4Args {
     int logI_cap;            // floats of compact log image that fit shared memory (0 = none)
     int rowtab_rows;         // rows whose row-axis tables fit shared memory (0 = keep them in global)
     int no_overlap;          // 1: run the convergence chain and the next iteration's phases one after the other
-                             // (2, 3: timing diagnostics only -- WRONG results: 2 = never run the chain, 3 = chain team idles the phases)
+                             // (same results; A/B timing of the overlap)
 };
 
 // debug record layout (floats): [0]=bmin [1]=bmax [2..4]=ncp [5]=n_trace, then
@@ -1361,7 +1363,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                         } else if (tid < TC.nt) {
                             const float cv = n4_convergence(c, TC, M);
                             if (tid == 0) s_conv = cv;
-                        } else if (room && !cap && a.no_overlap != 3) {
+                        } else if (room && !cap) {
                             n4_histogram(c, TP, bmin, bmax);
                             n4_sharpen(c, TP, bmin, bmax, a.p.fwhm, a.p.wiener_noise);
                             n4_contract<false>(c, TP, bmin, bmax);
@@ -1369,7 +1371,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                         __syncthreads();
                         conv = s_conv;
                         __syncthreads();
-                        fitted = !serial && room && !cap && a.no_overlap != 3;
+                        fitted = !serial && room && !cap;
                         pending = false;
                         tph[5] += vb_clock() - tq;
                         if (dbg_trace && tid == 0 && ntrace - 1 < trace_cap && ntrace > 0) dbg_trace[ntrace - 1] = conv;
@@ -1390,7 +1392,6 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                     ++it; ++total;
                     tq = vb_clock();
                     pending = n4_update(c, M, bmin, bmax, a.p.conv_threshold, dbg != nullptr || it >= a.p.max_iter[level], conv);
-                    if (a.no_overlap == 2 && pending) { pending = false; conv = (it >= 12 + 20 * (level == 0)) ? 0.0f : 1.0f; }
                     tph[4] += vb_clock() - tq;
                     if (!pending && dbg_trace && tid == 0 && ntrace < trace_cap) dbg_trace[ntrace] = conv;
                     ++ntrace;

@@ -9,7 +9,9 @@
 #include <float.h>
 #include "vb_common.cuh"
 
+#ifndef VB_VDP_THREADS
 #define VB_VDP_THREADS 1024
+#endif
 #define VB_SNR_MAX_AXIS 8192   // n0 + n1 + n2 must not exceed this (projection flags in smem)
 
 // ---------------------------------------------------------------------------------------------
@@ -378,7 +380,9 @@ VB_KERNEL void vdp_median_kernel(const uint8_t* VB_RESTRICT d0, const VbSubject*
 // forms the median (neighbour count >= 5, zero padded, per slice) for rows [i0 - 1, i0 + R + 1)
 // in a second shared tile and from it the border of rows [i0, i0 + R).  Traffic per voxel:
 // 5 B read (+ 4/R halo) and 3 B written, instead of three kernels and a d0 round trip.
+#ifndef VB_CLS_THREADS
 #define VB_CLS_THREADS 512
+#endif
 VB_KERNEL void VB_LAUNCH_BOUNDS(VB_CLS_THREADS, 2)
 vdp_classify_kernel(const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, float thresh,
                     int R, uint8_t* lb, uint8_t* defect, uint8_t* border, vb_subject_stats* stats) {

@@ -262,7 +262,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     a.ws_logI = (float*)W.logI.p; a.ws_colmask = (uint32_t*)W.colmask.p; a.ws_rbb = (uint32_t*)W.rbb.p;
     a.ws_wbase = (uint32_t*)W.wbase.p; a.ws_acol = (uint32_t*)W.acol.p; a.ws_order = (uint32_t*)W.order.p; a.ws_axis = (float*)W.axis.p;
     a.ws_ec = (float*)W.ec.p; a.rowtab_rows = (int)rowtab_rows;
-    { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] >= '1' && e[0] <= '9') ? e[0] - '0' : 0; }
+    { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] == '1') ? 1 : 0; }
     a.work_counter = (int*)W.counter.p; a.debug = dbg;
     a.Vmax = vmax; a.cmw_max = cmw; a.rbb_max = rbb; a.wb_max = wb; a.ncols_max = ncmax;
     a.axis_stride = (int)axis; a.debug_stride = dbg_stride;
