@@ -40,7 +40,9 @@
 #endif
 #define VB_N4_WARPS (VB_N4_THREADS / 32)
 #define VB_BSPLINE_EPS 1e-3f
+#ifndef VB_N4_EPT
 #define VB_N4_EPT 8                               /* convergence chain: elements per thread   */
+#endif
 #ifndef VB_N4_CHAIN_WARPS
 #define VB_N4_CHAIN_WARPS 16                      /* warps of the chain team while it overlaps  */
 #endif
@@ -64,8 +66,7 @@ struct N4Args {
     uint32_t* ws_acol;       // [grid][ncols_max] active (mask-carrying) columns, ascending
     uint32_t* ws_order;      // [grid][wb_max]    work items, largest first
     float* ws_axis;          // [grid][axis_stride]  (4-byte words)
-    float* ws_ec;            // [grid][2*Vmax]    convergence sequence in C order: pixel[M], then pixel/N [M]
-    const float2* rcp;       // [Vmax + 1]        1/N = x + y as two floats, N = index (shared by all CTAs)
+    float* ws_ec;            // [grid][Vmax]      convergence sequence exp(old - new) in C order
     int* work_counter;
     float* debug;            // may be null: [n][debug_stride]
     long long Vmax, cmw_max, rbb_max, wb_max, ncols_max;
@@ -197,8 +198,7 @@ struct N4Ctx {
     int* ctr;             // shared-memory work counters, one per team barrier id
     int nact, nseg, wps;  // active columns; row segments per block; 32-row words per segment
     float* axis_base;
-    float* ec;            // [M] pixel in C order, [M] pixel / N behind it (chain input)
-    const float2* rcp;    // 1/N split in two floats
+    float* ec;            // [M] exp(old - new) in C order (chain input)
     // row-axis tables (shared memory when they fit, else inside axis_base)
     const float4* r_evw;
     const float4* r_fit3;
@@ -893,18 +893,10 @@ struct N4Step {
 VB_DEV N4Step n4_step_consts(float pixel, int n) {
     N4Step s;
     const float nf = (float)n;
-    s.b = __fdiv_rn(pixel, nf);
     s.ch = __frcp_rn(nf);
     s.cl = __fmul_rn(fmaf(-s.ch, nf, 1.0f), s.ch);
+    s.b = n4_div(pixel, nf, s.ch);                      // == RN(pixel / N), the reference's float division
     return s;
-}
-// 1/N as two floats for every N up to nmax (one table per launch, shared by all subjects)
-VB_KERNEL void n4_rcp_table_kernel(float2* rcp, int nmax) {
-    for (int n = (int)(blockIdx.x * blockDim.x + threadIdx.x); n <= nmax; n += (int)(gridDim.x * blockDim.x)) {
-        const float nf = (float)(n > 0 ? n : 1);
-        const float ch = __frcp_rn(nf);
-        rcp[n] = make_float2(ch, __fmul_rn(fmaf(-ch, nf, 1.0f), ch));
-    }
 }
 VB_DEV float n4_mu_next(float mu, const N4Step& s) {
     const float t = fmaf(-mu, s.cl, fmaf(-mu, s.ch, s.b));      // pixel/N - mu/N
@@ -959,7 +951,6 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
     VB_SHARED int s_tot[2][32];               // warp totals, double buffered
     int buf = 0;
     const float* epx = c.ec;                  // pixel, C order
-    const float* epb = c.ec + ((M + 3) & ~3); // pixel / N
     const int S0 = min(M, VB_N4_SERIAL);
     VB_SHARED float s_px[VB_N4_SERIAL];
     long long tq = vb_clock();
@@ -988,21 +979,13 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
         N4Step st[VB_N4_EPT];
         if (cnt == VB_N4_EPT && VB_N4_EPT == 8) {             // lo is a multiple of 8 here: 16-byte loads
             const float4 p0 = *(const float4*)(epx + lo), p1 = *(const float4*)(epx + lo + 4);
-            const float4 b0 = *(const float4*)(epb + lo), b1 = *(const float4*)(epb + lo + 4);
             px[0] = p0.x; px[1] = p0.y; px[2] = p0.z; px[3] = p0.w; px[4] = p1.x; px[5] = p1.y; px[6] = p1.z; px[7] = p1.w;
-            st[0].b = b0.x; st[1].b = b0.y; st[2].b = b0.z; st[3].b = b0.w; st[4].b = b1.x; st[5].b = b1.y; st[6].b = b1.z; st[7].b = b1.w;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { const float2 r = c.rcp[lo + i + 1]; st[i].ch = r.x; st[i].cl = r.y; }
         } else {
 #pragma unroll
-            for (int i = 0; i < VB_N4_EPT; ++i) {
-                const bool on = i < cnt;
-                px[i] = on ? epx[lo + i] : 1.0f;
-                st[i].b = on ? epb[lo + i] : 1.0f;
-                const float2 r = c.rcp[on ? lo + i + 1 : 1];
-                st[i].ch = r.x; st[i].cl = r.y;
-            }
+            for (int i = 0; i < VB_N4_EPT; ++i) px[i] = (i < cnt) ? epx[lo + i] : 1.0f;
         }
+#pragma unroll
+        for (int i = 0; i < VB_N4_EPT; ++i) st[i] = n4_step_consts(px[i], lo + i + 1);
         // mu: a thread runs its steps sequentially (exactly) from its guessed start; the starts
         // are re-derived from the prefix sum of the threads' increments until none moves.  One
         // barrier per sweep: it publishes the warps' totals AND tells whether the previous sweep
@@ -1098,7 +1081,6 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
     const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     float tmin = FLT_MAX, tmax = -FLT_MAX;
     double s1 = 0.0, s2 = 0.0;
-    const unsigned Mpad = (unsigned)((M + 3) & ~3);
     float* Gn = c.G ? c.un_f : nullptr;                  // table of the new lattice (union region is free here)
     N4Team T;
     T.tid = (int)threadIdx.x; T.nt = nt; T.bar = 0;
@@ -1124,8 +1106,7 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
                 tmin = fminf(tmin, un);
                 tmax = fmaxf(tmax, un);
                 const float ev = n4_exp_small(bo - bn);
-                c.ec[rank] = ev;                                       // chain input, C order:
-                c.ec[Mpad + rank] = __fdiv_rn(ev, (float)(rank + 1)); // pixel and pixel / N (float division)
+                c.ec[rank] = ev;                                       // chain input, C order
                 const double em = (double)ev - 1.0;
                 s1 += em; s2 += em * em;
             }
@@ -1297,8 +1278,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         c.iorder = a.ws_order + (size_t)blockIdx.x * a.wb_max;
         c.ctr = s_ctr;
         c.axis_base = a.ws_axis + (size_t)blockIdx.x * a.axis_stride;
-        c.ec = a.ws_ec + (size_t)blockIdx.x * 2 * (size_t)((a.Vmax + 3) & ~3LL);
-        c.rcp = a.rcp;
+        c.ec = a.ws_ec + (size_t)blockIdx.x * (size_t)((a.Vmax + 3) & ~3LL);
         c.ncp[0] = a.p.ncp[0]; c.ncp[1] = a.p.ncp[1]; c.ncp[2] = a.p.ncp[2];
         {
             const int nn[3] = {S.n0, S.n1, S.n2};

@@ -45,12 +45,12 @@ struct vb_ctx {
     std::vector<VbSubject> last_subj;
     std::vector<long long> last_wordoff;
     Buf h_desc, h_stats, d_subj, d_wordoff;   // h_*: pinned host staging
-    long long v_total = 0, words_total = 0, rcp_n = -1;
+    long long v_total = 0, words_total = 0;
     // workspaces
     N4Ws n4ws[2];
     int wsi = 0;                         // workspace set the next N4 launch uses
     vbrt::stream_t stream2 = nullptr;    // second compute stream of the host pipeline
-    Buf ws_rcp, ws_d0, ws_bits, ws_list, ws_count, dbg;
+    Buf ws_d0, ws_bits, ws_list, ws_count, dbg;
     int dbg_stride = 0, dbg_nbins = 0, dbg_Lmax = 0, dbg_n = 0;
     // CI tables
     std::vector<TableHost> tables;
@@ -166,20 +166,6 @@ int upload_tables(vb_ctx* c, vbrt::stream_t s) {
 }
 
 // ------------------------------------------------------------------------------------- stages
-// 1/N table of the N4 convergence chain, (re)built only when it has to grow
-int ensure_rcp(vb_ctx* c, long long vmax, vbrt::stream_t s, bool* launched) {
-    if (launched) *launched = false;
-    if (c->rcp_n >= vmax) return VB_OK;
-    if (!ensure(c->ws_rcp, 8 * ((size_t)vmax + 8))) return VB_ERR_CUDA;
-    vbrt::clear_stale_error();
-    VB_LAUNCH(n4_rcp_table_kernel, dim3(c->sms), dim3(256), 0, s, (float2*)c->ws_rcp.p, (int)vmax);
-    ++c->launches;
-    if (!vbrt::last_launch_ok("n4_rcp_table_kernel")) return VB_ERR_CUDA;
-    c->rcp_n = vmax;
-    if (launched) *launched = true;
-    return VB_OK;
-}
-
 int run_snr(vb_ctx* c, const float* image, const uint8_t* mask, int n, int fov, vb_subject_stats* stats,
             vbrt::stream_t s) {
     vbrt::clear_stale_error();
@@ -241,7 +227,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     if (!ensure(W.logI, sizeof(float) * (size_t)grid * (size_t)vmax) ||
         !ensure(W.colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(W.rbb, 4 * (size_t)grid * (size_t)rbb) ||
         !ensure(W.wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(W.acol, 4 * (size_t)grid * (size_t)ncmax) ||
-        !ensure(W.order, 4 * (size_t)grid * (size_t)wb) || !ensure(W.ec, 8 * (size_t)grid * (size_t)((vmax + 3) & ~3LL)) ||
+        !ensure(W.order, 4 * (size_t)grid * (size_t)wb) || !ensure(W.ec, 4 * (size_t)grid * (size_t)((vmax + 3) & ~3LL)) ||
         !ensure(W.axis, 4 * (size_t)grid * (size_t)axis) || !ensure(W.counter, 64))
         return VB_ERR_CUDA;
     int trace = 0;
@@ -270,8 +256,6 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     // a mask that does not fit keeps its compact log image in global memory (L2)
     a.logI_cap = (int)std::min<long long>(std::max<long long>(cap, 0), vmax);
     const int smem = (int)(ub + fixed + 4LL * a.logI_cap);
-    if (int rcr = ensure_rcp(c, vmax, s, nullptr)) return rcr;
-    a.rcp = (const float2*)c->ws_rcp.p;
     if (!vbrt::allow_smem(n4_subject_kernel, smem)) return VB_ERR_CUDA;
     VB_LAUNCH(n4_subject_kernel, dim3(grid), dim3(VB_N4_THREADS), (size_t)smem, s, a);
     ++c->launches;
@@ -395,7 +379,7 @@ void vb_destroy(vb_ctx* c) {
         for (Buf* b : wb) vbrt::dev_free(b->p);
     }
     vbrt::stream_destroy(c->stream2);
-    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_rcp, &c->ws_d0,
+    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_d0,
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
                    &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats};
     for (Buf* b : bufs) vbrt::dev_free(b->p);
@@ -633,11 +617,6 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
         vbrt::event_t e;
         if (!vbrt::event_create(&e)) return VB_ERR_CUDA;
         c->ev_copy.push_back(e);
-    }
-    if (flags & VB_DO_N4) {                                // shared by both compute streams: finish it first
-        bool launched = false;
-        if ((rc = ensure_rcp(c, vmax_of(c), s, &launched))) return rc;
-        if (launched && !vbrt::stream_sync(s)) return VB_ERR_CUDA;
     }
     // the (small) stats records go through pinned staging: a copy into pageable user memory would
     // block the host until the chunk has finished and serialise the pipeline
