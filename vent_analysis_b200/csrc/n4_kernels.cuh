@@ -4,33 +4,38 @@
 // sitk.N4BiasFieldCorrectionImageFilter() with all defaults (ITK 5.3
 // itkN4BiasFieldCorrectionImageFilter.hxx; restated on the CPU in oracle/n4_oracle.c).
 //
-// Design:
-//   * A CTA pulls subjects from a global work counter and runs the WHOLE filter for one
-//     subject -- 4 levels x <=50 iterations x {histogram, Wiener sharpening, B-spline fit,
-//     update, convergence} -- with block barriers only; no host round trip, subjects converge
-//     independently.
+// Design (DESIGN.md §4 "N4"):
+//   * A CTA (1024 threads) pulls subjects from a global work counter and runs the WHOLE filter
+//     for one subject -- 4 levels x <=50 iterations x {histogram, Wiener sharpening, B-spline fit,
+//     update, convergence} -- with block / named barriers only; no host round trip, subjects
+//     converge independently.
 //   * Only mask voxels take part in the iterations, so the log image is COMPACTED once per
-//     subject: columns (col, slice) are grouped in blocks of 32 (one warp), and within a block
-//     the masked voxels are stored row by row, lane by lane.  A warp that walks the rows of its
-//     block therefore reads one contiguous, conflict-free stream.  For the benchmark volumes
-//     (128x128x14, ~36k mask voxels = 143 KB) the compact log image lives in SHARED MEMORY for
-//     the whole filter; larger masks fall back to a compact array in global memory (L2).
-//   * Nothing else is stored per voxel: U = logI - bias is re-evaluated from the control
-//     lattice (shared memory) wherever it is needed.  The row-axis B-spline weights are warp
-//     uniform; a lane keeps a 4-tap sliding window of column coefficients in registers.
+//     subject: the columns (col, slice) that carry mask voxels are grouped in blocks of 32 (one
+//     warp), and within a block the masked voxels are stored row by row, lane by lane.  A warp
+//     that walks the rows of its block therefore reads one contiguous, conflict-free stream.
+//     For the benchmark volumes (128x128x14, ~36k mask voxels = 143 KB) the compact log image
+//     lives in SHARED MEMORY for the whole filter; larger masks use the same code with the
+//     compact array in global memory (L2).  Work items (block x row segment) are drawn
+//     largest-first from a shared counter.
+//   * Nothing else is stored per voxel: U = logI - bias is re-evaluated wherever it is needed
+//     from per-column coefficient tables G[a][column] (rebuilt from the control lattice after
+//     every fit; spare shared memory) with warp-uniform row weights and a 4-tap sliding window.
 //   * Parzen histogram: fixed-point (count-conserving) shared-memory atomics into 8 copies
-//     => deterministic, no 200 KB of private bins.
+//     => exactly associative, deterministic.
 //   * Sharpening: 4 packed 512-point complex FFTs in double in shared memory.
 //   * B-spline fit: the Lee-Wolberg-Shin scatter is separable (t = tr*tc*ts,
 //     sum t^2 = Sr*Sc*Ss), so delta = sum w^3 z / sum w^2 is three small contractions:
-//     rows (registers, sliding 4-tap window) -> columns -> slices.  omega depends only on the
-//     mask and the lattice size: once per level.
+//     rows (registers, sliding 4-tap window) -> columns (64-bit fixed-point shared-memory adds
+//     built from two native 32-bit atomics with carry forwarding) -> slices.  omega depends only
+//     on the mask and the lattice size: once per level.
 //   * Convergence: ITK's CalculateConvergenceMeasurement is a SEQUENTIAL float32 Welford
 //     recurrence whose rounding (the running mean stalls once its update drops below half an
-//     ulp) decides when a level stops.  It is reproduced here in parallel: the recurrence is
-//     iterated Jacobi-style on float bit patterns in chunks (guess trajectory -> per-step
-//     increments -> prefix sum) until the trajectory reproduces itself, which proves it is the
-//     sequential one.
+//     ulp) decides when a level stops.  It is reproduced here in parallel: threads run their
+//     consecutive steps exactly from guessed start states, the float bit-pattern increments are
+//     prefix-summed, and this repeats until no start moves -- the trajectory then IS the
+//     sequential one.  The chain is skipped when a rigorous bound already decides "continue";
+//     otherwise it runs on half of the warps while the other half computes the next iteration's
+//     histogram / sharpening / fit speculatively (committed only if the chain says "continue").
 #pragma once
 #include <float.h>
 #include "vb_common.cuh"
