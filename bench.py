@@ -337,6 +337,14 @@ def run_ours(args, rank, local_rank, world):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = n4_bytes / (n4_launch_ms * 1e-3) / 1e9
+    # DRAM traffic of the kernel from the committed ncu --set full capture (per subject; a launch
+    # handles B subjects and the traffic is proportional to them)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_n4_dram_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["subjects_per_launch"] * B
+        traffic_src = f"profiles/r01_n4_dram_traffic.json (ncu capture of a {tj['subjects_per_launch']}-subject launch, scaled to {B})"
     line = {
         "metric": METRIC, "value": B * world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -355,7 +363,8 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "n4_subject_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": n4_bytes, "launch_ms": n4_launch_ms,
                      "definition": "(17 + 19*n_it)*V bytes per subject (SURVEY.md 8d), n_it = iterations actually run"},
         "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
@@ -373,7 +382,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1184, help="subjects per GPU per step (8 per SM; the cohort config is 1024)")
+    ap.add_argument("--batch", type=int, default=1776, help="subjects per GPU per step (12 per SM; the cohort config is 1024)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C2", "C5"],
                     help="C2: BASELINE.json configs[1] (default); C5: the cohort config, C1/C2 spacings alternating")

@@ -144,3 +144,104 @@ def check_edge_cases(ctx):
         assert np.array_equal(o["defect_border"].reshape(shape).astype(bool), r["defectBorder"])
         assert np.array_equal(o["mask_border"].reshape(shape), vdp_oracle.border(mask))
         off += V
+
+
+def _vdp_reference_given_stats(n4, mask, mean, p99, thresh=0.6):
+    """numpy restatement of Vent_Analysis.py:246-256 for a GIVEN float32 mean / p99 (exact
+    float32 divisions and comparisons), median and border from the oracle."""
+    n4 = np.asarray(n4, dtype=np.float32)
+    with np.errstate(all="ignore"):
+        d0 = (np.divide(n4, np.float32(mean)) < thresh) * (mask != 0)
+        x = np.divide(n4, np.float32(p99))
+    e = vdp_oracle.LB_EDGES
+    lb = ((x <= e[0]) * 1 + (x > e[0]) * (x <= e[1]) * 2 + (x > e[1]) * (x <= e[2]) * 3
+          + (x > e[2]) * (x <= e[3]) * 4 + (x > e[3]) * (x <= e[4]) * 5 + (x > e[4]) * 6) * (mask != 0)
+    defect = vdp_oracle.median3x3_binary(d0)
+    return defect.astype(np.uint8), lb.astype(np.uint8), vdp_oracle.border(defect).astype(np.uint8)
+
+
+def _near_threshold_volume(shape, seed, odd_in_mask=()):
+    """A volume whose in-mask values sit within a few ulps of the quotient thresholds
+    (0.6 * mean and the linear-binning edges * p99), with zero / negative / denormal voxels in
+    the mask; `odd_in_mask` (NaN / inf) makes the mean or p99 degenerate."""
+    rng = np.random.default_rng(seed)
+    n4 = (1000.0 * (1 + 0.2 * rng.standard_normal(shape))).astype(np.float32)
+    mask = (rng.random(shape) < 0.6).astype(np.uint8)
+    sel = np.flatnonzero(mask.ravel())
+    pick = rng.permutation(sel)
+    edge, odd = pick[:len(sel) // 2], pick[len(sel) // 2:len(sel) // 2 + 7 + len(odd_in_mask)]
+    cs = rng.choice(np.array([0.6, 0.16, 0.34, 0.52, 0.7, 0.88]), size=len(edge))
+    flat = n4.ravel().astype(np.float64)
+    flat[odd[:7]] = np.array([0.0, -0.0, -5.0, 1e-30, 7.0, -1e-40, 1e-45])
+    for _ in range(60):                                   # fixed point: edge voxels relative to the final mean / p99
+        cur = flat.astype(np.float32)
+        vals = np.sort(cur[sel])
+        mean = np.float32(vals.astype(np.float64).sum() / len(vals))
+        p99 = vals[int(len(vals) * .99)]
+        anchor = np.where(cs == 0.6, np.float64(mean), np.float64(p99))
+        flat[edge] = anchor * cs
+    out = flat.astype(np.float32)
+    bump = rng.integers(-3, 4, size=len(edge))
+    out[edge] = (out[edge].view(np.int32) + bump.astype(np.int32)).view(np.float32)
+    if len(odd_in_mask):
+        out[odd[7:]] = np.array(odd_in_mask, np.float32)
+    out[np.flatnonzero(mask.ravel() == 0)[:4]] = np.array([np.nan, np.inf, -np.inf, 3e38], np.float32)
+    return out.reshape(shape), mask
+
+
+def check_vdp_threshold_edges(ctx):
+    """Threshold / linear-binning / median / border kernels on values placed a few ulps around
+    every quotient threshold (word and byte versions, mixed in one batch), given the kernel's
+    own mean (= float32 of the float64 mean) and the exact p99."""
+    shapes = [(32, 20, 6), (35, 8, 3), (64, 12, 7), (16, 16, 14), (24, 8, 2), (20, 12, 1), (33, 9, 5), (21, 10, 6)]
+    odd = [(), (), (), (), (np.inf,), (np.nan, -np.inf), (), (np.inf, np.nan)]        # last two: byte version (unaligned)
+    vols = [_near_threshold_volume(s, 100 + i, o) for i, (s, o) in enumerate(zip(shapes, odd))]
+    n4 = np.concatenate([v[0].ravel() for v in vols])
+    mask = np.concatenate([v[1].ravel() for v in vols])
+    out = ctx.pipeline_host(shapes, _lib.DO_VDP, mask=mask, n4=n4)
+    off = 0
+    for (x, m), shape, st in zip(vols, shapes, out["stats"]):
+        V = x.size
+        with np.errstate(all="ignore"):
+            vals = np.sort(x[m > 0])
+        assert int(st["n_mask"]) == len(vals)
+        p99 = vals[int(len(vals) * .99)]
+        assert st["p99"] == p99 or (np.isnan(st["p99"]) and np.isnan(p99))
+        finite = vals[np.isfinite(vals)]
+        if len(finite) == len(vals):
+            assert st["mean"] == np.float32(vals.astype(np.float64).sum() / len(vals))
+        d, lb, bd = _vdp_reference_given_stats(x, m, st["mean"], st["p99"])
+        assert np.array_equal(out["defect"][off:off + V].reshape(shape), d), shape
+        assert np.array_equal(out["defect_lb"][off:off + V].reshape(shape), lb), shape
+        assert np.array_equal(out["defect_border"][off:off + V].reshape(shape), bd), shape
+        assert int(st["n_defect"]) == int(d.sum()) and int(st["n_lb12"]) == int(((lb == 1) | (lb == 2)).sum())
+        off += V
+
+
+def check_p99_select(ctx):
+    """Exact order statistic on clustered / duplicate-heavy / signed data, keys in shared memory
+    and (VB_VDP_KEY_CAP) re-streamed from global memory."""
+    import os
+    rng = np.random.default_rng(9)
+    shape = (24, 16, 5)
+    cases = [np.full(shape, 3.25, np.float32),
+             rng.choice(np.array([1.0, 1.0000001, 2.0, -3.0], np.float32), size=shape),
+             (1000 + rng.standard_normal(shape)).astype(np.float32),
+             (rng.standard_normal(shape) * 10.0 ** rng.integers(-20, 20, size=shape)).astype(np.float32),
+             np.abs(rng.standard_normal(shape)).astype(np.float32) * np.float32(1e-40)]
+    masks = [(rng.random(shape) < p).astype(np.uint8) for p in (1.0, 0.5, 0.3, 0.9, 0.7)]
+    masks[2][0, 0, 0] = 1
+    for cap in (None, "64"):
+        if cap is None:
+            os.environ.pop("VB_VDP_KEY_CAP", None)
+        else:
+            os.environ["VB_VDP_KEY_CAP"] = cap
+        try:
+            out = ctx.pipeline_host([shape] * len(cases), _lib.DO_VDP, mask=np.concatenate([m.ravel() for m in masks]),
+                                    n4=np.concatenate([c.ravel() for c in cases]))
+        finally:
+            os.environ.pop("VB_VDP_KEY_CAP", None)
+        for x, m, st in zip(cases, masks, out["stats"]):
+            vals = np.sort(x[m > 0])
+            assert int(st["n_mask"]) == len(vals)
+            assert st["p99"] == vals[int(len(vals) * .99)], (cap, st["p99"], vals[int(len(vals) * .99)])

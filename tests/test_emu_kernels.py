@@ -122,3 +122,11 @@ def test_class_surface_end_to_end(ctx, monkeypatch):
     # reference quirk: the array constructor without vox raises (Vent_Analysis.py:166)
     with pytest.raises(Exception):
         helpers.quiet(Vent_Analysis, xenon_array=img, mask_array=mask.astype(np.float64))
+
+
+def test_vdp_thresholds_a_few_ulps_around_every_edge(ctx):
+    helpers.check_vdp_threshold_edges(ctx)
+
+
+def test_vdp_p99_select_shared_and_restreamed(ctx):
+    helpers.check_p99_select(ctx)

@@ -100,6 +100,14 @@ def test_edge_cases_ragged_degenerate_inputs(ctx):
     helpers.check_edge_cases(ctx)
 
 
+def test_vdp_thresholds_a_few_ulps_around_every_edge(ctx):
+    helpers.check_vdp_threshold_edges(ctx)
+
+
+def test_vdp_p99_select_shared_and_restreamed(ctx):
+    helpers.check_p99_select(ctx)
+
+
 def test_class_surface_end_to_end_c2():
     from vent_analysis_b200 import CI, Vent_Analysis
     g, shape, vox, img, mask, n4 = helpers.golden_inputs("C2")

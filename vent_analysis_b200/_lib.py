@@ -295,7 +295,7 @@ class Context:
                                               lattice_capacity, _ptr(ncp), _ptr(trace), trace_capacity))
         L = int(np.prod(ncp))
         phases = dict(zip(("setup", "hist", "sharpen", "fit", "update", "chain", "finalize", "other",
-                           "chain_prefix", "chain_setup", "chain_mu", "chain_sigma"), (float(x) for x in trace[-12:])))
+                           "chain_prefix", "chain_warp", "chain_team", "chain_unused"), (float(x) for x in trace[-12:])))
         tr = trace[:-12]
         return dict(hist=hist, emap=emap, lattice=lat[:L].reshape(tuple(int(x) for x in ncp)).copy(), ncp=ncp,
                     conv=tr[tr >= 0], phase_us=phases)

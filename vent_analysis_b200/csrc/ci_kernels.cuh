@@ -51,6 +51,41 @@ VB_KERNEL void ci_pack_kernel(CiArgs a) {
     uint32_t* bits = a.bits + a.word_off[si];
     int* list = a.list + S.off;
     if (blockIdx.x == 0 && threadIdx.x == 0) a.stats[si].ci_error = 0;
+    const int ncols = n1 * n2;
+    if ((n0 & 31) == 0 && (ncols & 3) == 0 && (S.off & 3) == 0) {
+        // Fast path: a flat word is 32 consecutive rows of one (col, slice).  A thread takes four
+        // neighbouring (col, slice) positions and walks the 32 rows of one slab with 4-byte
+        // loads, so a warp reads 128 contiguous bytes per row (the volume is read exactly once,
+        // coalesced) instead of 32 single bytes one row stride apart per word.
+        const int G = ncols >> 2, slabs = n0 >> 5, W0 = n0 >> 5;
+        for (int t = (int)(blockIdx.x * blockDim.x + threadIdx.x); t < G * slabs; t += (int)(gridDim.x * blockDim.x)) {
+            const int g = t % G, sl = t / G;
+            const uint8_t* p = d + (size_t)(sl * 32) * ncols + 4 * g;
+            uint32_t acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 8
+            for (int b = 0; b < 32; ++b) {
+                const uint32_t v = *(const uint32_t*)(p + (size_t)b * ncols);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[e] |= (uint32_t)(((v >> (8 * e)) & 0xFFu) != 0u) << b;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int q = 4 * g + e, j = q / n2, k = q - j * n2;
+                const int w = sl + W0 * (j + n1 * k);
+                bits[w] = acc[e];
+                if (acc[e]) {
+                    int pos = atomicAdd(&a.count[si], __popc(acc[e]));
+                    uint32_t m = acc[e];
+                    while (m) {
+                        const int b = __ffs((int)m) - 1;
+                        m &= m - 1;
+                        list[pos++] = (w << 5) + b;
+                    }
+                }
+            }
+        }
+        return;
+    }
     for (int w = (int)(blockIdx.x * blockDim.x + threadIdx.x); w < words; w += (int)(gridDim.x * blockDim.x)) {
         uint32_t word = 0;
         int f = w << 5;

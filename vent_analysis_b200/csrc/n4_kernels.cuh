@@ -52,6 +52,9 @@
 #define VB_N4_CHAIN_WARPS 16                      /* warps of the chain team while it overlaps  */
 #endif
 #define VB_N4_SERIAL 64                           /* first elements: one thread, sequentially */
+#ifndef VB_N4_WARP_END
+#define VB_N4_WARP_END 2048                       /* ... then one warp up to here (multiple of 8), then the team */
+#endif
 #define VB_N4_HCOPIES 8                           /* histogram copies (warp & 7)              */
 
 struct N4Args {
@@ -64,7 +67,8 @@ struct N4Args {
     vb_n4_params p;
     vb_subject_stats* stats; // may be null
     // per-CTA workspace (slot = blockIdx.x)
-    float* ws_logI;          // [grid][Vmax]      compact log image when it does not fit smem
+    float* ws_logI;          // [grid][Vmax]      compact log image (L2 resident; read once per iteration)
+    float* ws_u;             // [grid][Vmax]      compact U = logI - bias when it does not fit smem
     uint32_t* ws_colmask;    // [grid][cmw_max]   per column: row bitmask words
     uint32_t* ws_rbb;        // [grid][rbb_max]   C-order rank of the first mask voxel of (row, block)
     uint32_t* ws_wbase;      // [grid][wb_max]    compact offset of every (block, 32-row word) (+1)
@@ -194,7 +198,8 @@ struct N4Ctx {
     const float* img;
     const uint8_t* msk;
     float* out;
-    float* logI;          // compact log image (shared or global memory)
+    float* logI;          // compact log image (global memory, L2)
+    float* U;             // compact U = logI - bias(L) of the committed lattice (shared or global memory)
     uint32_t* colmask;    // [W][ncols]
     uint32_t* rbb;        // [n0][nblk] (+1)
     uint32_t* wbase;      // [nblk][W] (+1)
@@ -546,7 +551,7 @@ VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float&
         }
         __syncthreads();
     }
-    if (M <= smem_cap) c.logI = smem_logI;             // the compact log image fits shared memory
+    if (M <= smem_cap) c.U = smem_logI;                // the compact U image fits shared memory
 
     float tmin = FLT_MAX, tmax = -FLT_MAX;
     const unsigned lt = (1u << lane) - 1u;
@@ -573,6 +578,7 @@ VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float&
                         const float l = (x[j] > 0.0f) ? logf(x[j]) : x[j];
                         const unsigned below = (unsigned)__popc(bal & lt);
                         c.logI[pos + below] = l;
+                        c.U[pos + below] = l;            // zero lattice: U = log image
                         tmin = fminf(tmin, l);
                         tmax = fmaxf(tmax, l);
                     }
@@ -600,6 +606,7 @@ VB_DEV void n4_range(N4Ctx& c, float& bmin, float& bmax) {
             n4_win_advance(win, c.L, c, col, c.r_bev[r], Gl, c.gstride);
             if (bit) {
                 const float u = c.logI[idx] - n4_win_eval(win, c.r_evw[r]);
+                c.U[idx] = u;
                 tmin = fminf(tmin, u);
                 tmax = fmaxf(tmax, u);
             }
@@ -626,13 +633,9 @@ VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     VB_N4_FOR_ITEMS(c, T, it) {
         const N4Item I = n4_item(c, it);
         if (I.empty) continue;
-        const N4Col col = n4_col(c, ac, as, I.q);
-        const float* Gl = c.G ? c.G + I.k : nullptr;
-        N4Win win; win.cur = -1; win.g0 = win.g1 = win.g2 = win.g3 = 0.0f;
         VB_N4_FOR_ROWS(c, I, {
-            n4_win_advance(win, c.L, c, col, c.r_bev[r], Gl, c.gstride);
             if (bit) {
-                const float u = c.logI[idx] - n4_win_eval(win, c.r_evw[r]);
+                const float u = c.U[idx];
                 const float cidx = n4_div(u - bmin, slope, rslope);
                 const float fl = floorf(cidx);
                 const int bi = (int)fl;
@@ -668,6 +671,9 @@ VB_DEV void n4_fft(const N4Team& T, double* re, double* im, int N, int logN, int
         }
     }
     n4_sync(T);
+    // The 32 butterflies b = 32 m .. 32 m + 31 of a stage with len <= 64 touch exactly the aligned
+    // elements 64 m .. 64 m + 63, and they always belong to the same warp (b = tid + j * nt, nt a
+    // multiple of 32): those stages only need the warp to be in step, not the team.
     for (int len = 2; len <= N; len <<= 1) {
         const int half = len >> 1, step = N / len;
         for (int b = tid; b < (N >> 1); b += nt) {
@@ -678,7 +684,7 @@ VB_DEV void n4_fft(const N4Team& T, double* re, double* im, int N, int logN, int
             re[i1] = re[i0] - xr; im[i1] = im[i0] - xi;
             re[i0] += xr; im[i0] += xi;
         }
-        n4_sync(T);
+        if (2 * len <= 64) __syncwarp(); else n4_sync(T);
     }
 }
 
@@ -806,12 +812,9 @@ VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     VB_N4_FOR_ITEMS(c, T, it) {
         const N4Item I = n4_item(c, it);
         if (I.empty) continue;
-        const N4Col col = n4_col(c, ac, as, I.q);
-        const float* Gl = c.G ? c.G + I.k : nullptr;
         const int cc = I.q / n2, ss = I.q - cc * n2;
         const int bc = ac.bfit[cc];
         const float4 wc = OMEGA ? ac.fit2[cc] : ac.fit3[cc];
-        N4Win win; win.cur = -1; win.g0 = win.g1 = win.g2 = win.g3 = 0.0f;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int cur = -1;                                    // window = coefficients cur .. cur+3
         VB_N4_FOR_ROWS(c, I, {
@@ -822,7 +825,6 @@ VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
                 a0 = a1; a1 = a2; a2 = a3; a3 = 0.f;
                 ++cur;
             }
-            if (!OMEGA) n4_win_advance(win, c.L, c, col, c.r_bev[r], Gl, c.gstride);
             if (bit) {
                 float val;
                 float4 wt;
@@ -830,7 +832,7 @@ VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
                     val = 1.0f;
                     wt = ar.fit2[r];
                 } else {
-                    const float u = c.logI[idx] - n4_win_eval(win, c.r_evw[r]);
+                    const float u = c.U[idx];
                     const float cidx = n4_div(u - bmin, slope, rslope);
                     const float fl = floorf(cidx);
                     const int bi = (int)fl;
@@ -930,15 +932,23 @@ VB_DEV int n4_chain_scan(const N4Team& T, int v, int& total, int* tot, int& flag
     }
     if (lane == 31) tot[w] = inc;
     flag = n4_sync_or(T, flag);
-    int wt = (lane < nw) ? tot[lane] : 0;
+    const int tv = (lane < nw) ? tot[lane] : 0;            // nw <= 32: two warp reductions
+    total = (int)__reduce_add_sync(VB_FULL, (unsigned)tv);
+    const int woff = (int)__reduce_add_sync(VB_FULL, (unsigned)((lane < w) ? tv : 0));
+    return woff + inc - v;
+}
+// the same for the 32 lanes of one warp: no shared memory, no barrier
+VB_DEV int n4_warp_scan(int v, int& total, int& flag) {
+    const int lane = vb_lane();
+    int inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(VB_FULL, wt, d);
-        if (lane >= d) wt += t;
+        const int t = __shfl_up_sync(VB_FULL, inc, d);
+        if (lane >= d) inc += t;
     }
-    total = __shfl_sync(VB_FULL, wt, 31);
-    const int woff = __shfl_sync(VB_FULL, wt, (w > 0) ? w - 1 : 0);
-    return ((w > 0) ? woff : 0) + inc - v;
+    total = __shfl_sync(VB_FULL, inc, 31);
+    flag = __any_sync(VB_FULL, flag);
+    return inc - v;
 }
 
 // sigma + (th + tl) rounded to float (TwoSum keeps the part of th that the first add drops)
@@ -950,9 +960,101 @@ VB_DEV float n4_sigma_add(float sigma, float th, float tl) {
 }
 VB_DEV int n4_binade(int bits) { return bits >> 23; }
 
+// One chunk [start, start + len) of the chain: every participating thread runs its <= VB_N4_EPT
+// consecutive steps exactly from a guessed start state; the starts are re-derived from the
+// prefix sum of the threads' bit-pattern increments until none moves.  WARP = false: the
+// threads of team T, one barrier per sweep.  WARP = true: the 32 lanes of ONE warp, no barrier
+// at all (used for the first elements, where a chunk may not be longer than the number of
+// elements before it and a block-wide sweep would cost a barrier for a handful of steps).
+// (mu_b, sg_b): float bit patterns of the state at the chunk start (in) / end (out), uniform.
+template <bool WARP>
+VB_DEV void n4_chain_chunk(N4Ctx& c, const N4Team& T, const float* epx, int start, int len, int& mu_b, int& sg_b,
+                           int (*s_tot)[32], int& buf) {
+    const int nt = WARP ? 32 : T.nt, tid = WARP ? (T.tid & 31) : T.tid;
+    const int ept = (len + nt - 1) / nt;                      // <= VB_N4_EPT
+    const int lo = start + min(len, tid * ept);
+    const int cnt = start + min(len, tid * ept + ept) - lo;   // steps of this thread
+    const int mu0 = mu_b, sg0 = sg_b;
+    float px[VB_N4_EPT];
+    N4Step st[VB_N4_EPT];
+    if (cnt == VB_N4_EPT && VB_N4_EPT == 8) {                 // lo is a multiple of 8 here: 16-byte loads
+        const float4 p0 = *(const float4*)(epx + lo), p1 = *(const float4*)(epx + lo + 4);
+        px[0] = p0.x; px[1] = p0.y; px[2] = p0.z; px[3] = p0.w; px[4] = p1.x; px[5] = p1.y; px[6] = p1.z; px[7] = p1.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < VB_N4_EPT; ++i) px[i] = (i < cnt) ? epx[lo + i] : 1.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < VB_N4_EPT; ++i) st[i] = n4_step_consts(px[i], lo + i + 1);
+    // mu: one scan per sweep; it also tells whether the previous sweep moved any start (if not,
+    // the sweep just computed has confirmed the trajectory).
+    int km = mu0, total = 0, changed = 1;
+    for (;;) {
+        float mu = __int_as_float(km);
+#pragma unroll
+        for (int i = 0; i < VB_N4_EPT; ++i)
+            if (i < cnt) mu = n4_mu_next(mu, st[i]);
+        const int off = WARP ? n4_warp_scan(__float_as_int(mu) - km, total, changed)
+                             : n4_chain_scan(T, __float_as_int(mu) - km, total, s_tot[buf], changed);
+        buf ^= 1;
+        ++c.n_sweeps;
+        if (!changed) break;
+        const int k = mu0 + off;
+        changed = (k != km);
+        km = k;
+    }
+    const int mu_end = mu0 + total;
+    // sigma, along the exact mu trajectory.  The terms dd*(N-1)/N do not depend on sigma:
+    // form them once (head in px[], tail in st[].b).  A step then only depends on sigma
+    // through the binade it rounds in, so a thread re-runs its steps only when a new start
+    // lies in another binade than the one it ran from (or its span crosses a binade).
+    {
+        float mu = __int_as_float(km);
+#pragma unroll
+        for (int i = 0; i < VB_N4_EPT; ++i)
+            if (i < cnt) {
+                const float d = __fsub_rn(px[i], mu);
+                const float dd = __fmul_rn(d, d);
+                const float th = fmaf(-dd, st[i].ch, dd);
+                const float tl = fmaf(-dd, st[i].cl, fmaf(-dd, st[i].ch, __fsub_rn(dd, th)));
+                mu = n4_mu_next(mu, st[i]);
+                px[i] = th; st[i].b = tl;
+            }
+    }
+    // first guess: sigma grows about linearly with N inside the chunk
+    int ks = __float_as_int(__int_as_float(sg0) * ((float)lo / (float)start));
+    if (tid == 0 || cnt == 0) ks = sg0;
+    int inc = 0;
+    bool rerun = true;
+    changed = 1;
+    for (;;) {
+        if (rerun) {
+            float sg = __int_as_float(ks);
+#pragma unroll
+            for (int i = 0; i < VB_N4_EPT; ++i)
+                if (i < cnt) sg = n4_sigma_add(sg, px[i], st[i].b);
+            inc = __float_as_int(sg) - ks;
+        }
+        const int off = WARP ? n4_warp_scan(inc, total, changed) : n4_chain_scan(T, inc, total, s_tot[buf], changed);
+        buf ^= 1;
+        c.n_sweeps += 1000;
+        if (!changed) break;
+        const int k = sg0 + off;
+        // the increments computed from `ks` also hold from `k` when start and end stay in
+        // the same single binade (every add then rounds to the same grid)
+        const bool same = (k == ks) || (n4_binade(k) == n4_binade(ks) && n4_binade(k + inc) == n4_binade(k) &&
+                                        n4_binade(ks + inc) == n4_binade(ks));
+        rerun = !same;
+        changed = rerun;
+        ks = k;
+    }
+    mu_b = mu_end;
+    sg_b = sg0 + total;
+}
+
 VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
-    const int nt = T.nt, tid = T.tid;
-    VB_SHARED int s_state[2];                 // float bit patterns of (mu, sigma) at the chunk start
+    const int tid = T.tid;
+    VB_SHARED int s_state[2];                 // float bit patterns of (mu, sigma) handed between the phases
     VB_SHARED int s_tot[2][32];               // warp totals, double buffered
     int buf = 0;
     const float* epx = c.ec;                  // pixel, C order
@@ -961,109 +1063,44 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
     long long tq = vb_clock();
     if (tid < S0) s_px[tid] = epx[tid];
     n4_sync(T);
-    if (tid == 0) {
-        float mu = 0.0f, sigma = 0.0f;
-        for (int j = 0; j < S0; ++j) {
-            const float px = s_px[j];
-            const N4Step s = n4_step_consts(px, j + 1);
-            if (j > 0) sigma = n4_sigma_next(sigma, mu, px, s);
-            mu = (j == 0) ? s.b : n4_mu_next(mu, s);
+    // phase 1: the first elements, one thread, sequentially.  Phase 2: up to VB_N4_WARP_END, one
+    // warp, chunks of <= 32 * VB_N4_EPT elements, no barrier.
+    const int wend = min(M, VB_N4_WARP_END);
+    if (tid < 32) {
+        int mu_b = 0, sg_b = 0;
+        if (tid == 0) {
+            float mu = 0.0f, sigma = 0.0f;
+            for (int j = 0; j < S0; ++j) {
+                const float px = s_px[j];
+                const N4Step s = n4_step_consts(px, j + 1);
+                if (j > 0) sigma = n4_sigma_next(sigma, mu, px, s);
+                mu = (j == 0) ? s.b : n4_mu_next(mu, s);
+            }
+            mu_b = __float_as_int(mu); sg_b = __float_as_int(sigma);
         }
-        s_state[0] = __float_as_int(mu); s_state[1] = __float_as_int(sigma);
+        mu_b = __shfl_sync(VB_FULL, mu_b, 0); sg_b = __shfl_sync(VB_FULL, sg_b, 0);
+        { const long long tn = vb_clock(); c.t_sub[0] += tn - tq; tq = tn; }
+        for (int start = S0; start < wend;) {
+            const int len = min(min(start, 32 * VB_N4_EPT), wend - start);
+            n4_chain_chunk<true>(c, T, epx, start, len, mu_b, sg_b, s_tot, buf);
+            start += len;
+        }
+        if (tid == 0) { s_state[0] = mu_b; s_state[1] = sg_b; }
+        { const long long tn = vb_clock(); c.t_sub[1] += tn - tq; tq = tn; }
     }
     n4_sync(T);
-    { const long long tn = vb_clock(); c.t_sub[0] += tn - tq; tq = tn; }
-    int start = S0;
-    while (start < M) {
-        const int len = min(min(start, nt * VB_N4_EPT), M - start);
-        const int ept = (len + nt - 1) / nt;                  // <= VB_N4_EPT
-        const int lo = start + min(len, tid * ept);
-        const int cnt = start + min(len, tid * ept + ept) - lo;   // steps of this thread
-        const int mu0 = s_state[0], sg0 = s_state[1];
-        float px[VB_N4_EPT];
-        N4Step st[VB_N4_EPT];
-        if (cnt == VB_N4_EPT && VB_N4_EPT == 8) {             // lo is a multiple of 8 here: 16-byte loads
-            const float4 p0 = *(const float4*)(epx + lo), p1 = *(const float4*)(epx + lo + 4);
-            px[0] = p0.x; px[1] = p0.y; px[2] = p0.z; px[3] = p0.w; px[4] = p1.x; px[5] = p1.y; px[6] = p1.z; px[7] = p1.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < VB_N4_EPT; ++i) px[i] = (i < cnt) ? epx[lo + i] : 1.0f;
-        }
-#pragma unroll
-        for (int i = 0; i < VB_N4_EPT; ++i) st[i] = n4_step_consts(px[i], lo + i + 1);
-        // mu: a thread runs its steps sequentially (exactly) from its guessed start; the starts
-        // are re-derived from the prefix sum of the threads' increments until none moves.  One
-        // barrier per sweep: it publishes the warps' totals AND tells whether the previous sweep
-        // moved any start (if not, the sweep just computed has confirmed the trajectory).
-        int km = mu0, total = 0, changed = 1;
-        { const long long tn = vb_clock(); c.t_sub[1] += tn - tq; tq = tn; }
-        for (;;) {
-            float mu = __int_as_float(km);
-#pragma unroll
-            for (int i = 0; i < VB_N4_EPT; ++i)
-                if (i < cnt) mu = n4_mu_next(mu, st[i]);
-            const int off = n4_chain_scan(T, __float_as_int(mu) - km, total, s_tot[buf], changed);
-            buf ^= 1;
-            ++c.n_sweeps;
-            if (!changed) break;
-            const int k = mu0 + off;
-            changed = (k != km);
-            km = k;
-        }
-        const int mu_end = mu0 + total;
-        { const long long tn = vb_clock(); c.t_sub[2] += tn - tq; tq = tn; }
-        // sigma, along the exact mu trajectory.  The terms dd*(N-1)/N do not depend on sigma:
-        // form them once (head in px[], tail in st[].b).  A step then only depends on sigma
-        // through the binade it rounds in, so a thread re-runs its steps only when a new start
-        // lies in another binade than the one it ran from (or its span crosses a binade).
-        {
-            float mu = __int_as_float(km);
-#pragma unroll
-            for (int i = 0; i < VB_N4_EPT; ++i)
-                if (i < cnt) {
-                    const float d = __fsub_rn(px[i], mu);
-                    const float dd = __fmul_rn(d, d);
-                    const float th = fmaf(-dd, st[i].ch, dd);
-                    const float tl = fmaf(-dd, st[i].cl, fmaf(-dd, st[i].ch, __fsub_rn(dd, th)));
-                    mu = n4_mu_next(mu, st[i]);
-                    px[i] = th; st[i].b = tl;
-                }
-        }
-        // first guess: sigma grows about linearly with N inside the chunk
-        int ks = __float_as_int(__int_as_float(sg0) * ((float)lo / (float)start));
-        if (tid == 0 || cnt == 0) ks = sg0;
-        int inc = 0;
-        bool rerun = true;
-        changed = 1;
-        for (;;) {
-            if (rerun) {
-                float sg = __int_as_float(ks);
-#pragma unroll
-                for (int i = 0; i < VB_N4_EPT; ++i)
-                    if (i < cnt) sg = n4_sigma_add(sg, px[i], st[i].b);
-                inc = __float_as_int(sg) - ks;
-            }
-            const int off = n4_chain_scan(T, inc, total, s_tot[buf], changed);
-            buf ^= 1;
-            c.n_sweeps += 1000;
-            if (!changed) break;
-            const int k = sg0 + off;
-            // the increments computed from `ks` also hold from `k` when start and end stay in
-            // the same single binade (every add then rounds to the same grid)
-            const bool same = (k == ks) || (n4_binade(k) == n4_binade(ks) && n4_binade(k + inc) == n4_binade(k) &&
-                                            n4_binade(ks + inc) == n4_binade(ks));
-            rerun = !same;
-            changed = rerun;
-            ks = k;
-        }
-        const int sg_end = sg0 + total;
-        if (tid == 0) { s_state[0] = mu_end; s_state[1] = sg_end; }
-        n4_sync(T);
-        { const long long tn = vb_clock(); c.t_sub[3] += tn - tq; tq = tn; }
+    int mu_b = s_state[0], sg_b = s_state[1];
+    buf = 0;
+    // phase 3: the team, chunks of <= nt * VB_N4_EPT elements (and never longer than the number
+    // of elements before them: the start perturbations then contract), one barrier per sweep
+    for (int start = max(S0, wend); start < M;) {
+        const int len = min(min(start, T.nt * VB_N4_EPT), M - start);
+        n4_chain_chunk<false>(c, T, epx, start, len, mu_b, sg_b, s_tot, buf);
         start += len;
     }
-    const float mu = __int_as_float(s_state[0]), sigma = __int_as_float(s_state[1]);
-    n4_sync(T);
+    { const long long tn = vb_clock(); c.t_sub[2] += tn - tq; tq = tn; }
+    const float mu = __int_as_float(mu_b), sigma = __int_as_float(sg_b);
+    n4_sync(T);                               // s_state / s_tot may be rewritten by the next call
     const float sd = (float)sqrt((double)sigma / ((double)(float)M - 1.0));
     return __fdiv_rn(sd, mu);
 }
@@ -1102,12 +1139,15 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
         wo.g0 = wo.g1 = wo.g2 = wo.g3 = wn.g0 = wn.g1 = wn.g2 = wn.g3 = 0.0f;
         VB_N4_FOR_ROWS_RANK(c, I, {
             const int base = c.r_bev[r];
+            float li = 0.0f;
+            if (bit) li = c.logI[idx];                               // L2; requested before the window updates
             n4_win_advance(wo, c.Lold, c, col, base, Go, c.gstride);
             n4_win_advance(wn, c.L, c, col, base, Gw, c.gstride);
             if (bit) {
                 const float4 rw = c.r_evw[r];
                 const float bo = n4_win_eval(wo, rw), bn = n4_win_eval(wn, rw);
-                const float un = c.logI[idx] - bn;
+                const float un = li - bn;
+                c.U[idx] = un;                                       // read by the next histogram / fit
                 tmin = fminf(tmin, un);
                 tmax = fmaxf(tmax, un);
                 const float ev = n4_exp_small(bo - bn);
@@ -1293,7 +1333,8 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                 c.slot[ax] = max(nn[ax], f);
             }
         }
-        c.logI = a.ws_logI + (size_t)blockIdx.x * a.Vmax;   // n4_setup moves it to shared memory if it fits
+        c.logI = a.ws_logI + (size_t)blockIdx.x * a.Vmax;
+        c.U = a.ws_u + (size_t)blockIdx.x * a.Vmax;         // n4_setup moves it to shared memory if it fits
         c.rowtab = (a.rowtab_rows > 0 && S.n0 <= a.rowtab_rows) ? smem_rowtab : nullptr;
 
         float bmin, bmax;
@@ -1304,7 +1345,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         n4_setup(c, a.p.mask_label, smem_logI, a.logI_cap, bmin, bmax, M);
         for (int e = tid; e < a.Lmax; e += (int)blockDim.x) { c.L[e] = 0.0f; c.Lold[e] = 0.0f; }
         {
-            const int used = (c.logI == smem_logI) ? ((M + 3) & ~3) : 0;
+            const int used = (c.U == smem_logI) ? ((M + 3) & ~3) : 0;
             c.gspace = smem_logI + used; c.gcap = a.logI_cap - used;
             c.gstride = (c.nact + 31) & ~31; c.G = nullptr;
         }

@@ -42,12 +42,33 @@ struct VbMaxF { VB_DEV_MEMBER float operator()(float a, float b) const { return 
 struct VbMinI { VB_DEV_MEMBER int operator()(int a, int b) const { return a < b ? a : b; } };
 struct VbMaxI { VB_DEV_MEMBER int operator()(int a, int b) const { return a > b ? a : b; } };
 
-// order-preserving float <-> uint key (radix select)
+// order-preserving float <-> uint key (radix select).  The bit pattern is moved through an opaque
+// register move: seen as `bitcast(f) | signbit`, the compiler emits -|f| as a FLOAT add, which
+// replaces a NaN by the canonical positive NaN and so changes its key (found on the B200 by the
+// NaN-in-mask parity case).
+VB_DEV unsigned vb_float_bits(float f) {
+#if defined(VB_EMULATE)
+    return __float_as_uint(f);
+#else
+    unsigned u;
+    asm("mov.b32 %0, %1;" : "=r"(u) : "f"(f));
+    return u;
+#endif
+}
+VB_DEV float vb_bits_float(unsigned u) {
+#if defined(VB_EMULATE)
+    return __uint_as_float(u);
+#else
+    float f;
+    asm("mov.b32 %0, %1;" : "=f"(f) : "r"(u));
+    return f;
+#endif
+}
 VB_DEV unsigned vb_float_key(float f) {
-    const unsigned u = __float_as_uint(f);
+    const unsigned u = vb_float_bits(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 VB_DEV float vb_key_float(unsigned k) {
     const unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-    return __uint_as_float(u);
+    return vb_bits_float(u);
 }

@@ -12,6 +12,9 @@
 #ifndef VB_VDP_THREADS
 #define VB_VDP_THREADS 1024
 #endif
+#ifndef VB_SNR_THREADS
+#define VB_SNR_THREADS VB_VDP_THREADS     /* threads per CTA of snr_kernel (<= VB_VDP_THREADS) */
+#endif
 #define VB_SNR_MAX_AXIS 8192   // n0 + n1 + n2 must not exceed this (projection flags in smem)
 
 // ---------------------------------------------------------------------------------------------
@@ -48,6 +51,19 @@ VB_DEV Vb4b vb_load4b(const uint8_t* p, int v, int V, bool aligned) {
         for (int e = 0; e < 4; ++e) r.v[e] = (v + e < V) ? p[v + e] : (uint8_t)0;
     }
     return r;
+}
+
+// four mask bytes as one word (0 beyond the volume); bit 7 of every non-zero byte
+VB_DEV uint32_t vb_load4b_word(const uint8_t* p, int v, int V, bool aligned) {
+    if (aligned && v + 3 < V) return *(const uint32_t*)(p + v);
+    uint32_t w = 0u;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (v + e < V) w |= (uint32_t)p[v + e] << (8 * e);
+    return w;
+}
+VB_DEV uint32_t vb_nonzero_bytes(uint32_t w) {
+    return ((((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u);
 }
 
 VB_KERNEL void VB_LAUNCH_BOUNDS(VB_VDP_THREADS, 1)
@@ -186,8 +202,8 @@ snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, cons
 
 // ---------------------------------------------------------------------------------------------
 // VDP statistics, one CTA per subject: M = #mask, mean (float32 of the float64 sum), and the
-// exact order statistic sorted(N4[mask>0])[int(M*.99)] by a 3-pass (11+11+10 bit) radix select
-// on the order-preserving key of the float bits.  Also zeroes the defect / LB counters.
+// exact order statistic sorted(N4[mask>0])[int(M*.99)] by a radix select on the order-preserving
+// key of the float bits.  Also zeroes the defect / LB counters.
 struct VbRun { int bin; unsigned cnt; };
 VB_DEV void vb_run_add(VbRun& r, unsigned* hist, int bin) {
     if (bin == r.bin) { ++r.cnt; return; }
@@ -235,85 +251,131 @@ VB_DEV int vdp_find_bin(unsigned* hist, int nb, long long& k, int* s_bin, long l
     return *s_bin;
 }
 
+// One pass over HBM: the mask is read once, the image only where the mask is set (16-byte loads,
+// four independent 20-byte groups per thread in flight); sum / count / key range go to registers
+// and the order-preserving keys of the mask voxels are compacted into shared memory (`key_cap`
+// keys of dynamic shared memory; warp-aggregated append).  The radix select then runs on the
+// shared-memory keys: the key range [kmin, kmax] is split into <= 2048 equal bins per level
+// (range-normalised, so clustered data still spread over the bins), <= 3 levels.  Subjects whose
+// mask does not fit `key_cap` re-stream the volume for every level instead.
+VB_DEV void vdp_hist_keys(unsigned* hist, unsigned key, unsigned lo, unsigned range, int sh, VbRun& run) {
+    const unsigned d = key - lo;
+    if (d <= range) vb_run_add(run, hist, (int)(d >> sh));
+}
+
 VB_KERNEL void VB_LAUNCH_BOUNDS(VB_VDP_THREADS, 1)
 vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, int n,
-                 vb_subject_stats* stats) {
+                 vb_subject_stats* stats, int key_cap) {
+    VB_DYN_SMEM(smem);
+    unsigned* keys = (unsigned*)smem;                    // [key_cap]
     VB_SHARED unsigned hist[2048];
     VB_SHARED double red[64];
-    VB_SHARED int s_bin;
+    VB_SHARED int s_bin, s_nkeys;
     VB_SHARED long long s_k;
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = tid & 31;
     for (int si = (int)blockIdx.x; si < n; si += (int)gridDim.x) {
         const VbSubject S = subj[si];
         const float* x = n4 + S.off;
         const uint8_t* msk = mask + S.off;
         const bool aligned = (S.off & 3) == 0;
         __syncthreads();
-        for (int i = tid; i < 2048; i += nt) hist[i] = 0;
+        if (tid == 0) s_nkeys = 0;
         __syncthreads();
         double sum = 0.0;
-        long long cnt = 0;
-        VbRun run; run.bin = 0; run.cnt = 0u;
-        for (int v = 4 * tid; v < S.V; v += 4 * nt) {
-            const Vb4b m = vb_load4b(msk, v, S.V, aligned);
-            if (!(m.v[0] | m.v[1] | m.v[2] | m.v[3])) continue;
-            const Vb4f f = vb_load4f(x, v, S.V, aligned);
+        int cnt = 0;
+        unsigned kmin = 0xffffffffu, kmax = 0u;
+        // software pipelined: the mask words of the next step are requested together with the
+        // image loads of the current one (one DRAM latency per step instead of two)
+        uint32_t mw[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (m.v[e]) {
-                    sum += (double)f.v[e]; ++cnt;
-                    vb_run_add(run, hist, (int)(vb_float_key(f.v[e]) >> 21));
+        for (int u = 0; u < 4; ++u) mw[u] = vb_load4b_word(msk, 4 * (u * nt + tid), S.V, aligned);
+        for (int base = 0; base < S.V; base += 16 * nt) {            // trip count is block uniform
+            Vb4f f[4];
+            uint32_t mn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (mw[u]) f[u] = vb_load4f(x, base + 4 * (u * nt + tid), S.V, aligned);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mn[u] = vb_load4b_word(msk, base + 16 * nt + 4 * (u * nt + tid), S.V, aligned);
+            int c = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c += __popc(vb_nonzero_bytes(mw[u]));
+            if (__any_sync(VB_FULL, c)) {
+                // warp-aggregated append: exclusive prefix of the lanes' counts, one atomic per warp
+                int inc = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(VB_FULL, inc, d);
+                    if (lane >= d) inc += t;
                 }
+                int wbase = 0;
+                if (lane == 31) wbase = atomicAdd(&s_nkeys, inc);
+                wbase = __shfl_sync(VB_FULL, wbase, 31);
+                int pos = wbase + inc - c;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!mw[u]) continue;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if ((mw[u] >> (8 * e)) & 0xFFu) {
+                            const float fv = f[u].v[e];
+                            const unsigned key = vb_float_key(fv);
+                            sum += (double)fv; ++cnt;
+                            kmin = min(kmin, key); kmax = max(kmax, key);
+                            if (pos < key_cap) keys[pos] = key;
+                            ++pos;
+                        }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mw[u] = mn[u];
         }
-        vb_run_flush(run, hist);
         sum = vb_block_reduce(sum, VbAddD(), 0.0, red);
-        cnt = vb_block_reduce(cnt, VbAddLL(), 0LL, (long long*)red);
+        const long long M = vb_block_reduce((long long)cnt, VbAddLL(), 0LL, (long long*)red);
+        // (signed reductions of key ^ 0x80000000 keep the unsigned order)
+        const unsigned lo0 = (unsigned)vb_block_reduce((int)(kmin ^ 0x80000000u), VbMinI(), 0x7fffffff, (int*)red) ^ 0x80000000u;
+        const unsigned hi0 = (unsigned)vb_block_reduce((int)(kmax ^ 0x80000000u), VbMaxI(), (int)0x80000000, (int*)red) ^ 0x80000000u;
         float p99 = 0.0f;
-        if (cnt > 0) {
-            long long k = (long long)((double)cnt * .99);            // int(len(signal_list)*.99)
-            if (k >= cnt) k = cnt - 1;
-            const unsigned b1 = (unsigned)vdp_find_bin(hist, 2048, k, &s_bin, &s_k);
-            __syncthreads();
-            for (int i = tid; i < 2048; i += nt) hist[i] = 0;
-            __syncthreads();
-            for (int v = 4 * tid; v < S.V; v += 4 * nt) {
-                const Vb4b m = vb_load4b(msk, v, S.V, aligned);
-                if (!(m.v[0] | m.v[1] | m.v[2] | m.v[3])) continue;
-                const Vb4f f = vb_load4f(x, v, S.V, aligned);
+        if (M > 0) {
+            const bool in_smem = M <= (long long)key_cap;
+            long long k = (long long)((double)M * .99);              // int(len(signal_list)*.99)
+            if (k >= M) k = M - 1;
+            unsigned lo = lo0, hi = hi0;
+            for (;;) {
+                const unsigned range = hi - lo;
+                if (range == 0u) break;
+                const int sh = max(0, (32 - __clz((int)range)) - 11);
+                const int nb = (int)(range >> sh) + 1;               // <= 2048
+                __syncthreads();
+                for (int i = tid; i < nb; i += nt) hist[i] = 0;
+                __syncthreads();
+                VbRun run; run.bin = 0; run.cnt = 0u;
+                if (in_smem) {
+                    for (int i = tid; i < (int)M; i += nt) vdp_hist_keys(hist, keys[i], lo, range, sh, run);
+                } else {
+                    for (int v = 4 * tid; v < S.V; v += 4 * nt) {
+                        const Vb4b m = vb_load4b(msk, v, S.V, aligned);
+                        if (!(m.v[0] | m.v[1] | m.v[2] | m.v[3])) continue;
+                        const Vb4f f = vb_load4f(x, v, S.V, aligned);
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (m.v[e]) {
-                        const unsigned key = vb_float_key(f.v[e]);
-                        if ((key >> 21) == b1) vb_run_add(run, hist, (int)((key >> 10) & 0x7FFu));
+                        for (int e = 0; e < 4; ++e)
+                            if (m.v[e]) vdp_hist_keys(hist, vb_float_key(f.v[e]), lo, range, sh, run);
                     }
+                }
+                vb_run_flush(run, hist);
+                __syncthreads();
+                const unsigned b = (unsigned)vdp_find_bin(hist, nb, k, &s_bin, &s_k);
+                lo += b << sh;
+                const unsigned w1 = (1u << sh) - 1u;                 // keys of the chosen bin: [lo, lo + w1]
+                if (hi - lo > w1) hi = lo + w1;
+                if (sh == 0) break;
             }
-            vb_run_flush(run, hist);
-            __syncthreads();
-            const unsigned b2 = (unsigned)vdp_find_bin(hist, 2048, k, &s_bin, &s_k);
-            __syncthreads();
-            for (int i = tid; i < 1024; i += nt) hist[i] = 0;
-            __syncthreads();
-            const unsigned pre = (b1 << 11) | b2;
-            for (int v = 4 * tid; v < S.V; v += 4 * nt) {
-                const Vb4b m = vb_load4b(msk, v, S.V, aligned);
-                if (!(m.v[0] | m.v[1] | m.v[2] | m.v[3])) continue;
-                const Vb4f f = vb_load4f(x, v, S.V, aligned);
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (m.v[e]) {
-                        const unsigned key = vb_float_key(f.v[e]);
-                        if ((key >> 10) == pre) vb_run_add(run, hist, (int)(key & 0x3FFu));
-                    }
-            }
-            vb_run_flush(run, hist);
-            __syncthreads();
-            const unsigned b3 = (unsigned)vdp_find_bin(hist, 1024, k, &s_bin, &s_k);
-            p99 = vb_key_float((pre << 10) | b3);
+            p99 = vb_key_float(lo);
         }
         if (tid == 0) {
             vb_subject_stats* st = stats + si;
-            st->n_mask = (int)cnt;
-            st->mean = (cnt > 0) ? (float)(sum / (double)cnt) : 0.0f;
+            st->n_mask = (int)M;
+            st->mean = (M > 0) ? (float)(sum / (double)M) : 0.0f;
             st->p99 = p99;
             st->n_defect = 0;
             st->n_lb12 = 0;
@@ -383,16 +445,12 @@ VB_KERNEL void vdp_median_kernel(const uint8_t* VB_RESTRICT d0, const VbSubject*
 #ifndef VB_CLS_THREADS
 #define VB_CLS_THREADS 512
 #endif
-VB_KERNEL void VB_LAUNCH_BOUNDS(VB_CLS_THREADS, 2)
-vdp_classify_kernel(const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, float thresh,
-                    int R, uint8_t* lb, uint8_t* defect, uint8_t* border, vb_subject_stats* stats) {
-    VB_DYN_SMEM(smem);
-    VB_SHARED int red[64];
-    const int si = (int)blockIdx.y;
-    const VbSubject S = subj[si];
+// byte-wise version: any shape / alignment
+VB_DEV void vdp_classify_bytes(unsigned char* smem, int* red, const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask,
+                               const VbSubject& S, int si, float thresh, int R, uint8_t* lb, uint8_t* defect,
+                               uint8_t* border, vb_subject_stats* stats) {
     const int n0 = S.n0, n1 = S.n1, n2 = S.n2, ncols = n1 * n2;
     const int i0 = (int)blockIdx.x * R;
-    if (i0 >= n0) return;
     const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
     const int ra = max(i0 - 2, 0), rb = min(i0 + R + 2, n0);          // rows of d0 held
     const int ma = max(i0 - 1, 0), mb = min(i0 + R + 1, n0);          // rows of the median held
@@ -499,6 +557,220 @@ vdp_classify_kernel(const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask
         if (nd) atomicAdd(&stats[si].n_defect, nd);
         if (c12) atomicAdd(&stats[si].n_lb12, c12);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Four-voxels-per-instruction version of the same tile (volumes whose row length is a multiple
+// of 4 at a 4-voxel aligned offset).
+//  * The float32 quotient tests are replaced by comparisons with per-subject thresholds: for
+//    d > 0 the rounded quotient RN(x / d) is non-decreasing in x, so {x : RN(x / d) <= c} is
+//    {x <= T} with T found by a few exact divisions next to c * d (same for <).  NaN fails every
+//    comparison, as in numpy.  Degenerate divisors (<= 0, non-finite, tiny) keep IEEE divisions.
+//  * d0 / median tiles are bytes handled as 32-bit words (four (col, slice) positions at once):
+//    the 3x3 count is three word additions, "count >= 5" one add/shift/and, the border two XORs.
+//    Column neighbours are n2 bytes away: two aligned words and a funnel shift; the per-byte
+//    "has a left / right neighbour" masks are constants of the thread.
+VB_DEV float vb_next_up_pos(float x) { return __uint_as_float(__float_as_uint(x) + 1u); }
+VB_DEV float vb_next_down_pos(float x) { return __uint_as_float(__float_as_uint(x) - 1u); }
+// largest x with RN(x / d) <= c (LE) or < c (!LE), for normal c, d > 0; NaN if not found
+template <bool LE>
+VB_DEV float vdp_quotient_threshold(float c, float d) {
+    float x = __fmul_rn(c, d);
+    int guard = 0;
+    for (; guard < 64; ++guard) {                        // first x that fails
+        const float q = __fdiv_rn(x, d);
+        if (!(LE ? (q <= c) : (q < c))) break;
+        x = vb_next_up_pos(x);
+    }
+    for (; guard < 128; ++guard) {                       // last x that passes
+        const float q = __fdiv_rn(x, d);
+        if (LE ? (q <= c) : (q < c)) return x;
+        x = vb_next_down_pos(x);
+    }
+    return __uint_as_float(0x7fc00000u);
+}
+VB_DEV uint32_t vb_funnel_r(uint32_t lo, uint32_t hi, int shift) {
+#if defined(VB_EMULATE)
+    return (uint32_t)((((uint64_t)hi << 32) | (uint64_t)lo) >> (shift & 31));
+#else
+    return __funnelshift_r(lo, hi, shift);
+#endif
+}
+struct VdpThr { float d, t1, t2, t3, t4, t5; };       // x <= d: below thresh; x <= t_i: LB code <= i
+struct VdpNbr { int wl, sl, wr, sr; uint32_t maskL, maskR; };
+VB_DEV VdpNbr vdp_nbr(int g, int n1, int n2) {
+    VdpNbr k;
+    k.maskL = k.maskR = 0u;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int j = (4 * g + e) / n2;
+        if (j > 0) k.maskL |= 0xFFu << (8 * e);
+        if (j < n1 - 1) k.maskR |= 0xFFu << (8 * e);
+    }
+    const int aL = 4 * g - n2, aR = 4 * g + n2;
+    k.wl = aL >> 2; k.sl = (aL & 3) * 8;                 // arithmetic shift: floor for negative aL
+    k.wr = aR >> 2; k.sr = (aR & 3) * 8;
+    return k;
+}
+
+VB_DEV void vdp_classify_words(unsigned char* smem, int* red, float* s_thr, int P, const float* VB_RESTRICT n4,
+                               const uint8_t* VB_RESTRICT mask, const VbSubject& S, int si, float thresh, int R,
+                               uint8_t* lb, uint8_t* defect, uint8_t* border, vb_subject_stats* stats) {
+    const int n0 = S.n0, n1 = S.n1, n2 = S.n2, ncols = n1 * n2, G = ncols >> 2;
+    const int i0 = (int)blockIdx.x * R;
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    const int ra = max(i0 - 2, 0), rb = min(i0 + R + 2, n0);          // rows of d0 held
+    const int ma = max(i0 - 1, 0), mb = min(i0 + R + 1, n0);          // rows of the median held
+    const int ib = min(i0 + R, n0);
+    uint32_t* d0w = (uint32_t*)smem + P;                              // [(R + 4) * G], P words of padding around
+    uint32_t* mdw = d0w + (size_t)(R + 4) * G + 2 * P;                // [(R + 2) * G]
+    const float mean = stats[si].mean, p99 = stats[si].p99;
+    // thresholds (threads 0..5), else exact divisions
+    const bool okdiv = mean >= 1e-30f && mean <= 1e30f && p99 >= 1e-30f && p99 <= 1e30f && thresh >= 1e-3f && thresh <= 1e3f;
+    if (okdiv && tid < 6) {
+        const float cs[5] = {0.16f, 0.34f, 0.52f, 0.7f, 0.88f};
+        s_thr[tid] = (tid == 0) ? vdp_quotient_threshold<false>(thresh, mean) : vdp_quotient_threshold<true>(cs[tid - 1], p99);
+    }
+    __syncthreads();
+    VdpThr T;
+    T.d = s_thr[0]; T.t1 = s_thr[1]; T.t2 = s_thr[2]; T.t3 = s_thr[3]; T.t4 = s_thr[4]; T.t5 = s_thr[5];
+    const bool fast = okdiv && T.d == T.d && T.t1 == T.t1 && T.t2 == T.t2 && T.t3 == T.t3 && T.t4 == T.t4 && T.t5 == T.t5;
+    const float* x = n4 + S.off + (size_t)ra * ncols;
+    const uint8_t* msk = mask + S.off + (size_t)ra * ncols;
+    uint8_t* lbo = lb + S.off + (size_t)ra * ncols;
+    const int ng = (rb - ra) * G;
+    const int own0 = (i0 - ra) * G, own1 = (ib - ra) * G;             // groups this CTA owns
+    int c12 = 0;
+    for (int gb = tid; gb < ng; gb += 4 * nt) {                       // four independent 20-byte loads in flight
+        // d0 and the code are zero outside the mask: the image is only read (and classified)
+        // where the mask word is set
+        float4 xv[4];
+        uint32_t mw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int gi = gb + u * nt;
+            mw[u] = (gi < ng) ? *(const uint32_t*)(msk + 4 * (size_t)gi) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int gi = gb + u * nt;
+            if (mw[u]) xv[u] = *(const float4*)(x + 4 * (size_t)gi);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int gi = gb + u * nt;
+            if (gi >= ng) break;
+            uint32_t dw = 0u, cw = 0u, w12 = 0u;
+            if (mw[u]) {
+            const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float xe = xs[e];
+                const bool in = ((mw[u] >> (8 * e)) & 0xFFu) != 0u;
+                int cd;
+                bool below;
+                if (fast) {
+                    below = xe <= T.d;
+                    cd = 6 - (int)(xe <= T.t1) - (int)(xe <= T.t2) - (int)(xe <= T.t3) - (int)(xe <= T.t4) - (int)(xe <= T.t5);
+                    cd = (xe == xe) ? cd : 0;                          // NaN compares false everywhere -> 0, as in numpy
+                } else {
+                    below = __fdiv_rn(xe, mean) < thresh;
+                    const float b = __fdiv_rn(xe, p99);
+                    cd = (b <= 0.16f) ? 1 : (b <= 0.34f) ? 2 : (b <= 0.52f) ? 3 : (b <= 0.7f) ? 4 : (b <= 0.88f) ? 5
+                       : (b > 0.88f) ? 6 : 0;
+                }
+                cd = in ? cd : 0;
+                dw |= (uint32_t)(below && in) << (8 * e);
+                cw |= (uint32_t)cd << (8 * e);
+                w12 |= (uint32_t)(cd == 1 || cd == 2) << e;
+            }
+            }
+            d0w[gi] = dw;
+            if (gi >= own0 && gi < own1) {
+                *(uint32_t*)(lbo + 4 * (size_t)gi) = cw;
+                c12 += __popc(w12);
+            }
+        }
+    }
+    __syncthreads();
+    // median of rows [ma, mb): a thread owns four (col, slice) positions and walks down the rows
+    // with a sliding window of the three-column sums
+    int nd = 0;
+    for (int g = tid; g < G; g += nt) {
+        const VdpNbr k = vdp_nbr(g, n1, n2);
+        uint32_t s_prev = 0u, s_cur;
+        if (ma > 0) {                                                 // row ma - 1 is held whenever it exists
+            const uint32_t* p = d0w + (size_t)(ma - 1 - ra) * G;
+            s_prev = p[g] + (vb_funnel_r(p[k.wl], p[k.wl + 1], k.sl) & k.maskL) + (vb_funnel_r(p[k.wr], p[k.wr + 1], k.sr) & k.maskR);
+        }
+        {
+            const uint32_t* p = d0w + (size_t)(ma - ra) * G;
+            s_cur = p[g] + (vb_funnel_r(p[k.wl], p[k.wl + 1], k.sl) & k.maskL) + (vb_funnel_r(p[k.wr], p[k.wr + 1], k.sr) & k.maskR);
+        }
+        for (int i = ma; i < mb; ++i) {
+            uint32_t s_next = 0u;
+            if (i + 1 < n0) {                                         // row i + 1 <= mb is held whenever it exists
+                const uint32_t* p = d0w + (size_t)(i + 1 - ra) * G;
+                s_next = p[g] + (vb_funnel_r(p[k.wl], p[k.wl + 1], k.sl) & k.maskL) + (vb_funnel_r(p[k.wr], p[k.wr + 1], k.sr) & k.maskR);
+            }
+            // per byte: count (<= 9) >= 5  <=>  bit 7 of count + 123
+            const uint32_t d = ((s_prev + s_cur + s_next + 0x7B7B7B7Bu) >> 7) & 0x01010101u;
+            mdw[(size_t)(i - ma) * G + g] = d;
+            if (i >= i0 && i < ib) {
+                *(uint32_t*)(defect + S.off + (size_t)i * ncols + 4 * g) = d;
+                nd += __popc(d);
+            }
+            s_prev = s_cur; s_cur = s_next;
+        }
+    }
+    __syncthreads();
+    if (border) {
+        for (int g = tid; g < G; g += nt) {
+            const VdpNbr k = vdp_nbr(g, n1, n2);
+            for (int i = i0; i < ib; ++i) {
+                const uint32_t* a = mdw + (size_t)(i - ma) * G;
+                const uint32_t c = a[g];
+                const uint32_t up = (i == 0) ? c : a[g - G], dn = (i == n0 - 1) ? c : a[g + G];
+                const uint32_t dl = (vb_funnel_r(a[k.wl], a[k.wl + 1], k.sl) & k.maskL) | (c & ~k.maskL);
+                const uint32_t dr = (vb_funnel_r(a[k.wr], a[k.wr + 1], k.sr) & k.maskR) | (c & ~k.maskR);
+                *(uint32_t*)(border + S.off + (size_t)i * ncols + 4 * g) = (dn ^ up) | (dr ^ dl);
+            }
+        }
+    }
+    nd = vb_block_reduce(nd, VbAddI(), 0, red);
+    c12 = vb_block_reduce(c12, VbAddI(), 0, red);
+    if (tid == 0) {
+        if (nd) atomicAdd(&stats[si].n_defect, nd);
+        if (c12) atomicAdd(&stats[si].n_lb12, c12);
+    }
+}
+
+// grid = (row tiles, subjects); dynamic shared memory: (2R + 6) * max row bytes + 16 * P.
+// A subject is handled by the word kernel when its rows are 4-voxel aligned, else by the byte
+// kernel (the host launches whichever the batch needs; each kernel skips the other's subjects).
+VB_DEV bool vdp_word_eligible(const VbSubject& S, int P) {
+    return ((S.n1 * S.n2) & 3) == 0 && (S.off & 3) == 0 && (S.n2 + 3) / 4 + 1 <= P;
+}
+VB_KERNEL void VB_LAUNCH_BOUNDS(VB_CLS_THREADS, 2)
+vdp_classify4_kernel(const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, float thresh,
+                     int R, int P, uint8_t* lb, uint8_t* defect, uint8_t* border, vb_subject_stats* stats) {
+    VB_DYN_SMEM(smem);
+    VB_SHARED int red[64];
+    VB_SHARED float s_thr[8];
+    const int si = (int)blockIdx.y;
+    const VbSubject S = subj[si];
+    if ((int)blockIdx.x * R >= S.n0 || !vdp_word_eligible(S, P)) return;
+    vdp_classify_words(smem, red, s_thr, P, n4, mask, S, si, thresh, R, lb, defect, border, stats);
+}
+VB_KERNEL void VB_LAUNCH_BOUNDS(VB_CLS_THREADS, 2)
+vdp_classify_kernel(const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, float thresh,
+                    int R, int P, uint8_t* lb, uint8_t* defect, uint8_t* border, vb_subject_stats* stats) {
+    VB_DYN_SMEM(smem);
+    VB_SHARED int red[64];
+    const int si = (int)blockIdx.y;
+    const VbSubject S = subj[si];
+    if ((int)blockIdx.x * R >= S.n0 || vdp_word_eligible(S, P)) return;
+    vdp_classify_bytes(smem, red, n4, mask, S, si, thresh, R, lb, defect, border, stats);
 }
 
 // calculateBorder: per slice, np.gradient != 0 along rows OR along columns (V_A.py:225-231)

@@ -1,6 +1,7 @@
 // libventb200: C ABI (include/ventb200.h) + host orchestration of the sm_100a kernels.
 // Also compiled for the host with -DVB_EMULATE by tests/emu (test infrastructure only).
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <unordered_set>
 #include <vector>
@@ -21,7 +22,7 @@ struct Buf {
 // per-resident-CTA workspace of the N4 kernel; two sets so that the launches of consecutive chunks
 // of the host pipeline (two compute streams) can overlap
 struct N4Ws {
-    Buf logI, colmask, rbb, wbase, acol, order, ec, axis, counter;
+    Buf logI, u, colmask, rbb, wbase, acol, order, ec, axis, counter;
 };
 
 struct TableHost {
@@ -172,7 +173,9 @@ int run_snr(vb_ctx* c, const float* image, const uint8_t* mask, int n, int fov, 
     for (const VbSubject& S : c->last_subj)
         if (S.n0 + S.n1 + S.n2 > VB_SNR_MAX_AXIS) return fail(VB_ERR_UNSUPPORTED, "SNR: n0+n1+n2 too large");
     const int grid = std::min(n, c->sms * 4);
-    VB_LAUNCH(snr_kernel, dim3(grid), dim3(VB_VDP_THREADS), 0, s, image, mask, subj_ptr(c), n,
+    int threads = VB_SNR_THREADS;
+    if (const char* e = getenv("VB_SNR_THREADS_RT")) threads = std::max(32, std::min(VB_VDP_THREADS, atoi(e) & ~31));   // tuning
+    VB_LAUNCH(snr_kernel, dim3(grid), dim3(threads), 0, s, image, mask, subj_ptr(c), n,
               fov, stats);
     ++c->launches;
     return vbrt::last_launch_ok("snr_kernel") ? VB_OK : VB_ERR_CUDA;
@@ -224,7 +227,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     const long long cap = ((long long)c->max_smem - ub - fixed - static_smem) / 4;
     const int grid = std::min(n, c->sms);
     N4Ws& W = c->n4ws[c->wsi & 1];
-    if (!ensure(W.logI, sizeof(float) * (size_t)grid * (size_t)vmax) ||
+    if (!ensure(W.logI, sizeof(float) * (size_t)grid * (size_t)vmax) || !ensure(W.u, sizeof(float) * (size_t)grid * (size_t)vmax) ||
         !ensure(W.colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(W.rbb, 4 * (size_t)grid * (size_t)rbb) ||
         !ensure(W.wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(W.acol, 4 * (size_t)grid * (size_t)ncmax) ||
         !ensure(W.order, 4 * (size_t)grid * (size_t)wb) || !ensure(W.ec, 4 * (size_t)grid * (size_t)((vmax + 3) & ~3LL)) ||
@@ -245,7 +248,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     N4Args a;
     a.image = image; a.mask = mask; a.out = out; a.logbias = logbias;
     a.subj = subj_ptr(c); a.n = n; a.p = p; a.stats = stats;
-    a.ws_logI = (float*)W.logI.p; a.ws_colmask = (uint32_t*)W.colmask.p; a.ws_rbb = (uint32_t*)W.rbb.p;
+    a.ws_logI = (float*)W.logI.p; a.ws_u = (float*)W.u.p; a.ws_colmask = (uint32_t*)W.colmask.p; a.ws_rbb = (uint32_t*)W.rbb.p;
     a.ws_wbase = (uint32_t*)W.wbase.p; a.ws_acol = (uint32_t*)W.acol.p; a.ws_order = (uint32_t*)W.order.p; a.ws_axis = (float*)W.axis.p;
     a.ws_ec = (float*)W.ec.p; a.rowtab_rows = (int)rowtab_rows;
     { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] == '1') ? 1 : 0; }
@@ -274,25 +277,50 @@ int run_vdp(vb_ctx* c, const float* n4, const uint8_t* mask, int n, float thresh
             uint8_t* dborder, vb_subject_stats* stats, vbrt::stream_t s) {
     vbrt::clear_stale_error();
     const VbSubject* subj = subj_ptr(c);
-    VB_LAUNCH(vdp_stats_kernel, dim3(std::min(n, c->sms * 4)), dim3(VB_VDP_THREADS), 0, s, n4, mask, subj, n, stats);
-    ++c->launches;
+    {
+        // keys of the mask voxels live in shared memory (one CTA per SM); 12 KB stay free for the
+        // kernel's static arrays
+        long long key_cap = std::max<long long>(32, std::min<long long>(vmax_of(c), ((long long)c->max_smem - 12 * 1024) / 4));
+        if (const char* e = getenv("VB_VDP_KEY_CAP"))          // tests: force the re-streaming path
+            key_cap = std::max<long long>(32, std::min<long long>(key_cap, atoll(e)));
+        if (!vbrt::allow_smem(vdp_stats_kernel, (int)(4 * key_cap))) return VB_ERR_CUDA;
+        VB_LAUNCH(vdp_stats_kernel, dim3(std::min(n, c->sms * 4)), dim3(VB_VDP_THREADS), (size_t)(4 * key_cap), s, n4, mask,
+                  subj, n, stats, (int)key_cap);
+        ++c->launches;
+    }
     // fused threshold + linear binning + median + border on row tiles held in shared memory
-    long long ncmax = 1, n0max = 1;
+    long long ncmax = 1, n0max = 1, n2max = 1;
     for (const VbSubject& S : c->last_subj) {
         ncmax = std::max<long long>(ncmax, (long long)S.n1 * S.n2);
         n0max = std::max<long long>(n0max, S.n0);
+        n2max = std::max<long long>(n2max, S.n2);
     }
-    const long long budget = std::min<long long>(c->max_smem - 1024, 96 * 1024);
+    const long long P = (n2max + 3) / 4 + 1;                   // padding words around the tiles (word version)
+    const long long budget = std::min<long long>(c->max_smem - 1024, 96 * 1024) - 16 * P;
     long long R = (budget / ncmax - 6) / 2;                    // (R + 4) + (R + 2) rows of bytes
     if (R >= 1) {
         R = std::min<long long>(R, 32);
         R = std::min<long long>(R, n0max);
-        const int smem = (int)((2 * R + 6) * ncmax);
-        if (!vbrt::allow_smem(vdp_classify_kernel, smem)) return VB_ERR_CUDA;
+        const int smem = (int)((2 * R + 6) * ncmax + 16 * P);
         const int gx = (int)((n0max + R - 1) / R);
-        VB_LAUNCH(vdp_classify_kernel, dim3(gx, n), dim3(VB_CLS_THREADS), (size_t)smem, s, n4, mask, subj, thresh, (int)R, lb,
-                  defect, dborder, stats);
-        ++c->launches;
+        bool any_words = false, any_bytes = false;             // subjects of this range per kernel flavour
+        for (int i = 0; i < n; ++i) {
+            const VbSubject& S = c->last_subj[(size_t)(c->r0 + i)];
+            const bool w = (((long long)S.n1 * S.n2) & 3) == 0 && (S.off & 3) == 0 && (S.n2 + 3) / 4 + 1 <= P;
+            (w ? any_words : any_bytes) = true;
+        }
+        if (any_words) {
+            if (!vbrt::allow_smem(vdp_classify4_kernel, smem)) return VB_ERR_CUDA;
+            VB_LAUNCH(vdp_classify4_kernel, dim3(gx, n), dim3(VB_CLS_THREADS), (size_t)smem, s, n4, mask, subj, thresh, (int)R,
+                      (int)P, lb, defect, dborder, stats);
+            ++c->launches;
+        }
+        if (any_bytes) {
+            if (!vbrt::allow_smem(vdp_classify_kernel, smem)) return VB_ERR_CUDA;
+            VB_LAUNCH(vdp_classify_kernel, dim3(gx, n), dim3(VB_CLS_THREADS), (size_t)smem, s, n4, mask, subj, thresh, (int)R,
+                      (int)P, lb, defect, dborder, stats);
+            ++c->launches;
+        }
         return vbrt::last_launch_ok("vdp kernels") ? VB_OK : VB_ERR_CUDA;
     }
     // rows too long for a shared-memory tile: three streaming kernels through a d0 array
@@ -375,7 +403,7 @@ void vb_destroy(vb_ctx* c) {
     vbrt::set_device(c->device);
     vbrt::stream_sync(c->stream);
     for (N4Ws& W : c->n4ws) {
-        Buf* wb[] = {&W.logI, &W.colmask, &W.rbb, &W.wbase, &W.acol, &W.order, &W.ec, &W.axis, &W.counter};
+        Buf* wb[] = {&W.logI, &W.u, &W.colmask, &W.rbb, &W.wbase, &W.acol, &W.order, &W.ec, &W.axis, &W.counter};
         for (Buf* b : wb) vbrt::dev_free(b->p);
     }
     vbrt::stream_destroy(c->stream2);
