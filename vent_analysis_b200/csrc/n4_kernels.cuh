@@ -671,10 +671,37 @@ VB_DEV void n4_fft(const N4Team& T, double* re, double* im, int N, int logN, int
         }
     }
     n4_sync(T);
-    // The 32 butterflies b = 32 m .. 32 m + 31 of a stage with len <= 64 touch exactly the aligned
-    // elements 64 m .. 64 m + 63, and they always belong to the same warp (b = tid + j * nt, nt a
-    // multiple of 32): those stages only need the warp to be in step, not the team.
-    for (int len = 2; len <= N; len <<= 1) {
+    // Two radix-2 stages (len, 2 len) per pass: a thread owns the four elements
+    // {i, i + len/2, i + len, i + len + len/2} of a block of 2 len and does both stages on them
+    // (the same butterflies, twiddles and operation order as the plain radix-2 loop, so the
+    // results are bit-identical) -- half the passes over shared memory and half the barriers.
+    // A warp covers 128 consecutive elements per pass, so while the next pass works on aligned
+    // blocks of <= 128 elements it only needs the warp to be in step, not the team.
+    int len = 2;
+    for (; 2 * len <= N; len <<= 2) {
+        const int half = len >> 1, step1 = N / len, step2 = N / (2 * len);
+        for (int q = tid; q < (N >> 2); q += nt) {
+            const int grp = q / half, k = q - grp * half;
+            const int i0 = grp * 2 * len + k, i1 = i0 + half, i2 = i0 + len, i3 = i2 + half;
+            const double w1r = twr[k * step1], w1i = (sign < 0) ? twi[k * step1] : -twi[k * step1];
+            // stage len: (i0, i1) and (i2, i3)
+            double ar = re[i0], ai = im[i0], br = re[i1], bi = im[i1];
+            double xr = br * w1r - bi * w1i, xi = br * w1i + bi * w1r;
+            br = ar - xr; bi = ai - xi; ar += xr; ai += xi;
+            double cr = re[i2], ci = im[i2], dr = re[i3], di = im[i3];
+            xr = dr * w1r - di * w1i; xi = dr * w1i + di * w1r;
+            dr = cr - xr; di = ci - xi; cr += xr; ci += xi;
+            // stage 2 len: (i0, i2) with twiddle k, (i1, i3) with twiddle k + half
+            const double w2r = twr[k * step2], w2i = (sign < 0) ? twi[k * step2] : -twi[k * step2];
+            const double w3r = twr[(k + half) * step2], w3i = (sign < 0) ? twi[(k + half) * step2] : -twi[(k + half) * step2];
+            xr = cr * w2r - ci * w2i; xi = cr * w2i + ci * w2r;
+            re[i2] = ar - xr; im[i2] = ai - xi; re[i0] = ar + xr; im[i0] = ai + xi;
+            xr = dr * w3r - di * w3i; xi = dr * w3i + di * w3r;
+            re[i3] = br - xr; im[i3] = bi - xi; re[i1] = br + xr; im[i1] = bi + xi;
+        }
+        if (8 * len <= 128) __syncwarp(); else n4_sync(T);
+    }
+    if (len <= N) {                                          // odd number of stages: the last one alone
         const int half = len >> 1, step = N / len;
         for (int b = tid; b < (N >> 1); b += nt) {
             const int grp = b / half, k = b - grp * half;
@@ -684,7 +711,7 @@ VB_DEV void n4_fft(const N4Team& T, double* re, double* im, int N, int logN, int
             re[i1] = re[i0] - xr; im[i1] = im[i0] - xi;
             re[i0] += xr; im[i0] += xi;
         }
-        if (2 * len <= 64) __syncwarp(); else n4_sync(T);
+        n4_sync(T);
     }
 }
 
@@ -986,22 +1013,25 @@ VB_DEV void n4_chain_chunk(N4Ctx& c, const N4Team& T, const float* epx, int star
     }
 #pragma unroll
     for (int i = 0; i < VB_N4_EPT; ++i) st[i] = n4_step_consts(px[i], lo + i + 1);
-    // mu: one scan per sweep; it also tells whether the previous sweep moved any start (if not,
-    // the sweep just computed has confirmed the trajectory).
-    int km = mu0, total = 0, changed = 1;
+    // mu: one scan per sweep.  The starts of a sweep are mu0 + prefix(increments of the previous
+    // sweep) (all mu0 for the first one: previous increments 0), so when NO thread's increment
+    // differs from its previous one the starts reproduce themselves: thread 0 starts from the exact
+    // state, hence its increment is exact, hence thread 1's start, ... -- the trajectory is the
+    // sequential one and the sweep that found this is the last (a stalled mean needs one sweep).
+    int km = mu0, total = 0, changed = 1, inc_prev = 0;
     for (;;) {
         float mu = __int_as_float(km);
 #pragma unroll
         for (int i = 0; i < VB_N4_EPT; ++i)
             if (i < cnt) mu = n4_mu_next(mu, st[i]);
-        const int off = WARP ? n4_warp_scan(__float_as_int(mu) - km, total, changed)
-                             : n4_chain_scan(T, __float_as_int(mu) - km, total, s_tot[buf], changed);
+        const int inc = __float_as_int(mu) - km;
+        changed = (inc != inc_prev);
+        const int off = WARP ? n4_warp_scan(inc, total, changed) : n4_chain_scan(T, inc, total, s_tot[buf], changed);
         buf ^= 1;
         ++c.n_sweeps;
         if (!changed) break;
-        const int k = mu0 + off;
-        changed = (k != km);
-        km = k;
+        inc_prev = inc;
+        km = mu0 + off;
     }
     const int mu_end = mu0 + total;
     // sigma, along the exact mu trajectory.  The terms dd*(N-1)/N do not depend on sigma:
@@ -1024,28 +1054,32 @@ VB_DEV void n4_chain_chunk(N4Ctx& c, const N4Team& T, const float* epx, int star
     // first guess: sigma grows about linearly with N inside the chunk
     int ks = __float_as_int(__int_as_float(sg0) * ((float)lo / (float)start));
     if (tid == 0 || cnt == 0) ks = sg0;
+    // Same stopping rule as for mu: once no thread's increment differs from the one it had in the
+    // previous sweep, the starts (sg0 + prefix of those increments) reproduce themselves.
     int inc = 0;
-    bool rerun = true;
-    changed = 1;
+    bool rerun = true, first = true;
     for (;;) {
+        changed = first ? 1 : 0;
         if (rerun) {
             float sg = __int_as_float(ks);
 #pragma unroll
             for (int i = 0; i < VB_N4_EPT; ++i)
                 if (i < cnt) sg = n4_sigma_add(sg, px[i], st[i].b);
-            inc = __float_as_int(sg) - ks;
+            const int inc_new = __float_as_int(sg) - ks;
+            if (inc_new != inc) changed = 1;
+            inc = inc_new;
         }
         const int off = WARP ? n4_warp_scan(inc, total, changed) : n4_chain_scan(T, inc, total, s_tot[buf], changed);
         buf ^= 1;
         c.n_sweeps += 1000;
         if (!changed) break;
+        first = false;
         const int k = sg0 + off;
         // the increments computed from `ks` also hold from `k` when start and end stay in
         // the same single binade (every add then rounds to the same grid)
         const bool same = (k == ks) || (n4_binade(k) == n4_binade(ks) && n4_binade(k + inc) == n4_binade(k) &&
                                         n4_binade(ks + inc) == n4_binade(ks));
         rerun = !same;
-        changed = rerun;
         ks = k;
     }
     mu_b = mu_end;
@@ -1137,10 +1171,12 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
         N4Win wo, wn;
         wo.cur = wn.cur = -1;
         wo.g0 = wo.g1 = wo.g2 = wo.g3 = wn.g0 = wn.g1 = wn.g2 = wn.g3 = 0.0f;
+        // The log image lives in L2 (a register stream buffer with shuffles and an L1 prefetch of the
+        // rows ahead were both measured slower than the plain load issued before the window updates).
         VB_N4_FOR_ROWS_RANK(c, I, {
             const int base = c.r_bev[r];
             float li = 0.0f;
-            if (bit) li = c.logI[idx];                               // L2; requested before the window updates
+            if (bit) li = c.logI[idx];
             n4_win_advance(wo, c.Lold, c, col, base, Go, c.gstride);
             n4_win_advance(wn, c.L, c, col, base, Gw, c.gstride);
             if (bit) {

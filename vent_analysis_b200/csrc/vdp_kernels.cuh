@@ -641,6 +641,7 @@ VB_DEV void vdp_classify_words(unsigned char* smem, int* red, float* s_thr, int 
     const int ng = (rb - ra) * G;
     const int own0 = (i0 - ra) * G, own1 = (ib - ra) * G;             // groups this CTA owns
     int c12 = 0;
+    uint32_t any_d0 = 0u;
     for (int gb = tid; gb < ng; gb += 4 * nt) {                       // four independent 20-byte loads in flight
         // d0 and the code are zero outside the mask: the image is only read (and classified)
         // where the mask word is set
@@ -686,16 +687,27 @@ VB_DEV void vdp_classify_words(unsigned char* smem, int* red, float* s_thr, int 
             }
             }
             d0w[gi] = dw;
+            any_d0 |= dw;
             if (gi >= own0 && gi < own1) {
                 *(uint32_t*)(lbo + 4 * (size_t)gi) = cw;
                 c12 += __popc(w12);
             }
         }
     }
-    __syncthreads();
+    int nd = 0;
+    if (!__syncthreads_or(any_d0 != 0u)) {
+        // nothing below the threshold in rows [ra, rb): median and border of the owned rows are zero
+        for (int g = tid; g < G; g += nt)
+            for (int i = i0; i < ib; ++i) {
+                *(uint32_t*)(defect + S.off + (size_t)i * ncols + 4 * g) = 0u;
+                if (border) *(uint32_t*)(border + S.off + (size_t)i * ncols + 4 * g) = 0u;
+            }
+        c12 = vb_block_reduce(c12, VbAddI(), 0, red);
+        if (tid == 0 && c12) atomicAdd(&stats[si].n_lb12, c12);
+        return;
+    }
     // median of rows [ma, mb): a thread owns four (col, slice) positions and walks down the rows
     // with a sliding window of the three-column sums
-    int nd = 0;
     for (int g = tid; g < G; g += nt) {
         const VdpNbr k = vdp_nbr(g, n1, n2);
         uint32_t s_prev = 0u, s_cur;
