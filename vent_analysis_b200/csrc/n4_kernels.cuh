@@ -49,13 +49,19 @@
 #define VB_N4_EPT 8                               /* convergence chain: elements per thread   */
 #endif
 #ifndef VB_N4_CHAIN_WARPS
-#define VB_N4_CHAIN_WARPS 16                      /* warps of the chain team while it overlaps  */
+#define VB_N4_CHAIN_WARPS 14                      /* warps of the chain team while it overlaps  */
 #endif
 #define VB_N4_SERIAL 64                           /* first elements: one thread, sequentially */
 #ifndef VB_N4_WARP_END
-#define VB_N4_WARP_END 2048                       /* ... then one warp up to here (multiple of 8), then the team */
+#define VB_N4_WARP_END 64                         /* ... then one warp up to here (multiple of 8; 64 = none), then the team */
 #endif
-#define VB_N4_HCOPIES 8                           /* histogram copies (warp & 7)              */
+#ifndef VB_N4_SIGMA_PREDICT_ALL
+#define VB_N4_SIGMA_PREDICT_ALL 0                 /* 1: every chunk predicts its sigma starts */
+#endif
+#ifndef VB_N4_PREDICT_END
+#define VB_N4_PREDICT_END 4096                    /* team chunks that start below this predict their starts (full length) */
+#endif
+#define VB_N4_HCOPIES 32                          /* histogram copies: one per lane (stride nbins | 1) */
 
 struct N4Args {
     const float* image;
@@ -207,6 +213,8 @@ struct N4Ctx {
     uint32_t* iorder;     // [nblk * nseg] work items sorted by voxel count, largest first
     int* ctr;             // shared-memory work counters, one per team barrier id
     int nact, nseg, wps;  // active columns; row segments per block; 32-row words per segment
+    int M;                // mask voxels (length of the compact arrays)
+    int union_bytes;      // size of the shared-memory union region
     float* axis_base;
     float* ec;            // [M] exp(old - new) in C order (chain input)
     // row-axis tables (shared memory when they fit, else inside axis_base)
@@ -345,6 +353,20 @@ VB_DEV void n4_win_advance(N4Win& w, const float* L, const N4Ctx& c, const N4Col
     } else {
         while (w.cur < base) {
             w.g0 = w.g1; w.g1 = w.g2; w.g2 = w.g3; w.g3 = n4_coef_t(L, c, k, G, gs, w.cur + 4);
+            ++w.cur;
+        }
+    }
+}
+// the same window over a precomputed coefficient column G[a * gs] (no lattice, no column weights)
+VB_DEV void n4_win_advance_tab(N4Win& w, int base, const float* G, int gs) {
+    if (base == w.cur) return;
+    if (w.cur < 0 || base - w.cur >= 4 || base < w.cur) {
+        w.g0 = G[(size_t)base * gs]; w.g1 = G[(size_t)(base + 1) * gs];
+        w.g2 = G[(size_t)(base + 2) * gs]; w.g3 = G[(size_t)(base + 3) * gs];
+        w.cur = base;
+    } else {
+        while (w.cur < base) {
+            w.g0 = w.g1; w.g1 = w.g2; w.g2 = w.g3; w.g3 = G[(size_t)(w.cur + 4) * gs];
             ++w.cur;
         }
     }
@@ -619,42 +641,41 @@ VB_DEV void n4_range(N4Ctx& c, float& bmin, float& bmax) {
 // ---------------------------------------------------------------------------------------------
 // P1: triangular Parzen histogram of U over the mask (SharpenImage, first half)
 VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
-    const int nt = T.nt, tid = T.tid, lane = (T.tid & 31), w = (T.tid >> 5), nw = nt >> 5;
-    const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
-    uint32_t* hc = (uint32_t*)c.un_f;                    // [VB_N4_HCOPIES][nbins]
-    for (int i = tid; i < c.nbins * VB_N4_HCOPIES; i += nt) hc[i] = 0u;
-    n4_items_begin(c, T);
+    const int nt = T.nt, tid = T.tid;
+    // One copy per LANE with an odd stride: lanes of a warp never share an address, and lanes that
+    // hit the same bin fall into 32 different banks (the U values cluster in a few bins, so copies
+    // per warp serialised most of the atomics: 21 -> 11 us per iteration flat, -> with lane copies)
+    const int hstride = c.nbins | 1;
+    uint32_t* hc = (uint32_t*)c.un_f;                    // [VB_N4_HCOPIES][hstride]
+    for (int i = tid; i < hstride * VB_N4_HCOPIES; i += nt) hc[i] = 0u;
     n4_sync(T);
     const float slope = (bmax - bmin) / (float)(c.nbins - 1);
     const float rslope = __frcp_rn(slope);
     const uint32_t one = 1u << c.hshift;
     const float fone = (float)one;
-    uint32_t* h = hc + (size_t)(w & (VB_N4_HCOPIES - 1)) * c.nbins;
-    VB_N4_FOR_ITEMS(c, T, it) {
-        const N4Item I = n4_item(c, it);
-        if (I.empty) continue;
-        VB_N4_FOR_ROWS(c, I, {
-            if (bit) {
-                const float u = c.U[idx];
-                const float cidx = n4_div(u - bmin, slope, rslope);
-                const float fl = floorf(cidx);
-                const int bi = (int)fl;
-                const float off = cidx - fl;
-                if (off == 0.0f) {
-                    if (bi >= 0 && bi < c.nbins) atomicAdd(&h[bi], one);
-                } else if (bi >= 0 && bi < c.nbins - 1) {
-                    const uint32_t o = (uint32_t)__float2uint_rn(off * fone);
-                    atomicAdd(&h[bi], one - o);
-                    atomicAdd(&h[bi + 1], o);
-                }
-            }
-        })
+    uint32_t* h = hc + (size_t)(tid & (VB_N4_HCOPIES - 1)) * hstride;
+    // U is stored per voxel, so the histogram needs no geometry: a flat, fully populated loop over
+    // the compact array (the fixed-point sums do not depend on the order)
+#pragma unroll 4
+    for (int i = tid; i < c.M; i += nt) {
+        const float u = c.U[i];
+        const float cidx = n4_div(u - bmin, slope, rslope);
+        const float fl = floorf(cidx);
+        const int bi = (int)fl;
+        const float off = cidx - fl;
+        if (off == 0.0f) {
+            if (bi >= 0 && bi < c.nbins) atomicAdd(&h[bi], one);
+        } else if (bi >= 0 && bi < c.nbins - 1) {
+            const uint32_t o = (uint32_t)__float2uint_rn(off * fone);
+            atomicAdd(&h[bi], one - o);
+            atomicAdd(&h[bi + 1], o);
+        }
     }
     n4_sync(T);
     for (int bin = tid; bin < c.nbins; bin += nt) {
         unsigned long long s = 0;
 #pragma unroll
-        for (int k = 0; k < VB_N4_HCOPIES; ++k) s += hc[(size_t)k * c.nbins + bin];
+        for (int k = 0; k < VB_N4_HCOPIES; ++k) s += hc[(size_t)k * hstride + bin];
         c.H[bin] = (float)((double)s / (double)one);
     }
     n4_sync(T);
@@ -823,13 +844,14 @@ VB_DEV void n4_qflush(unsigned* Q, int a, int ncp1, int n2, int bc, int s, const
 
 template <bool OMEGA>
 VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
-    const int nt = T.nt, tid = T.tid, w = (T.tid >> 5), nw = nt >> 5;
+    const int nt = T.nt, tid = T.tid;
     const int ncp0 = c.ncp[0], ncp1 = c.ncp[1], ncp2 = c.ncp[2];
     const int n2 = c.n2;
     const N4Axis ar = n4_ax(c, 0), ac = n4_ax(c, 1), as = n4_ax(c, 2);
     const float slope = (bmax - bmin) / (float)(c.nbins - 1);
     const float rslope = __frcp_rn(slope);
     const int nbm1 = c.nbins - 1;
+    // (private copies of Q per warp index were measured slower: 31.9 -> 34.9 us per iteration)
     unsigned* Q = (unsigned*)c.un_d;                     // [ncp0][ncp1][n2] x {low, high} words
     const int Qn = ncp0 * ncp1 * n2;
     for (int e = tid; e < 2 * Qn; e += nt) Q[e] = 0u;
@@ -978,6 +1000,33 @@ VB_DEV int n4_warp_scan(int v, int& total, int& flag) {
     return inc - v;
 }
 
+// exclusive prefix of a float over the team (WARP = false: one barrier) or the warp; only used
+// for start guesses, so the summation order does not matter
+template <bool WARP>
+VB_DEV float n4_guess_scan(const N4Team& T, float v, float* tot) {
+    const int lane = (T.tid & 31), w = (T.tid >> 5), nw = T.nt >> 5;
+    float inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float t = __shfl_up_sync(VB_FULL, inc, d);
+        if (lane >= d) inc += t;
+    }
+    float woff = 0.0f;
+    if (!WARP) {
+        if (lane == 31) tot[w] = inc;
+        n4_sync(T);
+        float tv = (lane < nw) ? tot[lane] : 0.0f;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float t = __shfl_up_sync(VB_FULL, tv, d);
+            if (lane >= d) tv += t;
+        }
+        woff = __shfl_sync(VB_FULL, tv, (w > 0) ? w - 1 : 0);
+        if (w == 0) woff = 0.0f;
+    }
+    return woff + inc - v;
+}
+
 // sigma + (th + tl) rounded to float (TwoSum keeps the part of th that the first add drops)
 VB_DEV float n4_sigma_add(float sigma, float th, float tl) {
     const float r = __fadd_rn(sigma, th);
@@ -994,9 +1043,13 @@ VB_DEV int n4_binade(int bits) { return bits >> 23; }
 // at all (used for the first elements, where a chunk may not be longer than the number of
 // elements before it and a block-wide sweep would cost a barrier for a handful of steps).
 // (mu_b, sg_b): float bit patterns of the state at the chunk start (in) / end (out), uniform.
-template <bool WARP>
+// PREDICT: the starts of the first mu sweep are guessed from the exact-arithmetic running mean
+// mu(lo) = mu0 + sum_{start <= i < lo} (px_i - mu0) / lo (one extra float scan) instead of mu0.
+// In the first few thousand elements the mean still moves by many ulps per element, and with
+// this guess a chunk there may be much longer than the number of elements before it.
+template <bool WARP, bool PREDICT>
 VB_DEV void n4_chain_chunk(N4Ctx& c, const N4Team& T, const float* epx, int start, int len, int& mu_b, int& sg_b,
-                           int (*s_tot)[32], int& buf) {
+                           int (*s_tot)[32], int& buf, float* s_guess) {
     const int nt = WARP ? 32 : T.nt, tid = WARP ? (T.tid & 31) : T.tid;
     const int ept = (len + nt - 1) / nt;                      // <= VB_N4_EPT
     const int lo = start + min(len, tid * ept);
@@ -1019,13 +1072,24 @@ VB_DEV void n4_chain_chunk(N4Ctx& c, const N4Team& T, const float* epx, int star
     // state, hence its increment is exact, hence thread 1's start, ... -- the trajectory is the
     // sequential one and the sweep that found this is the last (a stalled mean needs one sweep).
     int km = mu0, total = 0, changed = 1, inc_prev = 0;
+    bool first = PREDICT;                                     // guessed starts are not a prefix of increments
+    if (PREDICT) {
+        const float m0 = __int_as_float(mu0);
+        float ds = 0.0f;
+#pragma unroll
+        for (int i = 0; i < VB_N4_EPT; ++i)
+            if (i < cnt) ds += px[i] - m0;
+        const float ex = n4_guess_scan<WARP>(T, ds, s_guess);
+        if (tid > 0 && cnt > 0) km = __float_as_int(m0 + ex / (float)lo);
+    }
     for (;;) {
         float mu = __int_as_float(km);
 #pragma unroll
         for (int i = 0; i < VB_N4_EPT; ++i)
             if (i < cnt) mu = n4_mu_next(mu, st[i]);
         const int inc = __float_as_int(mu) - km;
-        changed = (inc != inc_prev);
+        changed = (inc != inc_prev) || first;
+        first = false;
         const int off = WARP ? n4_warp_scan(inc, total, changed) : n4_chain_scan(T, inc, total, s_tot[buf], changed);
         buf ^= 1;
         ++c.n_sweeps;
@@ -1051,15 +1115,23 @@ VB_DEV void n4_chain_chunk(N4Ctx& c, const N4Team& T, const float* epx, int star
                 px[i] = th; st[i].b = tl;
             }
     }
-    // first guess: sigma grows about linearly with N inside the chunk
+    // first guess: sigma grows about linearly with N inside the chunk; PREDICT: sigma at the
+    // thread's start is sg0 + the (float) prefix of the terms, which are known by now
     int ks = __float_as_int(__int_as_float(sg0) * ((float)lo / (float)start));
+    if (PREDICT || VB_N4_SIGMA_PREDICT_ALL) {
+        float ts = 0.0f;
+#pragma unroll
+        for (int i = 0; i < VB_N4_EPT; ++i)
+            if (i < cnt) ts += px[i];
+        ks = __float_as_int(__int_as_float(sg0) + n4_guess_scan<WARP>(T, ts, s_guess));
+    }
     if (tid == 0 || cnt == 0) ks = sg0;
     // Same stopping rule as for mu: once no thread's increment differs from the one it had in the
     // previous sweep, the starts (sg0 + prefix of those increments) reproduce themselves.
     int inc = 0;
-    bool rerun = true, first = true;
+    bool rerun = true, sfirst = true;
     for (;;) {
-        changed = first ? 1 : 0;
+        changed = sfirst ? 1 : 0;
         if (rerun) {
             float sg = __int_as_float(ks);
 #pragma unroll
@@ -1073,7 +1145,7 @@ VB_DEV void n4_chain_chunk(N4Ctx& c, const N4Team& T, const float* epx, int star
         buf ^= 1;
         c.n_sweeps += 1000;
         if (!changed) break;
-        first = false;
+        sfirst = false;
         const int k = sg0 + off;
         // the increments computed from `ks` also hold from `k` when start and end stay in
         // the same single binade (every add then rounds to the same grid)
@@ -1097,9 +1169,10 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
     long long tq = vb_clock();
     if (tid < S0) s_px[tid] = epx[tid];
     n4_sync(T);
-    // phase 1: the first elements, one thread, sequentially.  Phase 2: up to VB_N4_WARP_END, one
-    // warp, chunks of <= 32 * VB_N4_EPT elements, no barrier.
-    const int wend = min(M, VB_N4_WARP_END);
+    // phase 1: the first elements, one thread, sequentially.  Phase 2 (optional, VB_N4_WARP_END >
+    // VB_N4_SERIAL): up to VB_N4_WARP_END on one warp, chunks of <= 32 * VB_N4_EPT elements, no barrier.
+    VB_SHARED float s_guess[32];
+    const int wend = min(M, max(VB_N4_WARP_END, VB_N4_SERIAL));
     if (tid < 32) {
         int mu_b = 0, sg_b = 0;
         if (tid == 0) {
@@ -1116,7 +1189,7 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
         { const long long tn = vb_clock(); c.t_sub[0] += tn - tq; tq = tn; }
         for (int start = S0; start < wend;) {
             const int len = min(min(start, 32 * VB_N4_EPT), wend - start);
-            n4_chain_chunk<true>(c, T, epx, start, len, mu_b, sg_b, s_tot, buf);
+            n4_chain_chunk<true, false>(c, T, epx, start, len, mu_b, sg_b, s_tot, buf, s_guess);
             start += len;
         }
         if (tid == 0) { s_state[0] = mu_b; s_state[1] = sg_b; }
@@ -1125,12 +1198,20 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
     n4_sync(T);
     int mu_b = s_state[0], sg_b = s_state[1];
     buf = 0;
-    // phase 3: the team, chunks of <= nt * VB_N4_EPT elements (and never longer than the number
-    // of elements before them: the start perturbations then contract), one barrier per sweep
+    // phase 3: the team, chunks of <= nt * VB_N4_EPT elements, one barrier per sweep.  While the
+    // mean still moves (start < VB_N4_PREDICT_END) the starts are predicted and a chunk has the
+    // full length; after that a chunk is never longer than the number of elements before it (the
+    // start perturbations then contract) and the flat guess (a stalling mean) is the better one.
     for (int start = max(S0, wend); start < M;) {
-        const int len = min(min(start, T.nt * VB_N4_EPT), M - start);
-        n4_chain_chunk<false>(c, T, epx, start, len, mu_b, sg_b, s_tot, buf);
-        start += len;
+        if (start < VB_N4_PREDICT_END) {
+            const int len = min(T.nt * VB_N4_EPT, M - start);
+            n4_chain_chunk<false, true>(c, T, epx, start, len, mu_b, sg_b, s_tot, buf, s_guess);
+            start += len;
+        } else {
+            const int len = min(min(start, T.nt * VB_N4_EPT), M - start);
+            n4_chain_chunk<false, false>(c, T, epx, start, len, mu_b, sg_b, s_tot, buf, s_guess);
+            start += len;
+        }
     }
     { const long long tn = vb_clock(); c.t_sub[2] += tn - tq; tq = tn; }
     const float mu = __int_as_float(mu_b), sigma = __int_as_float(sg_b);
@@ -1152,22 +1233,18 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
 // iteration of a level, debug capture).
 // Returns true when the sequential chain has to be run on c.ec; otherwise `conv` holds the
 // (exact-arithmetic) value and the level certainly continues.
-VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool exact_needed, float& conv) {
-    const int nt = (int)blockDim.x, w = vb_warp(), nw = nt >> 5;
+// the walk of n4_update; TAB: both fields come from coefficient tables (the usual case), which
+// frees the registers of the column weights
+template <bool TAB>
+VB_DEV void n4_update_walk(N4Ctx& c, const N4Team& T, const float* Gn, float& tmin, float& tmax, double& s1, double& s2) {
     const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
-    float tmin = FLT_MAX, tmax = -FLT_MAX;
-    double s1 = 0.0, s2 = 0.0;
-    float* Gn = c.G ? c.un_f : nullptr;                  // table of the new lattice (union region is free here)
-    N4Team T;
-    T.tid = (int)threadIdx.x; T.nt = nt; T.bar = 0;
-    n4_items_begin(c, T);
-    if (Gn) n4_build_G(c, c.L, Gn); else __syncthreads();
     VB_N4_FOR_ITEMS(c, T, it) {
         const N4Item I = n4_item(c, it);
         if (I.empty) continue;
-        const N4Col col = n4_col(c, ac, as, I.q);
-        const float* Go = c.G ? c.G + I.k : nullptr;
-        const float* Gw = Gn ? Gn + I.k : nullptr;
+        N4Col col;
+        if (!TAB) col = n4_col(c, ac, as, I.q);
+        const float* Go = TAB ? c.G + I.k : nullptr;
+        const float* Gw = TAB ? Gn + I.k : nullptr;
         N4Win wo, wn;
         wo.cur = wn.cur = -1;
         wo.g0 = wo.g1 = wo.g2 = wo.g3 = wn.g0 = wn.g1 = wn.g2 = wn.g3 = 0.0f;
@@ -1177,8 +1254,13 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
             const int base = c.r_bev[r];
             float li = 0.0f;
             if (bit) li = c.logI[idx];
-            n4_win_advance(wo, c.Lold, c, col, base, Go, c.gstride);
-            n4_win_advance(wn, c.L, c, col, base, Gw, c.gstride);
+            if (TAB) {
+                n4_win_advance_tab(wo, base, Go, c.gstride);
+                n4_win_advance_tab(wn, base, Gw, c.gstride);
+            } else {
+                n4_win_advance(wo, c.Lold, c, col, base);
+                n4_win_advance(wn, c.L, c, col, base);
+            }
             if (bit) {
                 const float4 rw = c.r_evw[r];
                 const float bo = n4_win_eval(wo, rw), bn = n4_win_eval(wn, rw);
@@ -1193,6 +1275,19 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
             }
         })
     }
+}
+
+VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool exact_needed, float& conv) {
+    const int nt = (int)blockDim.x;
+    float tmin = FLT_MAX, tmax = -FLT_MAX;
+    double s1 = 0.0, s2 = 0.0;
+    float* Gn = c.G ? c.un_f : nullptr;                  // table of the new lattice (union region is free here)
+    N4Team T;
+    T.tid = (int)threadIdx.x; T.nt = nt; T.bar = 0;
+    n4_items_begin(c, T);
+    if (Gn) n4_build_G(c, c.L, Gn); else __syncthreads();
+    if (Gn) n4_update_walk<true>(c, T, Gn, tmin, tmax, s1, s2);
+    else n4_update_walk<false>(c, T, Gn, tmin, tmax, s1, s2);
     bmin = vb_block_reduce(tmin, VbMinF(), FLT_MAX, (float*)c.red);
     bmax = vb_block_reduce(tmax, VbMaxF(), -FLT_MAX, (float*)c.red);
     s1 = vb_block_reduce(s1, VbAddD(), 0.0, c.red);
@@ -1339,7 +1434,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
     c.red = (double*)p; p += 64 * sizeof(double);
     float* smem_rowtab = (float*)p; p += (size_t)40 * a.rowtab_rows;
     float* smem_logI = (float*)p;
-    c.nbins = a.p.n_bins; c.fftN = a.fftN;
+    c.nbins = a.p.n_bins; c.fftN = a.fftN; c.union_bytes = a.union_bytes;
 
     for (;;) {
         __syncthreads();
@@ -1379,6 +1474,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         long long tq = vb_clock();
         c.t_chain = 0; c.n_sweeps = 0; c.t_sub[0] = c.t_sub[1] = c.t_sub[2] = c.t_sub[3] = 0;
         n4_setup(c, a.p.mask_label, smem_logI, a.logI_cap, bmin, bmax, M);
+        c.M = M;
         for (int e = tid; e < a.Lmax; e += (int)blockDim.x) { c.L[e] = 0.0f; c.Lold[e] = 0.0f; }
         {
             const int used = (c.U == smem_logI) ? ((M + 3) & ~3) : 0;

@@ -216,7 +216,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     const long long Lb = 4 * ((Lmax + 3) & ~3LL), Hb = 4 * ((p.n_bins + 3) & ~3);
     const long long rowtab_rows = (40 * n0max <= 20480) ? ((n0max + 3) & ~3LL) : 0;
     const long long fixed = 4 * Lb + 2 * Hb + 64 * 8 + 40 * rowtab_rows;
-    long long ub = 4LL * VB_N4_HCOPIES * p.n_bins;                       // histogram copies
+    long long ub = 4LL * VB_N4_HCOPIES * (p.n_bins | 1);                 // histogram copies
     ub = std::max(ub, 8LL * 7 * fftN);                                   // FFT work arrays
     ub = std::max(ub, 8LL * (long long)ncpf[0] * ncpf[1] * n2max);       // Q[a][b][s], 64-bit fixed point
     ub = std::max(ub, 4LL * Lmax);                                       // refinement scratch
@@ -639,8 +639,21 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
     if (rc) return rc;
     // Chunks of about one wave of subjects: inputs of chunk k+1 go up and outputs of chunk k-1
     // come down (two copy streams) while chunk k computes.
+    // Large batches start with two smaller chunks (1/4 and 1/2 wave): nothing overlaps the first
+    // upload.  (Small chunks at the END were measured slower: a chunk cannot take less than one
+    // subject's latency, whatever its size.)
     const int per = std::max(c->sms, 1);
-    const int nchunks = std::max(1, std::min(16, n / per));
+    std::vector<int> bounds;                                   // first subject of every chunk, then n
+    if (n >= 6 * per) {
+        const int a = std::max(1, per / 4), b = std::max(1, per / 2);
+        const int rest = n - (a + b), nm = std::max(1, std::min(14, rest / per));
+        bounds.push_back(0); bounds.push_back(a); bounds.push_back(a + b);
+        for (int k = 1; k <= nm; ++k) bounds.push_back(a + b + (int)((long long)rest * k / nm));
+    } else {
+        const int nc = std::max(1, std::min(16, n / per));
+        for (int k = 0; k <= nc; ++k) bounds.push_back((int)((long long)n * k / nc));
+    }
+    const int nchunks = (int)bounds.size() - 1;
     while (c->ev_copy.size() < 2 * (size_t)nchunks) {
         vbrt::event_t e;
         if (!vbrt::event_create(&e)) return VB_ERR_CUDA;
@@ -657,7 +670,7 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
     }
     bool ok = true;
     for (int k = 0; k < nchunks && ok; ++k) {
-        const int r0 = (int)((long long)n * k / nchunks), r1 = (int)((long long)n * (k + 1) / nchunks);
+        const int r0 = bounds[(size_t)k], r1 = bounds[(size_t)k + 1];
         const size_t v0 = (size_t)c->last_subj[(size_t)r0].off;
         const size_t v1 = (size_t)c->last_subj[(size_t)(r1 - 1)].off + (size_t)c->last_subj[(size_t)(r1 - 1)].V;
         const size_t nv = v1 - v0;
