@@ -442,6 +442,22 @@ VB_DEV int n4_items_next(const N4Ctx& c, const N4Team& T) {
 #define VB_N4_FOR_ITEMS(c, T, it) \
     for (int i_ = n4_items_next(c, T), it = 0; i_ < (c).nblk * (c).nseg && ((it = (int)(c).iorder[i_]), true); i_ = n4_items_next(c, T))
 
+// What the row walks need from the context, as opaque local copies: otherwise the compiler
+// re-derives every pointer from the kernel parameters (blockIdx * stride + base, or shared-memory
+// base + offsets: up to 5 instructions) at each use inside the loops.
+struct N4Walk {
+    const uint32_t* colmask;
+    const uint32_t* rbb;
+    int ncols, nblk, n0;
+};
+VB_DEV N4Walk n4_walk(const N4Ctx& c) {
+    N4Walk w;
+    w.colmask = c.colmask; w.rbb = c.rbb; w.ncols = c.ncols; w.nblk = c.nblk; w.n0 = c.n0;
+    VB_OPAQUE_PTR(w.colmask);
+    VB_OPAQUE_PTR(w.rbb);
+    return w;
+}
+
 // Walk the mask voxels of one item row by row.  BODY sees: r (row), bit (this lane's voxel is
 // in the mask), idx (compact index of this lane's voxel when bit), bal (lane mask of the row).
 // Rows without any mask voxel in the block are skipped.
@@ -453,7 +469,7 @@ VB_DEV int n4_items_next(const N4Ctx& c, const N4Team& T) {
             const uint32_t mw_ = (I).valid ? (c).colmask[(size_t)wi_ * (c).ncols + (I).q] : 0u; \
             uint32_t rem_ = __reduce_or_sync(VB_FULL, mw_);                                  \
             while (rem_) {                                                                   \
-                const int b_ = __ffs((int)rem_) - 1;                                         \
+                const int b_ = __popc((rem_ - 1u) & ~rem_);                                        \
                 rem_ &= rem_ - 1u;                                                           \
                 const int r = wi_ * 32 + b_;                                                 \
                 const bool bit = (mw_ >> b_) & 1u;                                           \
@@ -479,7 +495,7 @@ VB_DEV int n4_items_next(const N4Ctx& c, const N4Team& T) {
             const int rr_ = wi_ * 32 + vb_lane();                                            \
             const unsigned rbw_ = (rr_ < (c).n0) ? (c).rbb[(size_t)rr_ * (c).nblk + (I).blk] : 0u; \
             while (rem_) {                                                                   \
-                const int b_ = __ffs((int)rem_) - 1;                                         \
+                const int b_ = __popc((rem_ - 1u) & ~rem_);                                        \
                 rem_ &= rem_ - 1u;                                                           \
                 const int r = wi_ * 32 + b_;                                                 \
                 const bool bit = (mw_ >> b_) & 1u;                                           \
@@ -853,6 +869,12 @@ VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     const int nbm1 = c.nbins - 1;
     // (private copies of Q per warp index were measured slower: 31.9 -> 34.9 us per iteration)
     unsigned* Q = (unsigned*)c.un_d;                     // [ncp0][ncp1][n2] x {low, high} words
+    const N4Walk wk = n4_walk(c);
+    const float* U = c.U;
+    const float* E = c.E;
+    const float4* rfit3 = c.r_fit3;
+    const int* rbfit = c.r_bfit;
+    VB_OPAQUE_PTR(Q); VB_OPAQUE_PTR(U); VB_OPAQUE_PTR(E); VB_OPAQUE_PTR(rfit3); VB_OPAQUE_PTR(rbfit);
     const int Qn = ncp0 * ncp1 * n2;
     for (int e = tid; e < 2 * Qn; e += nt) Q[e] = 0u;
     n4_items_begin(c, T);
@@ -866,8 +888,8 @@ VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
         const float4 wc = OMEGA ? ac.fit2[cc] : ac.fit3[cc];
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int cur = -1;                                    // window = coefficients cur .. cur+3
-        VB_N4_FOR_ROWS(c, I, {
-            const int base = c.r_bfit[r];
+        VB_N4_FOR_ROWS(wk, I, {
+            const int base = rbfit[r];
             if (cur < 0) cur = base;
             while (cur < base) {                         // warp uniform
                 if (I.valid) n4_qflush(Q, cur, ncp1, n2, bc, ss, wc, a0);
@@ -881,19 +903,19 @@ VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
                     val = 1.0f;
                     wt = ar.fit2[r];
                 } else {
-                    const float u = c.U[idx];
+                    const float u = U[idx];
                     const float cidx = n4_div(u - bmin, slope, rslope);
                     const float fl = floorf(cidx);
                     const int bi = (int)fl;
                     float s;
                     if (bi >= 0 && bi < nbm1) {
-                        const float e0 = c.E[bi], e1 = c.E[bi + 1];
+                        const float e0 = E[bi], e1 = E[bi + 1];
                         s = e0 + (e1 - e0) * (cidx - fl);
                     } else {
-                        s = c.E[nbm1];
+                        s = E[nbm1];
                     }
                     val = u - s;
-                    wt = c.r_fit3[r];
+                    wt = rfit3[r];
                 }
                 a0 += wt.x * val; a1 += wt.y * val; a2 += wt.z * val; a3 += wt.w * val;
             }
@@ -1238,6 +1260,15 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
 template <bool TAB>
 VB_DEV void n4_update_walk(N4Ctx& c, const N4Team& T, const float* Gn, float& tmin, float& tmax, double& s1, double& s2) {
     const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
+    // base pointers of this CTA's slots, made opaque: otherwise the compiler re-derives them from
+    // the kernel parameters (blockIdx * stride + base: 5 instructions) at every use in the loop
+    const N4Walk wk = n4_walk(c);
+    const float* logI = c.logI;
+    float* ec = c.ec;
+    float* U = c.U;
+    const float4* revw = c.r_evw;
+    const int* rbev = c.r_bev;
+    VB_OPAQUE_PTR(logI); VB_OPAQUE_PTR(ec); VB_OPAQUE_PTR(U); VB_OPAQUE_PTR(revw); VB_OPAQUE_PTR(rbev);
     VB_N4_FOR_ITEMS(c, T, it) {
         const N4Item I = n4_item(c, it);
         if (I.empty) continue;
@@ -1250,10 +1281,10 @@ VB_DEV void n4_update_walk(N4Ctx& c, const N4Team& T, const float* Gn, float& tm
         wo.g0 = wo.g1 = wo.g2 = wo.g3 = wn.g0 = wn.g1 = wn.g2 = wn.g3 = 0.0f;
         // The log image lives in L2 (a register stream buffer with shuffles and an L1 prefetch of the
         // rows ahead were both measured slower than the plain load issued before the window updates).
-        VB_N4_FOR_ROWS_RANK(c, I, {
-            const int base = c.r_bev[r];
+        VB_N4_FOR_ROWS_RANK(wk, I, {
+            const int base = rbev[r];
             float li = 0.0f;
-            if (bit) li = c.logI[idx];
+            if (bit) li = logI[idx];
             if (TAB) {
                 n4_win_advance_tab(wo, base, Go, c.gstride);
                 n4_win_advance_tab(wn, base, Gw, c.gstride);
@@ -1262,14 +1293,14 @@ VB_DEV void n4_update_walk(N4Ctx& c, const N4Team& T, const float* Gn, float& tm
                 n4_win_advance(wn, c.L, c, col, base);
             }
             if (bit) {
-                const float4 rw = c.r_evw[r];
+                const float4 rw = revw[r];
                 const float bo = n4_win_eval(wo, rw), bn = n4_win_eval(wn, rw);
                 const float un = li - bn;
-                c.U[idx] = un;                                       // read by the next histogram / fit
+                U[idx] = un;                                         // read by the next histogram / fit
                 tmin = fminf(tmin, un);
                 tmax = fmaxf(tmax, un);
                 const float ev = n4_exp_small(bo - bn);
-                c.ec[rank] = ev;                                       // chain input, C order
+                ec[rank] = ev;                                         // chain input, C order
                 const double em = (double)ev - 1.0;
                 s1 += em; s2 += em * em;
             }

@@ -47,6 +47,7 @@ VB_DEV int vb_bar_or(int id, int nthreads, int pred) {
     return out;
 }
 VB_DEV long long vb_clock() { return clock64(); }   // SM cycles
+#define VB_OPAQUE_PTR(p) asm volatile("" : "+l"(p))
 #else
 // ------------------------------------------------------------------------------- emulation
 #include <math.h>
@@ -333,6 +334,7 @@ template <class T> static inline T vb_ldg(const T* p) { return *p; }
 template <class T> static inline T vb_ld_stream(const T* p) { return *p; }
 static inline void vb_st_stream(float* p, float v) { *p = v; }
 static inline long long vb_clock() { return 0; }
+#define VB_OPAQUE_PTR(p) ((void)0)
 using std::max;
 using std::min;
 #endif
