@@ -672,16 +672,19 @@ VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     uint32_t* h = hc + (size_t)(tid & (VB_N4_HCOPIES - 1)) * hstride;
     // U is stored per voxel, so the histogram needs no geometry: a flat, fully populated loop over
     // the compact array (the fixed-point sums do not depend on the order)
+    const float* U = c.U;
+    VB_OPAQUE_PTR(U); VB_OPAQUE_PTR(h);
+    const int M = c.M, nbins = c.nbins;
 #pragma unroll 4
-    for (int i = tid; i < c.M; i += nt) {
-        const float u = c.U[i];
+    for (int i = tid; i < M; i += nt) {
+        const float u = U[i];
         const float cidx = n4_div(u - bmin, slope, rslope);
         const float fl = floorf(cidx);
         const int bi = (int)fl;
         const float off = cidx - fl;
         if (off == 0.0f) {
-            if (bi >= 0 && bi < c.nbins) atomicAdd(&h[bi], one);
-        } else if (bi >= 0 && bi < c.nbins - 1) {
+            if (bi >= 0 && bi < nbins) atomicAdd(&h[bi], one);
+        } else if (bi >= 0 && bi < nbins - 1) {
             const uint32_t o = (uint32_t)__float2uint_rn(off * fone);
             atomicAdd(&h[bi], one - o);
             atomicAdd(&h[bi + 1], o);
