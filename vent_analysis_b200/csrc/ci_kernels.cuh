@@ -62,11 +62,21 @@ VB_KERNEL void ci_pack_kernel(CiArgs a) {
             const int g = t % G, sl = t / G;
             const uint8_t* p = d + (size_t)(sl * 32) * ncols + 4 * g;
             uint32_t acc[4] = {0u, 0u, 0u, 0u};
-#pragma unroll 8
-            for (int b = 0; b < 32; ++b) {
-                const uint32_t v = *(const uint32_t*)(p + (size_t)b * ncols);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) acc[e] |= (uint32_t)(((v >> (8 * e)) & 0xFFu) != 0u) << b;
+            for (int b0 = 0; b0 < 32; b0 += 8) {
+                uint32_t v[8];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) v[b] = *(const uint32_t*)(p + (size_t)(b0 + b) * ncols);
+                // byte e of t: bit b = "row b0 + b of position e is set" (eight rows per word)
+                uint32_t t = 0u;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const uint32_t w = v[b];
+                    const uint32_t nz = ((((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u) >> 7;   // 0/1 per byte
+                    t |= nz << b;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[e] |= ((t >> (8 * e)) & 0xFFu) << b0;
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
