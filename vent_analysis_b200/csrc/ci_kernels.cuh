@@ -24,6 +24,7 @@
 struct CiTableDev {
     const int2* rows;   // [n_unique]  x = flat offset, y = (first boundary << 16) | boundary count
     const int* ii;      // [n_bounds]  row count at each boundary
+    const int* up;      // [ceil(n_unique / 32)]  largest ii of a boundary ending inside the 32-row step (0: none)
     int n_unique;
     int n_bounds;
 };
@@ -152,18 +153,24 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_CI_THREADS, 1) ci_grow_kernel(CiArgs a) {
                 if (g < V) hit = (bits[g >> 5] >> (g & 31u)) & 1u;
             }
             const unsigned hm = __ballot_sync(VB_FULL, hit);
-            const int pre = cum + __popc(hm & (0xffffffffu >> (31 - lane)));   // inclusive prefix
-            int cand = -1;
-            const int nb = row.y & 0xFFFF;
-            if (nb) {                                            // boundaries that end after row u
-                const int t0 = (int)((unsigned)row.y >> 16);
-                for (int t = t0; t < t0 + nb; ++t)
-                    if (2 * pre < T.ii[t]) { cand = t; break; }  // C < 0.5  (CI.py:97)
-            }
-            const unsigned cm = __ballot_sync(VB_FULL, cand >= 0);
-            if (cm) {
-                found = __shfl_sync(VB_FULL, cand, __ffs((int)cm) - 1);
-                break;
+            // A boundary t of this step can only stop the search if 2 * hits < ii[t], and the hits
+            // up to any row of the step are >= cum: with up = the largest ii[t] of the step, nothing
+            // can stop while 2 * cum >= up (most steps inside a cluster) -- warp uniform.
+            const int upv = T.up[base >> 5];
+            if (2 * cum < upv) {
+                const int pre = cum + __popc(hm & (0xffffffffu >> (31 - lane)));   // inclusive prefix
+                int cand = -1;
+                const int nb = row.y & 0xFFFF;
+                if (nb) {                                            // boundaries that end after row u
+                    const int t0 = (int)((unsigned)row.y >> 16);
+                    for (int t = t0; t < t0 + nb; ++t)
+                        if (2 * pre < T.ii[t]) { cand = t; break; }  // C < 0.5  (CI.py:97)
+                }
+                const unsigned cm = __ballot_sync(VB_FULL, cand >= 0);
+                if (cm) {
+                    found = __shfl_sync(VB_FULL, cand, __ffs((int)cm) - 1);
+                    break;
+                }
             }
             cum += __popc(hm);
         }

@@ -30,6 +30,7 @@ struct TableHost {
     int n_unique, n_bounds;
     void* d_rows = nullptr;
     void* d_ii = nullptr;
+    void* d_up = nullptr;      // per 32-row step: largest row count of a boundary that ends inside it (0: none)
     std::vector<double> radii;
 };
 
@@ -155,6 +156,7 @@ int upload_tables(vb_ctx* c, vbrt::stream_t s) {
     for (size_t i = 0; i < t.size(); ++i) {
         t[i].rows = (const int2*)c->tables[i].d_rows;
         t[i].ii = (const int*)c->tables[i].d_ii;
+        t[i].up = (const int*)c->tables[i].d_up;
         t[i].n_unique = c->tables[i].n_unique;
         t[i].n_bounds = c->tables[i].n_bounds;
     }
@@ -411,7 +413,7 @@ void vb_destroy(vb_ctx* c) {
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
                    &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats};
     for (Buf* b : bufs) vbrt::dev_free(b->p);
-    for (TableHost& t : c->tables) { vbrt::dev_free(t.d_rows); vbrt::dev_free(t.d_ii); }
+    for (TableHost& t : c->tables) { vbrt::dev_free(t.d_rows); vbrt::dev_free(t.d_ii); vbrt::dev_free(t.d_up); }
     vbrt::host_free(c->h_desc.p);
     vbrt::host_free(c->h_stats.p);
     for (vbrt::event_t e : c->ev) vbrt::event_destroy(e);
@@ -471,10 +473,17 @@ int vb_ci_table_create(vb_ctx* c, const double* table, int64_t nrows, int32_t n0
     T.n_unique = (int)rows.size(); T.n_bounds = (int)bnd.size();
     T.radii.resize(bnd.size());
     for (size_t t = 0; t < bnd.size(); ++t) T.radii[t] = table[4 * (size_t)(bnd[t] - 1)];   // CI.py:105
-    if (!vbrt::dev_malloc(&T.d_rows, rows.size() * sizeof(int2)) || !vbrt::dev_malloc(&T.d_ii, bnd.size() * sizeof(int)))
+    std::vector<int> up((rows.size() + 31) / 32, 0);
+    for (size_t u = 0; u < rows.size(); ++u) {
+        const int cnt = rows[u].y & 0xFFFF;
+        if (cnt) up[u >> 5] = std::max(up[u >> 5], bnd[(size_t)((unsigned)rows[u].y >> 16) + (size_t)cnt - 1]);
+    }
+    if (!vbrt::dev_malloc(&T.d_rows, rows.size() * sizeof(int2)) || !vbrt::dev_malloc(&T.d_ii, bnd.size() * sizeof(int)) ||
+        !vbrt::dev_malloc(&T.d_up, up.size() * sizeof(int)))
         return VB_ERR_CUDA;
     if (!vbrt::h2d(T.d_rows, rows.data(), rows.size() * sizeof(int2), c->stream) ||
-        !vbrt::h2d(T.d_ii, bnd.data(), bnd.size() * sizeof(int), c->stream) || !vbrt::stream_sync(c->stream))
+        !vbrt::h2d(T.d_ii, bnd.data(), bnd.size() * sizeof(int), c->stream) ||
+        !vbrt::h2d(T.d_up, up.data(), up.size() * sizeof(int), c->stream) || !vbrt::stream_sync(c->stream))
         return VB_ERR_CUDA;
     c->tables.push_back(T);
     c->tables_dirty = true;
