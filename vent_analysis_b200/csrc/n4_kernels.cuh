@@ -9,20 +9,21 @@
 //     for one subject -- 4 levels x <=50 iterations x {histogram, Wiener sharpening, B-spline fit,
 //     update, convergence} -- with block / named barriers only; no host round trip, subjects
 //     converge independently.
-//   * Only mask voxels take part in the iterations, so the log image is COMPACTED once per
-//     subject: the columns (col, slice) that carry mask voxels are grouped in blocks of 32 (one
-//     warp), and within a block the masked voxels are stored row by row, lane by lane.  A warp
-//     that walks the rows of its block therefore reads one contiguous, conflict-free stream.
-//     For the benchmark volumes (128x128x14, ~36k mask voxels = 143 KB) the compact log image
-//     lives in SHARED MEMORY for the whole filter; larger masks use the same code with the
-//     compact array in global memory (L2).  Work items (block x row segment) are drawn
-//     largest-first from a shared counter.
-//   * Nothing else is stored per voxel: U = logI - bias is re-evaluated wherever it is needed
-//     from per-column coefficient tables G[a][column] (rebuilt from the control lattice after
-//     every fit; spare shared memory) with warp-uniform row weights and a 4-tap sliding window.
-//   * Parzen histogram: fixed-point (count-conserving) shared-memory atomics into 8 copies
-//     => exactly associative, deterministic.
-//   * Sharpening: 4 packed 512-point complex FFTs in double in shared memory.
+//   * Only mask voxels take part in the iterations, so the volume is COMPACTED once per subject:
+//     the columns (col, slice) that carry mask voxels are grouped in blocks of 32 (one warp), and
+//     within a block the masked voxels are stored row by row, lane by lane.  A warp that walks the
+//     rows of its block therefore reads one contiguous, conflict-free stream.  Two compact arrays:
+//     the log image (global memory, L2 resident, read once per iteration) and U = logI - bias of
+//     the committed lattice, which for the benchmark volumes (128x128x14, ~36k mask voxels =
+//     143 KB) lives in SHARED MEMORY for the whole filter (larger masks: global memory, same
+//     code).  Work items (block x row segment) are drawn largest-first from a shared counter.
+//   * Only the update pass evaluates the bias (old and new field, from per-column coefficient
+//     tables G[a][column] rebuilt from the control lattice after every fit, warp-uniform row
+//     weights and a 4-tap sliding window) and writes the new U; histogram and fit read U.
+//   * Parzen histogram: a flat loop over the compact U array, fixed-point (count-conserving)
+//     shared-memory atomics into one copy per lane => exactly associative, deterministic.
+//   * Sharpening: 4 packed 512-point complex FFTs in double in shared memory, two radix-2 stages
+//     per pass.
 //   * B-spline fit: the Lee-Wolberg-Shin scatter is separable (t = tr*tc*ts,
 //     sum t^2 = Sr*Sc*Ss), so delta = sum w^3 z / sum w^2 is three small contractions:
 //     rows (registers, sliding 4-tap window) -> columns (64-bit fixed-point shared-memory adds
@@ -32,10 +33,13 @@
 //     recurrence whose rounding (the running mean stalls once its update drops below half an
 //     ulp) decides when a level stops.  It is reproduced here in parallel: threads run their
 //     consecutive steps exactly from guessed start states, the float bit-pattern increments are
-//     prefix-summed, and this repeats until no start moves -- the trajectory then IS the
-//     sequential one.  The chain is skipped when a rigorous bound already decides "continue";
-//     otherwise it runs on half of the warps while the other half computes the next iteration's
-//     histogram / sharpening / fit speculatively (committed only if the chain says "continue").
+//     prefix-summed, and this repeats until no increment changes -- the trajectory then IS the
+//     sequential one.  The first chunk predicts its starts from the exact-arithmetic running
+//     mean.  The chain is skipped when a rigorous bound already decides "continue"; otherwise it
+//     runs on a team of warps while the other warps compute the next iteration's histogram /
+//     sharpening / fit speculatively (committed only if the chain says "continue").
+//   * Inside the hot loops the slot / shared-memory pointers are opaque local copies: at the
+//     64-register cap the compiler otherwise re-derives them from the kernel parameters at each use.
 #pragma once
 #include <float.h>
 #include "vb_common.cuh"
