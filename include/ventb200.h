@@ -128,6 +128,18 @@ int vb_ci_batch_dev(vb_ctx* ctx, const uint8_t* defect, int32_t n, const int32_t
                     const int32_t* table_handles, uint16_t* ci_shell, vb_subject_stats* stats,
                     void* stream);
 
+/* Vent_Analysis.build4DdataArray (V_A.py:292-313), the step after the path: per
+   subject float32 [rows][cols][slices][6] = proton[0] HPvent[1] mask[2] N4HPvent[3] defectArray[4]
+   CIarray[5] (mm = float32(radius[shell] * vox_min[i]); 0 off the defect).  A null input leaves its
+   channel 0, like a missing attribute in the reference.  `out` holds 6 floats per voxel. */
+int vb_pack6_batch_dev(vb_ctx* ctx, int32_t n, const int32_t* shapes, const int32_t* table_handles,
+                       const double* vox_min, const float* proton, const float* image, const uint8_t* mask,
+                       const float* n4, const uint8_t* defect, const uint16_t* ci_shell, float* out,
+                       void* stream);
+int vb_pack6_batch_host(vb_ctx* ctx, int32_t n, const int32_t* shapes, const int32_t* table_handles,
+                        const double* vox_min, const float* proton, const float* image, const uint8_t* mask,
+                        const float* n4, const uint8_t* defect, const uint16_t* ci_shell, float* out);
+
 /* ---- whole path --------------------------------------------------------------------------- */
 int vb_pipeline_batch_dev(vb_ctx* ctx, int32_t n, const int32_t* shapes, const int32_t* table_handles,
                           const vb_n4_params* params, float thresh, uint32_t flags,

@@ -245,3 +245,47 @@ def check_p99_select(ctx):
             vals = np.sort(x[m > 0])
             assert int(st["n_mask"]) == len(vals)
             assert st["p99"] == vals[int(len(vals) * .99)], (cap, st["p99"], vals[int(len(vals) * .99)])
+
+
+def check_pack6(ctx):
+    """vb_pack6_batch_host (Vent_Analysis.build4DdataArray, V_A.py:292-313) against the numpy
+    statement of the reference: ragged batch, one subject without CI values, proton present /
+    absent, float32 bit-exact (CIarray = float32(float64 radius * min(vox)))."""
+    rng = np.random.default_rng(4)
+    vox = [1.5, 1.5, 10.0]
+    tbl = generate(vox, 50)
+    shapes = [(12, 10, 3), (9, 7, 5), (16, 8, 2)]
+    hs = [ctx.ci_table(tbl, s, key=(tuple(vox), 50, tbl.shape[0])) for s in shapes]
+    radii = ctx.ci_radii(hs[0])
+    vols = []
+    for s in shapes:
+        img = (1000 * rng.random(s)).astype(np.float32)
+        pro = (500 * rng.random(s)).astype(np.float32)
+        mask = (rng.random(s) < 0.5).astype(np.uint8)
+        n4 = (img * (1 + 0.1 * rng.random(s))).astype(np.float32)
+        defect = ((rng.random(s) < 0.2) & (mask > 0)).astype(np.uint8)
+        shell = np.where(defect > 0, rng.integers(0, len(radii), size=s), _lib.CI_OFF).astype(np.uint16)
+        vols.append((pro, img, mask, n4, defect, shell))
+    cat = lambda k: np.concatenate([v[k].ravel() for v in vols])
+    for with_proton in (True, False):
+        out = ctx.pack6_host(shapes, [min(vox)] * 3, proton=cat(0) if with_proton else None, image=cat(1), mask=cat(2),
+                             n4=cat(3), defect=cat(4), ci_shell=cat(5), handles=hs)
+        off = 0
+        for (pro, img, mask, n4, defect, shell), s in zip(vols, shapes):
+            V = img.size
+            ref = np.zeros(s + (6,), dtype=np.float32)                # V_A.py:294
+            if with_proton:
+                ref[..., 0] = pro
+            ref[..., 1] = img
+            ref[..., 2] = mask.astype(np.float64)
+            ref[..., 3] = n4
+            ref[..., 4] = defect.astype(np.float64)
+            ci = np.zeros(s)                                          # CI.py:139-142: float64 radius * min(vox)
+            sel = defect > 0
+            ci[sel] = radii[shell[sel]] * min(vox)
+            ref[..., 5] = ci
+            assert np.array_equal(out[6 * off:6 * (off + V)].reshape(s + (6,)), ref), (s, with_proton)
+            off += V
+    # channels whose input is missing stay zero
+    out = ctx.pack6_host(shapes, [min(vox)] * 3, image=cat(1), mask=cat(2))
+    assert not out.reshape(-1, 6)[:, [0, 3, 4, 5]].any() and np.array_equal(out.reshape(-1, 6)[:, 1], cat(1))

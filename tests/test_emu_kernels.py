@@ -130,3 +130,7 @@ def test_vdp_thresholds_a_few_ulps_around_every_edge(ctx):
 
 def test_vdp_p99_select_shared_and_restreamed(ctx):
     helpers.check_p99_select(ctx)
+
+
+def test_build4DdataArray_packing_bit_exact(ctx):
+    helpers.check_pack6(ctx)

@@ -176,3 +176,7 @@ def test_properties_at_full_size(ctx):
     assert (o1["ci_shell"][~sel] == _lib.CI_OFF).all() and (o1["ci_shell"][sel] < 5000).all()
     m3, o3, _ = cohort.run_cohort_host([img], [mask], [vox])
     assert np.array_equal(o3["ci_shell"], o1["ci_shell"])
+
+
+def test_build4DdataArray_packing_bit_exact(ctx):
+    helpers.check_pack6(ctx)

@@ -61,7 +61,7 @@ class VbError(RuntimeError):
 EXPORTS = ["vb_version", "vb_last_error", "vb_device_count", "vb_create", "vb_destroy", "vb_launch_count",
            "vb_n4_default_params", "vb_ci_table_create", "vb_ci_table_radii", "vb_snr_batch_dev", "vb_n4_batch_dev",
            "vb_vdp_batch_dev", "vb_border_batch_dev", "vb_ci_batch_dev", "vb_pipeline_batch_dev",
-           "vb_pipeline_batch_host", "vb_set_profiling", "vb_profile_fetch", "vb_set_debug", "vb_n4_debug_fetch"]
+           "vb_pipeline_batch_host", "vb_pack6_batch_dev", "vb_pack6_batch_host", "vb_set_profiling", "vb_profile_fetch", "vb_set_debug", "vb_n4_debug_fetch"]
 N_STAGES = 5
 STAGE_NAMES = ("snr", "n4", "vdp", "mask_border", "ci")
 
@@ -89,6 +89,8 @@ def bind(path):
     lib.vb_ci_batch_dev.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     lib.vb_pipeline_batch_dev.argtypes = [vp, i32, vp, vp, C.POINTER(N4Params), f32, u32, C.POINTER(Buffers), vp]
     lib.vb_pipeline_batch_host.argtypes = [vp, i32, vp, vp, C.POINTER(N4Params), f32, u32, C.POINTER(Buffers)]
+    lib.vb_pack6_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.vb_pack6_batch_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.vb_set_profiling.argtypes = [vp, i32]
     lib.vb_profile_fetch.argtypes = [vp, vp, C.POINTER(i32)]
     lib.vb_set_debug.argtypes = [vp, i32]
@@ -283,6 +285,33 @@ class Context:
         if rc not in (VB_OK, VB_ERR_CI_RMAX):
             self.check(rc)
         return shell, stats, rc
+
+    def pack6_host(self, shapes, vox_min, proton=None, image=None, mask=None, n4=None, defect=None, ci_shell=None,
+                   handles=None, out=None):
+        """``Vent_Analysis.build4DdataArray`` (Vent_Analysis.py:292-313) for a batch on host arrays:
+        float32 ``[6 * V]`` = per subject ``[rows][cols][slices][6]`` (proton, HPvent, mask, N4HPvent,
+        defectArray, CIarray in mm).  Inputs left ``None`` give a zero channel."""
+        shapes = np.ascontiguousarray(shapes, dtype=np.int32).reshape(-1, 3)
+        n = shapes.shape[0]
+        V = int(np.prod(shapes.astype(np.int64), axis=1).sum())
+
+        def arr(a, dt):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dt).reshape(-1)
+            assert a.size == V
+            return a
+        proton, image, n4 = arr(proton, np.float32), arr(image, np.float32), arr(n4, np.float32)
+        mask, defect, ci_shell = arr(mask, np.uint8), arr(defect, np.uint8), arr(ci_shell, np.uint16)
+        vm = np.ascontiguousarray(vox_min, dtype=np.float64).reshape(-1)
+        assert vm.size == n
+        hd = None if handles is None else np.ascontiguousarray(handles, dtype=np.int32)
+        if out is None:
+            out = np.empty(6 * V, dtype=np.float32)
+        assert out.dtype == np.float32 and out.size == 6 * V and out.flags.c_contiguous
+        self.check(self.lib.vb_pack6_batch_host(self.h, n, _ptr(shapes), _ptr(hd), _ptr(vm), _ptr(proton), _ptr(image),
+                                                _ptr(mask), _ptr(n4), _ptr(defect), _ptr(ci_shell), _ptr(out)))
+        return out
 
     def n4_debug(self, subject, nbins, lattice_capacity, trace_capacity=212):
         self.check(self.lib.vb_set_debug(self.h, 1))

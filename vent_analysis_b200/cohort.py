@@ -77,6 +77,27 @@ def run_cohort_host(images, masks, voxs, device=0, flags=ALL_STAGES, thresh=0.6,
     return metrics_from_stats(ctx, out["stats"], shapes, voxs, handles), out, out["stats"]
 
 
+def build4DdataArrays(images, masks, voxs, out, protons=None, device=0, ctx=None, rmax=50):
+    """``Vent_Analysis.build4DdataArray`` (Vent_Analysis.py:292-313) for a cohort, packed on the GPU
+    from the compact outputs of :func:`run_cohort_host` (``out``: n4 f32, defect u8, ci_shell u16).
+    Returns one float32 ``[rows, cols, slices, 6]`` array per subject: proton[0] HPvent[1] mask[2]
+    N4HPvent[3] defectArray[4] CIarray[5]."""
+    ctx = ctx if ctx is not None else _lib.context(device)
+    shapes = [tuple(int(s) for s in im.shape) for im in images]
+    handles = table_handles(ctx, shapes, voxs, rmax) if out.get("ci_shell") is not None else None
+    cat = lambda xs, dt: np.concatenate([np.asarray(x, dtype=dt).ravel() for x in xs])
+    packed = ctx.pack6_host(shapes, [min(float(v) for v in vox) for vox in voxs],
+                            proton=None if protons is None else cat(protons, np.float32),
+                            image=cat(images, np.float32), mask=cat(masks, np.uint8), n4=out.get("n4"),
+                            defect=out.get("defect"), ci_shell=out.get("ci_shell"), handles=handles)
+    res, off = [], 0
+    for shp in shapes:
+        V = int(np.prod(shp))
+        res.append(packed[6 * off:6 * (off + V)].reshape(shp + (6,)))
+        off += V
+    return res
+
+
 class DeviceCohort:
     """A batch resident in HBM.  ``step()`` enqueues the whole N4 -> VDP -> CI path on torch's
     current CUDA stream (no host synchronisation); ``stats()`` copies the per-subject record

@@ -25,6 +25,7 @@ struct CiTableDev {
     const int2* rows;   // [n_unique]  x = flat offset, y = (first boundary << 16) | boundary count
     const int* ii;      // [n_bounds]  row count at each boundary
     const int* up;      // [ceil(n_unique / 32)]  largest ii of a boundary ending inside the 32-row step (0: none)
+    const double* radii; // [n_bounds]  shell radius in min-voxel units (CI.py:105)
     int n_unique;
     int n_bounds;
 };
@@ -223,5 +224,48 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_CI_THREADS, 1) ci_percentile_kernel(CiArgs a)
             }
             st->ci_t95 = t95;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vent_Analysis.build4DdataArray (Vent_Analysis.py:292-313): the six result volumes of a subject
+// interleaved as float32 [row][col][slice][6]: proton[0] HPvent[1] mask[2] N4HPvent[3]
+// defectArray[4] CIarray[5], CIarray = float32(radius[shell] * min(vox)) on defect voxels, else 0
+// (the float64 product the reference stores, then its float32 cast).  A channel whose input is
+// null stays 0, as when the reference's attribute is missing.  One voxel per thread and step:
+// reads are coalesced per channel, a warp writes 768 contiguous bytes (three 8-byte stores each).
+struct Pack6Args {
+    const float* proton;
+    const float* image;
+    const uint8_t* mask;
+    const float* n4;
+    const uint8_t* defect;
+    const uint16_t* shell;
+    const VbSubject* subj;
+    const CiTableDev* tables;     // may be null when shell is null
+    const double* vox_min;        // [n]
+    float* out;                   // [6 * V_total]
+};
+VB_KERNEL void pack6_kernel(Pack6Args a) {
+    const int si = (int)blockIdx.y;
+    const VbSubject S = a.subj[si];
+    const double vmin = a.vox_min[si];
+    const double* radii = nullptr;
+    int nb = 0;
+    if (a.shell && S.table >= 0) { radii = a.tables[S.table].radii; nb = a.tables[S.table].n_bounds; }
+    for (int v = (int)(blockIdx.x * blockDim.x + threadIdx.x); v < S.V; v += (int)(gridDim.x * blockDim.x)) {
+        const size_t g = (size_t)S.off + (size_t)v;
+        const float c0 = a.proton ? a.proton[g] : 0.0f;
+        const float c1 = a.image ? a.image[g] : 0.0f;
+        const float c2 = a.mask ? (float)a.mask[g] : 0.0f;
+        const float c3 = a.n4 ? a.n4[g] : 0.0f;
+        const float c4 = a.defect ? (float)a.defect[g] : 0.0f;
+        float c5 = 0.0f;
+        if (radii) {
+            const int t = (int)a.shell[g];
+            if (t < nb) c5 = (float)__dmul_rn(radii[t], vmin);
+        }
+        float2* o = (float2*)(a.out + 6 * g);
+        o[0] = make_float2(c0, c1); o[1] = make_float2(c2, c3); o[2] = make_float2(c4, c5);
     }
 }

@@ -31,6 +31,7 @@ struct TableHost {
     void* d_rows = nullptr;
     void* d_ii = nullptr;
     void* d_up = nullptr;      // per 32-row step: largest row count of a boundary that ends inside it (0: none)
+    void* d_radii = nullptr;   // shell radii (double), for vb_pack6_*
     std::vector<double> radii;
 };
 
@@ -64,6 +65,7 @@ struct vb_ctx {
     size_t ev_used = 0;
     // host-API mirrors
     Buf m_image, m_mask, m_n4, m_logbias, m_defect, m_lb, m_dborder, m_mborder, m_shell, m_stats;
+    Buf m_proton, m_pack, d_voxmin;
 };
 
 namespace {
@@ -157,6 +159,7 @@ int upload_tables(vb_ctx* c, vbrt::stream_t s) {
         t[i].rows = (const int2*)c->tables[i].d_rows;
         t[i].ii = (const int*)c->tables[i].d_ii;
         t[i].up = (const int*)c->tables[i].d_up;
+        t[i].radii = (const double*)c->tables[i].d_radii;
         t[i].n_unique = c->tables[i].n_unique;
         t[i].n_bounds = c->tables[i].n_bounds;
     }
@@ -411,9 +414,9 @@ void vb_destroy(vb_ctx* c) {
     vbrt::stream_destroy(c->stream2);
     Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_d0,
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
-                   &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats};
+                   &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats, &c->m_proton, &c->m_pack, &c->d_voxmin};
     for (Buf* b : bufs) vbrt::dev_free(b->p);
-    for (TableHost& t : c->tables) { vbrt::dev_free(t.d_rows); vbrt::dev_free(t.d_ii); vbrt::dev_free(t.d_up); }
+    for (TableHost& t : c->tables) { vbrt::dev_free(t.d_rows); vbrt::dev_free(t.d_ii); vbrt::dev_free(t.d_up); vbrt::dev_free(t.d_radii); }
     vbrt::host_free(c->h_desc.p);
     vbrt::host_free(c->h_stats.p);
     for (vbrt::event_t e : c->ev) vbrt::event_destroy(e);
@@ -479,11 +482,12 @@ int vb_ci_table_create(vb_ctx* c, const double* table, int64_t nrows, int32_t n0
         if (cnt) up[u >> 5] = std::max(up[u >> 5], bnd[(size_t)((unsigned)rows[u].y >> 16) + (size_t)cnt - 1]);
     }
     if (!vbrt::dev_malloc(&T.d_rows, rows.size() * sizeof(int2)) || !vbrt::dev_malloc(&T.d_ii, bnd.size() * sizeof(int)) ||
-        !vbrt::dev_malloc(&T.d_up, up.size() * sizeof(int)))
+        !vbrt::dev_malloc(&T.d_up, up.size() * sizeof(int)) || !vbrt::dev_malloc(&T.d_radii, bnd.size() * sizeof(double)))
         return VB_ERR_CUDA;
     if (!vbrt::h2d(T.d_rows, rows.data(), rows.size() * sizeof(int2), c->stream) ||
         !vbrt::h2d(T.d_ii, bnd.data(), bnd.size() * sizeof(int), c->stream) ||
-        !vbrt::h2d(T.d_up, up.data(), up.size() * sizeof(int), c->stream) || !vbrt::stream_sync(c->stream))
+        !vbrt::h2d(T.d_up, up.data(), up.size() * sizeof(int), c->stream) ||
+        !vbrt::h2d(T.d_radii, T.radii.data(), bnd.size() * sizeof(double), c->stream) || !vbrt::stream_sync(c->stream))
         return VB_ERR_CUDA;
     c->tables.push_back(T);
     c->tables_dirty = true;
@@ -537,6 +541,56 @@ int vb_ci_batch_dev(vb_ctx* c, const uint8_t* defect, int32_t n, const int32_t* 
     vbrt::set_device(c->device);
     int rc = prepare(c, n, shapes, handles, (vbrt::stream_t)stream);
     return rc ? rc : run_ci(c, defect, n, shell, stats, (vbrt::stream_t)stream);
+}
+
+// Vent_Analysis.build4DdataArray for a batch (device pointers; null inputs leave their channel 0)
+int vb_pack6_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const int32_t* handles, const double* vox_min,
+                       const float* proton, const float* image, const uint8_t* mask, const float* n4,
+                       const uint8_t* defect, const uint16_t* shell, float* out, void* stream) {
+    if (!c || !vox_min || !out) return fail(VB_ERR_ARG, "pack6: null argument");
+    if (shell && !handles) return fail(VB_ERR_ARG, "pack6: ci_shell needs the CI table handles");
+    vbrt::set_device(c->device);
+    vbrt::stream_t s = (vbrt::stream_t)stream;
+    int rc = prepare(c, n, shapes, shell ? handles : nullptr, s);
+    if (rc) return rc;
+    if (shell && (rc = upload_tables(c, s))) return rc;
+    if (!ensure(c->d_voxmin, sizeof(double) * (size_t)n)) return VB_ERR_CUDA;
+    if (!vbrt::stream_sync(s)) return VB_ERR_CUDA;             // a previous upload from the caller's array
+    if (!vbrt::h2d(c->d_voxmin.p, vox_min, sizeof(double) * (size_t)n, s) || !vbrt::stream_sync(s)) return VB_ERR_CUDA;
+    vbrt::clear_stale_error();
+    c->r0 = 0;
+    Pack6Args a;
+    a.proton = proton; a.image = image; a.mask = mask; a.n4 = n4; a.defect = defect; a.shell = shell;
+    a.subj = subj_ptr(c); a.tables = (const CiTableDev*)c->d_tables.p; a.vox_min = (const double*)c->d_voxmin.p; a.out = out;
+    VB_LAUNCH(pack6_kernel, dim3(grid_x_for(c, n, vmax_of(c), 256), n), dim3(256), 0, s, a);
+    ++c->launches;
+    return vbrt::last_launch_ok("pack6_kernel") ? VB_OK : VB_ERR_CUDA;
+}
+
+// the same on host arrays (pageable or pinned); blocks until `out` is filled
+int vb_pack6_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const int32_t* handles, const double* vox_min,
+                        const float* proton, const float* image, const uint8_t* mask, const float* n4,
+                        const uint8_t* defect, const uint16_t* shell, float* out) {
+    if (!c || !shapes || n <= 0 || !out) return fail(VB_ERR_ARG, "pack6: null argument");
+    vbrt::set_device(c->device);
+    vbrt::stream_t s = c->stream;
+    size_t V = 0;
+    for (int i = 0; i < n; ++i) V += (size_t)shapes[3 * i] * shapes[3 * i + 1] * shapes[3 * i + 2];
+    bool ok = ensure(c->m_pack, 24 * V);
+    if (proton) ok = ok && ensure(c->m_proton, 4 * V) && vbrt::h2d(c->m_proton.p, proton, 4 * V, s);
+    if (image) ok = ok && ensure(c->m_image, 4 * V) && vbrt::h2d(c->m_image.p, image, 4 * V, s);
+    if (mask) ok = ok && ensure(c->m_mask, V) && vbrt::h2d(c->m_mask.p, mask, V, s);
+    if (n4) ok = ok && ensure(c->m_n4, 4 * V) && vbrt::h2d(c->m_n4.p, n4, 4 * V, s);
+    if (defect) ok = ok && ensure(c->m_defect, V) && vbrt::h2d(c->m_defect.p, defect, V, s);
+    if (shell) ok = ok && ensure(c->m_shell, 2 * V) && vbrt::h2d(c->m_shell.p, shell, 2 * V, s);
+    if (!ok) return VB_ERR_CUDA;
+    int rc = vb_pack6_batch_dev(c, n, shapes, handles, vox_min, proton ? (const float*)c->m_proton.p : nullptr,
+                                image ? (const float*)c->m_image.p : nullptr, mask ? (const uint8_t*)c->m_mask.p : nullptr,
+                                n4 ? (const float*)c->m_n4.p : nullptr, defect ? (const uint8_t*)c->m_defect.p : nullptr,
+                                shell ? (const uint16_t*)c->m_shell.p : nullptr, (float*)c->m_pack.p, s);
+    if (rc) return rc;
+    if (!vbrt::d2h(out, c->m_pack.p, 24 * V, s) || !vbrt::stream_sync(s)) return VB_ERR_CUDA;
+    return VB_OK;
 }
 
 // the selected stages on subjects [r0, r0 + cnt) of the prepared batch (buffers are whole-batch)
