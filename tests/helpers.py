@@ -289,3 +289,21 @@ def check_pack6(ctx):
     # channels whose input is missing stay zero
     out = ctx.pack6_host(shapes, [min(vox)] * 3, image=cat(1), mask=cat(2))
     assert not out.reshape(-1, 6)[:, [0, 3, 4, 5]].any() and np.array_equal(out.reshape(-1, 6)[:, 1], cat(1))
+
+
+def check_pack6_golden(ctx):
+    """The packing against the UNMODIFIED reference's build4DdataArray (tests/golden/pack6_small_b.npz,
+    made by tests/golden/make_golden_pack6.py): VDP + CI through our kernels on the fixture's
+    inputs, packed on the device, SHA-256 of the float32 [48, 40, 6, 6] array identical."""
+    import hashlib
+    gp = golden("pack6_small_b.npz")
+    g, shape, vox, img, mask, n4 = golden_inputs("small_b")
+    out = check_vdp_ci_against_golden(ctx, "small_b", True)
+    tbl = generate(vox, 50)
+    h = ctx.ci_table(tbl, shape, key=(tuple(vox), 50, tbl.shape[0]))
+    proton = (500.0 * np.random.default_rng(int(gp["proton_seed"])).random(shape)).astype(np.float32)
+    packed = ctx.pack6_host([shape], [min(vox)], proton=proton, image=img, mask=mask, n4=n4, defect=out["defect"],
+                            ci_shell=out["ci_shell"], handles=[h])
+    assert tuple(int(x) for x in gp["shape"]) == shape + (6,) and str(gp["dtype"]) == "float32"
+    assert np.allclose(packed.reshape(-1, 6).astype(np.float64).sum(axis=0), gp["channel_sums"], rtol=0, atol=0)
+    assert hashlib.sha256(packed.tobytes()).hexdigest() == str(gp["sha"])

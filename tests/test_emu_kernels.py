@@ -134,3 +134,7 @@ def test_vdp_p99_select_shared_and_restreamed(ctx):
 
 def test_build4DdataArray_packing_bit_exact(ctx):
     helpers.check_pack6(ctx)
+
+
+def test_build4DdataArray_identical_to_the_reference_output(ctx):
+    helpers.check_pack6_golden(ctx)

@@ -180,3 +180,7 @@ def test_properties_at_full_size(ctx):
 
 def test_build4DdataArray_packing_bit_exact(ctx):
     helpers.check_pack6(ctx)
+
+
+def test_build4DdataArray_identical_to_the_reference_output(ctx):
+    helpers.check_pack6_golden(ctx)
