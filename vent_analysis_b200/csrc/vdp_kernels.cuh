@@ -343,6 +343,8 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
             long long k = (long long)((double)M * .99);              // int(len(signal_list)*.99)
             if (k >= M) k = M - 1;
             unsigned lo = lo0, hi = hi0;
+            const unsigned* kp = keys;                               // keys still in the running (shared-memory path)
+            int kn = (int)M;
             for (;;) {
                 const unsigned range = hi - lo;
                 if (range == 0u) break;
@@ -353,7 +355,7 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
                 __syncthreads();
                 VbRun run; run.bin = 0; run.cnt = 0u;
                 if (in_smem) {
-                    for (int i = tid; i < (int)M; i += nt) vdp_hist_keys(hist, keys[i], lo, range, sh, run);
+                    for (int i = tid; i < kn; i += nt) vdp_hist_keys(hist, kp[i], lo, range, sh, run);
                 } else {
                     for (int v = 4 * tid; v < S.V; v += 4 * nt) {
                         const Vb4b m = vb_load4b(msk, v, S.V, aligned);
@@ -367,10 +369,26 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
                 vb_run_flush(run, hist);
                 __syncthreads();
                 const unsigned b = (unsigned)vdp_find_bin(hist, nb, k, &s_bin, &s_k);
+                const int nsel = (int)hist[b];                       // keys of the chosen bin
                 lo += b << sh;
                 const unsigned w1 = (1u << sh) - 1u;                 // keys of the chosen bin: [lo, lo + w1]
                 if (hi - lo > w1) hi = lo + w1;
                 if (sh == 0) break;
+                // the next levels only concern the keys of the chosen bin: gather them behind the
+                // key array when there is room (usually a few hundred of ~36 k), so that the
+                // remaining levels do not walk all keys again
+                if (in_smem && kp == keys && nsel <= key_cap - (int)M && nsel < kn) {
+                    if (tid == 0) s_nkeys = 0;
+                    __syncthreads();
+                    unsigned* dst = keys + M;
+                    const unsigned r2 = hi - lo;
+                    for (int i = tid; i < kn; i += nt) {
+                        const unsigned key = kp[i];
+                        if (key - lo <= r2) dst[atomicAdd(&s_nkeys, 1)] = key;
+                    }
+                    __syncthreads();
+                    kp = dst; kn = nsel;
+                }
             }
             p99 = vb_key_float(lo);
         }
