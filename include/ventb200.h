@@ -17,6 +17,7 @@
  */
 #ifndef VENTB200_H
 #define VENTB200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -149,6 +150,48 @@ int vb_pipeline_batch_dev(vb_ctx* ctx, int32_t n, const int32_t* shapes, const i
 int vb_pipeline_batch_host(vb_ctx* ctx, int32_t n, const int32_t* shapes, const int32_t* table_handles,
                            const vb_n4_params* params, float thresh, uint32_t flags,
                            const vb_buffers* host);
+
+/* ---- whole path, COMPACT host I/O ------------------------------------------------------------
+ * The same path with the fewest bytes over PCIe: the image as the reference reads it from DICOM
+ * (uint16 pixel data, Vent_Analysis.py:169-181) or float32, the 0/1 mask bit-packed, and on the way
+ * back one byte of codes per voxel plus the CI map as a sparse list (2.125 B/voxel up and about
+ * 5.2 B/voxel down instead of 5 and 9).  Arrays are whole-batch, subjects concatenated.
+ *   mask_bits   subject i owns ceil(V_i / 32) 32-bit words; bit b of word w = voxel 32 w + b of the
+ *               C-ordered volume (numpy: packbits(mask.ravel() != 0, bitorder='little'), padded to a
+ *               multiple of 4 bytes).  The mask is 0/1 here; multi-label masks use mask_u8.
+ *   codes       bits 0-2 defectArrayLB (0..6) | bit 3 defectArray | bit 4 defectBorder |
+ *               bit 5 mask_border (with VB_DO_MASK_BORDER)
+ *   ci_index / ci_value   for subject i the entries [ci_offset[i], ci_offset[i+1]): C-order flat
+ *               voxel index inside the subject and shell ordinal t (CIarray = radii[t]*min(vox)) of
+ *               every defect voxel, in no particular order.  VB_ERR_ARG if ci_capacity is too small
+ *               (a batch never needs more than its voxel count). */
+#define VB_CODE_LB_MASK 7u
+#define VB_CODE_DEFECT 8u
+#define VB_CODE_DEFECT_BORDER 16u
+#define VB_CODE_MASK_BORDER 32u
+typedef struct vb_host_io {
+    const uint16_t* image_u16; /* in   exactly one of image_u16 / image_f32                      */
+    const float* image_f32;    /* in                                                            */
+    const uint32_t* mask_bits; /* in   exactly one of mask_bits / mask_u8                        */
+    const uint8_t* mask_u8;    /* in                                                            */
+    float* n4;                 /* out  optional N4HPvent                                         */
+    float* logbias;            /* out  optional                                                  */
+    uint8_t* codes;            /* out  optional (needs VB_DO_VDP)                                */
+    uint32_t* ci_index;        /* out  with VB_DO_CI (optional: NULL = CI scalars only)          */
+    uint16_t* ci_value;        /* out                                                            */
+    int64_t ci_capacity;       /* entries available in ci_index / ci_value                       */
+    int64_t* ci_offset;        /* out  [n + 1]                                                   */
+    vb_subject_stats* stats;   /* out  [n]                                                       */
+} vb_host_io;
+int vb_pipeline_batch_host_packed(vb_ctx* ctx, int32_t n, const int32_t* shapes, const int32_t* table_handles,
+                                  const vb_n4_params* params, float thresh, uint32_t flags,
+                                  const vb_host_io* io);
+
+/* Page-locked host memory for the *_host entry points (asynchronous copies need it to overlap with
+ * compute).  The pages are touched by the calling thread, so a caller that has bound itself to the
+ * CPUs next to the context's GPU gets NUMA-local buffers. */
+int vb_host_alloc(vb_ctx* ctx, size_t bytes, void** ptr);
+int vb_host_free(vb_ctx* ctx, void* ptr);
 
 /* Per-stage device timing of vb_pipeline_batch_dev: with profiling on, every call records a
  * CUDA event on the launching stream before the first stage and after each of the VB_N_STAGES

@@ -176,7 +176,7 @@ def _near_threshold_volume(shape, seed, odd_in_mask=()):
     for _ in range(60):                                   # fixed point: edge voxels relative to the final mean / p99
         cur = flat.astype(np.float32)
         vals = np.sort(cur[sel])
-        mean = np.float32(vals.astype(np.float64).sum() / len(vals))
+        mean = np.mean(vals)                              # the reference's anchor (V_A.py:245-246)
         p99 = vals[int(len(vals) * .99)]
         anchor = np.where(cs == 0.6, np.float64(mean), np.float64(p99))
         flat[edge] = anchor * cs
@@ -189,10 +189,15 @@ def _near_threshold_volume(shape, seed, odd_in_mask=()):
     return out.reshape(shape), mask
 
 
+def _same_f32(a, b):
+    return a == b or (np.isnan(a) and np.isnan(b))
+
+
 def check_vdp_threshold_edges(ctx):
     """Threshold / linear-binning / median / border kernels on values placed a few ulps around
-    every quotient threshold (word and byte versions, mixed in one batch), given the kernel's
-    own mean (= float32 of the float64 mean) and the exact p99."""
+    every quotient threshold (word and byte versions, mixed in one batch) against the restatement
+    of the reference (oracle/vdp_oracle.vdp): the anchors are the reference's own -- numpy's float32
+    pairwise mean of the SORTED mask values and the exact p99 -- so every output is bit exact."""
     shapes = [(32, 20, 6), (35, 8, 3), (64, 12, 7), (16, 16, 14), (24, 8, 2), (20, 12, 1), (33, 9, 5), (21, 10, 6)]
     odd = [(), (), (), (), (np.inf,), (np.nan, -np.inf), (), (np.inf, np.nan)]        # last two: byte version (unaligned)
     vols = [_near_threshold_volume(s, 100 + i, o) for i, (s, o) in enumerate(zip(shapes, odd))]
@@ -203,19 +208,56 @@ def check_vdp_threshold_edges(ctx):
     for (x, m), shape, st in zip(vols, shapes, out["stats"]):
         V = x.size
         with np.errstate(all="ignore"):
-            vals = np.sort(x[m > 0])
-        assert int(st["n_mask"]) == len(vals)
-        p99 = vals[int(len(vals) * .99)]
-        assert st["p99"] == p99 or (np.isnan(st["p99"]) and np.isnan(p99))
-        finite = vals[np.isfinite(vals)]
-        if len(finite) == len(vals):
-            assert st["mean"] == np.float32(vals.astype(np.float64).sum() / len(vals))
-        d, lb, bd = _vdp_reference_given_stats(x, m, st["mean"], st["p99"])
-        assert np.array_equal(out["defect"][off:off + V].reshape(shape), d), shape
-        assert np.array_equal(out["defect_lb"][off:off + V].reshape(shape), lb), shape
-        assert np.array_equal(out["defect_border"][off:off + V].reshape(shape), bd), shape
-        assert int(st["n_defect"]) == int(d.sum()) and int(st["n_lb12"]) == int(((lb == 1) | (lb == 2)).sum())
+            r = vdp_oracle.vdp(x, m.astype(np.float64), [1.5, 1.5, 10.0])
+        assert int(st["n_mask"]) == int((m > 0).sum())
+        assert _same_f32(st["p99"], r["p99"]), (shape, st["p99"], r["p99"])
+        assert _same_f32(st["mean"], r["mean"]), (shape, st["mean"], r["mean"])
+        assert np.array_equal(out["defect"][off:off + V].reshape(shape), r["defectArray"]), shape
+        assert np.array_equal(out["defect_lb"][off:off + V].reshape(shape), r["defectArrayLB"]), shape
+        assert np.array_equal(out["defect_border"][off:off + V].reshape(shape).astype(bool), r["defectBorder"]), shape
+        assert 100 * np.float64(st["n_defect"]) / np.sum(m.astype(np.float64)) == r["VDP"]
+        assert 100 * np.int64(st["n_lb12"]) / np.sum(m.astype(np.float64)) == r["VDP_lb"]
         off += V
+
+
+def check_mean_bit_exact(ctx, n_phantoms=8, shape=(48, 40, 6), big=None):
+    """stats.mean == np.mean(sorted(N4[mask>0])) (Vent_Analysis.py:245-246: numpy's float32 PAIRWISE
+    sum of the sorted list / M) and stats.p99 == sorted[int(M*.99)], bit for bit: phantoms, mask
+    sizes around every corner of numpy's recursion (M < 8, M <= 128, just above, odd remainders),
+    duplicate-heavy and wide-range data, and the global-memory variant of the sort."""
+    import os
+    rng = np.random.default_rng(77)
+    vols = []
+    for i in range(n_phantoms):
+        img, mask = phantom(shape, [2.0, 2.0, 11.5], 900 + i)
+        vols.append((img, mask))
+    for M in (1, 5, 7, 8, 9, 15, 16, 127, 128, 129, 136, 137, 255, 256, 257, 1000, 1029):
+        x = (500 * (1 + 0.3 * rng.standard_normal((40, 30, 2)))).astype(np.float32)
+        m = np.zeros(x.size, np.uint8)
+        m[rng.permutation(x.size)[:M]] = 1
+        vols.append((x, m.reshape(x.shape)))
+    x = rng.choice(np.array([3.0, 3.0000002, 700.0, 1e-3, 2.5e7], np.float32), size=(30, 24, 3))      # few distinct values
+    vols.append((x, (rng.random(x.shape) < 0.8).astype(np.uint8)))
+    x = (rng.standard_normal((30, 24, 3)) * 10.0 ** rng.integers(-6, 6, size=(30, 24, 3))).astype(np.float32)   # signed, wide
+    vols.append((x, (rng.random(x.shape) < 0.7).astype(np.uint8)))
+    if big is not None:
+        vols.append(big)
+    shapes = [v[0].shape for v in vols]
+    for cap in (None, "64"):
+        if cap is None:
+            os.environ.pop("VB_VDP_KEY_CAP", None)
+        else:
+            os.environ["VB_VDP_KEY_CAP"] = cap
+        try:
+            out = ctx.pipeline_host(shapes, _lib.DO_VDP, mask=np.concatenate([v[1].ravel() for v in vols]),
+                                    n4=np.concatenate([v[0].ravel() for v in vols]))
+        finally:
+            os.environ.pop("VB_VDP_KEY_CAP", None)
+        for (x, m), st in zip(vols, out["stats"]):
+            vals = sorted(x[m > 0])                                   # the reference's expression, literally
+            assert int(st["n_mask"]) == len(vals)
+            assert st["mean"] == np.mean(vals), (cap, x.shape, len(vals), st["mean"], np.mean(vals))
+            assert st["p99"] == vals[int(len(vals) * .99)], (cap, x.shape, len(vals))
 
 
 def check_p99_select(ctx):

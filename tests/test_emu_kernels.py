@@ -132,6 +132,10 @@ def test_vdp_p99_select_shared_and_restreamed(ctx):
     helpers.check_p99_select(ctx)
 
 
+def test_vdp_anchor_mean_is_numpys_pairwise_mean_of_the_sorted_list(ctx):
+    helpers.check_mean_bit_exact(ctx, n_phantoms=3)
+
+
 def test_build4DdataArray_packing_bit_exact(ctx):
     helpers.check_pack6(ctx)
 

@@ -108,6 +108,13 @@ def test_vdp_p99_select_shared_and_restreamed(ctx):
     helpers.check_p99_select(ctx)
 
 
+def test_vdp_anchor_mean_is_numpys_pairwise_mean_of_the_sorted_list(ctx):
+    """64 C2-sized phantoms + the corner cases + a 128^3 volume (mask beyond shared memory and a
+    pairwise heap deeper than the shared-memory one)."""
+    shape, vox, seed = CONFIGS["C3"]
+    helpers.check_mean_bit_exact(ctx, n_phantoms=64, shape=CONFIGS["C2"][0], big=phantom(shape, vox, seed))
+
+
 def test_class_surface_end_to_end_c2():
     from vent_analysis_b200 import CI, Vent_Analysis
     g, shape, vox, img, mask, n4 = helpers.golden_inputs("C2")

@@ -173,9 +173,14 @@ class Context:
     def ci_table(self, table, shape, key=None):
         """Handle of the sphere table prepared for volume ``shape`` (memoised by ``key``)."""
         shape = tuple(int(s) for s in shape)
-        k = (key if key is not None else id(table), shape)
-        if k not in self._tables:
+        t = None
+        if key is None:                                  # content hash: an id() can be recycled
+            import hashlib
             t = np.ascontiguousarray(table, dtype=np.float64)
+            key = (t.shape, hashlib.sha1(t.tobytes()).hexdigest())
+        k = (key, shape)
+        if k not in self._tables:
+            t = np.ascontiguousarray(table, dtype=np.float64) if t is None else t
             h = C.c_int32(-1)
             self.check(self.lib.vb_ci_table_create(self.h, _ptr(t), t.shape[0], shape[0], shape[1], shape[2],
                                                    C.byref(h)))

@@ -24,12 +24,6 @@
 // {rows with mask, plus row 0} x {cols [first masked col > 0, last masked col)} x
 // {slices with mask, plus slice 0}, minus the first / last `fov` rows.  Population std.
 // 4 consecutive voxels per thread and step (16-byte image loads when the subject is aligned)
-// x / d from rd = RN(1/d) with one Newton correction of the quotient: the IEEE-rounded result
-// for normal operands (checked against 2e7 random float32 divisions), 3 instructions
-VB_DEV float vb_div_rcp(float x, float d, float rd) {
-    const float q = __fmul_rn(x, rd);
-    return fmaf(fmaf(-q, d, x), rd, q);
-}
 struct Vb4f { float v[4]; };
 struct Vb4b { uint8_t v[4]; };
 VB_DEV Vb4f vb_load4f(const float* p, int v, int V, bool aligned) {
@@ -203,78 +197,121 @@ snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// VDP statistics, one CTA per subject: M = #mask, mean (float32 of the float64 sum), and the
-// exact order statistic sorted(N4[mask>0])[int(M*.99)] by a radix select on the order-preserving
-// key of the float bits.  Also zeroes the defect / LB counters.
-struct VbRun { int bin; unsigned cnt; };
-VB_DEV void vb_run_add(VbRun& r, unsigned* hist, int bin) {
-    if (bin == r.bin) { ++r.cnt; return; }
-    if (r.cnt) atomicAdd(&hist[r.bin], r.cnt);
-    r.bin = bin; r.cnt = 1u;
-}
-VB_DEV void vb_run_flush(VbRun& r, unsigned* hist) {
-    if (r.cnt) atomicAdd(&hist[r.bin], r.cnt);
-    r.cnt = 0u;
-}
+// VDP statistics, one CTA per subject: M = #mask and the two anchors of Vent_Analysis.py:245-255,
+// both taken from the SORTED list of the mask voxels exactly as the reference does:
+//   mean = np.mean(sorted(N4[mask>0]))   numpy's float32 PAIRWISE sum of the sorted values (leaves
+//          of <= 128 elements with 8 strided accumulators, split at n/2 rounded down to a multiple
+//          of 8), divided by M in float64 and rounded to float32 -- bit for bit;
+//   p99  = sorted(...)[int(M*.99)].
+// The kernel therefore sorts the mask voxels (order-preserving key of the float bits):
+//   1. ONE pass over HBM: the mask is read once, the image only where the mask is set (16-byte
+//      loads, software pipelined); the keys are appended to a per-CTA scratch array A in global
+//      memory (L2 resident; warp-aggregated append), key range and count in registers;
+//   2. bucket sort: histogram over <= 2^13 range-normalised bins in shared memory, exclusive scan,
+//      scatter A -> B (B in shared memory when the mask fits, else a second scratch array);
+//   3. rank inside the bucket by counting (ties by position) and write the sorted keys back to A;
+//   4. numpy's pairwise summation tree evaluated in parallel on the sorted array (8 lanes per leaf,
+//      one per accumulator; the leaf sums combined bottom-up along numpy's recursion tree).
+// Also zeroes the defect / LB counters.
+#define VB_VDP_LOG_BINS 13          /* buckets when the keys live in shared memory */
 
-VB_DEV int vdp_find_bin(unsigned* hist, int nb, long long& k, int* s_bin, long long* s_k) {
-    // block-wide exclusive prefix over the bins (each thread owns a contiguous run); the thread
-    // whose run contains the k-th element publishes (bin, rank inside the bin)
-    VB_SHARED int wsum[32];
-    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = tid & 31, w = tid >> 5, nw = nt >> 5;
+// block-wide exclusive prefix sum of h[0..nb) in place (each thread owns a contiguous run)
+VB_DEV void vdp_block_exscan(unsigned* h, int nb, unsigned* wsum) {
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int per = (nb + nt - 1) / nt;
     const int lo = min(nb, tid * per), hi = min(nb, lo + per);
-    int s = 0;
-    for (int b = lo; b < hi; ++b) s += (int)hist[b];
-    int inc = s;
+    unsigned s = 0;
+    for (int b = lo; b < hi; ++b) s += h[b];
+    unsigned inc = s;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(VB_FULL, inc, d);
+        const unsigned t = __shfl_up_sync(VB_FULL, inc, d);
         if (lane >= d) inc += t;
     }
+    __syncthreads();                                   // wsum may still be read from a previous call
     if (lane == 31) wsum[w] = inc;
-    if (tid == 0) { *s_bin = nb - 1; *s_k = 0; }
     __syncthreads();
-    int woff = 0, total = 0;
-    for (int i = 0; i < nw; ++i) { const int t = wsum[i]; if (i < w) woff += t; total += t; }
-    long long cum = (long long)(woff + inc - s);
-    if (k >= (long long)total) {                       // cannot happen for k < count; keep the last bin
-        if (tid == 0) { *s_bin = nb - 1; *s_k = k - ((long long)total - (long long)hist[nb - 1]); }
-    } else if (k >= cum && k < cum + (long long)s) {
-        int b = lo;
-        for (; b < hi; ++b) {
-            if (cum + (long long)hist[b] > k) break;
-            cum += hist[b];
+    unsigned run = inc - s;
+    for (int i = 0; i < w; ++i) run += wsum[i];
+    for (int b = lo; b < hi; ++b) { const unsigned t = h[b]; h[b] = run; run += t; }
+    __syncthreads();
+}
+
+// depth of numpy's pairwise recursion for n elements (the right child is the larger one)
+VB_DEV int vdp_pw_depth(int n) {
+    int d = 0;
+    while (n > 128) { int n2 = n >> 1; n2 -= n2 & 7; n -= n2; ++d; }
+    return d;
+}
+
+// np.add.reduce of the float32 array a[0..M) given as sorted keys (numpy/_core/src/umath/
+// loops_utils.h.src, *_pairwise_sum: PW_BLOCKSIZE 128, unroll 8), evaluated by the whole block.
+// hv / hk: heap of 2^(D+1) partial sums / "has a value" flags, D = vdp_pw_depth(M).
+VB_DEV float vdp_pairwise_sum(const unsigned* keys, int M, int D, float* hv, unsigned char* hk) {
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    const int nslots = 1 << D;
+    for (int h = tid; h < 2 * nslots; h += nt) hk[h] = 0;
+    __syncthreads();
+    const int g = tid >> 3, j = tid & 7, ng = nt >> 3;
+    for (int base = 0; base < nslots; base += ng) {            // trip count is block uniform
+        const int slot = base + g;
+        int start = 0, len = 0, h = 1, d = 0;
+        bool owner = false;
+        if (slot < nslots) {
+            len = M;
+            while (len > 128) {                                // walk numpy's recursion along the bits of `slot`
+                int n2 = len >> 1;
+                n2 -= n2 & 7;
+                if ((slot >> (D - 1 - d)) & 1) { start += n2; len -= n2; h = 2 * h + 1; }
+                else { len = n2; h = 2 * h; }
+                ++d;
+            }
+            owner = (slot & ((1 << (D - d)) - 1)) == 0;        // one slot per leaf
         }
-        *s_bin = b; *s_k = k - cum;
+        float r = 0.0f;
+        const int n8 = len - (len & 7);
+        if (owner && len >= 8) {
+            r = vb_key_float(keys[start + j]);
+            for (int i = 8; i < n8; i += 8) r = __fadd_rn(r, vb_key_float(keys[start + i + j]));
+        }
+        // ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7))
+        r = __fadd_rn(r, __shfl_xor_sync(VB_FULL, r, 1));
+        r = __fadd_rn(r, __shfl_xor_sync(VB_FULL, r, 2));
+        r = __fadd_rn(r, __shfl_xor_sync(VB_FULL, r, 4));
+        if (owner && j == 0) {
+            if (len >= 8) {
+                for (int i = n8; i < len; ++i) r = __fadd_rn(r, vb_key_float(keys[start + i]));
+            } else {
+                r = 0.0f;
+                for (int i = 0; i < len; ++i) r = __fadd_rn(r, vb_key_float(keys[start + i]));
+            }
+            hv[h] = r;
+            hk[h] = 1;
+        }
     }
     __syncthreads();
-    k = *s_k;
-    return *s_bin;
+    for (int d = D - 1; d >= 0; --d) {
+        for (int h = (1 << d) + tid; h < (2 << d); h += nt)
+            if (!hk[h] && hk[2 * h] && hk[2 * h + 1]) { hv[h] = __fadd_rn(hv[2 * h], hv[2 * h + 1]); hk[h] = 1; }
+        __syncthreads();
+    }
+    return hv[1];
 }
 
-// One pass over HBM: the mask is read once, the image only where the mask is set (16-byte loads,
-// four independent 20-byte groups per thread in flight); sum / count / key range go to registers
-// and the order-preserving keys of the mask voxels are compacted into shared memory (`key_cap`
-// keys of dynamic shared memory; warp-aggregated append).  The radix select then runs on the
-// shared-memory keys: the key range [kmin, kmax] is split into <= 2048 equal bins per level
-// (range-normalised, so clustered data still spread over the bins), <= 3 levels.  Subjects whose
-// mask does not fit `key_cap` re-stream the volume for every level instead.
-VB_DEV void vdp_hist_keys(unsigned* hist, unsigned key, unsigned lo, unsigned range, int sh, VbRun& run) {
-    const unsigned d = key - lo;
-    if (d <= range) vb_run_add(run, hist, (int)(d >> sh));
-}
-
+#define VB_VDP_HEAP_DEPTH 10        /* pairwise heaps up to this depth live in shared memory */
 VB_KERNEL void VB_LAUNCH_BOUNDS(VB_VDP_THREADS, 1)
 vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, int n,
-                 vb_subject_stats* stats, int key_cap) {
+                 vb_subject_stats* stats, int key_cap, int dyn_words, unsigned* ws_a, unsigned* ws_b, long long ws_stride) {
     VB_DYN_SMEM(smem);
-    unsigned* keys = (unsigned*)smem;                    // [key_cap]
-    VB_SHARED unsigned hist[2048];
+    unsigned* hist = (unsigned*)smem;                    // [2^13] buckets, then [key_cap] keys (array B)
     VB_SHARED double red[64];
-    VB_SHARED int s_bin, s_nkeys;
-    VB_SHARED long long s_k;
+    VB_SHARED unsigned wsum[32];
+    VB_SHARED float pw_val[2 << VB_VDP_HEAP_DEPTH];
+    VB_SHARED unsigned char pw_kind[2 << VB_VDP_HEAP_DEPTH];
+    VB_SHARED int s_nkeys;
     const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = tid & 31;
+    unsigned* A = ws_a + (size_t)blockIdx.x * (size_t)ws_stride;
+    unsigned* Bg = ws_b + (size_t)blockIdx.x * (size_t)ws_stride;
     for (int si = (int)blockIdx.x; si < n; si += (int)gridDim.x) {
         const VbSubject S = subj[si];
         const float* x = n4 + S.off;
@@ -283,7 +320,6 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
         __syncthreads();
         if (tid == 0) s_nkeys = 0;
         __syncthreads();
-        double sum = 0.0;
         int cnt = 0;
         unsigned kmin = 0xffffffffu, kmax = 0u;
         // software pipelined: the mask words of the next step are requested together with the
@@ -320,82 +356,69 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
                         if ((mw[u] >> (8 * e)) & 0xFFu) {
-                            const float fv = f[u].v[e];
-                            const unsigned key = vb_float_key(fv);
-                            sum += (double)fv; ++cnt;
+                            const unsigned key = vb_float_key(f[u].v[e]);
+                            ++cnt;
                             kmin = min(kmin, key); kmax = max(kmax, key);
-                            if (pos < key_cap) keys[pos] = key;
-                            ++pos;
+                            A[pos++] = key;
                         }
                 }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) mw[u] = mn[u];
         }
-        sum = vb_block_reduce(sum, VbAddD(), 0.0, red);
-        const long long M = vb_block_reduce((long long)cnt, VbAddLL(), 0LL, (long long*)red);
+        const int M = (int)vb_block_reduce((long long)cnt, VbAddLL(), 0LL, (long long*)red);
         // (signed reductions of key ^ 0x80000000 keep the unsigned order)
         const unsigned lo0 = (unsigned)vb_block_reduce((int)(kmin ^ 0x80000000u), VbMinI(), 0x7fffffff, (int*)red) ^ 0x80000000u;
         const unsigned hi0 = (unsigned)vb_block_reduce((int)(kmax ^ 0x80000000u), VbMaxI(), (int)0x80000000, (int*)red) ^ 0x80000000u;
-        float p99 = 0.0f;
+        float p99 = 0.0f, mean = 0.0f;
         if (M > 0) {
-            const bool in_smem = M <= (long long)key_cap;
-            long long k = (long long)((double)M * .99);              // int(len(signal_list)*.99)
-            if (k >= M) k = M - 1;
-            unsigned lo = lo0, hi = hi0;
-            const unsigned* kp = keys;                               // keys still in the running (shared-memory path)
-            int kn = (int)M;
-            for (;;) {
-                const unsigned range = hi - lo;
-                if (range == 0u) break;
-                const int sh = max(0, (32 - __clz((int)range)) - 11);
-                const int nb = (int)(range >> sh) + 1;               // <= 2048
-                __syncthreads();
+            const unsigned range = hi0 - lo0;
+            if (range != 0u) {                                       // (all keys equal: A is sorted as it is)
+                const bool in_smem = M <= key_cap;
+                unsigned* B = in_smem ? hist + (1 << VB_VDP_LOG_BINS) : Bg;
+                int lognb = VB_VDP_LOG_BINS;                         // keys in global memory: all of it for buckets
+                if (!in_smem) while ((2 << lognb) <= dyn_words) ++lognb;
+                const int sh = max(0, (32 - __clz((int)range)) - lognb);
+                const int nb = (int)(range >> sh) + 1;               // <= 2^lognb
                 for (int i = tid; i < nb; i += nt) hist[i] = 0;
                 __syncthreads();
-                VbRun run; run.bin = 0; run.cnt = 0u;
-                if (in_smem) {
-                    for (int i = tid; i < kn; i += nt) vdp_hist_keys(hist, kp[i], lo, range, sh, run);
-                } else {
-                    for (int v = 4 * tid; v < S.V; v += 4 * nt) {
-                        const Vb4b m = vb_load4b(msk, v, S.V, aligned);
-                        if (!(m.v[0] | m.v[1] | m.v[2] | m.v[3])) continue;
-                        const Vb4f f = vb_load4f(x, v, S.V, aligned);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (m.v[e]) vdp_hist_keys(hist, vb_float_key(f.v[e]), lo, range, sh, run);
-                    }
-                }
-                vb_run_flush(run, hist);
+                for (int i = tid; i < M; i += nt) atomicAdd(&hist[(A[i] - lo0) >> sh], 1u);
                 __syncthreads();
-                const unsigned b = (unsigned)vdp_find_bin(hist, nb, k, &s_bin, &s_k);
-                const int nsel = (int)hist[b];                       // keys of the chosen bin
-                lo += b << sh;
-                const unsigned w1 = (1u << sh) - 1u;                 // keys of the chosen bin: [lo, lo + w1]
-                if (hi - lo > w1) hi = lo + w1;
-                if (sh == 0) break;
-                // the next levels only concern the keys of the chosen bin: gather them behind the
-                // key array when there is room (usually a few hundred of ~36 k), so that the
-                // remaining levels do not walk all keys again
-                if (in_smem && kp == keys && nsel <= key_cap - (int)M && nsel < kn) {
-                    if (tid == 0) s_nkeys = 0;
-                    __syncthreads();
-                    unsigned* dst = keys + M;
-                    const unsigned r2 = hi - lo;
-                    for (int i = tid; i < kn; i += nt) {
-                        const unsigned key = kp[i];
-                        if (key - lo <= r2) dst[atomicAdd(&s_nkeys, 1)] = key;
-                    }
-                    __syncthreads();
-                    kp = dst; kn = nsel;
+                vdp_block_exscan(hist, nb, wsum);                    // bucket starts
+                for (int i = tid; i < M; i += nt) {
+                    const unsigned key = A[i];
+                    B[atomicAdd(&hist[(key - lo0) >> sh], 1u)] = key;   // afterwards hist[b] = end of bucket b
                 }
+                __syncthreads();
+                for (int p = tid; p < M; p += nt) {
+                    const unsigned key = B[p];
+                    const int b = (int)((key - lo0) >> sh);
+                    const int o = b ? (int)hist[b - 1] : 0, e = (int)hist[b];
+                    int rank = p - o;                                // sh == 0: one key value per bucket
+                    if (sh != 0) {
+                        rank = 0;
+                        for (int q = o; q < e; ++q) {
+                            const unsigned y = B[q];
+                            rank += (int)((y < key) || (y == key && q < p));
+                        }
+                    }
+                    A[o + rank] = key;
+                }
+                __syncthreads();
             }
-            p99 = vb_key_float(lo);
+            long long k = (long long)((double)M * .99);              // int(len(signal_list)*.99)
+            if (k >= M) k = M - 1;
+            p99 = vb_key_float(A[k]);
+            const int D = vdp_pw_depth(M);
+            float total;
+            if (D <= VB_VDP_HEAP_DEPTH) total = vdp_pairwise_sum(A, M, D, pw_val, pw_kind);
+            else total = vdp_pairwise_sum(A, M, D, (float*)Bg, (unsigned char*)(Bg + ((size_t)2 << D)));
+            mean = (float)((double)total / (double)M);               // np.mean: float32 sum / intp count in float64
         }
         if (tid == 0) {
             vb_subject_stats* st = stats + si;
-            st->n_mask = (int)M;
-            st->mean = (M > 0) ? (float)(sum / (double)M) : 0.0f;
+            st->n_mask = M;
+            st->mean = mean;
             st->p99 = p99;
             st->n_defect = 0;
             st->n_lb12 = 0;
@@ -462,11 +485,61 @@ VB_KERNEL void vdp_median_kernel(const uint8_t* VB_RESTRICT d0, const VbSubject*
 // forms the median (neighbour count >= 5, zero padded, per slice) for rows [i0 - 1, i0 + R + 1)
 // in a second shared tile and from it the border of rows [i0, i0 + R).  Traffic per voxel:
 // 5 B read (+ 4/R halo) and 3 B written, instead of three kernels and a d0 round trip.
+// The float32 quotient tests of Vent_Analysis.py:246-256 as comparisons with per-subject thresholds:
+// for d > 0 the rounded quotient RN(x / d) is non-decreasing in x, so {x : RN(x / d) <= c} is
+// {x <= T} with T found by a few exact divisions next to c * d (same for <).  NaN fails every
+// comparison, as in numpy.  Degenerate divisors (<= 0, non-finite, tiny) keep IEEE divisions.
+VB_DEV float vb_next_up_pos(float x) { return __uint_as_float(__float_as_uint(x) + 1u); }
+VB_DEV float vb_next_down_pos(float x) { return __uint_as_float(__float_as_uint(x) - 1u); }
+// largest x with RN(x / d) <= c (LE) or < c (!LE), for normal c, d > 0; NaN if not found
+template <bool LE>
+VB_DEV float vdp_quotient_threshold(float c, float d) {
+    float x = __fmul_rn(c, d);
+    int guard = 0;
+    for (; guard < 64; ++guard) {                        // first x that fails
+        const float q = __fdiv_rn(x, d);
+        if (!(LE ? (q <= c) : (q < c))) break;
+        x = vb_next_up_pos(x);
+    }
+    for (; guard < 128; ++guard) {                       // last x that passes
+        const float q = __fdiv_rn(x, d);
+        if (LE ? (q <= c) : (q < c)) return x;
+        x = vb_next_down_pos(x);
+    }
+    return __uint_as_float(0x7fc00000u);
+}
+struct VdpThr { float d, t1, t2, t3, t4, t5; bool fast; };   // x <= d: below thresh; x <= t_i: LB code <= i
+// threads 0..5 find the thresholds (s_thr: 8 floats of shared memory); all threads must call
+VB_DEV VdpThr vdp_thresholds(float* s_thr, float thresh, float mean, float p99) {
+    const int tid = (int)threadIdx.x;
+    const bool okdiv = mean >= 1e-30f && mean <= 1e30f && p99 >= 1e-30f && p99 <= 1e30f && thresh >= 1e-3f && thresh <= 1e3f;
+    if (okdiv && tid < 6) {
+        const float cs[5] = {0.16f, 0.34f, 0.52f, 0.7f, 0.88f};
+        s_thr[tid] = (tid == 0) ? vdp_quotient_threshold<false>(thresh, mean) : vdp_quotient_threshold<true>(cs[tid - 1], p99);
+    }
+    __syncthreads();
+    VdpThr T;
+    T.d = s_thr[0]; T.t1 = s_thr[1]; T.t2 = s_thr[2]; T.t3 = s_thr[3]; T.t4 = s_thr[4]; T.t5 = s_thr[5];
+    T.fast = okdiv && T.d == T.d && T.t1 == T.t1 && T.t2 == T.t2 && T.t3 == T.t3 && T.t4 == T.t4 && T.t5 == T.t5;
+    return T;
+}
+VB_DEV void vdp_classify_one(const VdpThr& T, float xe, float thresh, float mean, float p99, bool& below, int& cd) {
+    if (T.fast) {
+        below = xe <= T.d;
+        cd = 6 - (int)(xe <= T.t1) - (int)(xe <= T.t2) - (int)(xe <= T.t3) - (int)(xe <= T.t4) - (int)(xe <= T.t5);
+        cd = (xe == xe) ? cd : 0;                          // NaN compares false everywhere -> 0, as in numpy
+    } else {
+        below = __fdiv_rn(xe, mean) < thresh;
+        const float b = __fdiv_rn(xe, p99);
+        cd = (b <= 0.16f) ? 1 : (b <= 0.34f) ? 2 : (b <= 0.52f) ? 3 : (b <= 0.7f) ? 4 : (b <= 0.88f) ? 5
+           : (b > 0.88f) ? 6 : 0;
+    }
+}
 #ifndef VB_CLS_THREADS
 #define VB_CLS_THREADS 512
 #endif
 // byte-wise version: any shape / alignment
-VB_DEV void vdp_classify_bytes(unsigned char* smem, int* red, const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask,
+VB_DEV void vdp_classify_bytes(unsigned char* smem, int* red, float* s_thr, const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask,
                                const VbSubject& S, int si, float thresh, int R, uint8_t* lb, uint8_t* defect,
                                uint8_t* border, vb_subject_stats* stats) {
     const int n0 = S.n0, n1 = S.n1, n2 = S.n2, ncols = n1 * n2;
@@ -477,8 +550,8 @@ VB_DEV void vdp_classify_bytes(unsigned char* smem, int* red, const float* VB_RE
     uint8_t* d0 = smem;                                               // [(R + 4) * ncols]
     uint8_t* md = smem + (size_t)(R + 4) * ncols;                     // [(R + 2) * ncols]
     const float mean = stats[si].mean, p99 = stats[si].p99;
-    const float rmean = __frcp_rn(mean), rp99 = __frcp_rn(p99);
-    const bool okdiv = isfinite(rmean) && isfinite(rp99) && rmean != 0.0f && rp99 != 0.0f;   // else: IEEE division
+    // the same exact per-subject thresholds as the word version (identical results by construction)
+    const VdpThr T = vdp_thresholds(s_thr, thresh, mean, p99);
     const float* x = n4 + S.off;
     const uint8_t* msk = mask + S.off;
     const bool aligned = ((S.off & 3) == 0) && ((ncols & 3) == 0);
@@ -505,12 +578,10 @@ VB_DEV void vdp_classify_bytes(unsigned char* smem, int* red, const float* VB_RE
             for (int e = 0; e < 4; ++e) {
                 if (v + e < v1) {
                     const bool in = m.v[e] != 0;
-                    const bool fin = okdiv && fabsf(f.v[e]) < 3.0e38f;      // inf / nan inputs: IEEE division
-                    const float qa = fin ? vb_div_rcp(f.v[e], mean, rmean) : __fdiv_rn(f.v[e], mean);
-                    d0[v + e - v0] = (uint8_t)((qa < thresh) && in);
-                    const float b = fin ? vb_div_rcp(f.v[e], p99, rp99) : __fdiv_rn(f.v[e], p99);
-                    int cd = (b <= 0.16f) ? 1 : (b <= 0.34f) ? 2 : (b <= 0.52f) ? 3 : (b <= 0.7f) ? 4 : (b <= 0.88f) ? 5
-                           : (b > 0.88f) ? 6 : 0;      // NaN compares false everywhere -> 0, as in numpy
+                    bool below;
+                    int cd;
+                    vdp_classify_one(T, f.v[e], thresh, mean, p99, below, cd);
+                    d0[v + e - v0] = (uint8_t)(below && in);
                     cd = in ? cd : 0;
                     code[e] = (uint8_t)cd;
                     if (v + e >= w0 && v + e < w1) c12 += (cd == 1 || cd == 2);
@@ -590,25 +661,6 @@ VB_DEV void vdp_classify_bytes(unsigned char* smem, int* red, const float* VB_RE
 //    the 3x3 count is three word additions, "count >= 5" one add/shift/and, the border two XORs.
 //    Column neighbours are n2 bytes away: two aligned words and a funnel shift; the per-byte
 //    "has a left / right neighbour" masks are constants of the thread.
-VB_DEV float vb_next_up_pos(float x) { return __uint_as_float(__float_as_uint(x) + 1u); }
-VB_DEV float vb_next_down_pos(float x) { return __uint_as_float(__float_as_uint(x) - 1u); }
-// largest x with RN(x / d) <= c (LE) or < c (!LE), for normal c, d > 0; NaN if not found
-template <bool LE>
-VB_DEV float vdp_quotient_threshold(float c, float d) {
-    float x = __fmul_rn(c, d);
-    int guard = 0;
-    for (; guard < 64; ++guard) {                        // first x that fails
-        const float q = __fdiv_rn(x, d);
-        if (!(LE ? (q <= c) : (q < c))) break;
-        x = vb_next_up_pos(x);
-    }
-    for (; guard < 128; ++guard) {                       // last x that passes
-        const float q = __fdiv_rn(x, d);
-        if (LE ? (q <= c) : (q < c)) return x;
-        x = vb_next_down_pos(x);
-    }
-    return __uint_as_float(0x7fc00000u);
-}
 VB_DEV uint32_t vb_funnel_r(uint32_t lo, uint32_t hi, int shift) {
 #if defined(VB_EMULATE)
     return (uint32_t)((((uint64_t)hi << 32) | (uint64_t)lo) >> (shift & 31));
@@ -616,7 +668,6 @@ VB_DEV uint32_t vb_funnel_r(uint32_t lo, uint32_t hi, int shift) {
     return __funnelshift_r(lo, hi, shift);
 #endif
 }
-struct VdpThr { float d, t1, t2, t3, t4, t5; };       // x <= d: below thresh; x <= t_i: LB code <= i
 struct VdpNbr { int wl, sl, wr, sr; uint32_t maskL, maskR; };
 VB_DEV VdpNbr vdp_nbr(int g, int n1, int n2) {
     VdpNbr k;
@@ -645,16 +696,7 @@ VB_DEV void vdp_classify_words(unsigned char* smem, int* red, float* s_thr, int 
     uint32_t* d0w = (uint32_t*)smem + P;                              // [(R + 4) * G], P words of padding around
     uint32_t* mdw = d0w + (size_t)(R + 4) * G + 2 * P;                // [(R + 2) * G]
     const float mean = stats[si].mean, p99 = stats[si].p99;
-    // thresholds (threads 0..5), else exact divisions
-    const bool okdiv = mean >= 1e-30f && mean <= 1e30f && p99 >= 1e-30f && p99 <= 1e30f && thresh >= 1e-3f && thresh <= 1e3f;
-    if (okdiv && tid < 6) {
-        const float cs[5] = {0.16f, 0.34f, 0.52f, 0.7f, 0.88f};
-        s_thr[tid] = (tid == 0) ? vdp_quotient_threshold<false>(thresh, mean) : vdp_quotient_threshold<true>(cs[tid - 1], p99);
-    }
-    __syncthreads();
-    VdpThr T;
-    T.d = s_thr[0]; T.t1 = s_thr[1]; T.t2 = s_thr[2]; T.t3 = s_thr[3]; T.t4 = s_thr[4]; T.t5 = s_thr[5];
-    const bool fast = okdiv && T.d == T.d && T.t1 == T.t1 && T.t2 == T.t2 && T.t3 == T.t3 && T.t4 == T.t4 && T.t5 == T.t5;
+    const VdpThr T = vdp_thresholds(s_thr, thresh, mean, p99);   // thresholds, else exact divisions
     const float* x = n4 + S.off + (size_t)ra * ncols;
     const uint8_t* msk = mask + S.off + (size_t)ra * ncols;
     uint8_t* lbo = lb + S.off + (size_t)ra * ncols;
@@ -690,16 +732,7 @@ VB_DEV void vdp_classify_words(unsigned char* smem, int* red, float* s_thr, int 
                 const bool in = ((mw[u] >> (8 * e)) & 0xFFu) != 0u;
                 int cd;
                 bool below;
-                if (fast) {
-                    below = xe <= T.d;
-                    cd = 6 - (int)(xe <= T.t1) - (int)(xe <= T.t2) - (int)(xe <= T.t3) - (int)(xe <= T.t4) - (int)(xe <= T.t5);
-                    cd = (xe == xe) ? cd : 0;                          // NaN compares false everywhere -> 0, as in numpy
-                } else {
-                    below = __fdiv_rn(xe, mean) < thresh;
-                    const float b = __fdiv_rn(xe, p99);
-                    cd = (b <= 0.16f) ? 1 : (b <= 0.34f) ? 2 : (b <= 0.52f) ? 3 : (b <= 0.7f) ? 4 : (b <= 0.88f) ? 5
-                       : (b > 0.88f) ? 6 : 0;
-                }
+                vdp_classify_one(T, xe, thresh, mean, p99, below, cd);
                 cd = in ? cd : 0;
                 dw |= (uint32_t)(below && in) << (8 * e);
                 cw |= (uint32_t)cd << (8 * e);
@@ -799,10 +832,11 @@ vdp_classify_kernel(const float* VB_RESTRICT n4, const uint8_t* VB_RESTRICT mask
                     int R, int P, uint8_t* lb, uint8_t* defect, uint8_t* border, vb_subject_stats* stats) {
     VB_DYN_SMEM(smem);
     VB_SHARED int red[64];
+    VB_SHARED float s_thr[8];
     const int si = (int)blockIdx.y;
     const VbSubject S = subj[si];
     if ((int)blockIdx.x * R >= S.n0 || vdp_word_eligible(S, P)) return;
-    vdp_classify_bytes(smem, red, n4, mask, S, si, thresh, R, lb, defect, border, stats);
+    vdp_classify_bytes(smem, red, s_thr, n4, mask, S, si, thresh, R, lb, defect, border, stats);
 }
 
 // calculateBorder: per slice, np.gradient != 0 along rows OR along columns (V_A.py:225-231)

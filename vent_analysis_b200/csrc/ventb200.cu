@@ -11,6 +11,7 @@
 #include "n4_kernels.cuh"
 #include "vdp_kernels.cuh"
 #include "ci_kernels.cuh"
+#include "io_kernels.cuh"
 
 namespace {
 
@@ -53,7 +54,7 @@ struct vb_ctx {
     N4Ws n4ws[2];
     int wsi = 0;                         // workspace set the next N4 launch uses
     vbrt::stream_t stream2 = nullptr;    // second compute stream of the host pipeline
-    Buf ws_d0, ws_bits, ws_list, ws_count, dbg;
+    Buf ws_d0, ws_bits, ws_list, ws_count, dbg, ws_keys_a, ws_keys_b;
     int dbg_stride = 0, dbg_nbins = 0, dbg_Lmax = 0, dbg_n = 0;
     // CI tables
     std::vector<TableHost> tables;
@@ -66,6 +67,8 @@ struct vb_ctx {
     // host-API mirrors
     Buf m_image, m_mask, m_n4, m_logbias, m_defect, m_lb, m_dborder, m_mborder, m_shell, m_stats;
     Buf m_proton, m_pack, d_voxmin;
+    Buf m_u16, m_bits, m_codes, m_ci_idx, m_ci_val, d_bitoff;   // compact host I/O
+    std::vector<long long> last_bitoff;
 };
 
 namespace {
@@ -130,6 +133,10 @@ int prepare(vb_ctx* c, int n, const int32_t* shapes, const int32_t* handles, vbr
     memcpy((char*)c->h_desc.p + sb, woff.data(), wb);
     if (!vbrt::h2d(c->d_subj.p, c->h_desc.p, sb, s)) return VB_ERR_CUDA;
     if (!vbrt::h2d(c->d_wordoff.p, (char*)c->h_desc.p + sb, wb, s)) return VB_ERR_CUDA;
+    // the descriptors are read by kernels on OTHER streams too (the host pipeline's second compute
+    // stream, a later *_dev call on a different caller stream): complete the upload here -- it
+    // happens once per distinct batch
+    if (!vbrt::stream_sync(s)) return VB_ERR_CUDA;
     c->last_subj.swap(subj);
     c->last_wordoff.swap(woff);
     return VB_OK;
@@ -244,9 +251,11 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     int dbg_stride = 0;
     if (c->debug) {
         dbg_stride = VB_DBG_HDR + 2 * p.n_bins + (int)Lmax + trace;
-        if (!ensure(c->dbg, sizeof(float) * (size_t)n * dbg_stride)) return VB_ERR_CUDA;
-        dbg = (float*)c->dbg.p;
-        c->dbg_stride = dbg_stride; c->dbg_nbins = p.n_bins; c->dbg_Lmax = (int)Lmax; c->dbg_n = n;
+        // one record per subject of the WHOLE batch (the host pipeline runs it in chunks)
+        const size_t ntot = c->last_subj.size();
+        if (!ensure(c->dbg, sizeof(float) * ntot * dbg_stride)) return VB_ERR_CUDA;
+        dbg = (float*)c->dbg.p + (size_t)c->r0 * dbg_stride;
+        c->dbg_stride = dbg_stride; c->dbg_nbins = p.n_bins; c->dbg_Lmax = (int)Lmax; c->dbg_n = (int)ntot;
         if (!vbrt::dev_memset(dbg, 0, sizeof(float) * (size_t)n * dbg_stride, s)) return VB_ERR_CUDA;
     }
     if (!vbrt::dev_memset(W.counter.p, 0, 64, s)) return VB_ERR_CUDA;
@@ -283,14 +292,21 @@ int run_vdp(vb_ctx* c, const float* n4, const uint8_t* mask, int n, float thresh
     vbrt::clear_stale_error();
     const VbSubject* subj = subj_ptr(c);
     {
-        // keys of the mask voxels live in shared memory (one CTA per SM); 12 KB stay free for the
-        // kernel's static arrays
-        long long key_cap = std::max<long long>(32, std::min<long long>(vmax_of(c), ((long long)c->max_smem - 12 * 1024) / 4));
-        if (const char* e = getenv("VB_VDP_KEY_CAP"))          // tests: force the re-streaming path
+        // sort buckets (2^13 words) + the scattered keys of a subject in shared memory (one CTA per
+        // SM); the unsorted / sorted key array and the fallback for masks that do not fit live in
+        // a per-CTA scratch in global memory (L2 resident)
+        const long long vmax = vmax_of(c);
+        const long long statics = vbrt::static_smem(vdp_stats_kernel);
+        long long key_cap = std::max<long long>(32, std::min<long long>(vmax, ((long long)c->max_smem - statics) / 4 - (1 << VB_VDP_LOG_BINS)));
+        if (const char* e = getenv("VB_VDP_KEY_CAP"))          // tests: force the global-memory path
             key_cap = std::max<long long>(32, std::min<long long>(key_cap, atoll(e)));
-        if (!vbrt::allow_smem(vdp_stats_kernel, (int)(4 * key_cap))) return VB_ERR_CUDA;
-        VB_LAUNCH(vdp_stats_kernel, dim3(std::min(n, c->sms * 4)), dim3(VB_VDP_THREADS), (size_t)(4 * key_cap), s, n4, mask,
-                  subj, n, stats, (int)key_cap);
+        const long long dyn_words = (1 << VB_VDP_LOG_BINS) + key_cap;
+        const int grid = std::min(n, c->sms * 2);
+        const size_t stride = (size_t)((vmax + 3) & ~3LL);
+        if (!ensure(c->ws_keys_a, 4 * stride * (size_t)grid) || !ensure(c->ws_keys_b, 4 * stride * (size_t)grid)) return VB_ERR_CUDA;
+        if (!vbrt::allow_smem(vdp_stats_kernel, (int)(4 * dyn_words))) return VB_ERR_CUDA;
+        VB_LAUNCH(vdp_stats_kernel, dim3(grid), dim3(VB_VDP_THREADS), (size_t)(4 * dyn_words), s, n4, mask,
+                  subj, n, stats, (int)key_cap, (int)dyn_words, (unsigned*)c->ws_keys_a.p, (unsigned*)c->ws_keys_b.p, (long long)stride);
         ++c->launches;
     }
     // fused threshold + linear binning + median + border on row tiles held in shared memory
@@ -412,9 +428,10 @@ void vb_destroy(vb_ctx* c) {
         for (Buf* b : wb) vbrt::dev_free(b->p);
     }
     vbrt::stream_destroy(c->stream2);
-    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_d0,
+    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_d0, &c->ws_keys_a, &c->ws_keys_b,
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
-                   &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats, &c->m_proton, &c->m_pack, &c->d_voxmin};
+                   &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats, &c->m_proton, &c->m_pack, &c->d_voxmin,
+                   &c->m_u16, &c->m_bits, &c->m_codes, &c->m_ci_idx, &c->m_ci_val, &c->d_bitoff};
     for (Buf* b : bufs) vbrt::dev_free(b->p);
     for (TableHost& t : c->tables) { vbrt::dev_free(t.d_rows); vbrt::dev_free(t.d_ii); vbrt::dev_free(t.d_up); vbrt::dev_free(t.d_radii); }
     vbrt::host_free(c->h_desc.p);
@@ -655,6 +672,34 @@ int vb_pipeline_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const int
     return pipeline_range(c, 0, n, params, thresh, flags, d, s, ev);
 }
 
+// Host pipelines work in chunks of about one wave of subjects: inputs of chunk k+1 go up and
+// outputs of chunk k-1 come down (two copy streams) while chunk k computes.  Large batches start
+// with two smaller chunks (1/4 and 1/2 wave): nothing overlaps the first upload.  (Small chunks at
+// the END were measured slower: a chunk cannot take less than one subject's latency.)
+static std::vector<int> chunk_bounds(const vb_ctx* c, int n) {
+    const int per = std::max(c->sms, 1);
+    std::vector<int> bounds;
+    if (n >= 6 * per) {
+        const int a = std::max(1, per / 4), b = std::max(1, per / 2);
+        const int rest = n - (a + b), nm = std::max(1, std::min(14, rest / per));
+        bounds.push_back(0); bounds.push_back(a); bounds.push_back(a + b);
+        for (int k = 1; k <= nm; ++k) bounds.push_back(a + b + (int)((long long)rest * k / nm));
+    } else {
+        const int nc = std::max(1, std::min(16, n / per));
+        for (int k = 0; k <= nc; ++k) bounds.push_back((int)((long long)n * k / nc));
+    }
+    return bounds;
+}
+// every exit path of a host pipeline waits for the copies it has enqueued: the caller may free its
+// buffers, and the next call reuses the device mirrors
+static bool drain(vb_ctx* c) {
+    bool ok = vbrt::stream_sync(c->stream_in);
+    ok = vbrt::stream_sync(c->stream) && ok;
+    ok = vbrt::stream_sync(c->stream2) && ok;
+    ok = vbrt::stream_sync(c->stream_out) && ok;
+    return ok;
+}
+
 int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const int32_t* handles,
                            const vb_n4_params* params, float thresh, uint32_t flags, const vb_buffers* h) {
     if (!c || !h || !h->mask || !h->stats || !shapes || n <= 0) return fail(VB_ERR_ARG, "pipeline_host: null argument");
@@ -700,22 +745,7 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
     if (rc) return rc;
     rc = prepare(c, n, shapes, (flags & VB_DO_CI) ? handles : nullptr, s);
     if (rc) return rc;
-    // Chunks of about one wave of subjects: inputs of chunk k+1 go up and outputs of chunk k-1
-    // come down (two copy streams) while chunk k computes.
-    // Large batches start with two smaller chunks (1/4 and 1/2 wave): nothing overlaps the first
-    // upload.  (Small chunks at the END were measured slower: a chunk cannot take less than one
-    // subject's latency, whatever its size.)
-    const int per = std::max(c->sms, 1);
-    std::vector<int> bounds;                                   // first subject of every chunk, then n
-    if (n >= 6 * per) {
-        const int a = std::max(1, per / 4), b = std::max(1, per / 2);
-        const int rest = n - (a + b), nm = std::max(1, std::min(14, rest / per));
-        bounds.push_back(0); bounds.push_back(a); bounds.push_back(a + b);
-        for (int k = 1; k <= nm; ++k) bounds.push_back(a + b + (int)((long long)rest * k / nm));
-    } else {
-        const int nc = std::max(1, std::min(16, n / per));
-        for (int k = 0; k <= nc; ++k) bounds.push_back((int)((long long)n * k / nc));
-    }
+    const std::vector<int> bounds = chunk_bounds(c, n);        // first subject of every chunk, then n
     const int nchunks = (int)bounds.size() - 1;
     while (c->ev_copy.size() < 2 * (size_t)nchunks) {
         vbrt::event_t e;
@@ -750,7 +780,7 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
         c->wsi = k & 1;
         rc = pipeline_range(c, r0, r1 - r0, params, thresh, flags, &d, cs, nullptr);
         c->wsi = 0;
-        if (rc) return rc;
+        if (rc) { drain(c); return rc; }
         vbrt::stream_t so = c->stream_out;
         ok = ok && vbrt::event_record(c->ev_copy[2 * (size_t)k + 1], cs) && vbrt::stream_wait(so, c->ev_copy[2 * (size_t)k + 1]);
         if (!so_only) {
@@ -765,13 +795,183 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
         }
         ok = ok && vbrt::d2h((vb_subject_stats*)c->h_stats.p + r0, d.stats + r0, sizeof(vb_subject_stats) * (size_t)(r1 - r0), so);
     }
-    if (!ok || !vbrt::stream_sync(c->stream_out) || !vbrt::stream_sync(s) || !vbrt::stream_sync(c->stream2) ||
-        !vbrt::stream_sync(c->stream_in))
-        return VB_ERR_CUDA;
+    if (!drain(c) || !ok) return VB_ERR_CUDA;
     memcpy(h->stats, c->h_stats.p, stb);
     if (flags & VB_DO_CI)
         for (int i = 0; i < n; ++i)
             if (h->stats[i].ci_error) return fail(VB_ERR_CI_RMAX, "CI: maximum sphere radius reached (table exhausted)");
+    return VB_OK;
+}
+
+// The whole path with compact host I/O (include/ventb200.h): per chunk, H2D of the uint16 image and
+// the mask bits -> io_unpack_kernel -> the stages -> io_codes_kernel / io_ci_sparse_kernel -> D2H of
+// N4HPvent, the code bytes and the per-subject records; the sparse CI lists follow once the host
+// knows their sizes (the records of a chunk arrive while later chunks compute).
+int vb_pipeline_batch_host_packed(vb_ctx* c, int32_t n, const int32_t* shapes, const int32_t* handles,
+                                  const vb_n4_params* params, float thresh, uint32_t flags, const vb_host_io* io) {
+    if (!c || !io || !io->stats || !shapes || n <= 0) return fail(VB_ERR_ARG, "pipeline_host_packed: null argument");
+    if (!io->image_u16 == !io->image_f32) return fail(VB_ERR_ARG, "pipeline_host_packed: exactly one of image_u16 / image_f32");
+    if (!io->mask_bits == !io->mask_u8) return fail(VB_ERR_ARG, "pipeline_host_packed: exactly one of mask_bits / mask_u8");
+    if ((flags & VB_DO_CI) && !(flags & VB_DO_VDP)) return fail(VB_ERR_ARG, "pipeline_host_packed: CI needs VDP");
+    if (io->codes && !(flags & VB_DO_VDP)) return fail(VB_ERR_ARG, "pipeline_host_packed: codes need VB_DO_VDP");
+    const bool want_sparse = (flags & VB_DO_CI) && io->ci_index && io->ci_value;
+    if ((flags & VB_DO_CI) && (!io->ci_index != !io->ci_value)) return fail(VB_ERR_ARG, "pipeline_host_packed: ci_index and ci_value go together");
+    if (want_sparse && !io->ci_offset) return fail(VB_ERR_ARG, "pipeline_host_packed: ci_offset required");
+    vbrt::set_device(c->device);
+    vbrt::stream_t s = c->stream;
+    size_t V = 0;
+    for (int i = 0; i < n; ++i) V += (size_t)shapes[3 * i] * shapes[3 * i + 1] * shapes[3 * i + 2];
+    const bool need_n4 = (flags & (VB_DO_N4 | VB_DO_VDP)) != 0;
+    if ((flags & VB_DO_VDP) && !(flags & VB_DO_N4)) return fail(VB_ERR_ARG, "pipeline_host_packed: VDP needs N4 here (use vb_pipeline_batch_host to pass an N4 volume in)");
+    const bool mb = (flags & VB_DO_MASK_BORDER) && io->codes;
+    vb_buffers d;
+    memset(&d, 0, sizeof(d));
+    if (!ensure(c->m_mask, V) || !ensure(c->m_image, 4 * V) || !ensure(c->m_stats, sizeof(vb_subject_stats) * (size_t)n)) return VB_ERR_CUDA;
+    d.mask = (const uint8_t*)c->m_mask.p; d.image = (const float*)c->m_image.p; d.stats = (vb_subject_stats*)c->m_stats.p;
+    if (need_n4) { if (!ensure(c->m_n4, 4 * V)) return VB_ERR_CUDA; d.n4 = (float*)c->m_n4.p; }
+    if (io->logbias && (flags & VB_DO_N4)) { if (!ensure(c->m_logbias, 4 * V)) return VB_ERR_CUDA; d.logbias = (float*)c->m_logbias.p; }
+    if (flags & VB_DO_VDP) {
+        if (!ensure(c->m_defect, V) || !ensure(c->m_lb, V)) return VB_ERR_CUDA;
+        d.defect = (uint8_t*)c->m_defect.p; d.defect_lb = (uint8_t*)c->m_lb.p;
+        if (io->codes) { if (!ensure(c->m_dborder, V) || !ensure(c->m_codes, V)) return VB_ERR_CUDA; d.defect_border = (uint8_t*)c->m_dborder.p; }
+    }
+    if (mb) { if (!ensure(c->m_mborder, V)) return VB_ERR_CUDA; d.mask_border = (uint8_t*)c->m_mborder.p; }
+    if (flags & VB_DO_CI) { if (!ensure(c->m_shell, 2 * V)) return VB_ERR_CUDA; d.ci_shell = (uint16_t*)c->m_shell.p; }
+    if (want_sparse && (!ensure(c->m_ci_idx, 4 * V) || !ensure(c->m_ci_val, 2 * V))) return VB_ERR_CUDA;
+    if (io->image_u16 && !ensure(c->m_u16, 2 * V)) return VB_ERR_CUDA;
+    int rc = pipeline_check(flags & ~VB_DO_MASK_BORDER, handles, params, &d);
+    if (rc) return rc;
+    rc = prepare(c, n, shapes, (flags & VB_DO_CI) ? handles : nullptr, s);
+    if (rc) return rc;
+    // mask words of every subject (host layout: ceil(V/32) words per subject, concatenated)
+    std::vector<long long> bitoff((size_t)n + 1);
+    {
+        long long w = 0;
+        for (int i = 0; i < n; ++i) { bitoff[(size_t)i] = w; w += (c->last_subj[(size_t)i].V + 31) / 32; }
+        bitoff[(size_t)n] = w;
+    }
+    if (io->mask_bits) {
+        if (!ensure(c->m_bits, 4 * (size_t)bitoff[(size_t)n])) return VB_ERR_CUDA;
+        if (bitoff != c->last_bitoff) {
+            if (!ensure(c->d_bitoff, 8 * bitoff.size())) return VB_ERR_CUDA;
+            if (!drain(c)) return VB_ERR_CUDA;
+            c->last_bitoff = bitoff;                        // (the upload reads the vector kept in the context)
+            if (!vbrt::h2d(c->d_bitoff.p, c->last_bitoff.data(), 8 * bitoff.size(), s) || !vbrt::stream_sync(s)) return VB_ERR_CUDA;
+        }
+    }
+    const std::vector<int> bounds = chunk_bounds(c, n);
+    const int nchunks = (int)bounds.size() - 1;
+    while (c->ev_copy.size() < 3 * (size_t)nchunks) {
+        vbrt::event_t e;
+        if (!vbrt::event_create(&e)) return VB_ERR_CUDA;
+        c->ev_copy.push_back(e);
+    }
+    const size_t stb = sizeof(vb_subject_stats) * (size_t)n;
+    if (c->h_stats.cap < stb) {
+        vbrt::host_free(c->h_stats.p);
+        c->h_stats.p = nullptr; c->h_stats.cap = 0;
+        if (!vbrt::host_malloc(&c->h_stats.p, stb * 2)) return VB_ERR_CUDA;
+        c->h_stats.cap = stb * 2;
+    }
+    bool ok = true;
+    for (int k = 0; k < nchunks && ok; ++k) {
+        const int r0 = bounds[(size_t)k], r1 = bounds[(size_t)k + 1], cnt = r1 - r0;
+        const size_t v0 = (size_t)c->last_subj[(size_t)r0].off;
+        const size_t v1 = (size_t)c->last_subj[(size_t)(r1 - 1)].off + (size_t)c->last_subj[(size_t)(r1 - 1)].V;
+        const size_t nv = v1 - v0;
+        vbrt::stream_t si = c->stream_in;
+        if (io->mask_bits) ok = ok && vbrt::h2d((uint32_t*)c->m_bits.p + bitoff[(size_t)r0], io->mask_bits + bitoff[(size_t)r0], 4 * (size_t)(bitoff[(size_t)r1] - bitoff[(size_t)r0]), si);
+        else ok = ok && vbrt::h2d((uint8_t*)c->m_mask.p + v0, io->mask_u8 + v0, nv, si);
+        if (io->image_u16) ok = ok && vbrt::h2d((uint16_t*)c->m_u16.p + v0, io->image_u16 + v0, 2 * nv, si);
+        else ok = ok && vbrt::h2d((float*)c->m_image.p + v0, io->image_f32 + v0, 4 * nv, si);
+        vbrt::stream_t cs = (k & 1) ? c->stream2 : s;
+        ok = ok && vbrt::event_record(c->ev_copy[3 * (size_t)k], si) && vbrt::stream_wait(cs, c->ev_copy[3 * (size_t)k]);
+        if (!ok) break;
+        vbrt::clear_stale_error();
+        long long vmax = 0;
+        for (int i = r0; i < r1; ++i) vmax = std::max<long long>(vmax, c->last_subj[(size_t)i].V);
+        if (io->image_u16 || io->mask_bits) {
+            UnpackArgs ua;
+            ua.image_u16 = io->image_u16 ? (const uint16_t*)c->m_u16.p : nullptr;
+            ua.mask_bits = io->mask_bits ? (const uint32_t*)c->m_bits.p : nullptr;
+            ua.bit_off = (const long long*)c->d_bitoff.p + r0;
+            ua.subj = (const VbSubject*)c->d_subj.p + r0;
+            ua.image = (float*)c->m_image.p; ua.mask = (uint8_t*)c->m_mask.p;
+            VB_LAUNCH(io_unpack_kernel, dim3(grid_x_for(c, cnt, (vmax + 31) / 32, 256), cnt), dim3(256), 0, cs, ua);
+            ++c->launches;
+            if (!vbrt::last_launch_ok("io_unpack_kernel")) { ok = false; break; }
+        }
+        c->wsi = k & 1;
+        rc = pipeline_range(c, r0, cnt, params, thresh, flags & ~(mb ? 0u : (uint32_t)VB_DO_MASK_BORDER), &d, cs, nullptr);
+        c->wsi = 0;
+        if (rc) { drain(c); return rc; }
+        if (io->codes) {
+            CodesArgs ca;
+            ca.lb = d.defect_lb; ca.defect = d.defect; ca.dborder = d.defect_border; ca.mborder = d.mask_border;
+            ca.codes = (uint8_t*)c->m_codes.p; ca.v0 = (long long)v0; ca.v1 = (long long)v1;
+            const int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->sms * 8, (nv / 16 + 255) / 256));
+            VB_LAUNCH(io_codes_kernel, dim3(blocks), dim3(256), 0, cs, ca);
+            ++c->launches;
+        }
+        if (want_sparse) {
+            SparseArgs sa;
+            sa.subj = (const VbSubject*)c->d_subj.p + r0; sa.count = (const int*)c->ws_count.p + r0;
+            sa.list = (const int*)c->ws_list.p; sa.shell = d.ci_shell;
+            sa.index = (uint32_t*)c->m_ci_idx.p + v0; sa.value = (uint16_t*)c->m_ci_val.p + v0; sa.n = cnt;
+            VB_LAUNCH(io_ci_sparse_kernel, dim3(cnt), dim3(256), 0, cs, sa);
+            ++c->launches;
+        }
+        if (!vbrt::last_launch_ok("io kernels")) { ok = false; break; }
+        vbrt::stream_t so = c->stream_out;
+        ok = ok && vbrt::event_record(c->ev_copy[3 * (size_t)k + 1], cs) && vbrt::stream_wait(so, c->ev_copy[3 * (size_t)k + 1]);
+        // records first: the host needs them to place the chunk's sparse CI list
+        ok = ok && vbrt::d2h((vb_subject_stats*)c->h_stats.p + r0, d.stats + r0, sizeof(vb_subject_stats) * (size_t)cnt, so);
+        ok = ok && vbrt::event_record(c->ev_copy[3 * (size_t)k + 2], so);
+        if (io->n4 && (flags & VB_DO_N4)) ok = ok && vbrt::d2h(io->n4 + v0, d.n4 + v0, 4 * nv, so);
+        if (io->logbias && d.logbias) ok = ok && vbrt::d2h(io->logbias + v0, d.logbias + v0, 4 * nv, so);
+        if (io->codes) ok = ok && vbrt::d2h(io->codes + v0, (uint8_t*)c->m_codes.p + v0, nv, so);
+    }
+    // sparse CI lists: as the records of each chunk arrive (later chunks are still computing)
+    int64_t total = 0;
+    bool too_small = false;
+    if (ok && want_sparse) {
+        io->ci_offset[0] = 0;
+        for (int k = 0; k < nchunks && ok; ++k) {
+            const int r0 = bounds[(size_t)k], r1 = bounds[(size_t)k + 1];
+            ok = ok && vbrt::event_sync(c->ev_copy[3 * (size_t)k + 2]);
+            if (!ok) break;
+            const vb_subject_stats* hs = (const vb_subject_stats*)c->h_stats.p;
+            const int64_t base = total;
+            for (int i = r0; i < r1; ++i) { total += hs[i].ci_n; io->ci_offset[i + 1] = total; }
+            if (total > io->ci_capacity) { too_small = true; continue; }
+            const size_t v0 = (size_t)c->last_subj[(size_t)r0].off, cntk = (size_t)(total - base);
+            if (cntk) {
+                ok = ok && vbrt::d2h(io->ci_index + base, (uint32_t*)c->m_ci_idx.p + v0, 4 * cntk, c->stream_out);
+                ok = ok && vbrt::d2h(io->ci_value + base, (uint16_t*)c->m_ci_val.p + v0, 2 * cntk, c->stream_out);
+            }
+        }
+    }
+    if (!drain(c) || !ok) return VB_ERR_CUDA;
+    memcpy(io->stats, c->h_stats.p, stb);
+    if (too_small) return fail(VB_ERR_ARG, "pipeline_host_packed: ci_capacity too small for the batch's defect voxels");
+    if (flags & VB_DO_CI)
+        for (int i = 0; i < n; ++i)
+            if (io->stats[i].ci_error) return fail(VB_ERR_CI_RMAX, "CI: maximum sphere radius reached (table exhausted)");
+    return VB_OK;
+}
+
+int vb_host_alloc(vb_ctx* c, size_t bytes, void** ptr) {
+    if (!c || !ptr) return fail(VB_ERR_ARG, "host_alloc: null argument");
+    vbrt::set_device(c->device);
+    *ptr = nullptr;
+    if (!vbrt::host_malloc(ptr, bytes)) return VB_ERR_CUDA;
+    return VB_OK;
+}
+
+int vb_host_free(vb_ctx* c, void* ptr) {
+    if (!c) return fail(VB_ERR_ARG, "host_free: null ctx");
+    vbrt::set_device(c->device);
+    vbrt::host_free(ptr);
     return VB_OK;
 }
 
