@@ -1,26 +1,34 @@
 #!/usr/bin/env python
 """Benchmark of the N4 -> VDP -> CI voxel hot path (BASELINE.json metric: subject volumes/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1|C2|C3|C4|C5] [--batch B]
+                    [--scaling weak|strong] [--cohort 1024] [--impl ours|reference]
 
 One "step" = one pass of the whole path (SNR + N4 + VDP + linear binning + borders + CI +
-percentile) over one batch of B synthetic subjects per GPU (BASELINE.json configs[1]: seeded
-xenon phantoms, 128x128x14 @ 2.0x2.0x11.5 mm; every subject is a distinct phantom).  Subjects
-are independent, so ranks shard them with no data-path collective (weak scaling: B per GPU);
-the per-subject metric blocks are all-gathered at the end of the run.
+percentile) over one batch of synthetic subjects per GPU.  Every subject is a distinct seeded
+phantom whose pixel values are integers, as DICOM pixel data are (the reference reads uint16,
+Vent_Analysis.py:169-181, and casts to float32 at :322).  Default workload: BASELINE.json
+configs[1] (C2: 128x128x14 @ 2.0x2.0x11.5 mm), 1776 subjects per GPU, weak scaling (subjects are
+independent, ranks shard them with no data-path collective; the per-subject metric blocks are
+all-gathered at the end of the run).  ``--workload`` selects the other configs (C1, C3: 128^3 with
+the regenerated isotropic table, C4: 256x256x64 N4 + linear binning without CI, C5: the mixed-spacing
+cohort); ``--scaling strong --cohort 1024`` splits a fixed cohort over the ranks.
 
 Prints ONE JSON line (rank 0):
   value     whole-job subjects/s with the batch resident in HBM (CUDA events, max over ranks)
-  e2e       same metric through the host-buffer C-ABI call (pinned host arrays in, every output
-            array of the reference's class surface copied back) -- copies inside the timed region
+  e2e       the same metric through the host-buffer C-ABI call vb_pipeline_batch_host_packed: pinned
+            host arrays in (uint16 image, bit-packed mask), N4HPvent + one code byte per voxel + the
+            sparse CI list + per-subject records out -- every copy inside the timed region
   roofline  the dominant kernel (n4_subject_kernel): algorithmic bytes / its CUDA-event duration
-            measured inside the timed region, against MEASURED_PEAKS.json
+            measured inside the timed region, against MEASURED_PEAKS.json; ``onchip`` puts the same
+            launch against the SM's issue-slot and shared-memory ceilings (the kernel's real bound)
   cpu_baseline  the oracle port of the reference CPU path timed on this box's host cores (N=1 only)
+  cohort_c5 (default run only) the 1024-subject mixed-spacing cohort split over the ranks
 
 ``--impl reference`` times the reference's CPU algorithm instead (the reference is pure Python +
 SimpleITK and cannot travel to the GPU box, so this is the oracle port: oracle/n4_oracle.c for
 SimpleITK's N4, oracle/vdp_oracle.py and the literal np.intersect1d sphere search of
-oracle/ci_oracle.py, one subject per host core).
+oracle/ci_oracle.py on EVERY defect voxel, one subject per host core, wall-clock timed).
 """
 from __future__ import annotations
 
@@ -39,46 +47,57 @@ if ROOT not in sys.path:
 
 METRIC = "subject volumes/sec (N4+VDP+CI)"
 UNIT = "subjects/s"
-SHAPE, VOX = (128, 128, 14), [2.0, 2.0, 11.5]          # BASELINE.json configs[1]
-WORKLOAD = "C2 xenon phantoms 128x128x14 @2.0x2.0x11.5 mm, N4(4 levels, 50 it max)+SNR+VDP+LB+borders+CI(Rmax 50)"
+STAGES_FULL = "N4(4 levels, 50 it max)+SNR+VDP+LB+borders+CI(Rmax 50)"
+# name -> (description, default subjects per GPU per step, runs CI)
+WORKLOADS = {
+    "C1": ("C1 xenon phantoms 128x128x14 @1.5x1.5x10 mm, " + STAGES_FULL, 1776, True),
+    "C2": ("C2 xenon phantoms 128x128x14 @2.0x2.0x11.5 mm, " + STAGES_FULL, 1776, True),
+    "C3": ("C3 isotropic xenon phantoms 128x128x128 @3.9 mm, CI table regenerated for that spacing (523k rows), " + STAGES_FULL, 148, True),
+    "C4": ("C4 high-res volumes 256x256x64, N4(4 levels, 50 it max)+SNR+VDP+LB+borders, no CI (BASELINE.json configs[3])", 148, False),
+    "C5": ("C5 cohort: xenon phantoms 128x128x14, spacings 1.5x1.5x10 / 2.0x2.0x11.5 mm alternating, " + STAGES_FULL, 1776, True),
+}
 
 
-# ------------------------------------------------------------------------------------------ inputs
-MIXED = False      # --workload C5: the cohort config, C1 / C2 geometry and spacing alternating
-
-
-def _subject_vox(seed):
+def subject_geometry(workload, seed):
     from vent_analysis_b200.phantom import CONFIGS
-    return list(CONFIGS["C1" if int(seed) % 2 == 0 else "C2"][1]) if MIXED else list(VOX)
+    name = workload if workload != "C5" else ("C1" if int(seed) % 2 == 0 else "C2")
+    shape, vox, _ = CONFIGS[name]
+    return tuple(shape), list(vox)
 
 
-def _make_subject(seed):
+def _make_subject(args):
+    """(uint16 pixel data, uint8 mask): the seeded phantom rounded to integers like DICOM pixels."""
     from vent_analysis_b200.phantom import phantom
-    return phantom(SHAPE, _subject_vox(seed), int(seed))
+    workload, seed = args
+    shape, vox = subject_geometry(workload, seed)
+    img, mask = phantom(shape, vox, int(seed))
+    return np.rint(np.clip(img, 0, 65535)).astype(np.uint16), mask
 
 
-def make_batch(seeds, procs):
+def make_batch(workload, seeds, procs):
     import multiprocessing as mp
-    if procs > 1 and len(seeds) > 4:
+    jobs = [(workload, int(s)) for s in seeds]
+    if procs > 1 and len(jobs) > 4:
         with mp.get_context("fork").Pool(procs) as pool:
-            subs = pool.map(_make_subject, list(seeds), chunksize=max(1, len(seeds) // (4 * procs)))
+            subs = pool.map(_make_subject, jobs, chunksize=max(1, len(jobs) // (4 * procs)))
     else:
-        subs = [_make_subject(s) for s in seeds]
-    imgs, masks = zip(*subs)
-    return list(imgs), list(masks)
+        subs = [_make_subject(j) for j in jobs]
+    u16, masks = zip(*subs)
+    return list(u16), list(masks)
 
 
 # ---------------------------------------------------------------------------- reference CPU path
 def _cpu_subject(args):
-    """The reference's algorithm for ONE subject on one core (oracle port).  CI runs the
-    reference's literal per-voxel np.intersect1d search on `ci_sample` defect voxels (all of
-    them when ci_sample <= 0) and its time is scaled to the subject's defect count."""
-    seed, ci_sample = args
+    """The reference's algorithm for ONE subject on one core (oracle port), wall-clock timed.  CI is
+    the reference's literal per-voxel np.intersect1d search on every defect voxel (`ci_sample` > 0
+    limits it to that many voxels: warm-up only)."""
+    workload, seed, ci_sample = args
     from oracle import ci_oracle, n4_oracle, vdp_oracle
     from vent_analysis_b200.sphere_table import generate
-    img, mask = _make_subject(seed)
-    vox = _subject_vox(seed)
-    table = generate(vox, 50)
+    u16, mask = _make_subject((workload, seed))
+    img = u16.astype(np.float32)
+    _, vox = subject_geometry(workload, seed)
+    table = generate(vox, 50) if WORKLOADS[workload][2] else None
     t0 = time.perf_counter()
     snr = vdp_oracle.snr(img, mask)
     n4 = n4_oracle.n4(img, mask)
@@ -87,62 +106,56 @@ def _cpu_subject(args):
     t1 = time.perf_counter()
     d = r["defectArray"]
     D = int(d.sum())
-    if ci_sample > 0 and ci_sample < D:
-        sample = np.random.default_rng(seed).choice(D, ci_sample, replace=False)
-    else:
+    if table is not None:
         sample = None
-    ci_oracle.calculate_ci_literal(d, vox, table, sample=sample)
+        if 0 < ci_sample < D:
+            sample = np.random.default_rng(seed).choice(D, ci_sample, replace=False)
+        ci_oracle.calculate_ci_literal(d, vox, table, sample=sample)
     t2 = time.perf_counter()
-    n_eval = D if sample is None else len(sample)
-    t_ci = (t2 - t1) * (D / max(n_eval, 1))
-    return dict(t_n4_vdp=t1 - t0, t_ci_measured=t2 - t1, t_ci_full=t_ci, D=D, n_eval=n_eval, snr=float(snr),
-                vdp=float(r["VDP"]))
+    return dict(t_n4_vdp=t1 - t0, t_ci=t2 - t1, D=D, snr=float(snr), vdp=float(r["VDP"]))
 
 
-def cpu_step(pool, seeds, ci_sample):
-    """One reference step: len(seeds) subjects, one per worker.  Returns (seconds the step takes
-    on these cores with the full CI, measured wall seconds, per-subject records)."""
+def cpu_step(pool, workload, seeds, ci_sample=0):
+    """One reference step: len(seeds) subjects, one per worker.  Returns (wall seconds, records)."""
     t0 = time.perf_counter()
-    recs = pool.map(_cpu_subject, [(s, ci_sample) for s in seeds], chunksize=1)
-    wall = time.perf_counter() - t0
-    # every worker handles one subject; the step ends when the slowest one does
-    full = max(r["t_n4_vdp"] + r["t_ci_full"] for r in recs)
-    full = max(full, wall) if ci_sample <= 0 else full
-    return full, wall, recs
+    recs = pool.map(_cpu_subject, [(workload, s, ci_sample) for s in seeds], chunksize=1)
+    return time.perf_counter() - t0, recs
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: rank 0 only."""
+    """`--impl reference`: rank 0 only.  Every step is `cores` subjects (one per core) through the
+    whole path with the literal CI on every defect voxel, timed by the wall clock; the number of
+    steps is cut to what fits the time budget (a step takes ~10 s) and the line says how many ran."""
     if rank != 0:
         return
     import multiprocessing as mp
     from oracle import _build
     _build.build()
     cores = os.cpu_count() or 1
-    est_subject_s = 30.0
-    budget_s = 150.0
-    total_steps = args.steps
-    ci_sample = 0 if total_steps * est_subject_s <= budget_s else max(32, int(1250 * budget_s / (total_steps * est_subject_s)))
+    budget_s = float(os.environ.get("VB_REF_BUDGET_S", "150"))
+    wl = args.workload
     seeds0 = 100000
+    walls, recs_all = [], []
     with mp.get_context("fork").Pool(cores) as pool:
-        for w in range(args.warmup):                          # untimed: page in numpy / the oracle .so
-            cpu_step(pool, [seeds0 + w * cores + i for i in range(cores)], 8)
-        times, walls, recs_all = [], [], []
-        for k in range(args.steps):
-            full, wall, recs = cpu_step(pool, [seeds0 + (args.warmup + k) * cores + i for i in range(cores)], ci_sample)
-            times.append(full); walls.append(wall); recs_all += recs
-    total = float(np.sum(times))
-    value = cores * args.steps / total
-    sample = (f"{cores} subjects per step (one per core), N4/VDP/SNR/borders in full; CI literal search on "
-              + ("every defect voxel" if ci_sample <= 0 else
-                 f"{ci_sample} sampled defect voxels per subject, its time scaled to the subject's defect count "
-                 f"(mean {np.mean([r['D'] for r in recs_all]):.0f}); measured wall {np.sum(walls):.1f} s"))
+        cpu_step(pool, wl, [seeds0 - 1 - i for i in range(cores)], ci_sample=4)      # untimed: page in numpy / the oracle .so
+        t_start = time.perf_counter()
+        for k in range(max(1, args.steps)):
+            if walls and (time.perf_counter() - t_start) + 1.15 * max(walls) > budget_s:
+                break
+            wall, recs = cpu_step(pool, wl, [seeds0 + k * cores + i for i in range(cores)])
+            walls.append(wall); recs_all += recs
+    steps = len(walls)
+    total = float(np.sum(walls))
+    value = cores * steps / total
+    sample = (f"{steps} steps of {cores} subjects (one per core), whole path in full incl. the literal CI search on every defect "
+              f"voxel (mean {np.mean([r['D'] for r in recs_all]):.0f} per subject); wall clock {total:.1f} s; "
+              f"{args.steps} steps were asked for, {steps} fit the {budget_s:.0f} s budget; warm-up = one untimed short step")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "subjects_per_step": cores,
-                   "note": "reference is pure Python + SimpleITK (absent, no network): oracle port of its CPU algorithm"},
+        "config": {"workload": WORKLOADS[wl][0], "subjects_per_step": cores, "steps_requested": args.steps,
+                   "note": "reference is pure Python + SimpleITK (absent, no network): oracle port of its CPU algorithm, wall-clock timed"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -150,18 +163,21 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg():
+def cpu_baseline_leg(workload):
     """Bounded CPU sample for the `cpu_baseline` object of our own arm: one step of `cores`
-    subjects with the full CI (about 15 s)."""
+    subjects with the full CI (about 10-15 s)."""
     import multiprocessing as mp
     from oracle import _build
     _build.build()
     cores = os.cpu_count() or 1
+    if workload in ("C3", "C4"):
+        return {"value": None, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "not timed for this workload: one subject takes minutes on a core (the default C2 run carries the CPU baseline)"}
     with mp.get_context("fork").Pool(cores) as pool:
-        cpu_step(pool, [200000 + i for i in range(cores)], 4)                 # page-in
-        full, wall, recs = cpu_step(pool, [300000 + i for i in range(cores)], 0)
-    return {"value": cores / full, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{cores} C2 subjects, one per core, full path incl. literal CI on every defect voxel "
+        cpu_step(pool, workload, [200000 + i for i in range(cores)], ci_sample=4)     # page-in
+        wall, recs = cpu_step(pool, workload, [300000 + i for i in range(cores)])
+    return {"value": cores / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{cores} {workload} subjects, one per core, full path incl. literal CI on every defect voxel "
                       f"(mean {np.mean([r['D'] for r in recs]):.0f} per subject); wall {wall:.1f} s; N4 is the C restatement "
                       "of SimpleITK's filter (SimpleITK itself is not installable here)"}
 
@@ -224,154 +240,251 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------------------------- ours
+class Leg:
+    """One batch on one GPU: resident (`value`) and host-buffer (`e2e`) measurements."""
+
+    def __init__(self, ctx, workload, seeds, local_rank, procs):
+        from vent_analysis_b200 import _lib, cohort
+        self.ctx, self.workload = ctx, workload
+        self.flags = cohort.ALL_STAGES if WORKLOADS[workload][2] else (_lib.DO_SNR | _lib.DO_N4 | _lib.DO_VDP)
+        self.u16, self.masks = make_batch(workload, seeds, procs)
+        self.voxs = [subject_geometry(workload, s)[1] for s in seeds]
+        self.B = len(seeds)
+        self.dc = cohort.DeviceCohort([u.astype(np.float32) for u in self.u16], self.masks, self.voxs, device=local_rank,
+                                      flags=self.flags)
+        self.V = self.dc.V
+
+    def resident(self, steps, warmup, barrier, sampler=None):
+        import torch
+        ctx, dc = self.ctx, self.dc
+        if sampler:
+            sampler.start()
+        for _ in range(warmup):
+            dc.step()
+        barrier()
+        ctx.set_profiling(True)
+        wall0 = time.time()
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            dc.step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count() - l0
+        stage_ms, ncalls = ctx.profile_fetch()
+        ctx.set_profiling(False)
+        clocks = sampler.stop(wall0, time.time()) if sampler else None
+        self.stats = dc.stats()
+        self.metrics = dc.metrics()
+        return dict(ms=ms, launches=launches, stage_ms=stage_ms, ncalls=ncalls, clocks=clocks)
+
+    def e2e(self, steps, warmup, barrier):
+        """Through vb_pipeline_batch_host_packed with page-locked host buffers (vb_host_alloc): uint16
+        image + mask bits up; N4HPvent, code bytes, sparse CI list and records down."""
+        from vent_analysis_b200 import _lib
+        ctx, V, B = self.ctx, self.V, self.B
+        shapes = self.dc.shapes
+        h_img = ctx.pinned_empty(V, np.uint16)
+        h_img[:] = np.concatenate([u.ravel() for u in self.u16])
+        bits = _lib.pack_mask_bits(self.masks)
+        h_bits = ctx.pinned_empty(bits.size, np.uint32)
+        h_bits[:] = bits
+        want_ci = bool(self.flags & _lib.DO_CI)
+        cap = max(1024, V // 8)                         # defect voxels are a few per cent of the volume
+        bufs = {"n4": ctx.pinned_empty(V, np.float32), "codes": ctx.pinned_empty(V, np.uint8),
+                "stats": ctx.pinned_empty(B, _lib.STATS_DTYPE)}
+        if want_ci:
+            bufs.update(ci_index=ctx.pinned_empty(cap, np.uint32), ci_value=ctx.pinned_empty(cap, np.uint16),
+                        ci_offset=ctx.pinned_empty(B + 1, np.int64))
+
+        def step(arrays=True):
+            out = ctx.pipeline_host_packed(shapes, self.flags, image_u16=h_img, mask_bits=h_bits, handles=self.dc.handles,
+                                           buffers=bufs, want_n4=arrays, want_codes=arrays, want_ci_map=arrays and want_ci)
+            assert out["rc"] == 0
+            return out
+        for _ in range(max(1, min(warmup, 2))):
+            out = step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        D_total = int(out["ci_offset"][B]) if want_ci else 0
+        # the two paths must agree bit for bit
+        st = self.stats
+        assert np.array_equal(out["stats"]["n_defect"], st["n_defect"]) and np.array_equal(out["stats"]["ci_t95"], st["ci_t95"])
+        assert np.array_equal(out["stats"]["n4_iters"], st["n4_iters"])
+        # the same call returning only the per-subject records (cohort screening): extra information
+        step(False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out_m = step(False)
+        barrier()
+        e2e_m_s = time.perf_counter() - t0
+        assert np.array_equal(out_m["stats"]["n_defect"], st["n_defect"])
+        h2d = 2 * V + 4 * bits.size
+        d2h = 4 * V + V + 6 * D_total + B * _lib.STATS_DTYPE.itemsize
+        return dict(e2e_s=e2e_s, e2e_m_s=e2e_m_s, h2d=h2d, d2h=d2h, d2h_m=B * _lib.STATS_DTYPE.itemsize)
+
+
+def _mean(x):
+    """nanmean that stays JSON-clean (None when nothing is finite, e.g. CI for the C4 workload)."""
+    x = np.asarray(x, dtype=np.float64)
+    return float(np.nanmean(x)) if np.isfinite(x).any() else None
+
+
+def n4_algorithmic_bytes(stats, shapes):
+    """(17 + 19 n_it) V bytes per subject, n_it = iterations actually run."""
+    n_it = stats["n4_iters"].sum(axis=1).astype(np.float64)
+    vox = np.prod(np.asarray(shapes, dtype=np.float64), axis=1)
+    return float(((17.0 + 19.0 * n_it) * vox).sum()), n_it
+
+
 def run_ours(args, rank, local_rank, world):
+    from vent_analysis_b200 import cohort as cohort_mod
+    cohort_mod.bind_near_gpu(local_rank)                     # host threads and pinned pages next to this rank's GPU
+    wl = args.workload
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_baseline_leg()                        # before CUDA is touched (fork pools)
-    B = args.batch
-    imgs, masks = make_batch([rank * B + i for i in range(B)], min(os.cpu_count() or 1, 16) // max(1, min(world, 8)) or 1)
+        cpu_base = cpu_baseline_leg(wl)                      # before CUDA is touched (fork pools)
+    strong = args.scaling == "strong"
+    if strong:
+        seeds = cohort_mod.shard_indices(args.cohort, rank, world)
+    else:
+        B = args.batch if args.batch > 0 else WORKLOADS[wl][1]
+        seeds = [rank * B + i for i in range(B)]
+    procs = max(1, min(os.cpu_count() or 1, 16) // max(1, min(world, 8)))
 
     import torch
     import torch.distributed as dist
-    from vent_analysis_b200 import _lib, cohort
+    from vent_analysis_b200 import _lib
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.context(local_rank)
-    voxs = [_subject_vox(rank * B + i) for i in range(B)]
-    dc = cohort.DeviceCohort(imgs, masks, voxs, device=local_rank)
-    V = dc.V
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: batch resident in HBM --------------------------------------------------------
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    for _ in range(args.warmup):
-        dc.step()
-    barrier()
-    ctx.set_profiling(True)
-    wall0 = time.time()
-    l0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        dc.step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count() - l0
-    stage_ms, ncalls = ctx.profile_fetch()
-    ctx.set_profiling(False)
-    clocks = sampler.stop(wall0, time.time()) if sampler else None
-    stats = dc.stats()
-    metrics = dc.metrics()
+    def reduce_max(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------------
-    def pinned(n, dtype):
-        t = torch.empty(n, dtype=dtype, pin_memory=True)
-        return t, t.numpy()
-    keep = []
-    t_img, h_img = pinned(V, torch.float32); t_msk, h_msk = pinned(V, torch.uint8)
-    h_img[:] = np.concatenate([im.ravel() for im in imgs]); h_msk[:] = np.concatenate([m.ravel() for m in masks])
-    bufs = {}
-    for key, dt in (("n4", torch.float32), ("defect", torch.uint8), ("defect_lb", torch.uint8),
-                    ("defect_border", torch.uint8), ("ci_shell", torch.uint16)):
-        t, a = pinned(V, dt); keep.append(t); bufs[key] = a
-    shapes = dc.shapes
-    handles = dc.handles
-    flags = cohort.ALL_STAGES
+    def reduce_sum(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.cpu()]
 
-    def e2e_step():
-        out = ctx.pipeline_host(shapes, flags, image=h_img, mask=h_msk, handles=handles, buffers=bufs)
-        assert out["rc"] == 0
-        return out
-    for _ in range(max(1, min(args.warmup, 2))):
-        out_h = e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out_h = e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    # the same call returning only the per-subject records (cohort screening): extra information
-    def e2e_metrics_step():
-        return ctx.pipeline_host(shapes, flags, image=h_img, mask=h_msk, handles=handles, stats_only=True)
-    e2e_metrics_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out_m = e2e_metrics_step()
-    barrier()
-    e2e_m_s = time.perf_counter() - t0
-    assert np.array_equal(out_m["stats"]["n_defect"], stats["n_defect"]) and np.array_equal(out_m["stats"]["ci_t95"], stats["ci_t95"])
-    h2d = V * 5
-    d2h = V * (4 + 1 + 1 + 1 + 2) + B * _lib.STATS_DTYPE.itemsize
-    # the two paths must agree bit for bit
-    assert np.array_equal(out_h["stats"]["n_defect"], stats["n_defect"]) and np.array_equal(out_h["stats"]["ci_t95"], stats["ci_t95"])
+    leg = Leg(ctx, wl, seeds, local_rank, procs)
+    B, V = leg.B, leg.V
+    r = leg.resident(args.steps, args.warmup, barrier, ClockSampler(local_rank) if rank == 0 else None)
+    e = leg.e2e(args.steps, args.warmup, barrier)
+    n4_bytes, n_it = n4_algorithmic_bytes(leg.stats, leg.dc.shapes)
+    ms, e2e_ms, n4_ms, e2e_m_ms = reduce_max([r["ms"], e["e2e_s"] * 1e3, r["stage_ms"]["n4"], e["e2e_m_s"] * 1e3])
+    n_total, = reduce_sum([float(B)])
+    n_total = int(round(n_total))
+    allm = cohort_mod.gather_metrics(leg.metrics, n_total, rank, world) if world > 1 and not strong else leg.metrics
+    if world > 1 and strong:
+        allm = cohort_mod.gather_metrics(leg.metrics, args.cohort, rank, world)
 
-    # ---- reduce over ranks --------------------------------------------------------------------
-    t = torch.tensor([ms, e2e_s * 1e3, stage_ms["n4"], e2e_m_s * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        allm = cohort.gather_metrics(metrics, B * world, rank, world)      # final metric gather (NCCL)
-    else:
-        allm = metrics
-    ms, e2e_ms, n4_ms, e2e_m_ms = (float(x) for x in t.cpu())
+    # ---- the cohort config (BASELINE.json configs[4]) beside the default run: 1024 mixed-spacing
+    # subjects split over the ranks (strong scaling), same two measurements
+    cohort_c5 = None
+    if wl == "C2" and not strong and args.cohort_leg and args.batch <= 0:
+        del leg.dc
+        torch.cuda.empty_cache()
+        cseeds = cohort_mod.shard_indices(1024, rank, world)
+        cl = Leg(ctx, "C5", cseeds, local_rank, procs)
+        cr = cl.resident(args.steps, args.warmup, barrier)
+        ce = cl.e2e(args.steps, args.warmup, barrier)
+        c_ms, c_e2e_ms = reduce_max([cr["ms"], ce["e2e_s"] * 1e3])
+        cm = cohort_mod.gather_metrics(cl.metrics, 1024, rank, world)
+        cohort_c5 = {"workload": WORKLOADS["C5"][0], "scaling": "strong", "cohort_subjects": 1024,
+                     "subjects_per_gpu": len(cseeds), "value": 1024 * args.steps / (c_ms * 1e-3), "unit": UNIT,
+                     "ms_per_step": c_ms / args.steps,
+                     "e2e": {"value": 1024 * args.steps / (c_e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": c_e2e_ms / args.steps,
+                             "h2d_bytes_per_step": int(ce["h2d"]), "d2h_bytes_per_step": int(ce["d2h"])},
+                     "mean_VDP": _mean(cm[:, 0]), "mean_CI_mm": _mean(cm[:, 2]),
+                     "subjects_gathered": int(np.isfinite(cm[:, 0]).sum()),
+                     "limiter": "148 persistent CTAs pull whole subjects (about 7 ms each): below one wave of subjects per GPU "
+                                "the step is one subject's latency, so strong scaling flattens once 1024 / N approaches 148"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    n_it = stats["n4_iters"].sum(axis=1).astype(np.float64)
-    vox_per = float(np.prod(SHAPE))
-    n4_bytes = float(((17.0 + 19.0 * n_it) * vox_per).sum())             # SURVEY.md §8d, per launch (= per step)
-    n4_launch_ms = n4_ms / max(ncalls, 1)
+    n4_launch_ms = n4_ms / max(r["ncalls"], 1)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = n4_bytes / (n4_launch_ms * 1e-3) / 1e9
-    # DRAM traffic of the kernel from the committed ncu --set full capture (per subject; a launch
-    # handles B subjects and the traffic is proportional to them)
-    traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_n4_dram_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["subjects_per_launch"] * B
-        traffic_src = f"profiles/r01_n4_dram_traffic.json (ncu capture of a {tj['subjects_per_launch']}-subject launch, scaled to {B})"
+    roof = {"kernel": "n4_subject_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": n4_bytes, "launch_ms": n4_launch_ms,
+            "definition": "(17 + 19*n_it)*V bytes per subject (SURVEY.md 8d), n_it = iterations actually run"}
+    # counters of the committed ncu --set full capture of this kernel (same build, C2 batch): DRAM
+    # traffic, warp instructions and shared-memory wavefronts per subject-iteration -- put against
+    # the time measured live
+    cpath = os.path.join(ROOT, "profiles", "n4_counters.json")
+    if os.path.exists(cpath) and wl in ("C1", "C2", "C5"):
+        cj = json.load(open(cpath))
+        scale = float(n_it.sum()) / cj["subject_iterations"]
+        roof["traffic"] = (cj["dram_bytes_read"] + cj["dram_bytes_write"]) / cj["subjects_per_launch"] * B
+        roof["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)"
+        roof["traffic_source"] = f"profiles/n4_counters.json ({cj['source']}), scaled to {B} subjects"
+        sm_hz = 1e6 * (r["clocks"]["sm_mhz"] if r["clocks"] and r["clocks"]["sm_mhz"] else 1965.0)
+        sms = 148
+        inst = cj["warp_instructions"] * scale
+        wav = cj["smem_wavefronts"] * scale
+        t = n4_launch_ms * 1e-3
+        roof["onchip"] = {
+            "issue": {"achieved": inst / t / 1e9, "peak": sms * 4 * sm_hz / 1e9, "unit": "G warp-instructions/s",
+                      "frac": inst / t / (sms * 4 * sm_hz)},
+            "shared_memory": {"achieved": 128 * wav / t / 1e9, "peak": sms * 128 * sm_hz / 1e9, "unit": "GB/s",
+                              "frac": wav / t / (sms * sm_hz)},
+            "warp_instructions_per_mask_voxel_iteration": cj["warp_instructions"] * 32 / cj["mask_voxel_iterations"],
+            "note": "instruction and shared-memory wavefront counts from the ncu capture (deterministic for a given batch), "
+                    "scaled by the iterations of this run; peak = 148 SMs x 4 issue slots (128 B of shared memory) per clock "
+                    "at the SM clock sampled during the timed region",
+        }
     line = {
-        "metric": METRIC, "value": B * world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "metric": METRIC, "value": n_total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "subjects_per_gpu_per_step": B, "global_subjects_per_step": B * world,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[wl][0], "subjects_per_gpu_per_step": B, "global_subjects_per_step": n_total,
                    "parallelism": f"subject-sharded x{world}, no data-path collective, final all_gather of [n,6] metrics",
-                   "l2": f"inputs larger than L2: {V * 5 / 1e6:.0f} MB in + {V * 9 / 1e6:.0f} MB out per GPU per step",
+                   "l2": f"inputs larger than L2: {V * 5 / 1e6:.0f} MB in + {V * 9 / 1e6:.0f} MB out per GPU per step (resident arrays)",
+                   "pixel_data": "integer-valued phantoms (DICOM-like uint16), float32 on the device",
                    "mean_n4_iterations": float(n_it.mean()),
-                   "mean_defect_voxels": float(stats["ci_n"].mean())},
-        "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
-                "api": "vb_pipeline_batch_host (cohort.run_cohort_host), pinned host buffers"},
-        "e2e_metrics_only": {"value": B * world * args.steps / (e2e_m_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                             "d2h_bytes_per_step": int(B * _lib.STATS_DTYPE.itemsize), "ms_per_step": e2e_m_ms / args.steps,
-                             "note": "same call with VB_HOST_STATS_ONLY: only the per-subject records come back"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": {"kernel": "n4_subject_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
-                     "traffic_source": traffic_src, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": n4_bytes, "launch_ms": n4_launch_ms,
-                     "definition": "(17 + 19*n_it)*V bytes per subject (SURVEY.md 8d), n_it = iterations actually run"},
-        "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
+                   "mean_defect_voxels": float(leg.stats["ci_n"].mean())},
+        "e2e": {"value": n_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(e["h2d"]),
+                "d2h_bytes_per_step": int(e["d2h"]), "ms_per_step": e2e_ms / args.steps,
+                "api": "vb_pipeline_batch_host_packed, page-locked host buffers (vb_host_alloc): uint16 image + mask bits in; "
+                       "N4HPvent f32 + code byte per voxel + sparse CI list + records out"},
+        "e2e_metrics_only": {"value": n_total * args.steps / (e2e_m_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(e["h2d"]),
+                             "d2h_bytes_per_step": int(e["d2h_m"]), "ms_per_step": e2e_m_ms / args.steps,
+                             "note": "same call with no output arrays: only the per-subject records come back"},
+        "gpu_launches": int(r["launches"]),
+        "clocks": r["clocks"],
+        "roofline": roof,
+        "stage_ms_per_step": {k: v / max(r["ncalls"], 1) for k, v in r["stage_ms"].items()},
         "cpu_baseline": cpu_base,
-        "results_check": {"mean_VDP": float(np.nanmean(allm[:, 0])), "mean_CI_mm": float(np.nanmean(allm[:, 2])),
-                          "subjects_gathered": int(allm.shape[0])},
+        "results_check": {"mean_VDP": _mean(allm[:, 0]), "mean_CI_mm": _mean(allm[:, 2]),
+                          "subjects_gathered": int(np.isfinite(allm[:, 0]).sum())},
     }
+    if cohort_c5 is not None:
+        line["cohort_c5"] = cohort_c5
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -382,17 +495,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1776, help="subjects per GPU per step (12 per SM; the cohort config is 1024)")
+    ap.add_argument("--batch", type=int, default=0, help="subjects per GPU per step (default: per workload; 1776 = 12 per SM for C1/C2/C5)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C2", "C5"],
-                    help="C2: BASELINE.json configs[1] (default); C5: the cohort config, C1/C2 spacings alternating")
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS),
+                    help="C2: BASELINE.json configs[1] (default); C1, C3, C4, C5: the other configs")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: a fixed cohort of --cohort subjects split over the ranks")
+    ap.add_argument("--cohort", type=int, default=1024)
+    ap.add_argument("--no-cohort-leg", dest="cohort_leg", action="store_false",
+                    help="skip the C5 cohort measurement that rides on the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    global MIXED, WORKLOAD
-    if args.workload == "C5":
-        MIXED = True
-        WORKLOAD = ("C5 cohort: xenon phantoms 128x128x14, spacings 1.5x1.5x10 / 2.0x2.0x11.5 mm alternating, "
-                    "N4(4 levels, 50 it max)+SNR+VDP+LB+borders+CI(Rmax 50)")
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

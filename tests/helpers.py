@@ -349,3 +349,43 @@ def check_pack6_golden(ctx):
     assert tuple(int(x) for x in gp["shape"]) == shape + (6,) and str(gp["dtype"]) == "float32"
     assert np.allclose(packed.reshape(-1, 6).astype(np.float64).sum(axis=0), gp["channel_sums"], rtol=0, atol=0)
     assert hashlib.sha256(packed.tobytes()).hexdigest() == str(gp["sha"])
+
+
+def check_packed_io(ctx, shapes=((33, 29, 5), (24, 20, 4), (36, 40, 1), (40, 32, 6)), max_iter=(4, 3)):
+    """vb_pipeline_batch_host_packed (uint16 image + bit-packed mask in; N4HPvent, code bytes and the
+    sparse CI list out) against vb_pipeline_batch_host on the same ragged batch: every array of the
+    class surface identical after unpacking; float32-image / byte-mask inputs likewise; a CI
+    capacity that is too small is an argument error."""
+    import pytest
+    vox = [1.5, 1.5, 10.0]
+    subs = [phantom(s, vox, 60 + i) for i, s in enumerate(shapes)]
+    u16 = [np.rint(np.clip(im, 0, 65535)).astype(np.uint16) for im, _ in subs]      # DICOM pixel data
+    masks = [m for _, m in subs]
+    img = np.concatenate([u.astype(np.float32).ravel() for u in u16])                # V_A.py:322 cast
+    msk = np.concatenate([m.ravel() for m in masks])
+    tbl = generate(vox, 50)
+    handles = [ctx.ci_table(tbl, s, key=(tuple(vox), 50, tbl.shape[0])) for s in shapes]
+    p = ctx.default_n4_params(max_iter=max_iter)
+    flags = _lib.DO_SNR | _lib.DO_N4 | _lib.DO_VDP | _lib.DO_CI | _lib.DO_MASK_BORDER
+    ref = ctx.pipeline_host(shapes, flags, image=img, mask=msk, handles=handles, params=p, want_logbias=True)
+    assert ref["rc"] == 0
+    keys = ("n4", "logbias", "defect", "defect_lb", "defect_border", "mask_border", "ci_shell")
+    for kw in (dict(image_u16=np.concatenate([u.ravel() for u in u16]), mask_bits=_lib.pack_mask_bits(masks)),
+               dict(image_f32=img, mask_u8=msk)):
+        pk = ctx.pipeline_host_packed(shapes, flags, handles=handles, params=p, want_logbias=True, **kw)
+        assert pk["rc"] == 0
+        got = _lib.unpack_outputs(pk, shapes)
+        for k in keys:
+            assert np.array_equal(got[k], ref[k]), (k, list(kw))
+        assert got["stats"].tobytes() == ref["stats"].tobytes()
+        D = ref["stats"]["ci_n"].astype(np.int64)
+        assert np.array_equal(pk["ci_offset"], np.concatenate([[0], np.cumsum(D)]))
+    # scalars only: no arrays wanted
+    pk = ctx.pipeline_host_packed(shapes, flags & ~_lib.DO_MASK_BORDER, image_f32=img, mask_u8=msk, handles=handles, params=p,
+                                  want_n4=False, want_codes=False, want_ci_map=False)
+    assert set(pk) == {"stats", "rc"} and np.array_equal(pk["stats"]["ci_t95"], ref["stats"]["ci_t95"])
+    assert np.array_equal(pk["stats"]["n_defect"], ref["stats"]["n_defect"])
+    small = dict(ci_index=np.empty(3, np.uint32), ci_value=np.empty(3, np.uint16))
+    with pytest.raises(_lib.VbError) as e:
+        ctx.pipeline_host_packed(shapes, flags, image_f32=img, mask_u8=msk, handles=handles, params=p, buffers=small)
+    assert e.value.code == _lib.VB_ERR_ARG

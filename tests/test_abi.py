@@ -35,11 +35,12 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_struct_sizes_match_the_c_side(tmp_path):
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include "ventb200.h"\nint main(){printf("%zu %zu %zu\\n",'
-                    'sizeof(vb_n4_params),sizeof(vb_subject_stats),sizeof(vb_buffers));return 0;}')
+    prog.write_text('#include <stdio.h>\n#include "ventb200.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
+                    'sizeof(vb_n4_params),sizeof(vb_subject_stats),sizeof(vb_buffers),sizeof(vb_host_io));return 0;}')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
-    a, b, c = (int(x) for x in subprocess.check_output([str(exe)]).split())
+    a, b, c, d = (int(x) for x in subprocess.check_output([str(exe)]).split())
+    assert d == ctypes.sizeof(_lib.HostIO)
     assert a == ctypes.sizeof(_lib.N4Params)
     assert b == ctypes.sizeof(_lib.SubjectStats) == _lib.STATS_DTYPE.itemsize
     assert c == ctypes.sizeof(_lib.Buffers)

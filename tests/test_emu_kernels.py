@@ -142,3 +142,7 @@ def test_build4DdataArray_packing_bit_exact(ctx):
 
 def test_build4DdataArray_identical_to_the_reference_output(ctx):
     helpers.check_pack6_golden(ctx)
+
+
+def test_compact_host_io_equals_the_dense_path(ctx):
+    helpers.check_packed_io(ctx)

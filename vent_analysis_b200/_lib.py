@@ -52,6 +52,32 @@ class Buffers(C.Structure):
                 ("mask_border", C.c_void_p), ("ci_shell", C.c_void_p), ("stats", C.c_void_p)]
 
 
+class HostIO(C.Structure):
+    """``vb_host_io`` -- compact host-side I/O of ``vb_pipeline_batch_host_packed``"""
+    _fields_ = [("image_u16", C.c_void_p), ("image_f32", C.c_void_p), ("mask_bits", C.c_void_p), ("mask_u8", C.c_void_p),
+                ("n4", C.c_void_p), ("logbias", C.c_void_p), ("codes", C.c_void_p), ("ci_index", C.c_void_p),
+                ("ci_value", C.c_void_p), ("ci_capacity", C.c_int64), ("ci_offset", C.c_void_p), ("stats", C.c_void_p)]
+
+
+CODE_LB_MASK, CODE_DEFECT, CODE_DEFECT_BORDER, CODE_MASK_BORDER = 7, 8, 16, 32
+
+
+def pack_mask_bits(masks):
+    """The ``mask_bits`` layout of ``vb_host_io``: per subject ``ceil(V/32)`` little-endian 32-bit
+    words, bit b of word w = voxel ``32 w + b`` of the C-ordered 0/1 volume; subjects concatenated."""
+    parts = []
+    for m in masks:
+        b = np.packbits(np.asarray(m).ravel() != 0, bitorder="little")
+        pad = (-b.size) % 4
+        parts.append(np.concatenate([b, np.zeros(pad, np.uint8)]) if pad else b)
+    return np.ascontiguousarray(np.concatenate(parts)).view(np.uint32)
+
+
+def mask_words(shapes):
+    """Number of ``mask_bits`` words of a batch."""
+    return int(sum((int(np.prod(s)) + 31) // 32 for s in shapes))
+
+
 class VbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"ventb200 error {code}: {msg}")
@@ -61,7 +87,7 @@ class VbError(RuntimeError):
 EXPORTS = ["vb_version", "vb_last_error", "vb_device_count", "vb_create", "vb_destroy", "vb_launch_count",
            "vb_n4_default_params", "vb_ci_table_create", "vb_ci_table_radii", "vb_snr_batch_dev", "vb_n4_batch_dev",
            "vb_vdp_batch_dev", "vb_border_batch_dev", "vb_ci_batch_dev", "vb_pipeline_batch_dev",
-           "vb_pipeline_batch_host", "vb_pack6_batch_dev", "vb_pack6_batch_host", "vb_set_profiling", "vb_profile_fetch", "vb_set_debug", "vb_n4_debug_fetch"]
+           "vb_pipeline_batch_host", "vb_pipeline_batch_host_packed", "vb_host_alloc", "vb_host_free", "vb_pack6_batch_dev", "vb_pack6_batch_host", "vb_set_profiling", "vb_profile_fetch", "vb_set_debug", "vb_n4_debug_fetch"]
 N_STAGES = 5
 STAGE_NAMES = ("snr", "n4", "vdp", "mask_border", "ci")
 
@@ -89,6 +115,9 @@ def bind(path):
     lib.vb_ci_batch_dev.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     lib.vb_pipeline_batch_dev.argtypes = [vp, i32, vp, vp, C.POINTER(N4Params), f32, u32, C.POINTER(Buffers), vp]
     lib.vb_pipeline_batch_host.argtypes = [vp, i32, vp, vp, C.POINTER(N4Params), f32, u32, C.POINTER(Buffers)]
+    lib.vb_pipeline_batch_host_packed.argtypes = [vp, i32, vp, vp, C.POINTER(N4Params), f32, u32, C.POINTER(HostIO)]
+    lib.vb_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.vb_host_free.argtypes = [vp, vp]
     lib.vb_pack6_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.vb_pack6_batch_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.vb_set_profiling.argtypes = [vp, i32]
@@ -135,9 +164,13 @@ class Context:
         self.device = int(device)
         self._tables = {}
         self._radii = {}
+        self._pinned = []
 
     def close(self):
         if getattr(self, "h", None):
+            for p in self._pinned:
+                self.lib.vb_host_free(self.h, p)
+            self._pinned = []
             self.lib.vb_destroy(self.h)
             self.h = None
 
@@ -269,6 +302,70 @@ class Context:
             self.check(rc)
         return out
 
+    # -- whole path, compact host I/O --------------------------------------------------------------
+    def pinned_empty(self, n, dtype):
+        """A page-locked numpy array (``vb_host_alloc``); freed with the context."""
+        dtype = np.dtype(dtype)
+        p = C.c_void_p()
+        nbytes = max(1, int(n) * dtype.itemsize)
+        self.check(self.lib.vb_host_alloc(self.h, nbytes, C.byref(p)))
+        self._pinned.append(p)
+        buf = (C.c_char * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def pipeline_host_packed(self, shapes, flags, image_u16=None, image_f32=None, mask_bits=None, mask_u8=None,
+                             handles=None, params=None, thresh=0.6, want_n4=True, want_logbias=False, want_codes=True,
+                             want_ci_map=True, buffers=None):
+        """``vb_pipeline_batch_host_packed``: the path on HOST arrays in their compact forms (uint16
+        or float32 image, bit-packed or byte mask in; N4HPvent, one code byte per voxel and the
+        sparse CI list out).  Returns the raw compact outputs; :func:`unpack_outputs` expands them
+        into the arrays of the reference's class surface.  ``buffers``: optional preallocated
+        (pinned) output arrays ``n4 / logbias / codes / ci_index / ci_value / ci_offset / stats``."""
+        shapes = np.ascontiguousarray(shapes, dtype=np.int32).reshape(-1, 3)
+        n = shapes.shape[0]
+        V = int(np.prod(shapes.astype(np.int64), axis=1).sum())
+        buffers = buffers or {}
+
+        def _buf(key, dtype, size):
+            if key in buffers:
+                a = buffers[key]
+                assert a.dtype == dtype and a.size >= size and a.flags.c_contiguous, key
+                return a.reshape(-1)
+            return np.empty(size, dtype=dtype)
+        io = HostIO()
+        keep = []
+        for name, arr, dt, size in (("image_u16", image_u16, np.uint16, V), ("image_f32", image_f32, np.float32, V),
+                                    ("mask_bits", mask_bits, np.uint32, mask_words(shapes)), ("mask_u8", mask_u8, np.uint8, V)):
+            if arr is not None:
+                a = np.ascontiguousarray(arr, dtype=dt).reshape(-1)
+                assert a.size == size, (name, a.size, size)
+                keep.append(a)
+                setattr(io, name, a.ctypes.data)
+        out = {}
+        if want_n4 and flags & DO_N4:
+            out["n4"] = _buf("n4", np.float32, V); io.n4 = out["n4"].ctypes.data
+        if want_logbias and flags & DO_N4:
+            out["logbias"] = _buf("logbias", np.float32, V); io.logbias = out["logbias"].ctypes.data
+        if want_codes and flags & DO_VDP:
+            out["codes"] = _buf("codes", np.uint8, V); io.codes = out["codes"].ctypes.data
+        if want_ci_map and flags & DO_CI:
+            cap = buffers["ci_index"].size if "ci_index" in buffers else V
+            out["ci_index"] = _buf("ci_index", np.uint32, cap); out["ci_value"] = _buf("ci_value", np.uint16, cap)
+            out["ci_offset"] = _buf("ci_offset", np.int64, n + 1)
+            io.ci_index = out["ci_index"].ctypes.data; io.ci_value = out["ci_value"].ctypes.data
+            io.ci_capacity = cap; io.ci_offset = out["ci_offset"].ctypes.data
+        stats = _buf("stats", STATS_DTYPE, n)
+        io.stats = stats.ctypes.data
+        hd = None if handles is None else np.ascontiguousarray(handles, dtype=np.int32)
+        p = params if params is not None else self.default_n4_params()
+        rc = self.lib.vb_pipeline_batch_host_packed(self.h, n, _ptr(shapes), _ptr(hd), C.byref(p), float(thresh),
+                                                    int(flags), C.byref(io))
+        out["stats"] = stats[:n]
+        out["rc"] = rc
+        if rc not in (VB_OK, VB_ERR_CI_RMAX):
+            self.check(rc)
+        return out
+
     def ci_host(self, defect, shapes, handles):
         """CI stage alone on host arrays: defect uint8 0/1 -> (ci_shell uint16, stats, rc)."""
         shapes = np.ascontiguousarray(shapes, dtype=np.int32).reshape(-1, 3)
@@ -346,6 +443,30 @@ class Context:
 
     def set_debug(self, on=True):
         self.check(self.lib.vb_set_debug(self.h, 1 if on else 0))
+
+
+def unpack_outputs(packed, shapes):
+    """Expand the compact outputs of :meth:`Context.pipeline_host_packed` into the dense arrays of
+    :meth:`Context.pipeline_host` (``defect``, ``defect_lb``, ``defect_border``, ``mask_border``
+    uint8, ``ci_shell`` uint16 with ``CI_OFF`` off the defect) -- format conversion only."""
+    shapes = np.asarray(shapes, dtype=np.int64).reshape(-1, 3)
+    vols = np.prod(shapes, axis=1)
+    V = int(vols.sum())
+    out = {k: packed[k] for k in ("n4", "logbias", "stats", "rc") if k in packed}
+    if "codes" in packed:
+        c = packed["codes"][:V]
+        out["defect_lb"] = c & CODE_LB_MASK
+        out["defect"] = (c >> 3) & 1
+        out["defect_border"] = (c >> 4) & 1
+        out["mask_border"] = (c >> 5) & 1
+    if "ci_index" in packed:
+        shell = np.full(V, CI_OFF, dtype=np.uint16)
+        off = packed["ci_offset"]
+        total = int(off[len(vols)])
+        base = np.repeat(np.concatenate([[0], np.cumsum(vols)[:-1]]), np.diff(off[:len(vols) + 1]))
+        shell[base + packed["ci_index"][:total].astype(np.int64)] = packed["ci_value"][:total]
+        out["ci_shell"] = shell
+    return out
 
 
 _CTX = {}

@@ -24,6 +24,38 @@ METRICS = ("VDP", "VDP_lb", "CI", "SNR", "LungVolume", "DefectVolume")
 ALL_STAGES = _lib.DO_SNR | _lib.DO_N4 | _lib.DO_VDP | _lib.DO_CI
 
 
+def bind_near_gpu(device=0):
+    """Restrict this process to the CPUs of the NUMA node the GPU hangs off (Linux sysfs), so that
+    the page-locked staging buffers it allocates afterwards (first touch) and the threads that feed
+    the copies are local to that GPU's PCIe root.  Returns the node, or None when the box has a
+    single node / the topology is not exposed (then nothing is changed)."""
+    import glob
+    import os
+    try:
+        nodes = [p for p in glob.glob("/sys/devices/system/node/node[0-9]*")]
+        if len(nodes) < 2:
+            return None
+        import torch
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def shard_indices(n, rank, world):
     """Subjects of ``rank``: round robin (CI cost varies per subject; interleaving balances it)."""
     return list(range(int(rank), int(n), int(world)))

@@ -79,6 +79,7 @@ struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 struct int2 { int x, y; };
 struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 static inline double2 make_double2(double a, double b) { return double2{a, b}; }

@@ -205,15 +205,25 @@ snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, cons
 //   p99  = sorted(...)[int(M*.99)].
 // The kernel therefore sorts the mask voxels (order-preserving key of the float bits):
 //   1. ONE pass over HBM: the mask is read once, the image only where the mask is set (16-byte
-//      loads, software pipelined); the keys are appended to a per-CTA scratch array A in global
-//      memory (L2 resident; warp-aggregated append), key range and count in registers;
-//   2. bucket sort: histogram over <= 2^13 range-normalised bins in shared memory, exclusive scan,
-//      scatter A -> B (B in shared memory when the mask fits, else a second scratch array);
-//   3. rank inside the bucket by counting (ties by position) and write the sorted keys back to A;
+//      loads, software pipelined); the keys are appended to array A (warp-aggregated append) --
+//      shared memory, overflowing into a per-CTA scratch in global memory when the mask does not
+//      fit -- key range and count in registers;
+//   2. bucket sort: histogram over two levels of range-normalised buckets in shared memory (about
+//      8-16 keys per bucket whatever the distribution), exclusive scan,
+//      scatter A -> B (B: per-CTA scratch in global memory, L2 resident) and a vectorised copy of
+//      the bucketed keys back into A (a global-memory read per comparison would expose the L2
+//      latency in step 3: measured 4x slower);
+//   3. rank inside the bucket by counting (ties by position), sorted keys to B, copied back to A;
 //   4. numpy's pairwise summation tree evaluated in parallel on the sorted array (8 lanes per leaf,
 //      one per accumulator; the leaf sums combined bottom-up along numpy's recursion tree).
 // Also zeroes the defect / LB counters.
-#define VB_VDP_LOG_BINS 13          /* buckets when the keys live in shared memory */
+#define VB_VDP_LOG_COARSE 11        /* level-1 buckets */
+#define VB_VDP_LOAD 8               /* keys per level-2 bucket aimed at (8..16 after rounding) */
+// level-2 bucket of a key (d = key - lowest key): cinfo[c] = first fine bucket | log2(parts) << 24
+VB_DEV int vdp_fine_bucket(const unsigned* cinfo, unsigned d, int sh1, unsigned m1) {
+    const unsigned ci = cinfo[d >> sh1];
+    return (int)((ci & 0xFFFFFFu) + ((d & m1) >> (sh1 - (int)(ci >> 24))));
+}
 
 // block-wide exclusive prefix sum of h[0..nb) in place (each thread owns a contiguous run)
 VB_DEV void vdp_block_exscan(unsigned* h, int nb, unsigned* wsum) {
@@ -298,20 +308,39 @@ VB_DEV float vdp_pairwise_sum(const unsigned* keys, int M, int D, float* hv, uns
     return hv[1];
 }
 
+// global -> shared copy of n keys by the whole block, 16 bytes per load, four loads in flight;
+// ends with a block barrier
+VB_DEV void vdp_copy_keys(unsigned* dst, const unsigned* src, int n) {
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x, n4 = n >> 2;
+    for (int i = tid; i < n4; i += 4 * nt) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i + u * nt < n4) v[u] = *(const uint4*)(src + 4 * (size_t)(i + u * nt));
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i + u * nt < n4) *(uint4*)(dst + 4 * (size_t)(i + u * nt)) = v[u];
+    }
+    for (int i = 4 * n4 + tid; i < n; i += nt) dst[i] = src[i];
+    __syncthreads();
+}
+
 #define VB_VDP_HEAP_DEPTH 10        /* pairwise heaps up to this depth live in shared memory */
 VB_KERNEL void VB_LAUNCH_BOUNDS(VB_VDP_THREADS, 1)
 vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, int n,
                  vb_subject_stats* stats, int key_cap, int dyn_words, unsigned* ws_a, unsigned* ws_b, long long ws_stride) {
     VB_DYN_SMEM(smem);
-    unsigned* hist = (unsigned*)smem;                    // [2^13] buckets, then [key_cap] keys (array B)
+    // dynamic shared memory: [2^11 coarse buckets][2^11 + key_cap / VB_VDP_LOAD fine buckets][key_cap keys (array A)]
+    unsigned* cinfo = (unsigned*)smem;
     VB_SHARED double red[64];
     VB_SHARED unsigned wsum[32];
     VB_SHARED float pw_val[2 << VB_VDP_HEAP_DEPTH];
     VB_SHARED unsigned char pw_kind[2 << VB_VDP_HEAP_DEPTH];
     VB_SHARED int s_nkeys;
     const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = tid & 31;
-    unsigned* A = ws_a + (size_t)blockIdx.x * (size_t)ws_stride;
-    unsigned* Bg = ws_b + (size_t)blockIdx.x * (size_t)ws_stride;
+    unsigned* As = cinfo + (2 << VB_VDP_LOG_COARSE) + key_cap / VB_VDP_LOAD;
+    unsigned* Ag = ws_a + (size_t)blockIdx.x * (size_t)ws_stride;
+    unsigned* B = ws_b + (size_t)blockIdx.x * (size_t)ws_stride;
     for (int si = (int)blockIdx.x; si < n; si += (int)gridDim.x) {
         const VbSubject S = subj[si];
         const float* x = n4 + S.off;
@@ -359,7 +388,8 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
                             const unsigned key = vb_float_key(f[u].v[e]);
                             ++cnt;
                             kmin = min(kmin, key); kmax = max(kmax, key);
-                            A[pos++] = key;
+                            if (pos < key_cap) As[pos] = key; else Ag[pos] = key;
+                            ++pos;
                         }
                 }
             }
@@ -373,38 +403,75 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
         float p99 = 0.0f, mean = 0.0f;
         if (M > 0) {
             const unsigned range = hi0 - lo0;
+            const bool in_smem = M <= key_cap;
+            unsigned* A = As;
+            if (!in_smem) {                                          // the mask does not fit: all keys in global memory
+                for (int i = tid; i < key_cap; i += nt) Ag[i] = As[i];
+                A = Ag;
+                __syncthreads();
+            }
             if (range != 0u) {                                       // (all keys equal: A is sorted as it is)
-                const bool in_smem = M <= key_cap;
-                unsigned* B = in_smem ? hist + (1 << VB_VDP_LOG_BINS) : Bg;
-                int lognb = VB_VDP_LOG_BINS;                         // keys in global memory: all of it for buckets
-                if (!in_smem) while ((2 << lognb) <= dyn_words) ++lognb;
-                const int sh = max(0, (32 - __clz((int)range)) - lognb);
-                const int nb = (int)(range >> sh) + 1;               // <= 2^lognb
-                for (int i = tid; i < nb; i += nt) hist[i] = 0;
+                // Two-level buckets.  Float keys are logarithmically spaced, so one zero or tiny voxel
+                // in the mask stretches [lo0, hi0] over dozens of binades and equal-width buckets
+                // would put the bulk of the keys into a handful of them (measured: 600 keys per
+                // bucket, 9x the instructions).  Level 1: <= 2^11 coarse buckets over the range;
+                // level 2: a coarse bucket with c keys is cut into pow2ceil(c / load) equal parts.
+                unsigned* fh = cinfo + (1 << VB_VDP_LOG_COARSE);     // fine buckets
+                const int fine_cap = (in_smem ? (1 << VB_VDP_LOG_COARSE) + key_cap / VB_VDP_LOAD : dyn_words - (1 << VB_VDP_LOG_COARSE));
+                const int sh1 = max(0, (32 - __clz((int)range)) - VB_VDP_LOG_COARSE);
+                const int nbc = (int)(range >> sh1) + 1;             // <= 2^11
+                const unsigned m1 = (1u << sh1) - 1u;
+                for (int i = tid; i < nbc; i += nt) cinfo[i] = 0;
                 __syncthreads();
-                for (int i = tid; i < M; i += nt) atomicAdd(&hist[(A[i] - lo0) >> sh], 1u);
+                for (int i = tid; i < M; i += nt) atomicAdd(&cinfo[(A[i] - lo0) >> sh1], 1u);
                 __syncthreads();
-                vdp_block_exscan(hist, nb, wsum);                    // bucket starts
-                for (int i = tid; i < M; i += nt) {
-                    const unsigned key = A[i];
-                    B[atomicAdd(&hist[(key - lo0) >> sh], 1u)] = key;   // afterwards hist[b] = end of bucket b
+                int lt = 0;                                          // log2 of the load aimed at per fine bucket
+                while ((1 << lt) < VB_VDP_LOAD) ++lt;
+                while (((M >> lt) << 1) + nbc > fine_cap) ++lt;
+                for (int c = tid; c < nbc; c += nt) {
+                    const unsigned want = cinfo[c] >> lt;            // parts = pow2ceil(want), at most 2^sh1
+                    int lg = (want > 1u) ? 32 - __clz((int)(want - 1u)) : 0;
+                    lg = min(lg, sh1);
+                    fh[c] = 1u << lg;
+                    cinfo[c] = (unsigned)lg << 24;
                 }
                 __syncthreads();
+                if (tid == 0) s_nkeys = (int)fh[nbc - 1];
+                vdp_block_exscan(fh, nbc, wsum);                     // first fine bucket of every coarse one
+                const int nf = (int)fh[nbc - 1] + s_nkeys;           // fine buckets in all
+                for (int c = tid; c < nbc; c += nt) cinfo[c] |= fh[c];
+                __syncthreads();
+                for (int i = tid; i < nf; i += nt) fh[i] = 0;
+                __syncthreads();
+                for (int i = tid; i < M; i += nt) atomicAdd(&fh[vdp_fine_bucket(cinfo, A[i] - lo0, sh1, m1)], 1u);
+                __syncthreads();
+                vdp_block_exscan(fh, nf, wsum);                      // bucket starts
+                for (int i = tid; i < M; i += nt) {
+                    const unsigned key = A[i];
+                    B[atomicAdd(&fh[vdp_fine_bucket(cinfo, key - lo0, sh1, m1)], 1u)] = key;   // afterwards fh[b] = end of bucket b
+                }
+                __syncthreads();
+                if (in_smem) vdp_copy_keys(A, B, M);                 // bucketed keys next to the SM
+                const unsigned* src = in_smem ? A : B;
+                unsigned* dst = in_smem ? B : A;
                 for (int p = tid; p < M; p += nt) {
-                    const unsigned key = B[p];
-                    const int b = (int)((key - lo0) >> sh);
-                    const int o = b ? (int)hist[b - 1] : 0, e = (int)hist[b];
-                    int rank = p - o;                                // sh == 0: one key value per bucket
-                    if (sh != 0) {
+                    const unsigned key = src[p];
+                    const unsigned d = key - lo0;
+                    const unsigned ci = cinfo[d >> sh1];
+                    const int b = (int)((ci & 0xFFFFFFu) + ((d & m1) >> (sh1 - (int)(ci >> 24))));
+                    const int o = b ? (int)fh[b - 1] : 0, e = (int)fh[b];
+                    int rank = p - o;                                // a bucket one key wide: all its keys are equal
+                    if (sh1 != (int)(ci >> 24)) {
                         rank = 0;
                         for (int q = o; q < e; ++q) {
-                            const unsigned y = B[q];
+                            const unsigned y = src[q];
                             rank += (int)((y < key) || (y == key && q < p));
                         }
                     }
-                    A[o + rank] = key;
+                    dst[o + rank] = key;
                 }
                 __syncthreads();
+                if (in_smem) vdp_copy_keys(A, B, M);                 // sorted keys back
             }
             long long k = (long long)((double)M * .99);              // int(len(signal_list)*.99)
             if (k >= M) k = M - 1;
@@ -412,7 +479,7 @@ vdp_stats_kernel(const float* n4, const uint8_t* VB_RESTRICT mask, const VbSubje
             const int D = vdp_pw_depth(M);
             float total;
             if (D <= VB_VDP_HEAP_DEPTH) total = vdp_pairwise_sum(A, M, D, pw_val, pw_kind);
-            else total = vdp_pairwise_sum(A, M, D, (float*)Bg, (unsigned char*)(Bg + ((size_t)2 << D)));
+            else total = vdp_pairwise_sum(A, M, D, (float*)B, (unsigned char*)(B + ((size_t)2 << D)));
             mean = (float)((double)total / (double)M);               // np.mean: float32 sum / intp count in float64
         }
         if (tid == 0) {

@@ -292,15 +292,16 @@ int run_vdp(vb_ctx* c, const float* n4, const uint8_t* mask, int n, float thresh
     vbrt::clear_stale_error();
     const VbSubject* subj = subj_ptr(c);
     {
-        // sort buckets (2^13 words) + the scattered keys of a subject in shared memory (one CTA per
-        // SM); the unsorted / sorted key array and the fallback for masks that do not fit live in
-        // a per-CTA scratch in global memory (L2 resident)
+        // sort buckets + the keys of a subject in shared memory (one CTA per SM); the bucketed copy
+        // and the fallback for masks that do not fit live in a per-CTA scratch in global memory (L2)
         const long long vmax = vmax_of(c);
         const long long statics = vbrt::static_smem(vdp_stats_kernel);
-        long long key_cap = std::max<long long>(32, std::min<long long>(vmax, ((long long)c->max_smem - statics) / 4 - (1 << VB_VDP_LOG_BINS)));
+        // words: 2^11 coarse + (2^11 + key_cap / LOAD) fine buckets + key_cap keys
+        const long long avail = ((long long)c->max_smem - statics) / 4 - (2 << VB_VDP_LOG_COARSE);
+        long long key_cap = std::max<long long>(64, std::min<long long>(vmax, avail * VB_VDP_LOAD / (VB_VDP_LOAD + 1))) & ~31LL;
         if (const char* e = getenv("VB_VDP_KEY_CAP"))          // tests: force the global-memory path
-            key_cap = std::max<long long>(32, std::min<long long>(key_cap, atoll(e)));
-        const long long dyn_words = (1 << VB_VDP_LOG_BINS) + key_cap;
+            key_cap = std::max<long long>(64, std::min<long long>(key_cap, atoll(e))) & ~31LL;
+        const long long dyn_words = (2 << VB_VDP_LOG_COARSE) + key_cap / VB_VDP_LOAD + key_cap;
         const int grid = std::min(n, c->sms * 2);
         const size_t stride = (size_t)((vmax + 3) & ~3LL);
         if (!ensure(c->ws_keys_a, 4 * stride * (size_t)grid) || !ensure(c->ws_keys_b, 4 * stride * (size_t)grid)) return VB_ERR_CUDA;
