@@ -243,11 +243,11 @@ class ClockSampler:
 class Leg:
     """One batch on one GPU: resident (`value`) and host-buffer (`e2e`) measurements."""
 
-    def __init__(self, ctx, workload, seeds, local_rank, procs):
+    def __init__(self, ctx, workload, seeds, local_rank, data):
         from vent_analysis_b200 import _lib, cohort
         self.ctx, self.workload = ctx, workload
         self.flags = cohort.ALL_STAGES if WORKLOADS[workload][2] else (_lib.DO_SNR | _lib.DO_N4 | _lib.DO_VDP)
-        self.u16, self.masks = make_batch(workload, seeds, procs)
+        self.u16, self.masks = data
         self.voxs = [subject_geometry(workload, s)[1] for s in seeds]
         self.B = len(seeds)
         self.dc = cohort.DeviceCohort([u.astype(np.float32) for u in self.u16], self.masks, self.voxs, device=local_rank,
@@ -358,6 +358,13 @@ def run_ours(args, rank, local_rank, world):
         B = args.batch if args.batch > 0 else WORKLOADS[wl][1]
         seeds = [rank * B + i for i in range(B)]
     procs = max(1, min(os.cpu_count() or 1, 16) // max(1, min(world, 8)))
+    # every phantom is made BEFORE CUDA / NCCL come up: the generator forks worker processes, and a
+    # fork of a process that already runs NCCL's threads can deadlock in the child
+    data = make_batch(wl, seeds, procs)
+    with_cohort = wl == "C2" and not strong and args.cohort_leg and args.batch <= 0
+    if with_cohort:
+        cseeds = cohort_mod.shard_indices(1024, rank, world)
+        cdata = make_batch("C5", cseeds, procs)
 
     import torch
     import torch.distributed as dist
@@ -384,7 +391,7 @@ def run_ours(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return [float(x) for x in t.cpu()]
 
-    leg = Leg(ctx, wl, seeds, local_rank, procs)
+    leg = Leg(ctx, wl, seeds, local_rank, data)
     B, V = leg.B, leg.V
     r = leg.resident(args.steps, args.warmup, barrier, ClockSampler(local_rank) if rank == 0 else None)
     e = leg.e2e(args.steps, args.warmup, barrier)
@@ -399,11 +406,10 @@ def run_ours(args, rank, local_rank, world):
     # ---- the cohort config (BASELINE.json configs[4]) beside the default run: 1024 mixed-spacing
     # subjects split over the ranks (strong scaling), same two measurements
     cohort_c5 = None
-    if wl == "C2" and not strong and args.cohort_leg and args.batch <= 0:
+    if with_cohort:
         del leg.dc
         torch.cuda.empty_cache()
-        cseeds = cohort_mod.shard_indices(1024, rank, world)
-        cl = Leg(ctx, "C5", cseeds, local_rank, procs)
+        cl = Leg(ctx, "C5", cseeds, local_rank, cdata)
         cr = cl.resident(args.steps, args.warmup, barrier)
         ce = cl.e2e(args.steps, args.warmup, barrier)
         c_ms, c_e2e_ms = reduce_max([cr["ms"], ce["e2e_s"] * 1e3])

@@ -35,11 +35,19 @@ def bind_near_gpu(device=0):
         nodes = [p for p in glob.glob("/sys/devices/system/node/node[0-9]*")]
         if len(nodes) < 2:
             return None
-        import torch
-        bus = torch.cuda.get_device_properties(device).pci_bus_id
-        dom = getattr(torch.cuda.get_device_properties(device), "pci_domain_id", 0)
-        dev = getattr(torch.cuda.get_device_properties(device), "pci_device_id", 0)
-        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        import subprocess
+        # (nvidia-smi, not the CUDA runtime: callers fork worker processes after this)
+        idx = str(device)
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis:
+            ent = [v.strip() for v in vis.split(",") if v.strip()]
+            if device < len(ent):
+                idx = ent[device]
+        bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", idx],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bdf:
+            return None
+        path = f"/sys/bus/pci/devices/{bdf[-12:]}/numa_node"
         node = int(open(path).read().strip())
         if node < 0:
             return None
