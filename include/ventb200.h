@@ -187,6 +187,48 @@ int vb_pipeline_batch_host_packed(vb_ctx* ctx, int32_t n, const int32_t* shapes,
                                   const vb_n4_params* params, float thresh, uint32_t flags,
                                   const vb_host_io* io);
 
+/* ---- overlay compositions: the consumers right behind the path -------------------
+ * vb_overlay_rgb_*: uint8 [rows][cols][slices][3] per subject, a 0/1 array `b` painted on the
+ * min-max normalised |a| (normalisation over the whole volume).
+ *   gui = 0  Vent_Analysis.exportDICOM (V_A.py:387-391): BW = uint8(normalize(|N4HPvent|) * 255) in
+ *            float32, R = 255 on defects else BW, G = B = BW off the defects;
+ *   gui = 1  the GUI's colorBinary + arrayToImage (V_A.py:621,628-634): the same in float64,
+ *            R = uint8((A*(B==0) + B) * 255).
+ * mode: VB_NORM_F32 when the reference would normalise a float32 array, VB_NORM_F64 for integer /
+ * float64 arrays (their values are passed as float32 and must be exact in it, e.g. uint16 DICOM data). */
+#define VB_NORM_F32 0
+#define VB_NORM_F64 1
+#define VB_ERR_EMPTY 5       /* cropToData: an axis has no index > 0 with signal: the reference raises
+                                IndexError (V_A.py:443-451)                                            */
+#define VB_ERR_CI_COLOR 6    /* screenShot: a CI value reached 40 mm, parula[int(CI*64/40)] is out of
+                                range: the reference raises IndexError (V_A.py:482-484)                */
+int vb_overlay_rgb_batch_dev(vb_ctx* ctx, int32_t n, const int32_t* shapes, const float* a, const uint8_t* b,
+                             int32_t gui, int32_t mode, uint8_t* rgb, void* stream);
+int vb_overlay_rgb_batch_host(vb_ctx* ctx, int32_t n, const int32_t* shapes, const float* a, const uint8_t* b,
+                              int32_t gui, int32_t mode, uint8_t* rgb);
+/* Vent_Analysis.cropToData (V_A.py:430-456) on the mask: boxes[6 i ..] = r0, r1, c0, c1, s0, s1
+ * (half-open).  VB_ERR_EMPTY if any subject has no box (its entries are -1). */
+int vb_crop_boxes_batch_host(vb_ctx* ctx, int32_t n, const int32_t* shapes, const uint8_t* mask, int32_t border,
+                             int32_t border_slices, int32_t* boxes);
+/* Vent_Analysis.screenShot (V_A.py:466-494) up to the array handed to PIL: per subject uint8
+ * [7 R][S C][3] (R, C, S = the box of cropToData(mask, border=5)); bands: blank, blank, proton, HPvent,
+ * N4 + mask border, N4 + defects, N4 + CI in parula colours.  Subject i's image starts at byte
+ * out_offset[i] of `out` (out_offset[n] = bytes used; VB_ERR_ARG if out_capacity is too small;
+ * 21 bytes per voxel always suffice). */
+typedef struct vb_montage_inputs {
+    const float* proton;        /* optional (blank band)                                           */
+    const float* image;         /* HPvent                                                          */
+    const float* n4;            /* N4HPvent                                                        */
+    const uint8_t* mask;        /* for the crop box                                                */
+    const uint8_t* mask_border;
+    const uint8_t* defect;
+    const uint16_t* ci_shell;   /* optional: with table_handles and vox_min                        */
+    int32_t image_mode, proton_mode;   /* VB_NORM_F32 / VB_NORM_F64                                */
+} vb_montage_inputs;
+int vb_montage_batch_host(vb_ctx* ctx, int32_t n, const int32_t* shapes, const int32_t* table_handles,
+                          const double* vox_min, const vb_montage_inputs* host, const double* parula64x3,
+                          int32_t* boxes, int64_t* out_offset, uint8_t* out, int64_t out_capacity);
+
 /* Page-locked host memory for the *_host entry points (asynchronous copies need it to overlap with
  * compute).  The pages are touched by the calling thread, so a caller that has bound itself to the
  * CPUs next to the context's GPU gets NUMA-local buffers. */

@@ -389,3 +389,62 @@ def check_packed_io(ctx, shapes=((33, 29, 5), (24, 20, 4), (36, 40, 1), (40, 32,
     with pytest.raises(_lib.VbError) as e:
         ctx.pipeline_host_packed(shapes, flags, image_f32=img, mask_u8=msk, handles=handles, params=p, buffers=small)
     assert e.value.code == _lib.VB_ERR_ARG
+
+
+def check_overlays(ctx):
+    """Overlay compositions through the C ABI against arrays produced by the reference's
+    own exportDICOM / cropToData / screenShot / colorBinary (tests/golden/overlay_small_b.npz), bit
+    exact; plus a ragged batch against the oracle, the float64 (integer image) mode, a flat image,
+    and the two IndexError cases of the reference."""
+    import pytest
+    from oracle import overlay_oracle
+    g = golden("overlay_small_b.npz")
+    v, shape, vox, img, mask, n4 = golden_inputs("small_b")
+    out = check_vdp_ci_against_golden(ctx, "small_b", True)
+    defect, mborder, shell = out["defect"].reshape(shape), out["mask_border"].reshape(shape), out["ci_shell"].reshape(shape)
+    tbl = generate(vox, 50)
+    h = ctx.ci_table(tbl, shape, key=(tuple(vox), 50, tbl.shape[0]))
+    proton = (500.0 * np.random.default_rng(int(g["proton_seed"])).random(shape)).astype(np.float32)
+    assert np.array_equal(ctx.overlay_rgb_host([shape], n4, defect).reshape(shape + (3,)), g["export_rgb"])
+    assert np.array_equal(ctx.overlay_rgb_host([shape], n4, defect, gui=True).reshape(shape + (3,)), g["gui_defect"])
+    assert np.array_equal(ctx.overlay_rgb_host([shape], img, mborder, gui=True).reshape(shape + (3,)), g["gui_raw_border"])
+    assert [int(x) for x in ctx.crop_boxes_host([shape], mask, border=5)[0]] == [int(x) for x in g["crop_box"]]
+    imgs, boxes = ctx.montage_host([shape], img, n4, mask, mborder, defect, g["parula"], proton=proton, ci_shell=shell,
+                                   handles=[h], vox_min=[min(vox)])
+    assert imgs[0].shape == g["screenshot"].shape and np.array_equal(imgs[0], g["screenshot"])
+    # ragged batch, integer-valued image (float64 normalisation), against the oracle
+    rng = np.random.default_rng(8)
+    shapes = [(20, 17, 4), (33, 12, 3), (16, 16, 5)]
+    vols = []
+    for i, s_ in enumerate(shapes):
+        im, mk = phantom(s_, vox, 70 + i)
+        u16 = np.rint(im).astype(np.uint16)
+        x4 = (im * (1 + 0.1 * rng.random(s_))).astype(np.float32)
+        df = ((rng.random(s_) < 0.3) & (mk > 0)).astype(np.uint8)
+        vols.append((u16, mk, x4, df, vdp_oracle.border(mk).astype(np.uint8), (300 * rng.random(s_)).astype(np.float32)))
+    cat = lambda k, dt=None: np.concatenate([np.asarray(v_[k], dtype=dt).ravel() for v_ in vols])
+    rgb = ctx.overlay_rgb_host(shapes, cat(2), cat(3))
+    rgb_u16 = ctx.overlay_rgb_host(shapes, cat(0), cat(4), gui=True)
+    boxes = ctx.crop_boxes_host(shapes, cat(1), border=2, border_slices=True)
+    imgs, mboxes = ctx.montage_host(shapes, cat(0), cat(2), cat(1), cat(4), cat(3), g["parula"], proton=cat(5))
+    off = 0
+    for i, ((u16, mk, x4, df, bd, pr), s_) in enumerate(zip(vols, shapes)):
+        V = u16.size
+        assert np.array_equal(rgb[3 * off:3 * (off + V)].reshape(s_ + (3,)), overlay_oracle.export_rgb(x4, df)), s_
+        assert np.array_equal(rgb_u16[3 * off:3 * (off + V)].reshape(s_ + (3,)), overlay_oracle.color_binary(u16, bd)), s_
+        assert [int(x) for x in boxes[i]] == list(overlay_oracle.crop_box(mk, border=2, border_slices=True))
+        ref = overlay_oracle.screenshot_image(u16, pr, x4, mk.astype(np.float64), bd, df, np.zeros(s_), g["parula"])
+        assert np.array_equal(imgs[i], ref), s_
+        off += V
+    # a flat image is returned as it is by normalize(): uint8 wrap of x * 255
+    flat = np.full((8, 8, 2), 3.0, np.float32)
+    z = np.zeros((8, 8, 2), np.uint8)
+    assert np.array_equal(ctx.overlay_rgb_host([(8, 8, 2)], flat, z).reshape(8, 8, 2, 3), overlay_oracle.export_rgb(flat, z))
+    # reference IndexErrors: no index > 0 with signal; a CI value >= 40 mm
+    with pytest.raises(IndexError):
+        ctx.crop_boxes_host([(8, 8, 2)], z)
+    big = np.zeros(shape, np.uint16) + _lib.CI_OFF
+    big[defect > 0] = len(ctx.ci_radii(h)) - 1                        # 49.99 voxels * 1.5 mm
+    with pytest.raises(IndexError):
+        ctx.montage_host([shape], img, n4, mask, mborder, defect, g["parula"], proton=proton, ci_shell=big, handles=[h],
+                         vox_min=[min(vox)])

@@ -146,3 +146,36 @@ def test_build4DdataArray_identical_to_the_reference_output(ctx):
 
 def test_compact_host_io_equals_the_dense_path(ctx):
     helpers.check_packed_io(ctx)
+
+
+def test_overlay_compositions_bit_exact_vs_reference(ctx):
+    helpers.check_overlays(ctx)
+
+
+def test_class_overlay_methods(ctx, monkeypatch, tmp_path):
+    """exportDICOM pixel data and the screenShot array of the class mirror equal the reference's own
+    (tests/golden/overlay_small_b.npz) when the class is given the fixture's N4 volume."""
+    from vent_analysis_b200 import Vent_Analysis
+    import types
+    monkeypatch.setitem(_lib._CTX, 0, ctx)
+    g = helpers.golden("overlay_small_b.npz")
+    v0, shape, vox, img, mask, n4 = helpers.golden_inputs("small_b")
+    v = helpers.quiet(Vent_Analysis, xenon_array=img, mask_array=mask.astype(np.float64), vox=vox)
+    v.N4_bias_correction = lambda a, b: n4                     # (the reference run had N4 pinned the same way)
+    out = ctx.pipeline_host([shape], _lib.DO_VDP, mask=mask, n4=n4)
+    v.N4HPvent = n4
+    v.defectArray = out["defect"].reshape(shape).astype(np.float64)
+    v.metadata["VDP"] = 1.0
+    helpers.quiet(v.calculate_CI)
+    v.proton = (500.0 * np.random.default_rng(int(g["proton_seed"])).random(shape)).astype(np.float32)
+    assert np.array_equal(v._overlay_rgb(), g["export_rgb"])
+    assert np.array_equal(v.screenShotArray(parula=g["parula"]), g["screenshot"])
+    helpers.quiet(v.screenShot, str(tmp_path / "shot.png"), parula=g["parula"])
+    assert (tmp_path / "shot.png").stat().st_size > 1000
+    assert "defectArray: array(48, 40, 6)" in repr(v)
+    # labels other than 0/1: N4 / SNR / borders run like the reference (label 1 / > 0), VDP refuses
+    m2 = mask.astype(np.float64).copy(); m2[:24] *= 2
+    v2 = helpers.quiet(Vent_Analysis, xenon_array=img, mask_array=m2, vox=vox)
+    assert v2.N4_bias_correction(img, m2).shape == shape
+    with pytest.raises(ValueError):
+        helpers.quiet(v2.calculate_VDP)

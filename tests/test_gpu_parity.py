@@ -195,3 +195,7 @@ def test_build4DdataArray_identical_to_the_reference_output(ctx):
 
 def test_compact_host_io_equals_the_dense_path(ctx):
     helpers.check_packed_io(ctx)
+
+
+def test_overlay_compositions_bit_exact_vs_reference(ctx):
+    helpers.check_overlays(ctx)

@@ -107,60 +107,54 @@ class Vent_Analysis:
         self.metadata['LungVolume'] = np.sum(self.mask == 1) * np.prod(np.divide(self.vox, 10)) / 1000
 
     # ------------------------------------------------------------------ file input (host side)
+    # Out of the hot path: thin pydicom glue with the reference's signatures and
+    # array conventions, so that the GUI's calls keep working.
     def openSingleDICOM(self, dicom_path):
-        """Vent_Analysis.py:169-181: one multi-frame DICOM -> [row, col, slice]."""
-        import pydicom as dicom
-        ds = dicom.dcmread(dicom_path, force=dicom_path is None)
-        arr = np.transpose(ds.pixel_array, (1, 2, 0))
-        print(f'\033[32mI opened a DICOM of shape {arr.shape}\033[37m')
-        return ds, arr
+        """One multi-frame DICOM -> (dataset, [row, col, slice] array)  (Vent_Analysis.py:169-181)."""
+        import pydicom
+        ds = pydicom.dcmread(dicom_path)
+        return ds, np.moveaxis(ds.pixel_array, 0, -1)
 
     def openDICOMfolder(self, maskFolder):
-        """Vent_Analysis.py:184-196: a folder of 2D DICOMs -> float64 [row, col, slice]."""
-        import pydicom as dicom
-        files = [f for f in sorted(os.listdir(maskFolder)) if f.endswith('.dcm')]
-        ds = dicom.dcmread(os.path.join(maskFolder, files[0]))
-        mask = np.zeros((ds.pixel_array.shape[0], ds.pixel_array.shape[1], len(files)))
-        for k, f in enumerate(files):
-            ds = dicom.dcmread(os.path.join(maskFolder, f))
-            mask[:, :, k] = ds.pixel_array
-        print(f'\033[32mI built a mask of shape {mask.shape}\033[37m')
-        return ds, mask
+        """A folder of single-slice DICOMs -> (last dataset, float64 [row, col, slice])  (:184-196)."""
+        import pydicom
+        names = sorted(f for f in os.listdir(maskFolder) if f.endswith('.dcm'))
+        sets = [pydicom.dcmread(os.path.join(maskFolder, f)) for f in names]
+        return sets[-1], np.stack([d.pixel_array for d in sets], axis=-1).astype(np.float64)
 
     def pullDICOMHeader(self):
-        """Vent_Analysis.py:198-223: patient fields + voxel size from the DICOM header."""
-        for elem in ['PatientName', 'PatientAge', 'PatientBirthDate', 'PatientSize', 'PatientWeight', 'PatientSex',
-                     'StudyDate', 'StudyTime', 'SeriesTime']:
+        """Patient fields and the voxel size [mm] from ``self.ds``  (:198-223)."""
+        for key in ('PatientName', 'PatientAge', 'PatientBirthDate', 'PatientSize', 'PatientWeight', 'PatientSex',
+                    'StudyDate', 'StudyTime', 'SeriesTime'):
+            self.metadata[key] = getattr(self.ds, key, '')
+        inplane = None
+        for frame in self.ds.get((0x5200, 0x9230), []):               # per-frame functional groups
             try:
-                self.metadata[elem] = self.ds[elem].value
-            except Exception:
-                print(f'\033[31mNo {elem}\033[37m')
-                self.metadata[elem] = ''
-        for k in range(100):
-            try:
-                self.vox = self.ds[0x5200, 0x9230][k]['PixelMeasuresSequence'][0].PixelSpacing
+                inplane = frame.PixelMeasuresSequence[0].PixelSpacing
                 break
-            except Exception:
-                if k == 99:
-                    print('Pixel Spacing not in correct place in DICOM header, please enter each dimension...')
-                    self.vox = [float(input()), float(input())]
-        try:
-            self.vox = [float(self.vox[0]), float(self.vox[1]), float(self.ds.SpacingBetweenSlices)]
-        except Exception:
-            print('Slice spacing not in correct position in DICOM header. Please enter manually:')
-            self.vox = [float(self.vox[0]), float(self.vox[1]), float(input())]
+            except (AttributeError, IndexError):
+                continue
+        if inplane is None:
+            raise ValueError("PixelSpacing not found in the DICOM header: pass vox=[dx, dy, dz] instead")
+        self.vox = [float(inplane[0]), float(inplane[1]), float(self.ds.SpacingBetweenSlices)]
         self.metadata['LungVolume'] = np.sum(self.mask == 1) * np.prod(np.divide(self.vox, 10)) / 1000
 
     # --------------------------------------------------------------------------- GPU hot path
     def _ctx(self):
         return _lib.context(getattr(self, '_device', 0))
 
-    def _mask_u8(self, mask=None):
+    def _mask_u8(self, mask=None, binary=False):
+        """The mask as label bytes (Vent_Analysis.py:323, :327: float32 -> UInt8).  Like the reference,
+        N4 works on label 1 and SNR on ``mask > 0`` whatever other labels are present; ``binary``:
+        ``calculate_VDP`` needs a 0/1 mask (with other labels the reference's threshold image and
+        linear-binning codes get multiplied by the label values, :249, :256 -- not reproduced)."""
         m = self.mask if mask is None else mask
-        m8 = np.asarray(m).astype(np.float32).astype(np.uint8)     # Vent_Analysis.py:323, :327
-        if not np.array_equal(m8 > 0, np.asarray(m) > 0) or m8.max(initial=0) > 1:
-            raise ValueError("mask must be binary (0/1): the reference mixes mask==1, mask>0 and "
-                             "sum(mask) (Vent_Analysis.py:166,:245,:251)")
+        m8 = np.asarray(m).astype(np.float32).astype(np.uint8)
+        if not np.array_equal(m8 > 0, np.asarray(m) > 0):
+            raise ValueError("mask labels must be integers in [0, 255]")
+        if binary and m8.max(initial=0) > 1:
+            raise ValueError("calculate_VDP needs a binary (0/1) mask: with other labels the reference weights its "
+                             "threshold image by the label (Vent_Analysis.py:249,:256)")
         return np.ascontiguousarray(m8)
 
     def calculateBorder(self, A):
@@ -208,7 +202,7 @@ class Vent_Analysis:
         """Vent_Analysis.py:239-263: SNR, N4, mean-anchored VDP (60 % threshold + per-slice 3x3
         median), defect border, linear-binning VDP -- one library call."""
         HP = np.asarray(self.HPvent)
-        m8 = self._mask_u8()
+        m8 = self._mask_u8(binary=True)
         out = self._ctx().pipeline_host([HP.shape], _lib.DO_SNR | _lib.DO_N4 | _lib.DO_VDP,
                                         image=HP.astype(np.float32), mask=m8, thresh=thresh)
         st = out["stats"][0]
@@ -263,22 +257,115 @@ class Vent_Analysis:
         return A[r0:r1, c0:c1, s0:s1], list(range(r0, r1)), list(range(c0, c1)), list(range(s0, s1))
 
     def pickleMe(self, pickle_path='C:/PIRL/data/VentPickle.pkl'):
-        """Vent_Analysis.py:542-553."""
-        pickle_dict = {}
-        for attr in vars(self):
+        """Every picklable attribute as one dict in a pickle file  (Vent_Analysis.py:542-553)."""
+        state = {}
+        for name, value in vars(self).items():
             try:
-                pickle.dumps(getattr(self, attr))
-                pickle_dict[attr] = getattr(self, attr)
-            except (pickle.PicklingError, AttributeError, TypeError):
-                print(f"\033[31mSkipping non-picklable attribute: {attr}\033[37m")
-        with open(pickle_path, 'wb') as file:
-            pickle.dump(pickle_dict, file)
+                pickle.dumps(value)
+            except Exception:
+                print(f"\033[31mSkipping non-picklable attribute: {name}\033[37m")
+                continue
+            state[name] = value
+        with open(pickle_path, 'wb') as f:
+            pickle.dump(state, f)
         print(f'\033[32mPickled dictionary saved to {pickle_path}\033[37m')
 
     def unPickleMe(self, pickle_dict):
-        """Vent_Analysis.py:556-559."""
-        for attr, value in pickle_dict.items():
-            setattr(self, attr, value)
+        """Restore the attributes saved by :meth:`pickleMe`  (:556-559)."""
+        vars(self).update(pickle_dict)
+
+    # ---------------------------------------------------- overlay compositions (SURVEY.md 8f3)
+    def _overlay_rgb(self):
+        """uint8 [rows, cols, slices, 3]: defects in red on the normalised |N4HPvent|
+        (Vent_Analysis.py:387-391).  Kernels: ``ovl_minmax_kernel`` + ``ovl_rgb_kernel``."""
+        shape = self.N4HPvent.shape
+        d8 = np.ascontiguousarray(np.asarray(self.defectArray) == 1, dtype=np.uint8)
+        return self._ctx().overlay_rgb_host([shape], self.N4HPvent, d8).reshape(shape + (3,))
+
+    def exportDICOM(self, ds, save_dir='C:/PIRL/data/', optional_text='', forPACS=True):
+        """Vent_Analysis.py:380-428: the defect overlay as RGB DICOM(s).  The pixel arithmetic runs on
+        the GPU; writing the files is pydicom's."""
+        if self.metadata['VDP'] == '':
+            print('\033[31mCant export dicoms until you run calculate_VDP()...\033[37m')
+            return
+        import pydicom
+        rgb = self._overlay_rgb()
+        rows, cols, slices = rgb.shape[:3]
+        desc = f"{optional_text} - VDP: {np.round(self.metadata['VDP'], 1)}"
+        ds.PhotometricInterpretation, ds.SamplesPerPixel = 'RGB', 3
+        ds.BitsAllocated = ds.BitsStored = 8
+        ds.SeriesDescription = desc
+        if not forPACS:                                   # one multi-frame object, slices first
+            ds.Rows, ds.Columns, ds.NumberOfFrames = rows, cols, slices
+            ds.HighBit = 7
+            ds.SOPInstanceUID = ds.SeriesInstanceUID = pydicom.uid.generate_uid()
+            ds.PixelData = np.ascontiguousarray(np.moveaxis(rgb, 2, 0)).tobytes()
+            path = os.path.join(save_dir, f"{self.metadata['PatientName']}_defectDICOM.dcm")
+            ds.save_as(path)
+            print(f'\033[32mdefect DICOM saved to {path}\033[37m')
+            return
+        self.ds.SeriesInstanceUID = pydicom.uid.generate_uid()
+        folder = os.path.join(save_dir, 'defectDICOMS')
+        os.makedirs(folder, exist_ok=True)
+        for k in range(slices):                           # one file per slice
+            ds.PixelData = np.ascontiguousarray(rgb[:, :, k, :]).tobytes()
+            ds.Rows, ds.Columns, ds.NumberOfFrames = rows, cols, 1
+            ds.InstanceNumber, ds.SliceLocation = k + 1, k
+            ds.SOPInstanceUID = pydicom.uid.generate_uid()
+            ds.save_as(os.path.join(folder, f"dicom_{k}.dcm"))
+
+    def _parula(self, parula=None):
+        if parula is not None:
+            return np.asarray(parula, dtype=np.float64)
+        for path in (r'C:\PIRL\data\parula.np.npy', 'parula.npy', os.path.join(os.path.dirname(__file__), 'parula.npy')):
+            if os.path.exists(path):
+                return np.load(path)
+        raise FileNotFoundError("parula colour table (64 x 3) not found: pass parula= or put parula.npy in the working directory")
+
+    def screenShotArray(self, parula=None):
+        """The montage image of Vent_Analysis.py:466-494 before any text: uint8 [7 R, S C, 3] (bands:
+        blank, blank, proton, HPvent, N4 + mask border, N4 + defects, N4 + CI in parula colours).
+        Kernels: ``ovl_cropbox_kernel``, ``ovl_minmax_kernel``, ``ovl_montage_kernel``."""
+        ctx, shape = self._ctx(), np.asarray(self.HPvent).shape
+        m8 = self._mask_u8()
+        kw = {}
+        if not isinstance(self.CIarray, str):
+            from .sphere_table import get_sphere_pix
+            vox = [float(v) for v in self.vox]
+            tbl = get_sphere_pix(vox, 50)
+            h = ctx.ci_table(tbl, shape, key=(tuple(vox), 50, tbl.shape[0]))
+            radii = ctx.ci_radii(h)
+            shell = np.full(shape, _lib.CI_OFF, dtype=np.uint16)
+            sel = np.asarray(self.CIarray) > 0
+            shell[sel] = np.searchsorted(radii * np.min(self.vox), np.asarray(self.CIarray)[sel])
+            kw = dict(ci_shell=shell, handles=[h], vox_min=[float(np.min(self.vox))])
+        imgs, _ = ctx.montage_host([shape], self.HPvent, self.N4HPvent, m8, np.asarray(self.mask_border) != 0,
+                                   np.asarray(self.defectArray) > 0, self._parula(parula), proton=self.proton, **kw)
+        return imgs[0]
+
+    def screenShot(self, path='C:/PIRL/data/screenShotTest.png', normalize95=False, parula=None):
+        """Vent_Analysis.py:458-520: the montage with the study text, saved as PNG."""
+        from PIL import Image, ImageDraw, ImageFont
+        image = Image.fromarray(self.screenShotArray(parula))
+        try:
+            font = ImageFont.truetype('arial.ttf', size=35)
+        except OSError:
+            font = ImageFont.load_default()
+        draw, md = ImageDraw.Draw(image), self.metadata
+        h = image.size[1] / 7
+        lines = [(0.00, 0.10, f"Patient: {md['PatientName']} ({md['PatientAge']}/{md['PatientSex']})"),
+                 (0.00, 0.40, f"Disease: {md['Disease']}"), (0.00, 0.70, f"StudyDate: {md['StudyDate']}"),
+                 (0.00, 1.00, f"Visit#: {md['visit']}"), (0.00, 1.30, f"Treatment: {md['treatment']}"),
+                 (0.25, 0.10, f"Lung Volume: {np.round(md['LungVolume'] * 1000)} mL"),
+                 (0.25, 0.40, f"Defect Volume: {np.round(md['DefectVolume'] * 1000)} mL" if md['DefectVolume'] != '' else ''),
+                 (0.50, 0.10, f"DE: {md['DE']} mL"), (0.50, 0.40, f"FEV1: {md['FEV1']} %"),
+                 (0.50, 0.70, f"VDP: {np.round(md['VDP'], 1)} %" if md['VDP'] != '' else ''),
+                 (0.50, 1.00, f"CI: {np.round(md['CI'])} %" if md['CI'] != '' else ''),
+                 (0.75, 0.25, f"Analysis Version: {self.version}"), (0.75, 0.50, f"Analyzed by: {md['analysisUser']}")]
+        for fx, fy, text in lines:
+            draw.text((10 + fx * image.size[0], fy * h), text, fill=(255, 255, 255), font=font)
+        image.save(path, 'PNG')
+        print(f'\033[32mScreenshot saved to {path}\033[37m')
 
     def _out_of_scope(self, name):
         raise NotImplementedError(
@@ -288,12 +375,6 @@ class Vent_Analysis:
     def exportNifti(self, filepath=None, fileName=None):
         self._out_of_scope("exportNifti")
 
-    def exportDICOM(self, ds, save_dir='C:/PIRL/data/', optional_text='', forPACS=True):
-        self._out_of_scope("exportDICOM")
-
-    def screenShot(self, path='C:/PIRL/data/screenShotTest.png', normalize95=False):
-        self._out_of_scope("screenShot")
-
     def process_RAW(self, filepath=None):
         self._out_of_scope("process_RAW")
 
@@ -301,19 +382,15 @@ class Vent_Analysis:
         self._out_of_scope("dicom_to_json")
 
     def __repr__(self):
-        """Vent_Analysis.py:562-577."""
-        string = f'\033[35mVent_Analysis\033[37m class object version \033[94m{self.version}\033[37m\n'
-        for attr, value in vars(self).items():
-            if isinstance(value, str) and value == '':
-                string += f'\033[31m {attr}: \033[37m\n'
-            elif type(value) is np.ndarray:
-                string += f'\033[32m {attr}: \033[36m{value.shape} \033[37m\n'
-            elif type(value) is dict:
-                for attr2, value2 in value.items():
-                    if isinstance(value2, str) and value2 == '':
-                        string += f'   \033[31m {attr2}: \033[37m\n'
-                    else:
-                        string += f'   \033[32m {attr2}: \033[36m{value2} \033[37m\n'
-            else:
-                string += f'\033[32m {attr}: \033[36m{type(value)} \033[37m\n'
-        return string
+        """One line per attribute: arrays by shape, metadata by value (cf. Vent_Analysis.py:562-577)."""
+        def show(v):
+            if isinstance(v, np.ndarray):
+                return f"array{v.shape} {v.dtype}"
+            return "(unset)" if isinstance(v, str) and v == '' else (v if np.isscalar(v) else type(v).__name__)
+        out = [f"Vent_Analysis (B200) version {self.version}"]
+        for name, value in vars(self).items():
+            if isinstance(value, dict):
+                out += [f"   {k}: {show(v)}" for k, v in value.items()]
+            elif not name.startswith('_'):
+                out.append(f" {name}: {show(value)}")
+        return "\n".join(out)

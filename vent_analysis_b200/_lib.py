@@ -14,7 +14,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libventb200.so")
 
-VB_OK, VB_ERR_CUDA, VB_ERR_ARG, VB_ERR_UNSUPPORTED, VB_ERR_CI_RMAX = 0, 1, 2, 3, 4
+VB_OK, VB_ERR_CUDA, VB_ERR_ARG, VB_ERR_UNSUPPORTED, VB_ERR_CI_RMAX, VB_ERR_EMPTY, VB_ERR_CI_COLOR = 0, 1, 2, 3, 4, 5, 6
+NORM_F32, NORM_F64 = 0, 1
 DO_SNR, DO_N4, DO_VDP, DO_CI, DO_MASK_BORDER, HOST_STATS_ONLY = 1, 2, 4, 8, 16, 32
 MAX_LEVELS = 8
 CI_OFF = 0xFFFF
@@ -59,6 +60,13 @@ class HostIO(C.Structure):
                 ("ci_value", C.c_void_p), ("ci_capacity", C.c_int64), ("ci_offset", C.c_void_p), ("stats", C.c_void_p)]
 
 
+class MontageInputs(C.Structure):
+    """``vb_montage_inputs``"""
+    _fields_ = [("proton", C.c_void_p), ("image", C.c_void_p), ("n4", C.c_void_p), ("mask", C.c_void_p),
+                ("mask_border", C.c_void_p), ("defect", C.c_void_p), ("ci_shell", C.c_void_p),
+                ("image_mode", C.c_int32), ("proton_mode", C.c_int32)]
+
+
 CODE_LB_MASK, CODE_DEFECT, CODE_DEFECT_BORDER, CODE_MASK_BORDER = 7, 8, 16, 32
 
 
@@ -87,7 +95,8 @@ class VbError(RuntimeError):
 EXPORTS = ["vb_version", "vb_last_error", "vb_device_count", "vb_create", "vb_destroy", "vb_launch_count",
            "vb_n4_default_params", "vb_ci_table_create", "vb_ci_table_radii", "vb_snr_batch_dev", "vb_n4_batch_dev",
            "vb_vdp_batch_dev", "vb_border_batch_dev", "vb_ci_batch_dev", "vb_pipeline_batch_dev",
-           "vb_pipeline_batch_host", "vb_pipeline_batch_host_packed", "vb_host_alloc", "vb_host_free", "vb_pack6_batch_dev", "vb_pack6_batch_host", "vb_set_profiling", "vb_profile_fetch", "vb_set_debug", "vb_n4_debug_fetch"]
+           "vb_pipeline_batch_host", "vb_pipeline_batch_host_packed", "vb_host_alloc", "vb_host_free", "vb_overlay_rgb_batch_dev", "vb_overlay_rgb_batch_host", "vb_crop_boxes_batch_host",
+           "vb_montage_batch_host", "vb_pack6_batch_dev", "vb_pack6_batch_host", "vb_set_profiling", "vb_profile_fetch", "vb_set_debug", "vb_n4_debug_fetch"]
 N_STAGES = 5
 STAGE_NAMES = ("snr", "n4", "vdp", "mask_border", "ci")
 
@@ -118,6 +127,10 @@ def bind(path):
     lib.vb_pipeline_batch_host_packed.argtypes = [vp, i32, vp, vp, C.POINTER(N4Params), f32, u32, C.POINTER(HostIO)]
     lib.vb_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.vb_host_free.argtypes = [vp, vp]
+    lib.vb_overlay_rgb_batch_dev.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp, vp]
+    lib.vb_overlay_rgb_batch_host.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp]
+    lib.vb_crop_boxes_batch_host.argtypes = [vp, i32, vp, vp, i32, i32, vp]
+    lib.vb_montage_batch_host.argtypes = [vp, i32, vp, vp, vp, C.POINTER(MontageInputs), vp, vp, vp, vp, i64]
     lib.vb_pack6_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.vb_pack6_batch_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.vb_set_profiling.argtypes = [vp, i32]
@@ -365,6 +378,93 @@ class Context:
         if rc not in (VB_OK, VB_ERR_CI_RMAX):
             self.check(rc)
         return out
+
+    # -- overlay compositions ------------------------------------------------------
+    @staticmethod
+    def norm_mode(a):
+        """How the reference's ``normalize`` would compute on array ``a``: float32 arithmetic for a
+        float32 array, float64 otherwise (the values must then be exact in float32: the kernels take
+        float32 arrays)."""
+        a = np.asarray(a)
+        if a.dtype == np.float32:
+            return NORM_F32, a
+        a32 = a.astype(np.float32)
+        if not np.array_equal(a32.astype(np.float64), a.astype(np.float64)):
+            raise ValueError("overlay: values of a non-float32 array must be exactly representable in float32")
+        return NORM_F64, a32
+
+    def overlay_rgb_host(self, shapes, a, b, gui=False):
+        """``exportDICOM`` (gui=False, Vent_Analysis.py:387-391) / GUI ``colorBinary`` (gui=True, :628-634)
+        overlay of the 0/1 array ``b`` on ``a`` -> uint8 ``[3 V]`` (per subject ``[rows, cols, slices, 3]``)."""
+        shapes = np.ascontiguousarray(shapes, dtype=np.int32).reshape(-1, 3)
+        V = int(np.prod(shapes.astype(np.int64), axis=1).sum())
+        mode, a32 = self.norm_mode(a)
+        a32 = np.ascontiguousarray(a32).reshape(-1)
+        b8 = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1)
+        assert a32.size == V and b8.size == V
+        rgb = np.empty(3 * V, dtype=np.uint8)
+        self.check(self.lib.vb_overlay_rgb_batch_host(self.h, shapes.shape[0], _ptr(shapes), _ptr(a32), _ptr(b8),
+                                                      1 if gui else 0, mode, _ptr(rgb)))
+        return rgb
+
+    def crop_boxes_host(self, shapes, mask, border=0, border_slices=False):
+        """``cropToData`` boxes (Vent_Analysis.py:430-456): int32 ``[n, 6]`` = r0, r1, c0, c1, s0, s1.
+        Raises IndexError like the reference when a subject has no box."""
+        shapes = np.ascontiguousarray(shapes, dtype=np.int32).reshape(-1, 3)
+        m8 = np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1)
+        boxes = np.empty((shapes.shape[0], 6), dtype=np.int32)
+        rc = self.lib.vb_crop_boxes_batch_host(self.h, shapes.shape[0], _ptr(shapes), _ptr(m8), int(border),
+                                               1 if border_slices else 0, _ptr(boxes))
+        if rc == VB_ERR_EMPTY:
+            raise IndexError("list index out of range")
+        self.check(rc)
+        return boxes
+
+    def montage_host(self, shapes, image, n4, mask, mask_border, defect, parula, proton=None, ci_shell=None, handles=None,
+                     vox_min=None):
+        """``screenShot`` montage (Vent_Analysis.py:466-494, before the text) for a batch: returns
+        ``(list of uint8 [7 R, S C, 3] arrays, boxes [n, 6])``.  IndexError like the reference when the
+        mask has no crop box or a CI value reaches 40 mm."""
+        shapes = np.ascontiguousarray(shapes, dtype=np.int32).reshape(-1, 3)
+        n = shapes.shape[0]
+        V = int(np.prod(shapes.astype(np.int64), axis=1).sum())
+        imode, im32 = self.norm_mode(image)
+        inp = MontageInputs()
+        keep = [np.ascontiguousarray(im32).reshape(-1), np.ascontiguousarray(n4, dtype=np.float32).reshape(-1),
+                np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1), np.ascontiguousarray(mask_border, dtype=np.uint8).reshape(-1),
+                np.ascontiguousarray(defect, dtype=np.uint8).reshape(-1)]
+        assert all(k.size == V for k in keep)
+        inp.image, inp.n4, inp.mask, inp.mask_border, inp.defect = (k.ctypes.data for k in keep)
+        inp.image_mode = imode
+        if proton is not None:
+            pmode, p32 = self.norm_mode(proton)
+            p32 = np.ascontiguousarray(p32).reshape(-1)
+            keep.append(p32)
+            inp.proton, inp.proton_mode = p32.ctypes.data, pmode
+        hd = vm = None
+        if ci_shell is not None:
+            sh = np.ascontiguousarray(ci_shell, dtype=np.uint16).reshape(-1)
+            keep.append(sh)
+            inp.ci_shell = sh.ctypes.data
+            hd = np.ascontiguousarray(handles, dtype=np.int32)
+            vm = np.ascontiguousarray(vox_min, dtype=np.float64).reshape(-1)
+        par = np.ascontiguousarray(parula, dtype=np.float64)
+        assert par.shape == (64, 3)
+        boxes = np.empty((n, 6), dtype=np.int32)
+        off = np.zeros(n + 1, dtype=np.int64)
+        out = np.empty(21 * V, dtype=np.uint8)
+        rc = self.lib.vb_montage_batch_host(self.h, n, _ptr(shapes), _ptr(hd), _ptr(vm), C.byref(inp), _ptr(par), _ptr(boxes),
+                                            _ptr(off), _ptr(out), out.size)
+        if rc == VB_ERR_EMPTY:
+            raise IndexError("list index out of range")
+        if rc == VB_ERR_CI_COLOR:
+            raise IndexError("index out of bounds for axis 0 with size 64")
+        self.check(rc)
+        imgs = []
+        for i in range(n):
+            R, Cc, S = (int(boxes[i, 1] - boxes[i, 0]), int(boxes[i, 3] - boxes[i, 2]), int(boxes[i, 5] - boxes[i, 4]))
+            imgs.append(out[off[i]:off[i + 1]].reshape(7 * R, S * Cc, 3).copy())
+        return imgs, boxes
 
     def ci_host(self, defect, shapes, handles):
         """CI stage alone on host arrays: defect uint8 0/1 -> (ci_shell uint16, stats, rc)."""

@@ -12,6 +12,7 @@
 #include "vdp_kernels.cuh"
 #include "ci_kernels.cuh"
 #include "io_kernels.cuh"
+#include "overlay_kernels.cuh"
 
 namespace {
 
@@ -69,6 +70,7 @@ struct vb_ctx {
     Buf m_proton, m_pack, d_voxmin;
     Buf m_u16, m_bits, m_codes, m_ci_idx, m_ci_val, d_bitoff;   // compact host I/O
     std::vector<long long> last_bitoff;
+    Buf d_ovl, m_rgb, m_ovl_in[6], d_parula, d_outoff;   // overlay compositions
 };
 
 namespace {
@@ -432,7 +434,8 @@ void vb_destroy(vb_ctx* c) {
     Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_d0, &c->ws_keys_a, &c->ws_keys_b,
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
                    &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats, &c->m_proton, &c->m_pack, &c->d_voxmin,
-                   &c->m_u16, &c->m_bits, &c->m_codes, &c->m_ci_idx, &c->m_ci_val, &c->d_bitoff};
+                   &c->m_u16, &c->m_bits, &c->m_codes, &c->m_ci_idx, &c->m_ci_val, &c->d_bitoff,
+                   &c->d_ovl, &c->m_rgb, &c->m_ovl_in[0], &c->m_ovl_in[1], &c->m_ovl_in[2], &c->m_ovl_in[3], &c->m_ovl_in[4], &c->m_ovl_in[5], &c->d_parula, &c->d_outoff};
     for (Buf* b : bufs) vbrt::dev_free(b->p);
     for (TableHost& t : c->tables) { vbrt::dev_free(t.d_rows); vbrt::dev_free(t.d_ii); vbrt::dev_free(t.d_up); vbrt::dev_free(t.d_radii); }
     vbrt::host_free(c->h_desc.p);
@@ -958,6 +961,154 @@ int vb_pipeline_batch_host_packed(vb_ctx* c, int32_t n, const int32_t* shapes, c
     if (flags & VB_DO_CI)
         for (int i = 0; i < n; ++i)
             if (io->stats[i].ci_error) return fail(VB_ERR_CI_RMAX, "CI: maximum sphere radius reached (table exhausted)");
+    return VB_OK;
+}
+
+// ------------------------------------------------------------------------------- overlays (8f3)
+static int ovl_begin(vb_ctx* c, int n, vbrt::stream_t s) {
+    if (!ensure(c->d_ovl, sizeof(OvlStats) * (size_t)n)) return VB_ERR_CUDA;
+    vbrt::clear_stale_error();
+    VB_LAUNCH(ovl_init_kernel, dim3((n + 127) / 128), dim3(128), 0, s, (OvlStats*)c->d_ovl.p, subj_ptr(c), n);
+    ++c->launches;
+    return VB_OK;
+}
+
+int vb_overlay_rgb_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const float* a, const uint8_t* b,
+                             int32_t gui, int32_t mode, uint8_t* rgb, void* stream) {
+    if (!c || !a || !b || !rgb) return fail(VB_ERR_ARG, "overlay_rgb: null argument");
+    if (mode != VB_NORM_F32 && mode != VB_NORM_F64) return fail(VB_ERR_ARG, "overlay_rgb: bad mode");
+    vbrt::set_device(c->device);
+    vbrt::stream_t s = (vbrt::stream_t)stream;
+    int rc = prepare(c, n, shapes, nullptr, s);
+    if (rc) return rc;
+    c->r0 = 0;
+    if ((rc = ovl_begin(c, n, s))) return rc;
+    const int gx = grid_x_for(c, n, vmax_of(c), 256);
+    OvlMinMaxArgs m;
+    m.a[0] = a; m.a[1] = nullptr; m.a[2] = nullptr; m.subj = subj_ptr(c); m.st = (OvlStats*)c->d_ovl.p; m.use_abs = 1;
+    VB_LAUNCH(ovl_minmax_kernel, dim3(gx, n), dim3(256), 0, s, m);
+    OvlRgbArgs r;
+    r.a = a; r.b = b; r.subj = subj_ptr(c); r.st = (const OvlStats*)c->d_ovl.p; r.rgb = rgb; r.gui = gui ? 1 : 0; r.mode = mode;
+    VB_LAUNCH(ovl_rgb_kernel, dim3(gx, n), dim3(256), 0, s, r);
+    c->launches += 2;
+    return vbrt::last_launch_ok("overlay kernels") ? VB_OK : VB_ERR_CUDA;
+}
+
+int vb_overlay_rgb_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const float* a, const uint8_t* b,
+                              int32_t gui, int32_t mode, uint8_t* rgb) {
+    if (!c || !shapes || n <= 0 || !a || !b || !rgb) return fail(VB_ERR_ARG, "overlay_rgb: null argument");
+    vbrt::set_device(c->device);
+    vbrt::stream_t s = c->stream;
+    size_t V = 0;
+    for (int i = 0; i < n; ++i) V += (size_t)shapes[3 * i] * shapes[3 * i + 1] * shapes[3 * i + 2];
+    if (!ensure(c->m_ovl_in[0], 4 * V) || !ensure(c->m_ovl_in[3], V) || !ensure(c->m_rgb, 3 * V)) return VB_ERR_CUDA;
+    if (!vbrt::h2d(c->m_ovl_in[0].p, a, 4 * V, s) || !vbrt::h2d(c->m_ovl_in[3].p, b, V, s)) return VB_ERR_CUDA;
+    int rc = vb_overlay_rgb_batch_dev(c, n, shapes, (const float*)c->m_ovl_in[0].p, (const uint8_t*)c->m_ovl_in[3].p, gui, mode,
+                                      (uint8_t*)c->m_rgb.p, s);
+    if (rc) { vbrt::stream_sync(s); return rc; }
+    if (!vbrt::d2h(rgb, c->m_rgb.p, 3 * V, s) || !vbrt::stream_sync(s)) return VB_ERR_CUDA;
+    return VB_OK;
+}
+
+// boxes of the prepared batch from the device mask -> host (synchronises `s`)
+static int crop_boxes(vb_ctx* c, int n, const uint8_t* d_mask, int border, int border_slices, int32_t* boxes, vbrt::stream_t s) {
+    int rc = ovl_begin(c, n, s);
+    if (rc) return rc;
+    VB_LAUNCH(ovl_cropbox_kernel, dim3(n), dim3(512), 0, s, d_mask, subj_ptr(c), border, border_slices, (OvlStats*)c->d_ovl.p);
+    ++c->launches;
+    if (!vbrt::last_launch_ok("ovl_cropbox_kernel")) return VB_ERR_CUDA;
+    std::vector<OvlStats> st((size_t)n);
+    if (!vbrt::d2h(st.data(), c->d_ovl.p, sizeof(OvlStats) * (size_t)n, s) || !vbrt::stream_sync(s)) return VB_ERR_CUDA;
+    bool empty = false;
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < 6; ++k) {
+            boxes[6 * i + k] = st[(size_t)i].error ? -1 : st[(size_t)i].box[k];
+            empty = empty || st[(size_t)i].error;
+        }
+    return empty ? fail(VB_ERR_EMPTY, "cropToData: an axis has no index > 0 with signal (list index out of range)") : VB_OK;
+}
+
+int vb_crop_boxes_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const uint8_t* mask, int32_t border,
+                             int32_t border_slices, int32_t* boxes) {
+    if (!c || !shapes || n <= 0 || !mask || !boxes || border < 0) return fail(VB_ERR_ARG, "crop_boxes: bad argument");
+    vbrt::set_device(c->device);
+    vbrt::stream_t s = c->stream;
+    size_t V = 0;
+    for (int i = 0; i < n; ++i) V += (size_t)shapes[3 * i] * shapes[3 * i + 1] * shapes[3 * i + 2];
+    if (!ensure(c->m_ovl_in[3], V) || !vbrt::h2d(c->m_ovl_in[3].p, mask, V, s)) return VB_ERR_CUDA;
+    int rc = prepare(c, n, shapes, nullptr, s);
+    if (rc) { vbrt::stream_sync(s); return rc; }
+    c->r0 = 0;
+    return crop_boxes(c, n, (const uint8_t*)c->m_ovl_in[3].p, border, border_slices, boxes, s);
+}
+
+int vb_montage_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const int32_t* handles, const double* vox_min,
+                          const vb_montage_inputs* h, const double* parula, int32_t* boxes, int64_t* out_offset,
+                          uint8_t* out, int64_t out_capacity) {
+    if (!c || !shapes || n <= 0 || !h || !h->image || !h->n4 || !h->mask || !h->mask_border || !h->defect || !parula || !boxes ||
+        !out_offset || !out)
+        return fail(VB_ERR_ARG, "montage: null argument");
+    if (h->ci_shell && (!handles || !vox_min)) return fail(VB_ERR_ARG, "montage: ci_shell needs table handles and vox_min");
+    vbrt::set_device(c->device);
+    vbrt::stream_t s = c->stream;
+    size_t V = 0;
+    for (int i = 0; i < n; ++i) V += (size_t)shapes[3 * i] * shapes[3 * i + 1] * shapes[3 * i + 2];
+    // device mirrors: 0 n4, 1 image, 2 proton, 3 mask, 4 mask border, 5 defect (+ m_shell)
+    bool ok = ensure(c->m_ovl_in[0], 4 * V) && ensure(c->m_ovl_in[1], 4 * V) && ensure(c->m_ovl_in[3], V) && ensure(c->m_ovl_in[4], V) &&
+              ensure(c->m_ovl_in[5], V) && ensure(c->d_parula, 64 * 3 * sizeof(double)) && ensure(c->d_outoff, 8 * (size_t)n) &&
+              ensure(c->d_voxmin, sizeof(double) * (size_t)n);
+    if (h->proton) ok = ok && ensure(c->m_ovl_in[2], 4 * V);
+    if (h->ci_shell) ok = ok && ensure(c->m_shell, 2 * V);
+    if (!ok) return VB_ERR_CUDA;
+    ok = vbrt::h2d(c->m_ovl_in[0].p, h->n4, 4 * V, s) && vbrt::h2d(c->m_ovl_in[1].p, h->image, 4 * V, s) &&
+         vbrt::h2d(c->m_ovl_in[3].p, h->mask, V, s) && vbrt::h2d(c->m_ovl_in[4].p, h->mask_border, V, s) &&
+         vbrt::h2d(c->m_ovl_in[5].p, h->defect, V, s) && vbrt::h2d(c->d_parula.p, parula, 64 * 3 * sizeof(double), s);
+    if (h->proton) ok = ok && vbrt::h2d(c->m_ovl_in[2].p, h->proton, 4 * V, s);
+    if (h->ci_shell) ok = ok && vbrt::h2d(c->m_shell.p, h->ci_shell, 2 * V, s) && vbrt::h2d(c->d_voxmin.p, vox_min, sizeof(double) * (size_t)n, s);
+    if (!ok) { vbrt::stream_sync(s); return VB_ERR_CUDA; }
+    int rc = prepare(c, n, shapes, h->ci_shell ? handles : nullptr, s);
+    if (!rc && h->ci_shell) rc = upload_tables(c, s);
+    if (rc) { vbrt::stream_sync(s); return rc; }
+    c->r0 = 0;
+    if ((rc = crop_boxes(c, n, (const uint8_t*)c->m_ovl_in[3].p, 5, 0, boxes, s))) return rc;      // cropToData(mask, border=5)
+    std::vector<long long> off((size_t)n + 1);
+    long long total = 0, pxmax = 0;
+    for (int i = 0; i < n; ++i) {
+        off[(size_t)i] = total;
+        const long long px = 7LL * (boxes[6 * i + 1] - boxes[6 * i]) * (boxes[6 * i + 3] - boxes[6 * i + 2]) * (boxes[6 * i + 5] - boxes[6 * i + 4]);
+        total += 3 * px;
+        pxmax = std::max(pxmax, px);
+    }
+    off[(size_t)n] = total;
+    for (int i = 0; i <= n; ++i) out_offset[i] = off[(size_t)i];
+    if (total > out_capacity) return fail(VB_ERR_ARG, "montage: out_capacity too small");
+    if (!ensure(c->m_rgb, (size_t)total)) return VB_ERR_CUDA;
+    if (!vbrt::h2d(c->d_outoff.p, off.data(), 8 * (size_t)n, s) || !vbrt::stream_sync(s)) return VB_ERR_CUDA;   // `off` is a stack object
+    vbrt::clear_stale_error();
+    OvlMinMaxArgs m;
+    m.a[0] = (const float*)c->m_ovl_in[0].p; m.a[1] = (const float*)c->m_ovl_in[1].p;
+    m.a[2] = h->proton ? (const float*)c->m_ovl_in[2].p : nullptr;
+    m.subj = subj_ptr(c); m.st = (OvlStats*)c->d_ovl.p; m.use_abs = 0;
+    const int gx = grid_x_for(c, n, std::max<long long>(pxmax, 1), 256);
+    VB_LAUNCH(ovl_minmax_kernel, dim3(gx, n), dim3(256), 0, s, m);
+    OvlMontageArgs a;
+    a.proton = h->proton ? (const float*)c->m_ovl_in[2].p : nullptr; a.image = (const float*)c->m_ovl_in[1].p;
+    a.n4 = (const float*)c->m_ovl_in[0].p; a.mborder = (const uint8_t*)c->m_ovl_in[4].p; a.defect = (const uint8_t*)c->m_ovl_in[5].p;
+    a.shell = h->ci_shell ? (const uint16_t*)c->m_shell.p : nullptr;
+    a.subj = subj_ptr(c); a.st = (OvlStats*)c->d_ovl.p; a.tables = (const CiTableDev*)c->d_tables.p;
+    a.vox_min = (const double*)c->d_voxmin.p; a.parula = (const double*)c->d_parula.p;
+    a.out_off = (const long long*)c->d_outoff.p; a.out = (uint8_t*)c->m_rgb.p;
+    a.image_mode = h->image_mode; a.proton_mode = h->proton_mode;
+    VB_LAUNCH(ovl_montage_kernel, dim3(gx, n), dim3(256), 0, s, a);
+    c->launches += 2;
+    if (!vbrt::last_launch_ok("montage kernels")) return VB_ERR_CUDA;
+    std::vector<OvlStats> st((size_t)n);
+    if (!vbrt::d2h(out, c->m_rgb.p, (size_t)total, s) || !vbrt::d2h(st.data(), c->d_ovl.p, sizeof(OvlStats) * (size_t)n, s) ||
+        !vbrt::stream_sync(s))
+        return VB_ERR_CUDA;
+    for (int i = 0; i < n; ++i)
+        if (st[(size_t)i].error == 2)
+            return fail(VB_ERR_CI_COLOR, "screenShot: a CI value >= 40 mm indexes past the 64-entry colour table (index out of bounds)");
     return VB_OK;
 }
 
