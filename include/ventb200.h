@@ -229,6 +229,14 @@ int vb_montage_batch_host(vb_ctx* ctx, int32_t n, const int32_t* shapes, const i
                           const double* vox_min, const vb_montage_inputs* host, const double* parula64x3,
                           int32_t* boxes, int64_t* out_offset, uint8_t* out, int64_t out_capacity);
 
+/* ---- k-space reconstruction: the step before the path for TWIX users ------------
+ * Vent_Analysis.process_RAW (V_A.py:536-540): per slice fftshift(fft2(fftshift(K[:, :, k]))), then
+ * transpose(., (1, 0, 2))[:, ::-1, :].  `kspace`: complex64 [rows][cols][slices] per subject as
+ * interleaved (re, im) float32; `image`: complex64 [cols][rows][slices] likewise (the reference
+ * keeps complex128; single precision holds it to about 1e-6 of the largest magnitude). */
+int vb_recon_batch_dev(vb_ctx* ctx, int32_t n, const int32_t* shapes, const float* kspace, float* image, void* stream);
+int vb_recon_batch_host(vb_ctx* ctx, int32_t n, const int32_t* shapes, const float* kspace, float* image);
+
 /* Page-locked host memory for the *_host entry points (asynchronous copies need it to overlap with
  * compute).  The pages are touched by the calling thread, so a caller that has bound itself to the
  * CPUs next to the context's GPU gets NUMA-local buffers. */

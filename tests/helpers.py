@@ -448,3 +448,35 @@ def check_overlays(ctx):
     with pytest.raises(IndexError):
         ctx.montage_host([shape], img, n4, mask, mborder, defect, g["parula"], proton=proton, ci_shell=big, handles=[h],
                          vox_min=[min(vox)])
+
+
+RECON_RTOL = 1e-5        # relative to the largest magnitude of the image (single-precision transforms)
+
+
+def check_recon(ctx):
+    """vb_recon_batch_host (process_RAW, Vent_Analysis.py:536-540) against images produced by the
+    reference's own source lines (tests/golden/recon_small.npz) and, on a ragged batch with
+    power-of-two, odd and DICOM-like (52 x 64) matrices, against the oracle: within 1e-5 of the
+    largest magnitude."""
+    from oracle import recon_oracle
+    g = golden("recon_small.npz")
+    names = ("pow2", "odd", "mixed")
+    imgs = ctx.recon_host([g[f"K_{n}"] for n in names])
+    for n, im in zip(names, imgs):
+        ref = g[f"img_{n}"]
+        assert im.shape == ref.shape
+        assert np.abs(im - ref).max() <= RECON_RTOL * np.abs(ref).max(), n
+    rng = np.random.default_rng(5)
+    ks = []
+    for shape in ((64, 64, 5), (52, 64, 18), (33, 20, 1), (128, 128, 14)):
+        K = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+        K[shape[0] // 2, shape[1] // 2] += 300.0
+        ks.append(K)
+    for K, im in zip(ks, ctx.recon_host(ks)):
+        ref = recon_oracle.reconstruct(K)
+        assert np.abs(im - ref).max() <= RECON_RTOL * np.abs(ref).max(), K.shape
+    # linearity and Parseval as size-independent properties
+    a, b = ks[3], np.roll(ks[3], 3, axis=0)
+    ia, ib, iab = ctx.recon_host([a, b, (a + 2 * b).astype(np.complex64)])
+    assert np.abs(iab - (ia + 2 * ib)).max() <= 4 * RECON_RTOL * np.abs(iab).max()
+    assert np.isclose(np.sum(np.abs(ia) ** 2), a.shape[0] * a.shape[1] * np.sum(np.abs(a) ** 2), rtol=1e-4)

@@ -179,3 +179,7 @@ def test_class_overlay_methods(ctx, monkeypatch, tmp_path):
     assert v2.N4_bias_correction(img, m2).shape == shape
     with pytest.raises(ValueError):
         helpers.quiet(v2.calculate_VDP)
+
+
+def test_kspace_reconstruction_matches_the_reference(ctx):
+    helpers.check_recon(ctx)

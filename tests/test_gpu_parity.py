@@ -199,3 +199,7 @@ def test_compact_host_io_equals_the_dense_path(ctx):
 
 def test_overlay_compositions_bit_exact_vs_reference(ctx):
     helpers.check_overlays(ctx)
+
+
+def test_kspace_reconstruction_matches_the_reference(ctx):
+    helpers.check_recon(ctx)

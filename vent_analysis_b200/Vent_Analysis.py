@@ -375,8 +375,24 @@ class Vent_Analysis:
     def exportNifti(self, filepath=None, fileName=None):
         self._out_of_scope("exportNifti")
 
+    def reconstruct_kspace(self, raw_K):
+        """The arithmetic of ``process_RAW`` (Vent_Analysis.py:536-540): per-slice
+        ``fftshift(fft2(fftshift(.)))``, then ``transpose(., (1, 0, 2))[:, ::-1, :]`` -> complex128.
+        Kernel: ``recon_pass_kernel`` (single precision transforms)."""
+        return self._ctx().recon_host([np.asarray(raw_K)])[0].astype(np.complex128)
+
     def process_RAW(self, filepath=None):
-        self._out_of_scope("process_RAW")
+        """Vent_Analysis.py:522-540: read a Siemens twix file (mapVBVD, host side) and reconstruct it."""
+        import mapvbvd
+        if filepath is None:
+            import tkinter.filedialog
+            filepath = tkinter.filedialog.askopenfilename()
+        self.raw_twix = mapvbvd.mapVBVD(filepath)
+        self.metadata['TWIXscanDateTime'] = self.raw_twix.hdr.Config['PrepareTimestamp']
+        self.metadata['TWIXprotocolName'] = self.raw_twix.hdr.Meas['tProtocolName']
+        self.raw_twix.image.squeeze = True
+        self.raw_K = self.raw_twix.image['']
+        self.raw_HPvent = self.reconstruct_kspace(self.raw_K)
 
     def dicom_to_json(self, ds, json_path='c:/pirl/data/DICOMjson.json', include_private=True):
         self._out_of_scope("dicom_to_json")

@@ -96,7 +96,7 @@ EXPORTS = ["vb_version", "vb_last_error", "vb_device_count", "vb_create", "vb_de
            "vb_n4_default_params", "vb_ci_table_create", "vb_ci_table_radii", "vb_snr_batch_dev", "vb_n4_batch_dev",
            "vb_vdp_batch_dev", "vb_border_batch_dev", "vb_ci_batch_dev", "vb_pipeline_batch_dev",
            "vb_pipeline_batch_host", "vb_pipeline_batch_host_packed", "vb_host_alloc", "vb_host_free", "vb_overlay_rgb_batch_dev", "vb_overlay_rgb_batch_host", "vb_crop_boxes_batch_host",
-           "vb_montage_batch_host", "vb_pack6_batch_dev", "vb_pack6_batch_host", "vb_set_profiling", "vb_profile_fetch", "vb_set_debug", "vb_n4_debug_fetch"]
+           "vb_montage_batch_host", "vb_recon_batch_dev", "vb_recon_batch_host", "vb_pack6_batch_dev", "vb_pack6_batch_host", "vb_set_profiling", "vb_profile_fetch", "vb_set_debug", "vb_n4_debug_fetch"]
 N_STAGES = 5
 STAGE_NAMES = ("snr", "n4", "vdp", "mask_border", "ci")
 
@@ -131,6 +131,8 @@ def bind(path):
     lib.vb_overlay_rgb_batch_host.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp]
     lib.vb_crop_boxes_batch_host.argtypes = [vp, i32, vp, vp, i32, i32, vp]
     lib.vb_montage_batch_host.argtypes = [vp, i32, vp, vp, vp, C.POINTER(MontageInputs), vp, vp, vp, vp, i64]
+    lib.vb_recon_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.vb_recon_batch_host.argtypes = [vp, i32, vp, vp, vp]
     lib.vb_pack6_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.vb_pack6_batch_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.vb_set_profiling.argtypes = [vp, i32]
@@ -465,6 +467,20 @@ class Context:
             R, Cc, S = (int(boxes[i, 1] - boxes[i, 0]), int(boxes[i, 3] - boxes[i, 2]), int(boxes[i, 5] - boxes[i, 4]))
             imgs.append(out[off[i]:off[i + 1]].reshape(7 * R, S * Cc, 3).copy())
         return imgs, boxes
+
+    def recon_host(self, kspaces):
+        """``process_RAW`` reconstruction (Vent_Analysis.py:536-540) of a list of complex k-space volumes
+        ``[rows, cols, slices]`` -> list of complex64 images ``[cols, rows, slices]``."""
+        shapes = np.ascontiguousarray([k.shape for k in kspaces], dtype=np.int32).reshape(-1, 3)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(k, dtype=np.complex64).ravel() for k in kspaces]))
+        out = np.empty_like(flat)
+        self.check(self.lib.vb_recon_batch_host(self.h, shapes.shape[0], _ptr(shapes), _ptr(flat), _ptr(out)))
+        res, off = [], 0
+        for n0, n1, n2 in shapes:
+            V = int(n0) * int(n1) * int(n2)
+            res.append(out[off:off + V].reshape(int(n1), int(n0), int(n2)))
+            off += V
+        return res
 
     def ci_host(self, defect, shapes, handles):
         """CI stage alone on host arrays: defect uint8 0/1 -> (ci_shell uint16, stats, rc)."""

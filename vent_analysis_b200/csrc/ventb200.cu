@@ -13,6 +13,7 @@
 #include "ci_kernels.cuh"
 #include "io_kernels.cuh"
 #include "overlay_kernels.cuh"
+#include "recon_kernels.cuh"
 
 namespace {
 
@@ -70,6 +71,7 @@ struct vb_ctx {
     Buf m_proton, m_pack, d_voxmin;
     Buf m_u16, m_bits, m_codes, m_ci_idx, m_ci_val, d_bitoff;   // compact host I/O
     std::vector<long long> last_bitoff;
+    Buf m_k[2], d_ktmp;                                     // k-space reconstruction
     Buf d_ovl, m_rgb, m_ovl_in[6], d_parula, d_outoff;   // overlay compositions
 };
 
@@ -435,6 +437,7 @@ void vb_destroy(vb_ctx* c) {
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
                    &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats, &c->m_proton, &c->m_pack, &c->d_voxmin,
                    &c->m_u16, &c->m_bits, &c->m_codes, &c->m_ci_idx, &c->m_ci_val, &c->d_bitoff,
+                   &c->m_k[0], &c->m_k[1], &c->d_ktmp,
                    &c->d_ovl, &c->m_rgb, &c->m_ovl_in[0], &c->m_ovl_in[1], &c->m_ovl_in[2], &c->m_ovl_in[3], &c->m_ovl_in[4], &c->m_ovl_in[5], &c->d_parula, &c->d_outoff};
     for (Buf* b : bufs) vbrt::dev_free(b->p);
     for (TableHost& t : c->tables) { vbrt::dev_free(t.d_rows); vbrt::dev_free(t.d_ii); vbrt::dev_free(t.d_up); vbrt::dev_free(t.d_radii); }
@@ -1109,6 +1112,49 @@ int vb_montage_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const int
     for (int i = 0; i < n; ++i)
         if (st[(size_t)i].error == 2)
             return fail(VB_ERR_CI_COLOR, "screenShot: a CI value >= 40 mm indexes past the 64-entry colour table (index out of bounds)");
+    return VB_OK;
+}
+
+// ------------------------------------------------------------------- k-space reconstruction (8f4)
+int vb_recon_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const float* kspace, float* image, void* stream) {
+    if (!c || !kspace || !image) return fail(VB_ERR_ARG, "recon: null argument");
+    vbrt::set_device(c->device);
+    vbrt::stream_t s = (vbrt::stream_t)stream;
+    int rc = prepare(c, n, shapes, nullptr, s);
+    if (rc) return rc;
+    c->r0 = 0;
+    int nmax = 1, n0max = 1, n1max = 1, n2max = 1;
+    for (const VbSubject& S : c->last_subj) {
+        n0max = std::max(n0max, S.n0); n1max = std::max(n1max, S.n1); n2max = std::max(n2max, S.n2);
+    }
+    nmax = std::max(n0max, n1max);
+    const size_t smem = sizeof(float) * 2 * ((size_t)2 * nmax * VB_RECON_NL + nmax);
+    if ((long long)smem > c->max_smem - 1024) return fail(VB_ERR_UNSUPPORTED, "recon: matrix size too large for the shared-memory transform");
+    if (!ensure(c->d_ktmp, 8 * (size_t)c->v_total)) return VB_ERR_CUDA;
+    if (!vbrt::allow_smem(recon_pass_kernel, (int)smem)) return VB_ERR_CUDA;
+    vbrt::clear_stale_error();
+    const int tiles = (n2max + VB_RECON_NL - 1) / VB_RECON_NL;
+    ReconArgs a;
+    a.subj = subj_ptr(c);
+    a.src = (const float2*)kspace; a.dst = (float2*)c->d_ktmp.p; a.pass = 0;
+    VB_LAUNCH(recon_pass_kernel, dim3(n1max, tiles, n), dim3(VB_RECON_THREADS), smem, s, a, nmax);
+    a.src = (const float2*)c->d_ktmp.p; a.dst = (float2*)image; a.pass = 1;
+    VB_LAUNCH(recon_pass_kernel, dim3(n0max, tiles, n), dim3(VB_RECON_THREADS), smem, s, a, nmax);
+    c->launches += 2;
+    return vbrt::last_launch_ok("recon_pass_kernel") ? VB_OK : VB_ERR_CUDA;
+}
+
+int vb_recon_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const float* kspace, float* image) {
+    if (!c || !shapes || n <= 0 || !kspace || !image) return fail(VB_ERR_ARG, "recon: null argument");
+    vbrt::set_device(c->device);
+    vbrt::stream_t s = c->stream;
+    size_t V = 0;
+    for (int i = 0; i < n; ++i) V += (size_t)shapes[3 * i] * shapes[3 * i + 1] * shapes[3 * i + 2];
+    if (!ensure(c->m_k[0], 8 * V) || !ensure(c->m_k[1], 8 * V)) return VB_ERR_CUDA;
+    if (!vbrt::h2d(c->m_k[0].p, kspace, 8 * V, s)) return VB_ERR_CUDA;
+    int rc = vb_recon_batch_dev(c, n, shapes, (const float*)c->m_k[0].p, (float*)c->m_k[1].p, s);
+    if (rc) { vbrt::stream_sync(s); return rc; }
+    if (!vbrt::d2h(image, c->m_k[1].p, 8 * V, s) || !vbrt::stream_sync(s)) return VB_ERR_CUDA;
     return VB_OK;
 }
 
