@@ -45,7 +45,9 @@
 #include "vb_common.cuh"
 
 #ifndef VB_N4_THREADS
-#define VB_N4_THREADS 1024
+/* 28 warps x 72 registers measured 1.1 % faster than 32 x 64 (and than 24 x 80, 30 x 64, 26 x 72):
+   the kernel is bound by instruction issue, a few more registers per thread trim the spills */
+#define VB_N4_THREADS 896
 #endif
 #define VB_N4_WARPS (VB_N4_THREADS / 32)
 #define VB_BSPLINE_EPS 1e-3f
@@ -53,7 +55,7 @@
 #define VB_N4_EPT 8                               /* convergence chain: elements per thread   */
 #endif
 #ifndef VB_N4_CHAIN_WARPS
-#define VB_N4_CHAIN_WARPS 14                      /* warps of the chain team while it overlaps  */
+#define VB_N4_CHAIN_WARPS 12                      /* warps of the chain team while it overlaps (10 / 14 of 28 measured slower) */
 #endif
 #define VB_N4_SERIAL 64                           /* first elements: one thread, sequentially */
 #ifndef VB_N4_WARP_END

@@ -1128,18 +1128,30 @@ int vb_recon_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const float*
         n0max = std::max(n0max, S.n0); n1max = std::max(n1max, S.n1); n2max = std::max(n2max, S.n2);
     }
     nmax = std::max(n0max, n1max);
-    const size_t smem = sizeof(float) * 2 * ((size_t)2 * nmax * VB_RECON_NL + nmax);
-    if ((long long)smem > c->max_smem - 1024) return fail(VB_ERR_UNSUPPORTED, "recon: matrix size too large for the shared-memory transform");
+    (void)n2max;
+    bool need_y = false;
+    for (const VbSubject& S : c->last_subj) need_y = need_y || (S.n0 & (S.n0 - 1)) || (S.n1 & (S.n1 - 1));
+    // transforms per CTA: as many as keep three CTAs per SM (at least 8)
+    const long long budget = std::min<long long>(c->max_smem - 1024, 72 * 1024);
+    int nl = (int)std::min<long long>(VB_RECON_NL_MAX, (budget / 8 - nmax) / ((need_y ? 2 : 1) * (long long)nmax));
+    if (nl < 8) nl = (int)std::min<long long>(8, (((long long)c->max_smem - 1024) / 8 - nmax) / ((need_y ? 2 : 1) * (long long)nmax));
+    if (nl < 1) return fail(VB_ERR_UNSUPPORTED, "recon: matrix size too large for the shared-memory transform");
+    const size_t smem = sizeof(float) * 2 * ((size_t)(need_y ? 2 : 1) * nmax * nl + nmax);
     if (!ensure(c->d_ktmp, 8 * (size_t)c->v_total)) return VB_ERR_CUDA;
     if (!vbrt::allow_smem(recon_pass_kernel, (int)smem)) return VB_ERR_CUDA;
     vbrt::clear_stale_error();
-    const int tiles = (n2max + VB_RECON_NL - 1) / VB_RECON_NL;
+    long long inner_max = 1, t2max = 1;
+    for (const VbSubject& S : c->last_subj) {
+        inner_max = std::max<long long>(inner_max, (long long)S.n1 * S.n2);
+        const int KS = std::min(S.n2, nl), LU = std::max(1, nl / KS);
+        t2max = std::max<long long>(t2max, (long long)((S.n0 + LU - 1) / LU) * ((S.n2 + KS - 1) / KS));
+    }
     ReconArgs a;
-    a.subj = subj_ptr(c);
+    a.subj = subj_ptr(c); a.nl = nl; a.need_y = need_y ? 1 : 0;
     a.src = (const float2*)kspace; a.dst = (float2*)c->d_ktmp.p; a.pass = 0;
-    VB_LAUNCH(recon_pass_kernel, dim3(n1max, tiles, n), dim3(VB_RECON_THREADS), smem, s, a, nmax);
+    VB_LAUNCH(recon_pass_kernel, dim3((unsigned)((inner_max + nl - 1) / nl), 1, n), dim3(VB_RECON_THREADS), smem, s, a, nmax);
     a.src = (const float2*)c->d_ktmp.p; a.dst = (float2*)image; a.pass = 1;
-    VB_LAUNCH(recon_pass_kernel, dim3(n0max, tiles, n), dim3(VB_RECON_THREADS), smem, s, a, nmax);
+    VB_LAUNCH(recon_pass_kernel, dim3((unsigned)t2max, 1, n), dim3(VB_RECON_THREADS), smem, s, a, nmax);
     c->launches += 2;
     return vbrt::last_launch_ok("recon_pass_kernel") ? VB_OK : VB_ERR_CUDA;
 }
