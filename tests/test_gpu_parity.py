@@ -203,3 +203,62 @@ def test_overlay_compositions_bit_exact_vs_reference(ctx):
 
 def test_kspace_reconstruction_matches_the_reference(ctx):
     helpers.check_recon(ctx)
+
+
+@pytest.mark.parametrize("name", ["small_a", "C1", "C2"])
+def test_n4_against_the_committed_pins(ctx, name):
+    """The CUDA N4 against tests/golden/n4_pins.npz: identical per-level iteration counts, final
+    control lattice within 1e-4, sampled corrected voxels within the north-star 1e-3.  (The pins are
+    outputs of the restatement; SimpleITK is not installable on either box,
+    profiles/r02_probe_box_simpleitk.txt.)"""
+    g = helpers.golden("n4_pins.npz")
+    shape, vox, seed = tuple(int(x) for x in g[f"{name}_shape"]), [float(x) for x in g[f"{name}_vox"]], int(g[f"{name}_seed"])
+    img, mask = phantom(shape, vox, seed)
+    ctx.set_debug(True)
+    out = ctx.pipeline_host([shape], _lib.DO_N4, image=img, mask=mask)
+    dbg = ctx.n4_debug(0, 200, 11 ** 3)
+    ctx.set_debug(False)
+    assert [int(x) for x in out["stats"]["n4_iters"][0][:4]] == [int(x) for x in g[f"{name}_iters"]]
+    assert np.abs(dbg["lattice"] - g[f"{name}_lattice"]).max() < 1e-4
+    got = out["n4"].ravel()[::max(1, out["n4"].size // 4096)][:4096]
+    ref = g[f"{name}_samples"]
+    assert (np.abs(got - ref) <= helpers.N4_BIAS_RTOL * np.maximum(np.abs(ref), 1e-6)).all()
+
+
+def test_stress_slice_64_cohort_phantoms(ctx):
+    """A 64-subject slice of the three stress tools (tools/stress_parity.py, stress_vdp_ci.py,
+    stress_shapes.py) in ONE batch: N4 iteration counts identical to the restatement and bias field
+    within 1e-3 on every subject (oracle on the host cores), VDP / LB / CI bit-exact downstream of
+    our N4 on eight of them."""
+    import multiprocessing as mp
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import stress_parity
+    from vent_analysis_b200 import cohort
+    seeds = list(range(2000, 2064))
+    with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+        refs = pool.map(stress_parity.ref, seeds, chunksize=1)
+    subs = [cohort_member(i) for i in seeds]
+    imgs, masks, voxs = zip(*subs)
+    shapes = [im.shape for im in imgs]
+    handles = cohort.table_handles(ctx, shapes, voxs)
+    out = ctx.pipeline_host(shapes, cohort.ALL_STAGES, image=np.concatenate([i.ravel() for i in imgs]),
+                            mask=np.concatenate([m.ravel() for m in masks]), handles=handles, want_logbias=True)
+    assert out["rc"] == 0
+    off = 0
+    for k, (i, it_ref, lb_ref) in enumerate(refs):
+        V = imgs[k].size
+        assert out["stats"]["n4_iters"][k][:4].tolist() == it_ref, (i, out["stats"]["n4_iters"][k][:4].tolist(), it_ref)
+        lb = out["logbias"][off:off + V].reshape(shapes[k]).astype(np.float64)
+        assert np.abs(np.expm1(lb - lb_ref)).max() < helpers.N4_BIAS_RTOL
+        if k % 8 == 0:
+            n4 = out["n4"][off:off + V].reshape(shapes[k])
+            r = vdp_oracle.vdp(n4, masks[k].astype(np.float64), voxs[k])
+            assert np.array_equal(out["defect"][off:off + V].reshape(shapes[k]), r["defectArray"])
+            assert np.array_equal(out["defect_lb"][off:off + V].reshape(shapes[k]), r["defectArrayLB"])
+            assert out["stats"]["mean"][k] == r["mean"] and out["stats"]["p99"][k] == r["p99"]
+            ci_ref, shell_ref = ci_oracle.calculate_ci(r["defectArray"], voxs[k], generate(voxs[k], 50))
+            sel = r["defectArray"] > 0
+            assert np.array_equal(out["ci_shell"][off:off + V].reshape(shapes[k])[sel].astype(np.int32), shell_ref[sel])
+        off += V

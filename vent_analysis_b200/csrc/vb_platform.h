@@ -48,6 +48,41 @@ VB_DEV int vb_bar_or(int id, int nthreads, int pred) {
 }
 VB_DEV long long vb_clock() { return clock64(); }   // SM cycles
 #define VB_OPAQUE_PTR(p) asm volatile("" : "+l"(p))
+// ---- bulk asynchronous copies (TMA, 1-D form) with mbarrier completion --------------------------
+// global -> shared through the async proxy: one thread arms the barrier with the byte count and
+// issues the copy; the bytes land without occupying registers or issue slots, and every consumer
+// waits on the barrier's phase.  Source, destination and size are multiples of 16 bytes.
+typedef unsigned long long vb_mbar_t;
+VB_DEV unsigned vb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+VB_DEV void vb_mbar_init(vb_mbar_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vb_smem_addr(bar)), "r"(count) : "memory");
+}
+VB_DEV void vb_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+VB_DEV void vb_mbar_expect_tx(vb_mbar_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(vb_smem_addr(bar)), "r"(bytes) : "memory");
+}
+VB_DEV void vb_bulk_g2s(void* dst_smem, const void* src_global, unsigned bytes, vb_mbar_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(vb_smem_addr(dst_smem)), "l"(src_global), "r"(bytes), "r"(vb_smem_addr(bar)) : "memory");
+}
+VB_DEV void vb_mbar_wait(vb_mbar_t* bar, unsigned parity);
+// ring-of-stages helpers shared with the emulation: fill number `k` (0, 1, 2, ...) of a stage
+VB_DEV void vb_stage_begin(vb_mbar_t* bar, unsigned bytes) { vb_mbar_expect_tx(bar, bytes); }
+VB_DEV void vb_stage_end(vb_mbar_t*) {}
+VB_DEV void vb_stage_wait(vb_mbar_t* bar, unsigned k) { vb_mbar_wait(bar, k & 1u); }
+// "stage is free again" barrier: `consumers` arrivals complete a phase; the producer waits for
+// the consumers of fill k - 1 before it starts fill k (nothing to wait for before fill 0)
+VB_DEV void vb_free_arrive(vb_mbar_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(vb_smem_addr(bar)) : "memory");
+}
+VB_DEV void vb_free_wait(vb_mbar_t* bar, unsigned k, int) { if (k > 0u) vb_mbar_wait(bar, (k - 1u) & 1u); }
+VB_DEV void vb_mbar_wait(vb_mbar_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tVB_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra VB_DONE_%=;\n\tbra VB_WAIT_%=;\n\tVB_DONE_%=:\n\t}"
+        ::"r"(vb_smem_addr(bar)), "r"(parity) : "memory");
+}
 #else
 // ------------------------------------------------------------------------------- emulation
 #include <math.h>
@@ -341,6 +376,23 @@ template <class T> static inline T vb_ld_stream(const T* p) { return *p; }
 static inline void vb_st_stream(float* p, float v) { *p = v; }
 static inline long long vb_clock() { return 0; }
 #define VB_OPAQUE_PTR(p) ((void)0)
+// bulk copies: the issuing thread copies synchronously and bumps a completion counter; a phase
+// `parity` of the barrier is complete once the counter has passed it (phases complete in order)
+typedef unsigned long long vb_mbar_t;
+static inline void vb_mbar_init(vb_mbar_t* bar, int) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
+static inline void vb_mbar_fence_init() {}
+// emulation: (pending copies << 32) | completed phases
+static inline void vb_mbar_expect_tx(vb_mbar_t*, unsigned) {}
+static inline void vb_bulk_g2s(void* dst, const void* src, unsigned bytes, vb_mbar_t*) { memcpy(dst, src, bytes); }
+static inline void vb_mbar_complete_emu(vb_mbar_t* bar) { __atomic_fetch_add(bar, 1ull, __ATOMIC_SEQ_CST); }
+static inline void vb_mbar_wait_emu(vb_mbar_t* bar, unsigned long long phases_done) {
+    while (__atomic_load_n(bar, __ATOMIC_SEQ_CST) < phases_done) std::this_thread::yield();
+}
+static inline void vb_stage_begin(vb_mbar_t*, unsigned) {}
+static inline void vb_stage_end(vb_mbar_t* bar) { vb_mbar_complete_emu(bar); }
+static inline void vb_stage_wait(vb_mbar_t* bar, unsigned k) { vb_mbar_wait_emu(bar, (unsigned long long)k + 1ull); }
+static inline void vb_free_arrive(vb_mbar_t* bar) { vb_mbar_complete_emu(bar); }
+static inline void vb_free_wait(vb_mbar_t* bar, unsigned k, int consumers) { vb_mbar_wait_emu(bar, (unsigned long long)k * (unsigned long long)consumers); }
 using std::max;
 using std::min;
 #endif

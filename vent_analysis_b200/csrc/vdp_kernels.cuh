@@ -17,7 +17,7 @@
    pass / barriers overlap the other's image pass (measured 5 % faster than one CTA of 1024) */
 #define VB_SNR_THREADS (VB_VDP_THREADS >= 1024 ? 512 : VB_VDP_THREADS)
 #endif
-#define VB_SNR_MAX_AXIS 8192   // n0 + n1 + n2 must not exceed this (projection flags in smem)
+#define VB_SNR_MAX_AXIS 3072   // n0 + n1 + n2 must not exceed this (projection flags in smem)
 
 // ---------------------------------------------------------------------------------------------
 // calculate_SNR: one CTA per subject.  Signal = mask > 0.  Noise = voxels outside
@@ -62,13 +62,67 @@ VB_DEV uint32_t vb_nonzero_bytes(uint32_t w) {
     return ((((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u);
 }
 
+// Row streaming through a ring of shared-memory stages filled by bulk asynchronous copies (TMA,
+// cp.async.bulk + mbarrier), warp specialised: lane 0 of the PRODUCER warp (the first warp that owns
+// no column group) keeps VB_SNR_STAGES chunks of `R` rows in flight; the consumer warps wait on a
+// stage's "full" barrier, reduce its rows and hand the stage back through its "free" barrier (one
+// arrival per warp) -- no block-wide barrier inside a pass.  `chunk` counts the chunks this CTA
+// has streamed so far (it selects stage and barrier phase, so it runs on across passes and
+// subjects).  BODY(row0, rows, simg, smsk) runs on the consumer warps.
+#ifndef VB_SNR_STAGES
+#define VB_SNR_STAGES 3      /* 3 stages of three C2 rows measured 0.50 ms per 1776 subjects; 4 x 2 rows 0.55, 6 x 1 row 0.61; direct loads 0.55 */
+#endif
+struct SnrRing {
+    unsigned char* base;          // VB_SNR_STAGES stages of `stage_bytes`
+    vb_mbar_t* full;
+    vb_mbar_t* free_;
+    int stage_bytes, R, ncw;      // consumer warps
+    unsigned chunk;
+};
+template <class F>
+VB_DEV void snr_stream(SnrRing& g, const float* img, const uint8_t* msk, int n0, int ncols, F body) {
+    g.R = max(1, min(n0, g.stage_bytes / ((img ? 5 : 1) * ncols)));     // rows per stage: mask-only passes take five times more
+    const int nch = (n0 + g.R - 1) / g.R, w = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+    const unsigned c0 = g.chunk;
+    if (w == g.ncw) {                                     // producer
+        if (lane == 0)
+            for (int c = 0; c < nch; ++c) {
+                const unsigned cg = c0 + (unsigned)c, st = cg % VB_SNR_STAGES;
+                vb_free_wait(&g.free_[st], cg / VB_SNR_STAGES, g.ncw);
+                const int row0 = c * g.R, rows = min(g.R, n0 - row0);
+                unsigned char* dst = g.base + (size_t)st * g.stage_bytes;
+                const unsigned mb = (unsigned)(rows * ncols), ib = img ? 4u * mb : 0u;
+                vb_stage_begin(&g.full[st], mb + ib);
+                if (img) vb_bulk_g2s(dst, img + (size_t)row0 * ncols, ib, &g.full[st]);
+                vb_bulk_g2s(dst + (img ? 4 * (size_t)g.R * ncols : 0), msk + (size_t)row0 * ncols, mb, &g.full[st]);
+                vb_stage_end(&g.full[st]);
+            }
+    } else if (w < g.ncw) {                               // consumers
+        for (int c = 0; c < nch; ++c) {
+            const unsigned cg = c0 + (unsigned)c, st = cg % VB_SNR_STAGES;
+            vb_stage_wait(&g.full[st], cg / VB_SNR_STAGES);
+            const unsigned char* sp = g.base + (size_t)st * g.stage_bytes;
+            body(c * g.R, min(g.R, n0 - c * g.R), (const float*)sp, (const uint8_t*)(sp + (img ? 4 * (size_t)g.R * ncols : 0)));
+            __syncwarp();
+            if (lane == 0) vb_free_arrive(&g.free_[st]);
+        }
+    }
+    g.chunk = c0 + (unsigned)nch;
+    __syncthreads();
+}
+
 VB_KERNEL void VB_LAUNCH_BOUNDS(VB_VDP_THREADS, 1)
 snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, const VbSubject* subj, int n,
-           int fov, vb_subject_stats* stats) {
+           int fov, vb_subject_stats* stats, int ring_bytes) {
+    VB_DYN_SMEM(ring_smem);
     VB_SHARED int flags[VB_SNR_MAX_AXIS];
     VB_SHARED double red[64];
     VB_SHARED int s_cmin, s_cmax;
+    VB_SHARED vb_mbar_t s_full[VB_SNR_STAGES], s_free[VB_SNR_STAGES];
     const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    SnrRing ring;
+    ring.base = ring_smem; ring.full = s_full; ring.free_ = s_free; ring.chunk = 0u; ring.stage_bytes = 0; ring.R = 1; ring.ncw = 0;
+    int ring_ncw = -1;                                   // consumer-warp count the "free" barriers were set up for
     for (int si = (int)blockIdx.x; si < n; si += (int)gridDim.x) {
         const VbSubject S = subj[si];
         const float* img = image + S.off;
@@ -85,7 +139,45 @@ snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, cons
         const int G = ncols >> 2, RP = fast ? max(1, nt / max(G, 1)) : 1;
         const int g = fast ? tid % G : 0, ph = fast ? tid / G : 0;
         const bool mine = fast && ph < RP;
-        if (fast) {
+        // bulk path: whole rows as 16-byte multiples at a 16-byte aligned offset, and a stage of at
+        // least one row must fit the ring
+        const int stage_bytes = (ring_bytes / VB_SNR_STAGES) & ~15;
+        const int stage_rows = fast ? stage_bytes / (5 * ncols) : 0;
+        const int ncw = fast ? (G * RP + 31) >> 5 : 0;            // warps that own column groups; the next one produces
+        const bool bulk = stage_rows >= 1 && (S.off & 15) == 0 && (ncols & 15) == 0 && ncw < (nt >> 5);
+        if (bulk) {
+            ring.stage_bytes = stage_bytes;
+            ring.ncw = ncw;
+            if (ring_ncw != ncw) {                                // (block uniform) first use / another geometry
+                __syncthreads();
+                if (tid == 0) {
+                    for (int k = 0; k < VB_SNR_STAGES; ++k) { vb_mbar_init(&s_full[k], 1); vb_mbar_init(&s_free[k], ncw); }
+                    vb_mbar_fence_init();
+                }
+                ring.chunk = 0u;
+                ring_ncw = ncw;
+                __syncthreads();
+            }
+        }
+        if (bulk) {
+            uint32_t colacc = 0;
+            snr_stream(ring, (const float*)nullptr, msk, n0, ncols, [&](int row0, int rows, const float*, const uint8_t* sm) {
+                if (mine)
+                    for (int i = ph; i < rows; i += RP) {
+                        const uint32_t wv = *(const uint32_t*)(sm + (size_t)i * ncols + 4 * g);
+                        colacc |= wv;
+                        if (wv) atomicOr((unsigned*)&rowf[row0 + i], 1u);
+                    }
+            });
+            if (mine) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if ((colacc >> (8 * e)) & 0xFFu) {
+                        const int rem = 4 * g + e, j = rem / n2, k = rem - j * n2;
+                        atomicOr((unsigned*)&colf[j], 1u); atomicOr((unsigned*)&slcf[k], 1u);
+                    }
+            }
+        } else if (fast) {
             uint32_t colacc = 0;
             if (mine) {
 #pragma unroll 4
@@ -134,7 +226,34 @@ snr_kernel(const float* VB_RESTRICT image, const uint8_t* VB_RESTRICT mask, cons
         const float pivot = img[0];
         double ssum = 0.0, nsum = 0.0, nsq = 0.0;
         long long scnt = 0, ncnt = 0;
-        if (fast) {
+        if (bulk) {
+            unsigned cs = 0;                       // bit e: (col, slice) of my e-th position is inside the box
+            if (mine) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int rem = 4 * g + e, j = rem / n2, k = rem - j * n2;
+                    if ((j >= cmin && j < cmax && cmin >= 0) && slcf[k]) cs |= 1u << e;
+                }
+            }
+            snr_stream(ring, img, msk, n0, ncols, [&](int row0, int rows, const float* sx, const uint8_t* sm) {
+                if (mine)
+                    for (int ii = ph; ii < rows; ii += RP) {
+                        const int i = row0 + ii;
+                        const float4 xv = *(const float4*)(sx + (size_t)ii * ncols + 4 * g);
+                        const uint32_t wv = *(const uint32_t*)(sm + (size_t)ii * ncols + 4 * g);
+                        const bool rowin = rowf[i] != 0, band = i >= lo && i < hi;
+                        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if ((wv >> (8 * e)) & 0xFFu) { ssum += (double)xs[e]; ++scnt; }
+                            if (band && !(rowin && ((cs >> e) & 1u))) {
+                                const double d = (double)xs[e] - (double)pivot;
+                                nsum += d; nsq += d * d; ++ncnt;
+                            }
+                        }
+                    }
+            });
+        } else if (fast) {
             if (mine) {
                 unsigned cs = 0;                   // bit e: (col, slice) of my e-th position is inside the box
 #pragma unroll

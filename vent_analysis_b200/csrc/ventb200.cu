@@ -191,8 +191,16 @@ int run_snr(vb_ctx* c, const float* image, const uint8_t* mask, int n, int fov, 
     const int grid = std::min(n, c->sms * 4);
     int threads = VB_SNR_THREADS;
     if (const char* e = getenv("VB_SNR_THREADS_RT")) threads = std::max(32, std::min(VB_VDP_THREADS, atoi(e) & ~31));   // tuning
-    VB_LAUNCH(snr_kernel, dim3(grid), dim3(threads), 0, s, image, mask, subj_ptr(c), n,
-              fov, stats);
+    // ring of bulk-copy stages (two CTAs per SM): 6 stages of whole rows; rows that do not fit keep
+    // the direct-load path inside the kernel
+    int ring = 0;
+    if (!getenv("VB_SNR_NO_BULK")) {
+        const long long statics = vbrt::static_smem(snr_kernel);
+        ring = (int)std::max<long long>(0, std::min<long long>(100 * 1024, ((long long)c->max_smem - 4096) / 2 - statics)) & ~255;
+        if (!vbrt::allow_smem(snr_kernel, ring)) return VB_ERR_CUDA;
+    }
+    VB_LAUNCH(snr_kernel, dim3(grid), dim3(threads), (size_t)ring, s, image, mask, subj_ptr(c), n,
+              fov, stats, ring);
     ++c->launches;
     return vbrt::last_launch_ok("snr_kernel") ? VB_OK : VB_ERR_CUDA;
 }
