@@ -262,3 +262,25 @@ def test_stress_slice_64_cohort_phantoms(ctx):
             sel = r["defectArray"] > 0
             assert np.array_equal(out["ci_shell"][off:off + V].reshape(shapes[k])[sel].astype(np.int32), shell_ref[sel])
         off += V
+
+
+def test_resident_batch_in_parts_on_two_streams_changes_nothing(ctx, monkeypatch):
+    """vb_pipeline_batch_dev splits large resident batches into parts that alternate between two
+    streams (the tail of one part's persistent N4 kernel is filled by the next part and by the small
+    kernels of the earlier ones): every output array identical to the unsplit run."""
+    from vent_analysis_b200 import cohort
+    subs = [cohort_member(i) for i in range(40, 54)]
+    imgs, masks, voxs = zip(*subs)
+    res = {}
+    for parts in ("1", "3", "4"):
+        monkeypatch.setenv("VB_PARTS", parts)
+        dc = cohort.DeviceCohort(imgs, masks, voxs, want_logbias=True)
+        for _ in range(2):
+            dc.step()
+        dc.torch.cuda.synchronize()
+        res[parts] = (dc.stats().tobytes(), dc.n4.cpu().numpy(), dc.defect.cpu().numpy(), dc.defect_lb.cpu().numpy(),
+                      dc.defect_border.cpu().numpy(), dc.ci_shell.cpu().numpy())
+    for parts in ("3", "4"):
+        assert res[parts][0] == res["1"][0]
+        for a, b in zip(res[parts][1:], res["1"][1:]):
+            assert np.array_equal(a, b)

@@ -11,6 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libventb200.so")
 SOURCES = ["ventb200.cu"]
 HEADERS = ["vb_platform.h", "vb_rt.h", "vb_common.cuh", "n4_kernels.cuh", "vdp_kernels.cuh", "ci_kernels.cuh",
+           "overlay_kernels.cuh", "recon_kernels.cuh", "io_kernels.cuh",
            os.path.join("..", "..", "include", "ventb200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

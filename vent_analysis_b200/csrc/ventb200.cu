@@ -55,8 +55,10 @@ struct vb_ctx {
     // workspaces
     N4Ws n4ws[2];
     int wsi = 0;                         // workspace set the next N4 launch uses
-    vbrt::stream_t stream2 = nullptr;    // second compute stream of the host pipeline
-    Buf ws_d0, ws_bits, ws_list, ws_count, dbg, ws_keys_a, ws_keys_b;
+    vbrt::stream_t stream2 = nullptr;    // second compute stream (host pipeline chunks; parts of a resident batch)
+    vbrt::event_t ev_fork = nullptr, ev_join = nullptr;
+    Buf ws_d0, ws_bits, ws_list, ws_count, dbg;
+    Buf ws_keys_a[2], ws_keys_b[2];     // sort scratch of vdp_stats_kernel, one set per compute stream (like n4ws)
     int dbg_stride = 0, dbg_nbins = 0, dbg_Lmax = 0, dbg_n = 0;
     // CI tables
     std::vector<TableHost> tables;
@@ -316,10 +318,12 @@ int run_vdp(vb_ctx* c, const float* n4, const uint8_t* mask, int n, float thresh
         const long long dyn_words = (2 << VB_VDP_LOG_COARSE) + key_cap / VB_VDP_LOAD + key_cap;
         const int grid = std::min(n, c->sms * 2);
         const size_t stride = (size_t)((vmax + 3) & ~3LL);
-        if (!ensure(c->ws_keys_a, 4 * stride * (size_t)grid) || !ensure(c->ws_keys_b, 4 * stride * (size_t)grid)) return VB_ERR_CUDA;
+        Buf& ka = c->ws_keys_a[c->wsi & 1];
+        Buf& kb = c->ws_keys_b[c->wsi & 1];
+        if (!ensure(ka, 4 * stride * (size_t)grid) || !ensure(kb, 4 * stride * (size_t)grid)) return VB_ERR_CUDA;
         if (!vbrt::allow_smem(vdp_stats_kernel, (int)(4 * dyn_words))) return VB_ERR_CUDA;
         VB_LAUNCH(vdp_stats_kernel, dim3(grid), dim3(VB_VDP_THREADS), (size_t)(4 * dyn_words), s, n4, mask,
-                  subj, n, stats, (int)key_cap, (int)dyn_words, (unsigned*)c->ws_keys_a.p, (unsigned*)c->ws_keys_b.p, (long long)stride);
+                  subj, n, stats, (int)key_cap, (int)dyn_words, (unsigned*)ka.p, (unsigned*)kb.p, (long long)stride);
         ++c->launches;
     }
     // fused threshold + linear binning + median + border on row tiles held in shared memory
@@ -441,7 +445,7 @@ void vb_destroy(vb_ctx* c) {
         for (Buf* b : wb) vbrt::dev_free(b->p);
     }
     vbrt::stream_destroy(c->stream2);
-    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_d0, &c->ws_keys_a, &c->ws_keys_b,
+    Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_d0, &c->ws_keys_a[0], &c->ws_keys_a[1], &c->ws_keys_b[0], &c->ws_keys_b[1],
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
                    &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats, &c->m_proton, &c->m_pack, &c->d_voxmin,
                    &c->m_u16, &c->m_bits, &c->m_codes, &c->m_ci_idx, &c->m_ci_val, &c->d_bitoff,
@@ -453,6 +457,7 @@ void vb_destroy(vb_ctx* c) {
     vbrt::host_free(c->h_stats.p);
     for (vbrt::event_t e : c->ev) vbrt::event_destroy(e);
     for (vbrt::event_t e : c->ev_copy) vbrt::event_destroy(e);
+    vbrt::event_destroy(c->ev_fork); vbrt::event_destroy(c->ev_join);
     vbrt::stream_destroy(c->stream_in);
     vbrt::stream_destroy(c->stream_out);
     vbrt::stream_destroy(c->stream);
@@ -627,12 +632,12 @@ int vb_pack6_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const int32
 
 // the selected stages on subjects [r0, r0 + cnt) of the prepared batch (buffers are whole-batch)
 static int pipeline_range(vb_ctx* c, int r0, int cnt, const vb_n4_params* params, float thresh, uint32_t flags,
-                          const vb_buffers* d, vbrt::stream_t s, vbrt::event_t* ev) {
+                          const vb_buffers* d, vbrt::stream_t s, vbrt::event_t* ev, bool clear_stats = true) {
     int rc = VB_OK;
     c->r0 = r0;
     vb_subject_stats* st = d->stats + r0;
     do {
-        if (!vbrt::dev_memset(st, 0, sizeof(vb_subject_stats) * (size_t)cnt, s)) { rc = VB_ERR_CUDA; break; }
+        if (clear_stats && !vbrt::dev_memset(st, 0, sizeof(vb_subject_stats) * (size_t)cnt, s)) { rc = VB_ERR_CUDA; break; }
         if (ev && !vbrt::event_record(ev[0], s)) { rc = VB_ERR_CUDA; break; }
         if (flags & VB_DO_SNR)
             if ((rc = run_snr(c, d->image, d->mask, cnt, 20, st, s))) break;
@@ -684,7 +689,38 @@ int vb_pipeline_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const int
         ev = c->ev.data() + c->ev_used;
         c->ev_used += VB_N_STAGES + 1;
     }
-    return pipeline_range(c, 0, n, params, thresh, flags, d, s, ev);
+    // Large batches run in parts on two streams: while the persistent N4 kernel of part k + 1 holds
+    // the SMs, the CTAs of part k that run out of subjects free theirs one by one -- part k + 1's
+    // CTAs and the (small) VDP / CI kernels of the earlier parts fill that tail instead of leaving
+    // it idle, and only the last part's VDP / CI are exposed.  SNR of the whole batch goes first.
+    int nparts = (n >= 6 * std::max(c->sms, 1)) ? 2 : 1;      // measured on 1776 C2 subjects: 2 parts 85.6 ms, 1: 87.6, 4: 86.4, 6: 86.6
+    if (const char* e = getenv("VB_PARTS")) nparts = std::max(1, std::min(8, atoi(e)));
+    if (!(flags & VB_DO_N4) || c->debug) nparts = 1;
+    if (nparts == 1) return pipeline_range(c, 0, n, params, thresh, flags, d, s, ev);
+    if (!c->ev_fork) {
+        if (!vbrt::event_create(&c->ev_fork) || !vbrt::event_create(&c->ev_join)) return VB_ERR_CUDA;
+    }
+    if (!vbrt::dev_memset(d->stats, 0, sizeof(vb_subject_stats) * (size_t)n, s)) return VB_ERR_CUDA;
+    if (ev && !vbrt::event_record(ev[0], s)) return VB_ERR_CUDA;
+    c->r0 = 0;
+    if ((flags & VB_DO_SNR) && (rc = run_snr(c, d->image, d->mask, n, 20, d->stats, s))) return rc;
+    if (ev && !vbrt::event_record(ev[1], s)) return VB_ERR_CUDA;
+    if (!vbrt::event_record(c->ev_fork, s) || !vbrt::stream_wait(c->stream2, c->ev_fork)) return VB_ERR_CUDA;
+    for (int k = 0; k < nparts; ++k) {
+        const int r0 = (int)((long long)n * k / nparts), r1 = (int)((long long)n * (k + 1) / nparts);
+        vbrt::stream_t ps = (k & 1) ? c->stream2 : s;
+        c->wsi = k & 1;
+        rc = pipeline_range(c, r0, r1 - r0, params, thresh, flags & ~(uint32_t)VB_DO_SNR, d, ps, nullptr, false);
+        c->wsi = 0;
+        if (rc) break;
+    }
+    // join: the caller's stream continues when both are done
+    if (!vbrt::event_record(c->ev_join, c->stream2) || !vbrt::stream_wait(s, c->ev_join)) return VB_ERR_CUDA;
+    if (ev) {                                                  // the stages overlap: N4 = everything up to the join, the rest reads 0
+        for (int k = 2; k <= VB_N_STAGES; ++k)
+            if (!vbrt::event_record(ev[k], s)) return VB_ERR_CUDA;
+    }
+    return rc;
 }
 
 // Host pipelines work in chunks of about one wave of subjects: inputs of chunk k+1 go up and
