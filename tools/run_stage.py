@@ -33,3 +33,9 @@ torch.cuda.synchronize()
 ms, n = ctx.profile_fetch()
 print(os.environ.get("VENTB200_LIB", "default"), {k: round(v / n, 4) for k, v in ms.items()}, "ms per step of", B, "subjects",
       "iters", int(dc.stats()["n4_iters"].sum()))
+if os.environ.get("VB_DUMP_INFO"):
+    import json
+    st = dc.stats()
+    it = st["n4_iters"].sum(axis=1).astype(np.int64)
+    json.dump({"subjects_per_launch": B, "subject_iterations": int(it.sum()),
+               "mask_voxel_iterations": int((it * st["n4_n_mask"].astype(np.int64)).sum())}, open(os.environ["VB_DUMP_INFO"], "w"))

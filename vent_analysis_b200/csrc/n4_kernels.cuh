@@ -67,6 +67,26 @@
 #ifndef VB_N4_PREDICT_END
 #define VB_N4_PREDICT_END 4096                    /* team chunks that start below this predict their starts (full length) */
 #endif
+#ifndef VB_N4_STREAM
+#define VB_N4_STREAM 0                            /* per-iteration streams (log image, voxel codes, chain sequence) bypass L1: the small walk tables stay there */
+#endif
+#if VB_N4_STREAM
+#define VB_N4_LDS(p) vb_ld_stream(p)
+#define VB_N4_STS(p, v) vb_st_stream(p, v)
+#else
+#define VB_N4_LDS(p) (*(p))
+#define VB_N4_STS(p, v) (*(p) = (v))
+#endif
+#ifndef VB_N4_UB
+#define VB_N4_UB 6                                 /* flat update pass: voxels per trip (loads issued together) */
+#endif
+#ifndef VB_N4_MERGED_RED
+#define VB_N4_MERGED_RED 1                        /* n4_update: its four block reductions behind one pair of barriers */
+#endif
+#ifndef VB_N4_G2
+#define VB_N4_G2 1                                /* two coefficient tables (swap) instead of table + copy when both fit */
+#endif
+#define VB_N4_RED 128                             /* doubles of block-reduction scratch */
 #define VB_N4_HCOPIES 32                          /* histogram copies: one per lane (stride nbins | 1) */
 
 struct N4Args {
@@ -88,6 +108,7 @@ struct N4Args {
     uint32_t* ws_order;      // [grid][wb_max]    work items, largest first
     float* ws_axis;          // [grid][axis_stride]  (4-byte words)
     float* ws_ec;            // [grid][Vmax]      convergence sequence exp(old - new) in C order
+    uint32_t* ws_code;       // [grid][Vmax]      per mask voxel (C order): row << 16 | index of its column among the active ones
     int* work_counter;
     float* debug;            // may be null: [n][debug_stride]
     long long Vmax, cmw_max, rbb_max, wb_max, ncols_max;
@@ -212,6 +233,7 @@ struct N4Ctx {
     float* out;
     float* logI;          // compact log image (global memory, L2)
     float* U;             // compact U = logI - bias(L) of the committed lattice (shared or global memory)
+    bool u_smem;          // U lives in shared memory
     uint32_t* colmask;    // [W][ncols]
     uint32_t* rbb;        // [n0][nblk] (+1)
     uint32_t* wbase;      // [nblk][W] (+1)
@@ -223,6 +245,7 @@ struct N4Ctx {
     int union_bytes;      // size of the shared-memory union region
     float* axis_base;
     float* ec;            // [M] exp(old - new) in C order (chain input)
+    uint32_t* code;       // [M] row << 16 | active-column index of every mask voxel (null: volume too large for the packing)
     // row-axis tables (shared memory when they fit, else inside axis_base)
     const float4* r_evw;
     const float4* r_fit3;
@@ -237,11 +260,13 @@ struct N4Ctx {
     float* Om;            // omega lattice of the current level
     float* Phi;           // lattice increment of the last fit (committed by n4_commit)
     float* G;             // [ncp0][gstride] column coefficients of c.L per active column (null: evaluate on the fly)
+    float* G2;            // second table behind G when both fit: the update pass builds the new lattice's table there and swaps
     float* gspace;        // spare shared memory behind the compact log image
     int gcap, gstride;    // floats available there; row stride of G (active columns rounded up to 32)
     float* E;             // E(u|v) table
     float* H;             // histogram
-    double* red;          // 64 doubles reduction scratch
+    double* red;          // VB_N4_RED doubles reduction scratch
+    double* tw;           // FFT twiddles cos | sin, fftN doubles (constant for the launch)
     int ncp[3];
     int slot[3];          // per-axis table length: max(samples, final control points)
     int nbins, fftN, hshift;
@@ -420,7 +445,6 @@ VB_DEV float n4_exp_small(float x) {
 struct N4Item {
     int blk, seg, wi0, wi1, q, k;        // k: index of this lane's column among the active columns
     bool valid, empty;
-    unsigned pos;
 };
 VB_DEV N4Item n4_item(const N4Ctx& c, int it) {
     N4Item I;
@@ -430,8 +454,7 @@ VB_DEV N4Item n4_item(const N4Ctx& c, int it) {
     I.valid = k < c.nact;
     I.k = I.valid ? k : c.nact - 1;
     I.q = (int)c.acol[I.k];
-    I.pos = c.wbase[(size_t)I.blk * c.W + I.wi0];
-    I.empty = c.wbase[(size_t)I.blk * c.W + I.wi1] == I.pos;
+    I.empty = c.wbase[(size_t)I.blk * c.W + I.wi1] == c.wbase[(size_t)I.blk * c.W + I.wi0];
     return I;
 }
 
@@ -464,36 +487,16 @@ VB_DEV N4Walk n4_walk(const N4Ctx& c) {
     return w;
 }
 
-// Walk the mask voxels of one item row by row.  BODY sees: r (row), bit (this lane's voxel is
-// in the mask), idx (compact index of this lane's voxel when bit), bal (lane mask of the row).
-// Rows without any mask voxel in the block are skipped.
+// Walk the mask voxels of one item row by row.  The compact arrays are in C ORDER (row-major over
+// the mask voxels of the volume, the order of the reference's convergence loop): the voxels of one
+// row inside a block of 32 consecutive active columns are contiguous there, starting at the rank
+// rbb[row][block].  BODY sees: r (row), bit (this lane's voxel is in the mask), idx (compact index =
+// C-order rank of this lane's voxel when bit), bal (lane mask of the row).  Rows without any mask
+// voxel in the block are skipped; the per-(row, block) bases of a 32-row word are fetched once by
+// the lanes and broadcast by shuffle.
 #define VB_N4_FOR_ROWS(c, I, ...)                                                            \
     {                                                                                        \
-        unsigned pos_ = (I).pos;                                                             \
-        const unsigned lt_ = (1u << vb_lane()) - 1u;                                         \
-        for (int wi_ = (I).wi0; wi_ < (I).wi1; ++wi_) {                                      \
-            const uint32_t mw_ = (I).valid ? (c).colmask[(size_t)wi_ * (c).ncols + (I).q] : 0u; \
-            uint32_t rem_ = __reduce_or_sync(VB_FULL, mw_);                                  \
-            while (rem_) {                                                                   \
-                const int b_ = __popc((rem_ - 1u) & ~rem_);                                        \
-                rem_ &= rem_ - 1u;                                                           \
-                const int r = wi_ * 32 + b_;                                                 \
-                const bool bit = (mw_ >> b_) & 1u;                                           \
-                const unsigned bal = __ballot_sync(VB_FULL, bit);                            \
-                const unsigned idx = pos_ + (unsigned)__popc(bal & lt_);                     \
-                __VA_ARGS__                                                                  \
-                pos_ += (unsigned)__popc(bal);                                               \
-            }                                                                                \
-        }                                                                                    \
-    }
-
-// Same walk; BODY additionally sees `rank`, the C-order rank of this lane's voxel among the mask
-// voxels (row-major over the whole volume): the per-(row, block) bases of a 32-row word are
-// fetched once by the lanes and broadcast by shuffle.
-#define VB_N4_FOR_ROWS_RANK(c, I, ...)                                                       \
-    {                                                                                        \
-        unsigned pos_ = (I).pos;                                                             \
-        const unsigned lt_ = (1u << vb_lane()) - 1u;                                         \
+        const unsigned lt_ = vb_lanemask_lt();                                                     \
         for (int wi_ = (I).wi0; wi_ < (I).wi1; ++wi_) {                                      \
             const uint32_t mw_ = (I).valid ? (c).colmask[(size_t)wi_ * (c).ncols + (I).q] : 0u; \
             uint32_t rem_ = __reduce_or_sync(VB_FULL, mw_);                                  \
@@ -501,16 +504,13 @@ VB_DEV N4Walk n4_walk(const N4Ctx& c) {
             const int rr_ = wi_ * 32 + vb_lane();                                            \
             const unsigned rbw_ = (rr_ < (c).n0) ? (c).rbb[(size_t)rr_ * (c).nblk + (I).blk] : 0u; \
             while (rem_) {                                                                   \
-                const int b_ = __popc((rem_ - 1u) & ~rem_);                                        \
+                const int b_ = __popc((rem_ - 1u) & ~rem_);                                  \
                 rem_ &= rem_ - 1u;                                                           \
                 const int r = wi_ * 32 + b_;                                                 \
                 const bool bit = (mw_ >> b_) & 1u;                                           \
                 const unsigned bal = __ballot_sync(VB_FULL, bit);                            \
-                const unsigned below_ = (unsigned)__popc(bal & lt_);                         \
-                const unsigned idx = pos_ + below_;                                          \
-                const unsigned rank = __shfl_sync(VB_FULL, rbw_, b_) + below_;               \
+                const unsigned idx = __shfl_sync(VB_FULL, rbw_, b_) + (unsigned)__popc(bal & lt_); \
                 __VA_ARGS__                                                                  \
-                pos_ += (unsigned)__popc(bal);                                               \
             }                                                                                \
         }                                                                                    \
     }
@@ -595,18 +595,20 @@ VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float&
         }
         __syncthreads();
     }
-    if (M <= smem_cap) c.U = smem_logI;                // the compact U image fits shared memory
+    c.u_smem = M <= smem_cap;
+    if (c.u_smem) c.U = smem_logI;                     // the compact U image fits shared memory
 
     float tmin = FLT_MAX, tmax = -FLT_MAX;
     const unsigned lt = (1u << lane) - 1u;
     for (int it = w; it < c.nblk * c.nseg; it += nw) {
         const N4Item I = n4_item(c, it);
         if (I.empty) continue;
-        unsigned pos = I.pos;
         for (int wi = I.wi0; wi < I.wi1; ++wi) {
             const uint32_t mw = I.valid ? c.colmask[(size_t)wi * c.ncols + I.q] : 0u;
             const uint32_t wm = __reduce_or_sync(VB_FULL, mw);
             if (!wm) continue;
+            const int rr = wi * 32 + lane;
+            const unsigned rbw = (rr < c.n0) ? c.rbb[(size_t)rr * c.nblk + I.blk] : 0u;   // C-order rank of the first voxel of (row, block)
 #pragma unroll 1
             for (int b0 = 0; b0 < 32; b0 += 8) {
                 if (((wm >> b0) & 0xFFu) == 0) continue;
@@ -618,15 +620,16 @@ VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float&
                 for (int j = 0; j < 8; ++j) {
                     const bool bit = (mw >> (b0 + j)) & 1u;
                     const unsigned bal = __ballot_sync(VB_FULL, bit);
+                    const unsigned base = __shfl_sync(VB_FULL, rbw, b0 + j);
                     if (bit) {
                         const float l = (x[j] > 0.0f) ? logf(x[j]) : x[j];
-                        const unsigned below = (unsigned)__popc(bal & lt);
-                        c.logI[pos + below] = l;
-                        c.U[pos + below] = l;            // zero lattice: U = log image
+                        const unsigned at = base + (unsigned)__popc(bal & lt);
+                        c.logI[at] = l;
+                        c.U[at] = l;                     // zero lattice: U = log image
+                        if (c.code) c.code[at] = ((uint32_t)(wi * 32 + b0 + j) << 16) | (uint32_t)I.k;
                         tmin = fminf(tmin, l);
                         tmax = fmaxf(tmax, l);
                     }
-                    pos += (unsigned)__popc(bal);
                 }
             }
         }
@@ -676,10 +679,11 @@ VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     const uint32_t one = 1u << c.hshift;
     const float fone = (float)one;
     uint32_t* h = hc + (size_t)(tid & (VB_N4_HCOPIES - 1)) * hstride;
+    const vb_saddr sh = vb_saddr_of(h);                 // this lane's copy, as a 32-bit shared address (RED.shared)
     // U is stored per voxel, so the histogram needs no geometry: a flat, fully populated loop over
     // the compact array (the fixed-point sums do not depend on the order)
     const float* U = c.U;
-    VB_OPAQUE_PTR(U); VB_OPAQUE_PTR(h);
+    VB_OPAQUE_PTR(U);
     const int M = c.M, nbins = c.nbins;
 #pragma unroll 4
     for (int i = tid; i < M; i += nt) {
@@ -689,11 +693,11 @@ VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
         const int bi = (int)fl;
         const float off = cidx - fl;
         if (off == 0.0f) {
-            if (bi >= 0 && bi < nbins) atomicAdd(&h[bi], one);
+            if (bi >= 0 && bi < nbins) vb_reds_add_u32(sh + 4u * (unsigned)bi, one);
         } else if (bi >= 0 && bi < nbins - 1) {
             const uint32_t o = (uint32_t)__float2uint_rn(off * fone);
-            atomicAdd(&h[bi], one - o);
-            atomicAdd(&h[bi + 1], o);
+            vb_reds_add_u32(sh + 4u * (unsigned)bi, one - o);
+            vb_reds_add_u32(sh + 4u * (unsigned)bi + 4u, o);
         }
     }
     n4_sync(T);
@@ -706,6 +710,8 @@ VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     n4_sync(T);
 }
 
+// (Running the whole sharpening step on a sub-team of four or eight warps behind its own named barrier
+// was measured slower: 14.6 -> 16.3 us per iteration, the pointwise passes lose more than the barriers gain.)
 // in-place radix-2 FFT on shared (re, im); tw = exp(-2 pi i k / N); sign<0 forward, >0 backward
 VB_DEV void n4_fft(const N4Team& T, double* re, double* im, int N, int logN, int sign, const double* twr, const double* twi) {
     const int nt = T.nt, tid = T.tid;
@@ -763,6 +769,16 @@ VB_DEV void n4_fft(const N4Team& T, double* re, double* im, int N, int logN, int
 
 // SharpenImage, second half: Wiener-deconvolve the histogram with the Gaussian bias model and
 // build E(u|v).  Two real sequences share one complex FFT (4 FFTs instead of ITK's 7).
+// The twiddles depend only on the (launch-constant) padded histogram size: c.tw, computed once per CTA.
+VB_DEV void n4_twiddles(N4Ctx& c) {
+    const int N = c.fftN;
+    for (int n = (int)threadIdx.x; n < (N >> 1); n += (int)blockDim.x) {
+        double sn, co;
+        vb_sincospi(-2.0 * (double)n / (double)N, &sn, &co);
+        c.tw[n] = co; c.tw[(N >> 1) + n] = sn;
+    }
+    __syncthreads();
+}
 VB_DEV void n4_sharpen(N4Ctx& c, const N4Team& T, float bmin, float bmax, float fwhm, float wiener) {
     const int nt = T.nt, tid = T.tid;
     const int N = c.fftN;
@@ -772,7 +788,7 @@ VB_DEV void n4_sharpen(N4Ctx& c, const N4Team& T, float bmin, float bmax, float 
     double* Ar = c.un_d;          double* Ai = Ar + N;
     double* Br = Ai + N;          double* Bi = Br + N;
     double* Fr = Bi + N;          double* Fi = Fr + N;     // Ff
-    double* twr = Fi + N;         double* twi = twr + (N >> 1);
+    const double* twr = c.tw;     const double* twi = twr + (N >> 1);
     const float slope = (bmax - bmin) / (float)(c.nbins - 1);
     const float sF = fwhm / slope;
     const float expFactor = (float)(4.0 * 0.69314718055994530942 / (double)(sF * sF));
@@ -792,11 +808,6 @@ VB_DEV void n4_sharpen(N4Ctx& c, const N4Team& T, float bmin, float bmax, float 
             const float fn = (float)(n < half ? n : N - n);
             f = scaleFactor * expf(-(fn * fn) * expFactor);
             Ai[n] = (double)f;
-        }
-        if (n < half) {
-            double s, co;
-            vb_sincospi(-2.0 * (double)n / (double)N, &s, &co);
-            twr[n] = co; twi[n] = s;
         }
     }
     n4_sync(T);
@@ -852,23 +863,26 @@ VB_DEV void n4_sharpen(N4Ctx& c, const N4Team& T, float bmin, float bmax, float 
 // 64-bit add from two native 32-bit shared-memory atomics: every wrap of the low word is seen
 // by exactly one adder (the one whose old value + addend overflowed), which forwards the carry.
 // Once all adders are done the pair holds the exact 64-bit sum, whatever the interleaving.
-VB_DEV void n4_add64(unsigned* q, long long x) {
+// Q is addressed through its 32-bit shared address (ATOMS / RED.shared, 32-bit address arithmetic).
+VB_DEV void n4_add64(vb_saddr q, long long x) {
     const unsigned xlo = (unsigned)(unsigned long long)x;
-    const unsigned old = atomicAdd(q, xlo);
+    const unsigned old = vb_atoms_add_u32(q, xlo);
     const unsigned carry = (unsigned)(old + xlo < old);
-    atomicAdd(q + 1, (unsigned)((unsigned long long)x >> 32) + carry);
+    vb_reds_add_u32(q + 4u, (unsigned)((unsigned long long)x >> 32) + carry);
 }
-VB_DEV void n4_qflush(unsigned* Q, int a, int ncp1, int n2, int bc, int s, const float4 wc, float v) {
+VB_DEV void n4_qflush(vb_saddr Q, int a, int ncp1, int n2, int bc, int s, const float4 wc, float v) {
     if (v == 0.0f) return;
-    unsigned* qp = Q + 2 * (((size_t)a * ncp1 + bc) * n2 + s);
+    const vb_saddr qp = Q + 8u * (unsigned)((a * ncp1 + bc) * n2 + s);
+    const unsigned st = 8u * (unsigned)n2;
     n4_add64(qp, __float2ll_rn(wc.x * v * VB_N4_QSCALE));
-    n4_add64(qp + 2 * n2, __float2ll_rn(wc.y * v * VB_N4_QSCALE));
-    n4_add64(qp + 4 * n2, __float2ll_rn(wc.z * v * VB_N4_QSCALE));
-    n4_add64(qp + 6 * n2, __float2ll_rn(wc.w * v * VB_N4_QSCALE));
+    n4_add64(qp + st, __float2ll_rn(wc.y * v * VB_N4_QSCALE));
+    n4_add64(qp + 2u * st, __float2ll_rn(wc.z * v * VB_N4_QSCALE));
+    n4_add64(qp + 3u * st, __float2ll_rn(wc.w * v * VB_N4_QSCALE));
 }
 
-template <bool OMEGA>
-VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
+// SM: U and the row tables live in shared memory (LDS through 32-bit shared addresses in the walk).
+template <bool OMEGA, bool SM>
+VB_DEV void n4_contract_t(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     const int nt = T.nt, tid = T.tid;
     const int ncp0 = c.ncp[0], ncp1 = c.ncp[1], ncp2 = c.ncp[2];
     const int n2 = c.n2;
@@ -880,10 +894,11 @@ VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     unsigned* Q = (unsigned*)c.un_d;                     // [ncp0][ncp1][n2] x {low, high} words
     const N4Walk wk = n4_walk(c);
     const float* U = c.U;
-    const float* E = c.E;
     const float4* rfit3 = c.r_fit3;
     const int* rbfit = c.r_bfit;
-    VB_OPAQUE_PTR(Q); VB_OPAQUE_PTR(U); VB_OPAQUE_PTR(E); VB_OPAQUE_PTR(rfit3); VB_OPAQUE_PTR(rbfit);
+    VB_OPAQUE_PTR(Q); VB_OPAQUE_PTR(U); VB_OPAQUE_PTR(rfit3); VB_OPAQUE_PTR(rbfit);
+    const vb_saddr sQ = vb_saddr_of(Q), sE = vb_saddr_of(c.E);
+    const vb_saddr sU = SM ? vb_saddr_of(c.U) : 0, sW = SM ? vb_saddr_of(c.r_fit3) : 0, sB = SM ? vb_saddr_of(c.r_bfit) : 0;
     const int Qn = ncp0 * ncp1 * n2;
     for (int e = tid; e < 2 * Qn; e += nt) Q[e] = 0u;
     n4_items_begin(c, T);
@@ -898,10 +913,10 @@ VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int cur = -1;                                    // window = coefficients cur .. cur+3
         VB_N4_FOR_ROWS(wk, I, {
-            const int base = rbfit[r];
+            const int base = SM ? vb_lds_s32(sB + 4u * (unsigned)r) : rbfit[r];
             if (cur < 0) cur = base;
             while (cur < base) {                         // warp uniform
-                if (I.valid) n4_qflush(Q, cur, ncp1, n2, bc, ss, wc, a0);
+                if (I.valid) n4_qflush(sQ, cur, ncp1, n2, bc, ss, wc, a0);
                 a0 = a1; a1 = a2; a2 = a3; a3 = 0.f;
                 ++cur;
             }
@@ -912,28 +927,28 @@ VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
                     val = 1.0f;
                     wt = ar.fit2[r];
                 } else {
-                    const float u = U[idx];
+                    const float u = SM ? vb_lds_f32(sU + 4u * idx) : U[idx];
                     const float cidx = n4_div(u - bmin, slope, rslope);
                     const float fl = floorf(cidx);
                     const int bi = (int)fl;
                     float s;
                     if (bi >= 0 && bi < nbm1) {
-                        const float e0 = E[bi], e1 = E[bi + 1];
+                        const float e0 = vb_lds_f32(sE + 4u * (unsigned)bi), e1 = vb_lds_f32(sE + 4u * (unsigned)bi + 4u);
                         s = e0 + (e1 - e0) * (cidx - fl);
                     } else {
-                        s = E[nbm1];
+                        s = vb_lds_f32(sE + 4u * (unsigned)nbm1);
                     }
                     val = u - s;
-                    wt = rfit3[r];
+                    wt = SM ? vb_lds_f32x4(sW + 16u * (unsigned)r) : rfit3[r];
                 }
                 a0 += wt.x * val; a1 += wt.y * val; a2 += wt.z * val; a3 += wt.w * val;
             }
         })
         if (I.valid && cur >= 0) {
-            n4_qflush(Q, cur, ncp1, n2, bc, ss, wc, a0);
-            n4_qflush(Q, cur + 1, ncp1, n2, bc, ss, wc, a1);
-            n4_qflush(Q, cur + 2, ncp1, n2, bc, ss, wc, a2);
-            n4_qflush(Q, cur + 3, ncp1, n2, bc, ss, wc, a3);
+            n4_qflush(sQ, cur, ncp1, n2, bc, ss, wc, a0);
+            n4_qflush(sQ, cur + 1, ncp1, n2, bc, ss, wc, a1);
+            n4_qflush(sQ, cur + 2, ncp1, n2, bc, ss, wc, a2);
+            n4_qflush(sQ, cur + 3, ncp1, n2, bc, ss, wc, a3);
         }
     }
     n4_sync(T);
@@ -963,6 +978,12 @@ VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
         }
     }
     n4_sync(T);
+}
+
+template <bool OMEGA>
+VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
+    if (!OMEGA && c.u_smem && c.rowtab) n4_contract_t<OMEGA, true>(c, T, bmin, bmax);
+    else n4_contract_t<OMEGA, false>(c, T, bmin, bmax);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1089,7 +1110,7 @@ VB_DEV void n4_chain_chunk(N4Ctx& c, const N4Team& T, const float* epx, int star
     float px[VB_N4_EPT];
     N4Step st[VB_N4_EPT];
     if (cnt == VB_N4_EPT && VB_N4_EPT == 8) {                 // lo is a multiple of 8 here: 16-byte loads
-        const float4 p0 = *(const float4*)(epx + lo), p1 = *(const float4*)(epx + lo + 4);
+        const float4 p0 = VB_N4_LDS((const float4*)(epx + lo)), p1 = VB_N4_LDS((const float4*)(epx + lo + 4));
         px[0] = p0.x; px[1] = p0.y; px[2] = p0.z; px[3] = p0.w; px[4] = p1.x; px[5] = p1.y; px[6] = p1.z; px[7] = p1.w;
     } else {
 #pragma unroll
@@ -1264,56 +1285,115 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
 // iteration of a level, debug capture).
 // Returns true when the sequential chain has to be run on c.ec; otherwise `conv` holds the
 // (exact-arithmetic) value and the level certainly continues.
-// the walk of n4_update; TAB: both fields come from coefficient tables (the usual case), which
-// frees the registers of the column weights
-template <bool TAB>
-VB_DEV void n4_update_walk(N4Ctx& c, const N4Team& T, const float* Gn, float& tmin, float& tmax, double& s1, double& s2) {
-    const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
-    // base pointers of this CTA's slots, made opaque: otherwise the compiler re-derives them from
-    // the kernel parameters (blockIdx * stride + base: 5 instructions) at every use in the loop
-    const N4Walk wk = n4_walk(c);
+// The update pass proper.  TAB (the usual case: both fields come from per-column coefficient tables):
+// a FLAT loop over the compact arrays -- thread i takes mask voxel i, i + nt, ... (C order), whose row
+// and active-column index come from the per-voxel code written by n4_setup; the four collapsed
+// coefficients of each field are read from the tables (lanes of a warp sit on consecutive columns of
+// at most a few rows: conflict-free or broadcast).  No row walk, no ballots, every lane busy: 2.3x
+// fewer warp instructions than walking the columns with a sliding window (lane utilisation of the
+// walk is 73 % on the benchmark masks, and its row bookkeeping costs more than the 8 extra loads).
+// !TAB (tables do not fit, or the volume is too large for the code packing): the column walk.
+// s1 / s2: sums of (e - 1) and (e - 1)^2 for the skip bound of n4_update; at most 64 terms are added
+// in float before they move to the double accumulators (relative error of a partial <= 64 * 2^-24,
+// accounted for in the bound).
+// SM: U and the row tables live in shared memory too (the benchmark volumes): every table access of
+// the loop is an LDS / STS through a 32-bit shared address.
+template <bool SM>
+VB_DEV void n4_update_flat(N4Ctx& c, const N4Team& T, const float* Gn, float& tmin, float& tmax, double& s1, double& s2) {
+    const float* logI = c.logI;
+    float* ec = c.ec;
+    const uint32_t* code = c.code;
+    VB_OPAQUE_PTR(logI); VB_OPAQUE_PTR(ec); VB_OPAQUE_PTR(code);
+    float* U = c.U;
+    const float4* revw = c.r_evw;
+    const int* rbev = c.r_bev;
+    if (!SM) { VB_OPAQUE_PTR(U); VB_OPAQUE_PTR(revw); VB_OPAQUE_PTR(rbev); }
+    const vb_saddr sU = SM ? vb_saddr_of(c.U) : 0, sW = SM ? vb_saddr_of(c.r_evw) : 0, sB = SM ? vb_saddr_of(c.r_bev) : 0;
+    const vb_saddr sGo = vb_saddr_of(c.G), sGn = vb_saddr_of(Gn);
+    const int M = c.M, nt = T.nt;
+    const unsigned gs4 = 4u * (unsigned)c.gstride;
+    // VB_N4_UB voxels per trip: their codes and log-image values (L2) are requested together, before
+    // the first of them is evaluated -- the stores of the loop body would otherwise keep the compiler
+    // from moving the next loads up, and a thread would wait one L2 round trip per voxel
+    for (int i0 = T.tid; i0 < M; i0 += 64 * nt) {
+        float f1 = 0.0f, f2 = 0.0f;
+        const int iend = min(M, i0 + 64 * nt);
+        for (int ib = i0; ib < iend; ib += VB_N4_UB * nt) {
+            uint32_t cd[VB_N4_UB];
+            float li[VB_N4_UB];
+#pragma unroll
+            for (int u = 0; u < VB_N4_UB; ++u) {
+                const int i = ib + u * nt;
+                cd[u] = (i < iend) ? VB_N4_LDS(code + i) : 0u;
+                li[u] = (i < iend) ? VB_N4_LDS(logI + i) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < VB_N4_UB; ++u) {
+                const int i = ib + u * nt;
+                if (i < iend) {
+                    const unsigned r = cd[u] >> 16, k = cd[u] & 0xffffu;
+                    const int base = SM ? vb_lds_s32(sB + 4u * r) : rbev[r];
+                    const float4 rw = SM ? vb_lds_f32x4(sW + 16u * r) : revw[r];
+                    const unsigned at = (unsigned)base * gs4 + 4u * k;
+                    const vb_saddr ao = sGo + at, an = sGn + at;
+                    N4Win wo, wn;
+                    wo.g0 = vb_lds_f32(ao); wo.g1 = vb_lds_f32(ao + gs4); wo.g2 = vb_lds_f32(ao + 2u * gs4); wo.g3 = vb_lds_f32(ao + 3u * gs4);
+                    wn.g0 = vb_lds_f32(an); wn.g1 = vb_lds_f32(an + gs4); wn.g2 = vb_lds_f32(an + 2u * gs4); wn.g3 = vb_lds_f32(an + 3u * gs4);
+                    const float bo = n4_win_eval(wo, rw), bn = n4_win_eval(wn, rw);
+                    const float un = li[u] - bn;
+                    if (SM) vb_sts_f32(sU + 4u * (unsigned)i, un); else U[i] = un;   // read by the next histogram / fit
+                    tmin = fminf(tmin, un);
+                    tmax = fmaxf(tmax, un);
+                    const float ev = n4_exp_small(bo - bn);
+                    VB_N4_STS(ec + i, ev);                               // chain input (C order = compact order)
+                    const float em = ev - 1.0f;                          // exact (Sterbenz) for 0.5 <= ev <= 2
+                    f1 += em; f2 = fmaf(em, em, f2);
+                }
+            }
+        }
+        s1 += (double)f1; s2 += (double)f2;
+    }
+}
+
+VB_DEV void n4_update_walk(N4Ctx& c, const N4Team& T, float& tmin, float& tmax, double& s1, double& s2) {
     const float* logI = c.logI;
     float* ec = c.ec;
     float* U = c.U;
     const float4* revw = c.r_evw;
     const int* rbev = c.r_bev;
     VB_OPAQUE_PTR(logI); VB_OPAQUE_PTR(ec); VB_OPAQUE_PTR(U); VB_OPAQUE_PTR(revw); VB_OPAQUE_PTR(rbev);
+    const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
+    const N4Walk wk = n4_walk(c);
     VB_N4_FOR_ITEMS(c, T, it) {
         const N4Item I = n4_item(c, it);
         if (I.empty) continue;
-        N4Col col;
-        if (!TAB) col = n4_col(c, ac, as, I.q);
-        const float* Go = TAB ? c.G + I.k : nullptr;
-        const float* Gw = TAB ? Gn + I.k : nullptr;
+        const N4Col col = n4_col(c, ac, as, I.q);
         N4Win wo, wn;
         wo.cur = wn.cur = -1;
         wo.g0 = wo.g1 = wo.g2 = wo.g3 = wn.g0 = wn.g1 = wn.g2 = wn.g3 = 0.0f;
-        // The log image lives in L2 (a register stream buffer with shuffles and an L1 prefetch of the
-        // rows ahead were both measured slower than the plain load issued before the window updates).
-        VB_N4_FOR_ROWS_RANK(wk, I, {
+        float f1 = 0.0f, f2 = 0.0f;
+        int nf = 0;
+        VB_N4_FOR_ROWS(wk, I, {
             const int base = rbev[r];
             float li = 0.0f;
             if (bit) li = logI[idx];
-            if (TAB) {
-                n4_win_advance_tab(wo, base, Go, c.gstride);
-                n4_win_advance_tab(wn, base, Gw, c.gstride);
-            } else {
-                n4_win_advance(wo, c.Lold, c, col, base);
-                n4_win_advance(wn, c.L, c, col, base);
-            }
+            n4_win_advance(wo, c.Lold, c, col, base);
+            n4_win_advance(wn, c.L, c, col, base);
             if (bit) {
                 const float4 rw = revw[r];
                 const float bo = n4_win_eval(wo, rw), bn = n4_win_eval(wn, rw);
                 const float un = li - bn;
-                U[idx] = un;                                         // read by the next histogram / fit
+                U[idx] = un;
                 tmin = fminf(tmin, un);
                 tmax = fmaxf(tmax, un);
                 const float ev = n4_exp_small(bo - bn);
-                ec[rank] = ev;                                         // chain input, C order
-                const double em = (double)ev - 1.0;
-                s1 += em; s2 += em * em;
+                ec[idx] = ev;
+                const float em = ev - 1.0f;
+                f1 += em; f2 = fmaf(em, em, f2);
             }
+            if (++nf == 64) { s1 += (double)f1; s2 += (double)f2; f1 = f2 = 0.0f; nf = 0; }     // warp uniform
         })
+        s1 += (double)f1; s2 += (double)f2;
     }
 }
 
@@ -1321,25 +1401,62 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
     const int nt = (int)blockDim.x;
     float tmin = FLT_MAX, tmax = -FLT_MAX;
     double s1 = 0.0, s2 = 0.0;
-    float* Gn = c.G ? c.un_f : nullptr;                  // table of the new lattice (union region is free here)
+    float* Gn = c.G ? (c.G2 ? c.G2 : c.un_f) : nullptr;  // table of the new lattice (spare table, else the union region: free here)
     N4Team T;
     T.tid = (int)threadIdx.x; T.nt = nt; T.bar = 0;
     n4_items_begin(c, T);
     if (Gn) n4_build_G(c, c.L, Gn); else __syncthreads();
-    if (Gn) n4_update_walk<true>(c, T, Gn, tmin, tmax, s1, s2);
-    else n4_update_walk<false>(c, T, Gn, tmin, tmax, s1, s2);
+    if (Gn) {
+        if (c.u_smem && c.rowtab) n4_update_flat<true>(c, T, Gn, tmin, tmax, s1, s2);
+        else n4_update_flat<false>(c, T, Gn, tmin, tmax, s1, s2);
+    } else {
+        n4_update_walk(c, T, tmin, tmax, s1, s2);
+    }
+#if !VB_N4_MERGED_RED
     bmin = vb_block_reduce(tmin, VbMinF(), FLT_MAX, (float*)c.red);
     bmax = vb_block_reduce(tmax, VbMaxF(), -FLT_MAX, (float*)c.red);
     s1 = vb_block_reduce(s1, VbAddD(), 0.0, c.red);
     s2 = vb_block_reduce(s2, VbAddD(), 0.0, c.red);
+#else
+    {   // the four block reductions of vb_block_reduce (same trees, same results) behind ONE pair of barriers
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            tmin = fminf(tmin, __shfl_xor_sync(VB_FULL, tmin, m));
+            tmax = fmaxf(tmax, __shfl_xor_sync(VB_FULL, tmax, m));
+            s1 += __shfl_xor_sync(VB_FULL, s1, m);
+            s2 += __shfl_xor_sync(VB_FULL, s2, m);
+        }
+        const int nw = nt >> 5, lane = vb_lane(), w = vb_warp();
+        float* redf = (float*)(c.red + 64);
+        __syncthreads();
+        if (lane == 0) { c.red[w] = s1; c.red[32 + w] = s2; redf[w] = tmin; redf[32 + w] = tmax; }
+        __syncthreads();
+        s1 = (lane < nw) ? c.red[lane] : 0.0;
+        s2 = (lane < nw) ? c.red[32 + lane] : 0.0;
+        tmin = (lane < nw) ? redf[lane] : FLT_MAX;
+        tmax = (lane < nw) ? redf[32 + lane] : -FLT_MAX;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            tmin = fminf(tmin, __shfl_xor_sync(VB_FULL, tmin, m));
+            tmax = fmaxf(tmax, __shfl_xor_sync(VB_FULL, tmax, m));
+            s1 += __shfl_xor_sync(VB_FULL, s1, m);
+            s2 += __shfl_xor_sync(VB_FULL, s2, m);
+        }
+        bmin = tmin; bmax = tmax;
+    }
+#endif
     __syncthreads();
-    if (Gn) {                                            // the new lattice's table becomes the current one
+    if (c.G2) {                                          // the new lattice's table becomes the current one
+        c.G2 = c.G; c.G = Gn;
+    } else if (Gn) {
         for (int e = (int)threadIdx.x; e < c.ncp[0] * c.gstride; e += (int)blockDim.x) c.G[e] = Gn[e];
         __syncthreads();
     }
     if (!exact_needed) {
         const double N = (double)M;
-        double var = (s2 - s1 * s1 / N) / (N - 1.0);
+        // the float partials of s1 / s2 carry a relative error <= 64 * 2^-24 each; |s1| <= sqrt(N s2), so
+        // (N - 1) var is known to within 3 * 4e-6 * s2: the bound uses the low end
+        double var = (s2 * (1.0 - 1.2e-5) - s1 * s1 / N) / (N - 1.0);
         if (var < 0.0) var = 0.0;
         const double mean = 1.0 + s1 / N;
         const double lag = 1.1920929e-7 * N / (4.0 * 1.7320508) * 1.05;
@@ -1471,10 +1588,12 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
     c.Phi = (float*)p;  p += Lb;
     c.E = (float*)p;    p += sizeof(float) * (size_t)((a.p.n_bins + 3) & ~3);
     c.H = (float*)p;    p += sizeof(float) * (size_t)((a.p.n_bins + 3) & ~3);
-    c.red = (double*)p; p += 64 * sizeof(double);
+    c.red = (double*)p; p += VB_N4_RED * sizeof(double);
+    c.tw = (double*)p;  p += sizeof(double) * (size_t)a.fftN;
     float* smem_rowtab = (float*)p; p += (size_t)40 * a.rowtab_rows;
     float* smem_logI = (float*)p;
     c.nbins = a.p.n_bins; c.fftN = a.fftN; c.union_bytes = a.union_bytes;
+    n4_twiddles(c);
 
     for (;;) {
         __syncthreads();
@@ -1495,6 +1614,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         c.ctr = s_ctr;
         c.axis_base = a.ws_axis + (size_t)blockIdx.x * a.axis_stride;
         c.ec = a.ws_ec + (size_t)blockIdx.x * (size_t)((a.Vmax + 3) & ~3LL);
+        c.code = (S.n0 <= 65536 && S.n1 * S.n2 <= 65536) ? a.ws_code + (size_t)blockIdx.x * a.Vmax : nullptr;
         c.ncp[0] = a.p.ncp[0]; c.ncp[1] = a.p.ncp[1]; c.ncp[2] = a.p.ncp[2];
         {
             const int nn[3] = {S.n0, S.n1, S.n2};
@@ -1519,7 +1639,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         {
             const int used = (c.U == smem_logI) ? ((M + 3) & ~3) : 0;
             c.gspace = smem_logI + used; c.gcap = a.logI_cap - used;
-            c.gstride = (c.nact + 31) & ~31; c.G = nullptr;
+            c.gstride = (c.nact + 31) & ~31; c.G = nullptr; c.G2 = nullptr;
         }
         __syncthreads();
         tph[0] = vb_clock() - tq;
@@ -1536,7 +1656,9 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                 n4_build_tables(c);
                 {
                     const int need = c.ncp[0] * c.gstride;
-                    c.G = (need <= c.gcap && need * 4 <= a.union_bytes) ? c.gspace : nullptr;
+                    c.G2 = (VB_N4_G2 && 2 * need <= c.gcap) ? c.gspace + need : nullptr;
+                    c.G = (c.code && need <= c.gcap && (c.G2 || need * 4 <= a.union_bytes)) ? c.gspace : nullptr;
+                    if (!c.G) c.G2 = nullptr;
                     if (c.G) n4_build_G(c, c.L, c.G);
                 }
                 n4_contract<true>(c, full, bmin, bmax);

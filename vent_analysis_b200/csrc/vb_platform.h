@@ -36,6 +36,8 @@ VB_DEV float4 vb_ldg(const float4* p) { return __ldg(p); }
 // streaming (read-once) loads: keep them out of L1
 VB_DEV float vb_ld_stream(const float* p) { return __ldcs(p); }
 VB_DEV uint8_t vb_ld_stream(const uint8_t* p) { return __ldcs(p); }
+VB_DEV uint32_t vb_ld_stream(const uint32_t* p) { return __ldcs(p); }
+VB_DEV float4 vb_ld_stream(const float4* p) { return __ldcs(p); }
 VB_DEV void vb_st_stream(float* p, float v) { __stcs(p, v); }
 // named barriers (ids 1..15) over a warp-aligned subset of the block
 VB_DEV void vb_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -47,7 +49,33 @@ VB_DEV int vb_bar_or(int id, int nthreads, int pred) {
     return out;
 }
 VB_DEV long long vb_clock() { return clock64(); }   // SM cycles
+VB_DEV unsigned vb_lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }   // lanes below this one
 #define VB_OPAQUE_PTR(p) asm volatile("" : "+l"(p))
+// ---- explicit shared-memory accesses through a 32-bit shared-window address ---------------------
+// A pointer into shared memory that has been made opaque (VB_OPAQUE_PTR) is a GENERIC pointer to the
+// compiler: every access through it is a generic LD / ST with 64-bit address arithmetic.  Hot loops
+// take the 32-bit shared address once (opaque as well, so that it is not re-derived from the kernel
+// parameters at each use) and go through LDS / STS with 32-bit address arithmetic instead.
+typedef unsigned vb_saddr;
+VB_DEV vb_saddr vb_saddr_of(const void* p) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+VB_DEV float vb_lds_f32(vb_saddr a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+VB_DEV int vb_lds_s32(vb_saddr a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+VB_DEV float4 vb_lds_f32x4(vb_saddr a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+VB_DEV void vb_sts_f32(vb_saddr a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+VB_DEV unsigned vb_atoms_add_u32(vb_saddr a, unsigned v) {        // ATOMS: returns the old value
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
+VB_DEV void vb_reds_add_u32(vb_saddr a, unsigned v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 // ---- bulk asynchronous copies (TMA, 1-D form) with mbarrier completion --------------------------
 // global -> shared through the async proxy: one thread arms the barrier with the byte count and
 // issues the copy; the bytes land without occupying registers or issue slots, and every consumer
@@ -117,6 +145,7 @@ struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
 static inline double2 make_double2(double a, double b) { return double2{a, b}; }
 static inline int2 make_int2(int a, int b) { return int2{a, b}; }
 
@@ -375,7 +404,16 @@ template <class T> static inline T vb_ldg(const T* p) { return *p; }
 template <class T> static inline T vb_ld_stream(const T* p) { return *p; }
 static inline void vb_st_stream(float* p, float v) { *p = v; }
 static inline long long vb_clock() { return 0; }
+static inline unsigned vb_lanemask_lt() { return (1u << (threadIdx.x & 31u)) - 1u; }
 #define VB_OPAQUE_PTR(p) ((void)0)
+typedef uintptr_t vb_saddr;                  // emulation: the "shared address" is the host address
+static inline vb_saddr vb_saddr_of(const void* p) { return (vb_saddr)p; }
+static inline float vb_lds_f32(vb_saddr a) { return *(const float*)a; }
+static inline int vb_lds_s32(vb_saddr a) { return *(const int*)a; }
+static inline float4 vb_lds_f32x4(vb_saddr a) { return *(const float4*)a; }
+static inline void vb_sts_f32(vb_saddr a, float v) { *(float*)a = v; }
+static inline unsigned vb_atoms_add_u32(vb_saddr a, unsigned v) { return __atomic_fetch_add((unsigned*)a, v, __ATOMIC_SEQ_CST); }
+static inline void vb_reds_add_u32(vb_saddr a, unsigned v) { __atomic_fetch_add((unsigned*)a, v, __ATOMIC_SEQ_CST); }
 // bulk copies: the issuing thread copies synchronously and bumps a completion counter; a phase
 // `parity` of the barrier is complete once the counter has passed it (phases complete in order)
 typedef unsigned long long vb_mbar_t;

@@ -25,7 +25,7 @@ struct Buf {
 // per-resident-CTA workspace of the N4 kernel; two sets so that the launches of consecutive chunks
 // of the host pipeline (two compute streams) can overlap
 struct N4Ws {
-    Buf logI, u, colmask, rbb, wbase, acol, order, ec, axis, counter;
+    Buf logI, u, colmask, rbb, wbase, acol, order, ec, code, axis, counter;
 };
 
 struct TableHost {
@@ -241,9 +241,9 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     // shared memory: [union][L][Lold][Om][Phi][E][H][red][row tables][compact log image]
     const long long Lb = 4 * ((Lmax + 3) & ~3LL), Hb = 4 * ((p.n_bins + 3) & ~3);
     const long long rowtab_rows = (40 * n0max <= 20480) ? ((n0max + 3) & ~3LL) : 0;
-    const long long fixed = 4 * Lb + 2 * Hb + 64 * 8 + 40 * rowtab_rows;
+    const long long fixed = 4 * Lb + 2 * Hb + VB_N4_RED * 8 + 8LL * fftN + 40 * rowtab_rows;
     long long ub = 4LL * VB_N4_HCOPIES * (p.n_bins | 1);                 // histogram copies
-    ub = std::max(ub, 8LL * 7 * fftN);                                   // FFT work arrays
+    ub = std::max(ub, 8LL * 6 * fftN);                                   // FFT work arrays (the twiddles have their own place)
     ub = std::max(ub, 8LL * (long long)ncpf[0] * ncpf[1] * n2max);       // Q[a][b][s], 64-bit fixed point
     ub = std::max(ub, 4LL * Lmax);                                       // refinement scratch
     ub = (ub + 15) & ~15LL;
@@ -257,6 +257,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
         !ensure(W.colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(W.rbb, 4 * (size_t)grid * (size_t)rbb) ||
         !ensure(W.wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(W.acol, 4 * (size_t)grid * (size_t)ncmax) ||
         !ensure(W.order, 4 * (size_t)grid * (size_t)wb) || !ensure(W.ec, 4 * (size_t)grid * (size_t)((vmax + 3) & ~3LL)) ||
+        !ensure(W.code, 4 * (size_t)grid * (size_t)vmax) ||
         !ensure(W.axis, 4 * (size_t)grid * (size_t)axis) || !ensure(W.counter, 64))
         return VB_ERR_CUDA;
     int trace = 0;
@@ -278,7 +279,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     a.subj = subj_ptr(c); a.n = n; a.p = p; a.stats = stats;
     a.ws_logI = (float*)W.logI.p; a.ws_u = (float*)W.u.p; a.ws_colmask = (uint32_t*)W.colmask.p; a.ws_rbb = (uint32_t*)W.rbb.p;
     a.ws_wbase = (uint32_t*)W.wbase.p; a.ws_acol = (uint32_t*)W.acol.p; a.ws_order = (uint32_t*)W.order.p; a.ws_axis = (float*)W.axis.p;
-    a.ws_ec = (float*)W.ec.p; a.rowtab_rows = (int)rowtab_rows;
+    a.ws_ec = (float*)W.ec.p; a.ws_code = (uint32_t*)W.code.p; a.rowtab_rows = (int)rowtab_rows;
     { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] == '1') ? 1 : 0; }
     a.work_counter = (int*)W.counter.p; a.debug = dbg;
     a.Vmax = vmax; a.cmw_max = cmw; a.rbb_max = rbb; a.wb_max = wb; a.ncols_max = ncmax;
@@ -441,7 +442,7 @@ void vb_destroy(vb_ctx* c) {
     vbrt::set_device(c->device);
     vbrt::stream_sync(c->stream);
     for (N4Ws& W : c->n4ws) {
-        Buf* wb[] = {&W.logI, &W.u, &W.colmask, &W.rbb, &W.wbase, &W.acol, &W.order, &W.ec, &W.axis, &W.counter};
+        Buf* wb[] = {&W.logI, &W.u, &W.colmask, &W.rbb, &W.wbase, &W.acol, &W.order, &W.ec, &W.code, &W.axis, &W.counter};
         for (Buf* b : wb) vbrt::dev_free(b->p);
     }
     vbrt::stream_destroy(c->stream2);
