@@ -52,6 +52,12 @@ template <class K> inline int static_smem(K kernel) {
     return (int)fa.sharedSizeBytes;
 }
 inline bool stream_create(stream_t* s) { return ok(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking), "cudaStreamCreate"); }
+// a stream whose kernels the block scheduler prefers over those of the default-priority streams
+inline bool stream_create_high(stream_t* s) {
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); greatest = 0; }
+    return ok(cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, greatest), "cudaStreamCreateWithPriority");
+}
 inline void stream_destroy(stream_t s) { if (s) cudaStreamDestroy(s); }
 typedef cudaEvent_t event_t;
 inline bool event_create(event_t* e) { return ok(cudaEventCreate(e), "cudaEventCreate"); }
@@ -80,6 +86,7 @@ inline int max_smem_optin(int) { return 232448; }
 template <class K> inline bool allow_smem(K, int) { return true; }
 template <class K> inline int static_smem(K) { return 0; }
 inline bool stream_create(stream_t* s) { *s = nullptr; return true; }
+inline bool stream_create_high(stream_t* s) { *s = nullptr; return true; }
 inline void stream_destroy(stream_t) {}
 typedef void* event_t;
 inline bool event_create(event_t* e) { *e = nullptr; return true; }

@@ -24,6 +24,7 @@ struct Buf {
 
 // per-resident-CTA workspace of the N4 kernel; two sets so that the launches of consecutive chunks
 // of the host pipeline (two compute streams) can overlap
+#define VB_MAX_CSTREAMS 4
 struct N4Ws {
     Buf logI, u, colmask, rbb, wbase, acol, order, ec, code, axis, counter;
 };
@@ -53,10 +54,17 @@ struct vb_ctx {
     Buf h_desc, h_stats, d_subj, d_wordoff;   // h_*: pinned host staging
     long long v_total = 0, words_total = 0;
     // workspaces
-    N4Ws n4ws[2];
-    int wsi = 0;                         // workspace set the next N4 launch uses
+    N4Ws n4ws[VB_MAX_CSTREAMS];
+    int wsi = 0;                         // N4 workspace set the next N4 launch uses (= compute stream of the chunk)
+    int ksi = 0;                         // sort-scratch set the next vdp_stats launch uses (= parity of the chunk)
+    vbrt::stream_t cextra[VB_MAX_CSTREAMS - 2] = {};   // further compute streams of the host pipelines (after stream, stream2)
+    int n_cstreams = 4;                  // compute streams the host pipelines rotate over (measured on 1776 C2 subjects: 2: 88.2, 3: 86.4, 4: 85.8 ms)
     vbrt::stream_t stream2 = nullptr;    // second compute stream (host pipeline chunks; parts of a resident batch)
-    vbrt::event_t ev_fork = nullptr, ev_join = nullptr;
+    vbrt::stream_t post[2] = {nullptr, nullptr};   // high-priority streams of the stages after N4 (VDP, borders, CI, output packing)
+    vbrt::stream_t pre[2] = {nullptr, nullptr};    // high-priority streams of the stages before N4 (input unpacking, SNR)
+    std::vector<vbrt::event_t> ev_pre;   // inputs of chunk k unpacked, SNR done -> its N4 may start
+    std::vector<vbrt::event_t> ev_post;  // N4 of chunk k done -> its later stages may start
+    vbrt::event_t ev_fork = nullptr, ev_joins[3] = {nullptr, nullptr, nullptr};
     Buf ws_d0, ws_bits, ws_list, ws_count, dbg;
     Buf ws_keys_a[2], ws_keys_b[2];     // sort scratch of vdp_stats_kernel, one set per compute stream (like n4ws)
     int dbg_stride = 0, dbg_nbins = 0, dbg_Lmax = 0, dbg_n = 0;
@@ -252,7 +260,7 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
         return fail(VB_ERR_UNSUPPORTED, "N4: working set does not fit the 227 KB of shared memory");
     const long long cap = ((long long)c->max_smem - ub - fixed - static_smem) / 4;
     const int grid = std::min(n, c->sms);
-    N4Ws& W = c->n4ws[c->wsi & 1];
+    N4Ws& W = c->n4ws[c->wsi % VB_MAX_CSTREAMS];
     if (!ensure(W.logI, sizeof(float) * (size_t)grid * (size_t)vmax) || !ensure(W.u, sizeof(float) * (size_t)grid * (size_t)vmax) ||
         !ensure(W.colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(W.rbb, 4 * (size_t)grid * (size_t)rbb) ||
         !ensure(W.wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(W.acol, 4 * (size_t)grid * (size_t)ncmax) ||
@@ -319,8 +327,8 @@ int run_vdp(vb_ctx* c, const float* n4, const uint8_t* mask, int n, float thresh
         const long long dyn_words = (2 << VB_VDP_LOG_COARSE) + key_cap / VB_VDP_LOAD + key_cap;
         const int grid = std::min(n, c->sms * 2);
         const size_t stride = (size_t)((vmax + 3) & ~3LL);
-        Buf& ka = c->ws_keys_a[c->wsi & 1];
-        Buf& kb = c->ws_keys_b[c->wsi & 1];
+        Buf& ka = c->ws_keys_a[c->ksi & 1];
+        Buf& kb = c->ws_keys_b[c->ksi & 1];
         if (!ensure(ka, 4 * stride * (size_t)grid) || !ensure(kb, 4 * stride * (size_t)grid)) return VB_ERR_CUDA;
         if (!vbrt::allow_smem(vdp_stats_kernel, (int)(4 * dyn_words))) return VB_ERR_CUDA;
         VB_LAUNCH(vdp_stats_kernel, dim3(grid), dim3(VB_VDP_THREADS), (size_t)(4 * dyn_words), s, n4, mask,
@@ -429,10 +437,13 @@ int vb_create(int device, vb_ctx** out) {
     c->sms = vbrt::sm_count(device);
     c->max_smem = vbrt::max_smem_optin(device);
     if (!vbrt::stream_create(&c->stream) || !vbrt::stream_create(&c->stream_in) || !vbrt::stream_create(&c->stream_out) ||
-        !vbrt::stream_create(&c->stream2)) {
+        !vbrt::stream_create(&c->stream2) || !vbrt::stream_create_high(&c->post[0]) || !vbrt::stream_create_high(&c->post[1]) ||
+        !vbrt::stream_create_high(&c->pre[0]) || !vbrt::stream_create_high(&c->pre[1]) ||
+        !vbrt::stream_create(&c->cextra[0]) || !vbrt::stream_create(&c->cextra[1])) {
         delete c;
         return VB_ERR_CUDA;
     }
+    if (const char* e = getenv("VB_N4_STREAMS")) c->n_cstreams = std::max(1, std::min(VB_MAX_CSTREAMS, atoi(e)));   // tuning
     *out = c;
     return VB_OK;
 }
@@ -446,6 +457,11 @@ void vb_destroy(vb_ctx* c) {
         for (Buf* b : wb) vbrt::dev_free(b->p);
     }
     vbrt::stream_destroy(c->stream2);
+    vbrt::stream_destroy(c->post[0]); vbrt::stream_destroy(c->post[1]);
+    for (vbrt::event_t e : c->ev_post) vbrt::event_destroy(e);
+    vbrt::stream_destroy(c->pre[0]); vbrt::stream_destroy(c->pre[1]);
+    vbrt::stream_destroy(c->cextra[0]); vbrt::stream_destroy(c->cextra[1]);
+    for (vbrt::event_t e : c->ev_pre) vbrt::event_destroy(e);
     Buf* bufs[] = {&c->d_subj, &c->d_wordoff, &c->ws_d0, &c->ws_keys_a[0], &c->ws_keys_a[1], &c->ws_keys_b[0], &c->ws_keys_b[1],
                    &c->ws_bits, &c->ws_list, &c->ws_count, &c->dbg, &c->d_tables, &c->m_image, &c->m_mask, &c->m_n4,
                    &c->m_logbias, &c->m_defect, &c->m_lb, &c->m_dborder, &c->m_mborder, &c->m_shell, &c->m_stats, &c->m_proton, &c->m_pack, &c->d_voxmin,
@@ -458,7 +474,8 @@ void vb_destroy(vb_ctx* c) {
     vbrt::host_free(c->h_stats.p);
     for (vbrt::event_t e : c->ev) vbrt::event_destroy(e);
     for (vbrt::event_t e : c->ev_copy) vbrt::event_destroy(e);
-    vbrt::event_destroy(c->ev_fork); vbrt::event_destroy(c->ev_join);
+    vbrt::event_destroy(c->ev_fork);
+    for (vbrt::event_t e : c->ev_joins) vbrt::event_destroy(e);
     vbrt::stream_destroy(c->stream_in);
     vbrt::stream_destroy(c->stream_out);
     vbrt::stream_destroy(c->stream);
@@ -660,6 +677,52 @@ static int pipeline_range(vb_ctx* c, int r0, int cnt, const vb_n4_params* params
     return rc;
 }
 
+// Chunk k of a host pipeline (or part k of a large resident batch), on three streams:
+//   `pre`  the chunk's inputs are ready there (the caller has queued the unpacking); SNR runs there too.
+//          The host pipelines pass a HIGH-PRIORITY stream: these small kernels would otherwise sit in
+//          front of the chunk's N4 launch on the compute stream and could only start once SMs held by
+//          the other chunk's N4 CTAs retire -- N4 of chunk k then waited for a trickle of SNR CTAs.
+//   `cs`   the persistent N4 kernel; consecutive chunks alternate between two compute streams (and N4
+//          workspace sets), so the stragglers of one chunk's N4 overlap the next chunk's CTAs.
+//   *ps    (returned) the stages after N4 on a high-priority stream of their own: N4 of chunk k + 2
+//          only waits for N4 of chunk k, not for chunk k's VDP / CI kernels, and those get a retiring
+//          SM before the next N4 CTA does.  The chunk's outputs are complete on *ps.
+static bool chunk_edge(std::vector<vbrt::event_t>& evs, int k, vbrt::stream_t from, vbrt::stream_t to) {
+    if (from == to) return true;
+    while (evs.size() <= (size_t)k) {
+        vbrt::event_t e;
+        if (!vbrt::event_create(&e)) return false;
+        evs.push_back(e);
+    }
+    return vbrt::event_record(evs[(size_t)k], from) && vbrt::stream_wait(to, evs[(size_t)k]);
+}
+static int chunk_stages(vb_ctx* c, int k, int r0, int cnt, const vb_n4_params* params, float thresh, uint32_t flags,
+                        const vb_buffers* d, vbrt::stream_t pre, vbrt::stream_t cs, int ws, vbrt::stream_t* ps, bool clear_stats) {
+    const uint32_t f_pre = flags & (uint32_t)VB_DO_SNR, f_n4 = flags & (uint32_t)VB_DO_N4, f_post = flags & ~(f_pre | f_n4);
+    const bool split = f_n4 && !getenv("VB_NO_POST_STREAMS");
+    *ps = cs;
+    int rc = VB_OK;
+    c->wsi = ws; c->ksi = k & 1;
+    if (!split) {                                            // no N4 kernel to work around: one stream
+        if (!chunk_edge(c->ev_pre, k, pre, cs)) rc = VB_ERR_CUDA;
+        if (!rc) rc = pipeline_range(c, r0, cnt, params, thresh, flags, d, cs, nullptr, clear_stats);
+        c->wsi = 0; c->ksi = 0;
+        return rc;
+    }
+    rc = pipeline_range(c, r0, cnt, params, thresh, f_pre, d, pre, nullptr, clear_stats);       // (clears the records,) SNR
+    if (!rc && !chunk_edge(c->ev_pre, k, pre, cs)) rc = VB_ERR_CUDA;
+    c->wsi = ws; c->ksi = k & 1;
+    if (!rc) rc = pipeline_range(c, r0, cnt, params, thresh, f_n4, d, cs, nullptr, false);
+    if (!rc && f_post) {
+        *ps = c->post[k & 1];
+        if (!chunk_edge(c->ev_post, k, cs, *ps)) rc = VB_ERR_CUDA;
+        c->wsi = ws; c->ksi = k & 1;
+        if (!rc) rc = pipeline_range(c, r0, cnt, params, thresh, f_post, d, *ps, nullptr, false);
+    }
+    c->wsi = 0; c->ksi = 0;
+    return rc;
+}
+
 static int pipeline_check(uint32_t flags, const int32_t* handles, const vb_n4_params* params, const vb_buffers* d) {
     if ((flags & VB_DO_CI) && !handles) return fail(VB_ERR_ARG, "pipeline: CI needs table handles");
     if ((flags & VB_DO_SNR) && !d->image) return fail(VB_ERR_ARG, "pipeline: SNR needs image");
@@ -699,7 +762,7 @@ int vb_pipeline_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const int
     if (!(flags & VB_DO_N4) || c->debug) nparts = 1;
     if (nparts == 1) return pipeline_range(c, 0, n, params, thresh, flags, d, s, ev);
     if (!c->ev_fork) {
-        if (!vbrt::event_create(&c->ev_fork) || !vbrt::event_create(&c->ev_join)) return VB_ERR_CUDA;
+        if (!vbrt::event_create(&c->ev_fork)) return VB_ERR_CUDA;
     }
     if (!vbrt::dev_memset(d->stats, 0, sizeof(vb_subject_stats) * (size_t)n, s)) return VB_ERR_CUDA;
     if (ev && !vbrt::event_record(ev[0], s)) return VB_ERR_CUDA;
@@ -709,14 +772,19 @@ int vb_pipeline_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const int
     if (!vbrt::event_record(c->ev_fork, s) || !vbrt::stream_wait(c->stream2, c->ev_fork)) return VB_ERR_CUDA;
     for (int k = 0; k < nparts; ++k) {
         const int r0 = (int)((long long)n * k / nparts), r1 = (int)((long long)n * (k + 1) / nparts);
-        vbrt::stream_t ps = (k & 1) ? c->stream2 : s;
-        c->wsi = k & 1;
-        rc = pipeline_range(c, r0, r1 - r0, params, thresh, flags & ~(uint32_t)VB_DO_SNR, d, ps, nullptr, false);
-        c->wsi = 0;
+        vbrt::stream_t ps;
+        vbrt::stream_t cs = (k & 1) ? c->stream2 : s;
+        rc = chunk_stages(c, k, r0, r1 - r0, params, thresh, flags & ~(uint32_t)VB_DO_SNR, d, cs, cs, k & 1, &ps, false);
         if (rc) break;
     }
-    // join: the caller's stream continues when both are done
-    if (!vbrt::event_record(c->ev_join, c->stream2) || !vbrt::stream_wait(s, c->ev_join)) return VB_ERR_CUDA;
+    // join: the caller's stream continues when all of them are done
+    {
+        vbrt::stream_t js[3] = {c->stream2, c->post[0], c->post[1]};
+        for (int j = 0; j < 3; ++j) {
+            if (!c->ev_joins[j] && !vbrt::event_create(&c->ev_joins[j])) return VB_ERR_CUDA;
+            if (!vbrt::event_record(c->ev_joins[j], js[j]) || !vbrt::stream_wait(s, c->ev_joins[j])) return VB_ERR_CUDA;
+        }
+    }
     if (ev) {                                                  // the stages overlap: N4 = everything up to the join, the rest reads 0
         for (int k = 2; k <= VB_N_STAGES; ++k)
             if (!vbrt::event_record(ev[k], s)) return VB_ERR_CUDA;
@@ -724,16 +792,19 @@ int vb_pipeline_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const int
     return rc;
 }
 
-// Host pipelines work in chunks of about one wave of subjects: inputs of chunk k+1 go up and
-// outputs of chunk k-1 come down (two copy streams) while chunk k computes.  Large batches start
-// with two smaller chunks (1/4 and 1/2 wave): nothing overlaps the first upload.  (Small chunks at
-// the END were measured slower: a chunk cannot take less than one subject's latency.)
+// Host pipelines work in chunks of a bit less than one wave of subjects: inputs of chunk k+1 go up
+// and outputs of chunk k-1 come down (two copy streams) while chunk k computes; up to four chunks'
+// N4 kernels are in flight (compute streams), so an SM that retires a subject always finds a CTA of
+// a later chunk waiting.  Large batches start with two smaller chunks (1/4 and 1/2 wave): nothing
+// overlaps the first upload.  (Small chunks at the END were measured slower: a chunk cannot take
+// less than one subject's latency.)
 static std::vector<int> chunk_bounds(const vb_ctx* c, int n) {
-    const int per = std::max(c->sms, 1);
+    int per = std::max(c->sms, 1);
+    if (const char* e = getenv("VB_CHUNK_PER")) per = std::max(1, atoi(e));     // tuning: subjects per chunk
     std::vector<int> bounds;
     if (n >= 6 * per) {
         const int a = std::max(1, per / 4), b = std::max(1, per / 2);
-        const int rest = n - (a + b), nm = std::max(1, std::min(14, rest / per));
+        const int rest = n - (a + b), nm = std::max(1, std::min(14, 2 * rest / per));       // about 0.8 waves per chunk
         bounds.push_back(0); bounds.push_back(a); bounds.push_back(a + b);
         for (int k = 1; k <= nm; ++k) bounds.push_back(a + b + (int)((long long)rest * k / nm));
     } else {
@@ -748,6 +819,12 @@ static bool drain(vb_ctx* c) {
     bool ok = vbrt::stream_sync(c->stream_in);
     ok = vbrt::stream_sync(c->stream) && ok;
     ok = vbrt::stream_sync(c->stream2) && ok;
+    ok = vbrt::stream_sync(c->post[0]) && ok;
+    ok = vbrt::stream_sync(c->post[1]) && ok;
+    ok = vbrt::stream_sync(c->pre[0]) && ok;
+    ok = vbrt::stream_sync(c->pre[1]) && ok;
+    ok = vbrt::stream_sync(c->cextra[0]) && ok;
+    ok = vbrt::stream_sync(c->cextra[1]) && ok;
     ok = vbrt::stream_sync(c->stream_out) && ok;
     return ok;
 }
@@ -826,15 +903,15 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
         if (need_def && !(flags & VB_DO_VDP)) ok = ok && vbrt::h2d((uint8_t*)c->m_defect.p + v0, h->defect + v0, nv, si);
         // consecutive chunks alternate between two compute streams (and N4 workspace sets), so the
         // stragglers of one chunk's persistent N4 kernel overlap the next chunk's CTAs
-        vbrt::stream_t cs = (k & 1) ? c->stream2 : s;
-        ok = ok && vbrt::event_record(c->ev_copy[2 * (size_t)k], si) && vbrt::stream_wait(cs, c->ev_copy[2 * (size_t)k]);
+        const int ci = k % c->n_cstreams;                    // compute stream (and N4 workspace set) of this chunk
+        vbrt::stream_t cs = ci == 0 ? s : ci == 1 ? c->stream2 : c->cextra[ci - 2], pre = c->pre[k & 1];
+        ok = ok && vbrt::event_record(c->ev_copy[2 * (size_t)k], si) && vbrt::stream_wait(pre, c->ev_copy[2 * (size_t)k]);
         if (!ok) break;
-        c->wsi = k & 1;
-        rc = pipeline_range(c, r0, r1 - r0, params, thresh, flags, &d, cs, nullptr);
-        c->wsi = 0;
+        vbrt::stream_t ps = cs;
+        rc = chunk_stages(c, k, r0, r1 - r0, params, thresh, flags, &d, pre, cs, ci, &ps, true);
         if (rc) { drain(c); return rc; }
         vbrt::stream_t so = c->stream_out;
-        ok = ok && vbrt::event_record(c->ev_copy[2 * (size_t)k + 1], cs) && vbrt::stream_wait(so, c->ev_copy[2 * (size_t)k + 1]);
+        ok = ok && vbrt::event_record(c->ev_copy[2 * (size_t)k + 1], ps) && vbrt::stream_wait(so, c->ev_copy[2 * (size_t)k + 1]);
         if (!so_only) {
         if (flags & VB_DO_N4) ok = ok && vbrt::d2h(h->n4 + v0, d.n4 + v0, 4 * nv, so);
         if (d.logbias) ok = ok && vbrt::d2h(h->logbias + v0, d.logbias + v0, 4 * nv, so);
@@ -936,8 +1013,9 @@ int vb_pipeline_batch_host_packed(vb_ctx* c, int32_t n, const int32_t* shapes, c
         else ok = ok && vbrt::h2d((uint8_t*)c->m_mask.p + v0, io->mask_u8 + v0, nv, si);
         if (io->image_u16) ok = ok && vbrt::h2d((uint16_t*)c->m_u16.p + v0, io->image_u16 + v0, 2 * nv, si);
         else ok = ok && vbrt::h2d((float*)c->m_image.p + v0, io->image_f32 + v0, 4 * nv, si);
-        vbrt::stream_t cs = (k & 1) ? c->stream2 : s;
-        ok = ok && vbrt::event_record(c->ev_copy[3 * (size_t)k], si) && vbrt::stream_wait(cs, c->ev_copy[3 * (size_t)k]);
+        const int ci = k % c->n_cstreams;                    // compute stream (and N4 workspace set) of this chunk
+        vbrt::stream_t cs = ci == 0 ? s : ci == 1 ? c->stream2 : c->cextra[ci - 2], pre = c->pre[k & 1];
+        ok = ok && vbrt::event_record(c->ev_copy[3 * (size_t)k], si) && vbrt::stream_wait(pre, c->ev_copy[3 * (size_t)k]);
         if (!ok) break;
         vbrt::clear_stale_error();
         long long vmax = 0;
@@ -949,14 +1027,12 @@ int vb_pipeline_batch_host_packed(vb_ctx* c, int32_t n, const int32_t* shapes, c
             ua.bit_off = (const long long*)c->d_bitoff.p + r0;
             ua.subj = (const VbSubject*)c->d_subj.p + r0;
             ua.image = (float*)c->m_image.p; ua.mask = (uint8_t*)c->m_mask.p;
-            VB_LAUNCH(io_unpack_kernel, dim3(grid_x_for(c, cnt, (vmax + 31) / 32, 256), cnt), dim3(256), 0, cs, ua);
+            VB_LAUNCH(io_unpack_kernel, dim3(grid_x_for(c, cnt, (vmax + 31) / 32, 256), cnt), dim3(256), 0, pre, ua);
             ++c->launches;
             if (!vbrt::last_launch_ok("io_unpack_kernel")) { ok = false; break; }
         }
-        c->wsi = k & 1;
-        rc = pipeline_range(c, r0, cnt, params, thresh, flags & ~(mb ? 0u : (uint32_t)VB_DO_MASK_BORDER), &d, cs, nullptr);
-        c->wsi = 0;
-        if (rc) { drain(c); return rc; }
+        rc = chunk_stages(c, k, r0, cnt, params, thresh, flags & ~(mb ? 0u : (uint32_t)VB_DO_MASK_BORDER), &d, pre, cs, ci, &cs, true);
+        if (rc) { drain(c); return rc; }                    // (cs is now the stream the chunk's later stages ran on)
         if (io->codes) {
             CodesArgs ca;
             ca.lb = d.defect_lb; ca.defect = d.defect; ca.dborder = d.defect_border; ca.mborder = d.mask_border;
