@@ -284,3 +284,35 @@ def test_resident_batch_in_parts_on_two_streams_changes_nothing(ctx, monkeypatch
         assert res[parts][0] == res["1"][0]
         for a, b in zip(res[parts][1:], res["1"][1:]):
             assert np.array_equal(a, b)
+
+
+def test_host_pipelines_in_many_chunks_over_four_streams_change_nothing(ctx, monkeypatch):
+    """The host pipelines cut a batch into chunks whose N4 kernels rotate over four compute streams while
+    the stages before / after N4 run on high-priority streams of their own: with chunks of three
+    subjects (ten or more chunks in flight over all the streams) every output is identical to the
+    one-chunk run, call after call, for the dense and for the compact entry point."""
+    from vent_analysis_b200 import cohort
+    subs = [cohort_member(i) for i in range(60, 90)]
+    imgs, masks, voxs = zip(*subs)
+    shapes = np.ascontiguousarray([im.shape for im in imgs], dtype=np.int32)
+    handles = cohort.table_handles(ctx, shapes, voxs)
+    img = np.concatenate([np.rint(np.clip(im, 0, 65535)).astype(np.float32).ravel() for im in imgs])
+    msk = np.concatenate([m.ravel() for m in masks])
+    p = ctx.default_n4_params(max_iter=(6, 4, 3))
+    flags = cohort.ALL_STAGES | _lib.DO_MASK_BORDER
+    keys = ("n4", "defect", "defect_lb", "defect_border", "mask_border", "ci_shell")
+    monkeypatch.setenv("VB_CHUNK_PER", "100000")                       # one chunk
+    ref = ctx.pipeline_host(shapes, flags, image=img, mask=msk, handles=handles, params=p)
+    assert ref["rc"] == 0
+    monkeypatch.setenv("VB_CHUNK_PER", "3")
+    for rep in range(3):
+        got = ctx.pipeline_host(shapes, flags, image=img, mask=msk, handles=handles, params=p)
+        assert got["rc"] == 0 and got["stats"].tobytes() == ref["stats"].tobytes(), rep
+        for k in keys:
+            assert np.array_equal(got[k], ref[k]), (k, rep)
+        pk = ctx.pipeline_host_packed(shapes, flags, image_f32=img, mask_u8=msk, handles=handles, params=p)
+        assert pk["rc"] == 0
+        un = _lib.unpack_outputs(pk, shapes)
+        assert un["stats"].tobytes() == ref["stats"].tobytes(), rep
+        for k in keys:
+            assert np.array_equal(un[k], ref[k]), (k, rep)
