@@ -732,6 +732,9 @@ VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
 
 // (Running the whole sharpening step on a sub-team of four or eight warps behind its own named barrier
 // was measured slower: 14.6 -> 16.3 us per iteration, the pointwise passes lose more than the barriers gain.)
+// (Out-of-place transforms with three radix-2 stages per pass -- bit reversal folded into the first pass,
+// 13 instead of 21 team barriers per sharpening step -- measured 14.2 -> 14.1 us: the step is not bound by its
+// barriers; the 16 doubles a thread then holds cost the other phases registers: 74.4 -> 78.0 ms per 1776 subjects.)
 // in-place radix-2 FFT on shared (re, im); tw = exp(-2 pi i k / N); sign<0 forward, >0 backward
 VB_DEV void n4_fft(const N4Team& T, double* re, double* im, int N, int logN, int sign, const double* twr, const double* twi) {
     const int nt = T.nt, tid = T.tid;
@@ -1275,7 +1278,8 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
     // full length; after that a chunk is never longer than the number of elements before it (the
     // start perturbations then contract) and the flat guess (a stalling mean) is the better one.
     // (requesting the elements of chunk k + 1 before chunk k sweeps was measured slower: the eight
-    // values do not survive the sweeps in registers, 75.3 -> 77.2 ms per 1776 subjects)
+    // values do not survive the sweeps in registers, 75.3 -> 77.2 ms per 1776 subjects; a
+    // prefetch.global.L1 of them changed nothing, loads that do not allocate in L1 cost 2 %)
     for (int start = max(S0, wend); start < M;) {
         if (start < VB_N4_PREDICT_END) {
             const int len = min(T.nt * VB_N4_EPT, M - start);
