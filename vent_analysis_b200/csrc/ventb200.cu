@@ -771,7 +771,17 @@ int vb_pipeline_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const int
     if (ev && !vbrt::event_record(ev[1], s)) return VB_ERR_CUDA;
     if (!vbrt::event_record(c->ev_fork, s) || !vbrt::stream_wait(c->stream2, c->ev_fork)) return VB_ERR_CUDA;
     for (int k = 0; k < nparts; ++k) {
-        const int r0 = (int)((long long)n * k / nparts), r1 = (int)((long long)n * (k + 1) / nparts);
+        // two parts: the last one is a single wave of subjects -- its VDP / CI kernels are the only ones
+        // nothing overlaps
+        int r0 = (int)((long long)n * k / nparts), r1 = (int)((long long)n * (k + 1) / nparts);
+        // (measured on 1776 C2 subjects, first part 50 / 67 / 75 / 84 / 92 %: 74.5 / 73.9 / 73.5 / 73.2 / 73.0 ms)
+        const int sm = std::max(c->sms, 1);
+        if (nparts == 2 && n >= 2 * sm) {
+            int cut = n - sm;                                  // last part: one wave
+            if (const char* e = getenv("VB_PART_SPLIT"))       // tuning: first part in per cent
+                cut = std::max(sm, std::min(n - sm, (int)((long long)n * std::max(10, std::min(95, atoi(e))) / 100) / sm * sm));
+            r0 = k == 0 ? 0 : cut; r1 = k == 0 ? cut : n;
+        }
         vbrt::stream_t ps;
         vbrt::stream_t cs = (k & 1) ? c->stream2 : s;
         rc = chunk_stages(c, k, r0, r1 - r0, params, thresh, flags & ~(uint32_t)VB_DO_SNR, d, cs, cs, k & 1, &ps, false);
@@ -807,6 +817,16 @@ static std::vector<int> chunk_bounds(const vb_ctx* c, int n) {
         const int rest = n - (a + b), nm = std::max(1, std::min(14, 2 * rest / per));       // about 0.8 waves per chunk
         bounds.push_back(0); bounds.push_back(a); bounds.push_back(a + b);
         for (int k = 1; k <= nm; ++k) bounds.push_back(a + b + (int)((long long)rest * k / nm));
+        {   // the last chunk in two halves: its download is the one nothing overlaps (measured 85.4 -> 84.3 ms
+            // per 1776 C2 subjects; four quarters: 87.7)
+            int t = 2;
+            if (const char* e = getenv("VB_CHUNK_TAIL")) t = std::max(1, std::min(8, atoi(e)));      // tuning
+            const int lo = bounds[bounds.size() - 2], hi = bounds.back();
+            if (t > 1 && hi - lo >= 2 * t) {
+                bounds.pop_back();
+                for (int k = 1; k <= t; ++k) bounds.push_back(lo + (int)((long long)(hi - lo) * k / t));
+            }
+        }
     } else {
         const int nc = std::max(1, std::min(16, n / per));
         for (int k = 0; k <= nc; ++k) bounds.push_back((int)((long long)n * k / nc));
