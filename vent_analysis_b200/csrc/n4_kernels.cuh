@@ -5,30 +5,34 @@
 // itkN4BiasFieldCorrectionImageFilter.hxx; restated on the CPU in oracle/n4_oracle.c).
 //
 // Design (DESIGN.md §4 "N4"):
-//   * A CTA (1024 threads) pulls subjects from a global work counter and runs the WHOLE filter
-//     for one subject -- 4 levels x <=50 iterations x {histogram, Wiener sharpening, B-spline fit,
-//     update, convergence} -- with block / named barriers only; no host round trip, subjects
-//     converge independently.
-//   * Only mask voxels take part in the iterations, so the volume is COMPACTED once per subject:
-//     the columns (col, slice) that carry mask voxels are grouped in blocks of 32 (one warp), and
-//     within a block the masked voxels are stored row by row, lane by lane.  A warp that walks the
-//     rows of its block therefore reads one contiguous, conflict-free stream.  Two compact arrays:
-//     the log image (global memory, L2 resident, read once per iteration) and U = logI - bias of
-//     the committed lattice, which for the benchmark volumes (128x128x14, ~36k mask voxels =
-//     143 KB) lives in SHARED MEMORY for the whole filter (larger masks: global memory, same
-//     code).  Work items (block x row segment) are drawn largest-first from a shared counter.
-//   * Only the update pass evaluates the bias (old and new field, from per-column coefficient
-//     tables G[a][column] rebuilt from the control lattice after every fit, warp-uniform row
-//     weights and a 4-tap sliding window) and writes the new U; histogram and fit read U.
+//   * A CTA (VB_N4_THREADS = 896 threads, 72 registers) pulls subjects from a global work counter and
+//     runs the WHOLE filter for one subject -- 4 levels x <=50 iterations x {histogram, Wiener
+//     sharpening, B-spline fit, update, convergence} -- with block / named barriers only; no host
+//     round trip, subjects converge independently.
+//   * Only mask voxels take part in the iterations, so the volume is COMPACTED once per subject into
+//     arrays of length M in C ORDER (row-major over the mask voxels: the order of the reference's
+//     convergence loop): the log image and the convergence sequence (global memory, L2 resident),
+//     U = logI - bias of the committed lattice -- for the benchmark volumes (128x128x14, ~36k mask
+//     voxels = 143 KB) in SHARED MEMORY for the whole filter, larger masks in global memory, same
+//     code -- and a per-voxel code (row << 16 | active-column index).  The columns (col, slice) that
+//     carry mask voxels are grouped in blocks of 32 (one warp); the voxels of one row inside a block
+//     are contiguous in the compact arrays (rank base rbb[row][block]), so a warp that walks the
+//     rows of its block reads one conflict-free stream.  Walk items (block x row segment) are drawn
+//     largest-first from a shared counter.
+//   * Only the update pass evaluates the bias (old and new field) and writes the new U; histogram
+//     and fit read U.  It is a FLAT loop over the compact arrays: row and column from the per-voxel
+//     code, the collapsed coefficients of both fields from per-column tables G[a][column] (rebuilt
+//     from the control lattice after every fit) -- no row walk, every lane busy.  (Tables that do
+//     not fit, or volumes too large for the code packing: the column walk with a sliding window.)
 //   * Parzen histogram: a flat loop over the compact U array, fixed-point (count-conserving)
-//     shared-memory atomics into one copy per lane => exactly associative, deterministic.
+//     shared-memory reductions into one copy per lane => exactly associative, deterministic.
 //   * Sharpening: 4 packed 512-point complex FFTs in double in shared memory, two radix-2 stages
-//     per pass.
+//     per pass, twiddles computed once per CTA.
 //   * B-spline fit: the Lee-Wolberg-Shin scatter is separable (t = tr*tc*ts,
 //     sum t^2 = Sr*Sc*Ss), so delta = sum w^3 z / sum w^2 is three small contractions:
-//     rows (registers, sliding 4-tap window) -> columns (64-bit fixed-point shared-memory adds
-//     built from two native 32-bit atomics with carry forwarding) -> slices.  omega depends only
-//     on the mask and the lattice size: once per level.
+//     rows (registers, sliding 4-tap window along the column walk) -> columns (64-bit fixed-point
+//     shared-memory adds built from two native 32-bit atomics with carry forwarding) -> slices.
+//     omega depends only on the mask and the lattice size: once per level.
 //   * Convergence: ITK's CalculateConvergenceMeasurement is a SEQUENTIAL float32 Welford
 //     recurrence whose rounding (the running mean stalls once its update drops below half an
 //     ulp) decides when a level stops.  It is reproduced here in parallel: threads run their
@@ -38,8 +42,11 @@
 //     mean.  The chain is skipped when a rigorous bound already decides "continue"; otherwise it
 //     runs on a team of warps while the other warps compute the next iteration's histogram /
 //     sharpening / fit speculatively (committed only if the chain says "continue").
-//   * Inside the hot loops the slot / shared-memory pointers are opaque local copies: at the
-//     64-register cap the compiler otherwise re-derives them from the kernel parameters at each use.
+//   * Shared-memory tables, U and the atomics of the hot loops go through 32-bit SHARED addresses
+//     (vb_saddr: LDS / STS / ATOMS / RED.shared).  Pointers into global memory are opaque local
+//     copies: at the register cap the compiler otherwise re-derives them from the kernel parameters
+//     at each use -- but an opaque pointer into shared memory is a GENERIC pointer (64-bit address
+//     arithmetic, generic LD / ATOM), which is what the shared addresses avoid.
 #pragma once
 #include <float.h>
 #include "vb_common.cuh"
