@@ -438,7 +438,9 @@ def run_ours(args, rank, local_rank, world):
     roof = {"kernel": "n4_subject_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": n4_bytes, "launch_ms": n4_launch_ms,
-            "definition": "(17 + 19*n_it)*V bytes per subject (SURVEY.md 8d), n_it = iterations actually run"}
+            "definition": "(17 + 19*n_it)*V bytes per subject (SURVEY.md 8d), n_it = iterations actually run; launch_ms = CUDA events "
+                          "from the first N4 launch of a step to the join of its streams (large batches run in two parts whose "
+                          "N4 kernels overlap: the small VDP / CI kernels of the last part are inside this time)"}
     # counters of the committed ncu --set full capture of this kernel (same build, C2 batch): DRAM
     # traffic, warp instructions and shared-memory wavefronts per subject-iteration -- put against
     # the time measured live
