@@ -451,7 +451,11 @@ int vb_create(int device, vb_ctx** out) {
 void vb_destroy(vb_ctx* c) {
     if (!c) return;
     vbrt::set_device(c->device);
-    vbrt::stream_sync(c->stream);
+    {   // every stream of the context is idle before anything is freed
+        vbrt::stream_t all[] = {c->stream, c->stream2, c->cextra[0], c->cextra[1], c->pre[0], c->pre[1], c->post[0], c->post[1],
+                                c->stream_in, c->stream_out};
+        for (vbrt::stream_t st : all) vbrt::stream_sync(st);
+    }
     for (N4Ws& W : c->n4ws) {
         Buf* wb[] = {&W.logI, &W.u, &W.colmask, &W.rbb, &W.wbase, &W.acol, &W.order, &W.ec, &W.code, &W.axis, &W.counter};
         for (Buf* b : wb) vbrt::dev_free(b->p);
