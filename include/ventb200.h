@@ -252,6 +252,15 @@ int vb_host_free(vb_ctx* ctx, void* ptr);
 int vb_set_profiling(vb_ctx* ctx, int32_t on);
 int vb_profile_fetch(vb_ctx* ctx, double* stage_ms, int32_t* n_calls);
 
+/* N4 on small batches (the reference's use: ONE subject per Vent_Analysis object,
+ * Vent_Analysis.py:316-334).  A batch that would leave most SMs idle runs with a thread-block
+ * cluster of K CTAs (K SMs) per subject; results are bit-identical to one CTA per subject.
+ * vb_set_n4_cluster: max_k = 0 automatic (largest K in {8, 4, 2, 1} with n * K <= SM count),
+ * 1 = always one CTA per subject, 2 / 4 / 8 = upper bound for the automatic choice.
+ * vb_n4_cluster_size: K of the most recent N4 launch of this context (1 before any launch). */
+int vb_set_n4_cluster(vb_ctx* ctx, int32_t max_k);
+int32_t vb_n4_cluster_size(const vb_ctx* ctx);
+
 /* debug: last Parzen histogram / E(u|v) table / lattice of subject `i` of the most recent
  * vb_n4_batch_* call (needs ctx debug capture; see vb_set_debug). */
 int vb_set_debug(vb_ctx* ctx, int32_t on);

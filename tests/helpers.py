@@ -100,6 +100,38 @@ def check_n4(ctx, img, mask, max_iter=(50, 50, 50, 50), require_same_iters=True)
     return out, ref, float(rel.max())
 
 
+def check_n4_cluster(ctx, cases, ks=(2, 4, 8), max_iter=(50, 50, 50, 50), sms=None):
+    """Cluster mode of the N4 kernel (K CTAs per subject, vb_set_n4_cluster): every output and the
+    iteration counts are BIT-IDENTICAL to one CTA per subject -- the cross-CTA sums are integer
+    (fixed point), min / max are exact, and the float sums that differ only feed a bound with margins.
+    `cases`: list of batches, each a list of (image, mask)."""
+    p = ctx.default_n4_params(max_iter=max_iter)
+    try:
+        for subs in cases:
+            shapes = [s[0].shape for s in subs]
+            img = np.concatenate([s[0].ravel() for s in subs])
+            msk = np.concatenate([s[1].ravel() for s in subs])
+            res = {}
+            for k in (1,) + tuple(ks):
+                ctx.set_n4_cluster(k)
+                out = ctx.pipeline_host(shapes, _lib.DO_N4, image=img, mask=msk, params=p, want_logbias=True)
+                used = ctx.n4_cluster_size()
+                if sms is not None:
+                    want = k
+                    while want > 1 and len(subs) * want > sms:
+                        want //= 2
+                    assert used == want, (k, used, want)
+                res[k] = (used, out["n4"].copy(), out["logbias"].copy(), out["stats"].copy())
+            assert res[1][0] == 1
+            for k in ks:
+                assert res[k][1].tobytes() == res[1][1].tobytes(), f"N4 output differs at K={k}"
+                assert res[k][2].tobytes() == res[1][2].tobytes(), f"log bias differs at K={k}"
+                for f in ("n4_iters", "n4_last_conv", "n4_n_mask"):
+                    assert res[k][3][f].tobytes() == res[1][3][f].tobytes(), (f, k)
+    finally:
+        ctx.set_n4_cluster(0)
+
+
 def check_edge_cases(ctx):
     """Degenerate and ragged inputs through the whole path in ONE batch (odd voxel offsets, a
     single-slice volume, an empty mask, a one-voxel mask, a mask with a foreign label):

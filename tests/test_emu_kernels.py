@@ -61,6 +61,47 @@ def test_n4_full_run_matches_restatement(ctx):
     assert rel < 1e-4
 
 
+@pytest.fixture(scope="module")
+def ctx8(monkeypatch_module=None):
+    """An emulated device with 8 SMs: single subjects run with clusters of up to 8 CTAs."""
+    import os
+    import build_emu
+    old = os.environ.get("VB_EMU_SMS")
+    os.environ["VB_EMU_SMS"] = "8"
+    try:
+        c = _lib.Context(0, lib=_lib.bind(os.environ.get("VB_EMU_LIB") or build_emu.build()))
+    finally:
+        if old is None:
+            del os.environ["VB_EMU_SMS"]
+        else:
+            os.environ["VB_EMU_SMS"] = old
+    return c
+
+
+def _cluster_cases():
+    a = phantom((24, 20, 5), [1.5, 1.5, 10.0], 21)
+    b = phantom((18, 30, 4), [2.0, 2.0, 11.5], 22)
+    e_img, e_m = phantom((20, 16, 3), [2.0, 2.0, 11.5], 23)
+    one = np.zeros_like(e_m)
+    one[3, 4, 1] = 1
+    return [[a], [a, b], [a, (e_img, np.zeros_like(e_m)), (e_img, one), b]]
+
+
+def test_n4_cluster_of_ctas_per_subject_is_bit_identical(ctx8):
+    """K = 2, 4, 8 CTAs per subject (the CTAs of an emulated cluster run concurrently, one forked
+    process each): outputs, log bias, iteration counts and the last convergence value equal the
+    one-CTA run bit for bit -- single subject, two ragged subjects, a batch with an empty and a
+    one-voxel mask."""
+    helpers.check_n4_cluster(ctx8, _cluster_cases(), max_iter=(6, 4, 3), sms=8)
+    helpers.check_n4_cluster(ctx8, [[phantom((40, 36, 6), [1.5, 1.5, 10.0], 5)]], ks=(4,), max_iter=(50, 50, 6, 4), sms=8)   # the first two levels run to convergence
+
+
+def test_n4_cluster_with_the_column_walk_update_and_u_in_global_memory(ctx8, monkeypatch):
+    """Same with no shared-memory room for the compact arrays / coefficient tables (the path of large volumes)."""
+    monkeypatch.setenv("VB_N4_SMEM_CAP", "0")
+    helpers.check_n4_cluster(ctx8, _cluster_cases()[:2], ks=(2, 8), max_iter=(5, 3), sms=8)
+
+
 def test_n4_ragged_batch_and_label_semantics(ctx):
     """Two subjects of different shapes in one launch; mask label 2 is ignored (MaskLabel=1)."""
     a_img, a_m = phantom((24, 20, 5), [1.5, 1.5, 10.0], 21)

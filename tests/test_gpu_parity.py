@@ -50,6 +50,27 @@ def test_n4_bias_field_within_1e3_of_restatement(ctx, shape, vox, seed):
     assert rel < helpers.N4_BIAS_RTOL
 
 
+def test_n4_cluster_of_ctas_per_subject_is_bit_identical(ctx, monkeypatch):
+    """Small batches run N4 with a thread-block cluster of K CTAs (K SMs) per subject
+    (vb_set_n4_cluster; the reference's own use is one subject at a time): corrected volume, log
+    bias, per-level iteration counts and last convergence value equal the one-CTA-per-subject run
+    BIT FOR BIT at K = 2, 4, 8 -- one C2 subject, a ragged batch with an empty and a one-voxel mask,
+    16 C1 subjects (K <= 8), 30 (K <= 4), and a subject whose compact arrays do not fit shared
+    memory (208x256x18); then the same with the column-walk update (no table space)."""
+    a = phantom((48, 40, 6), [1.5, 1.5, 10.0], 21)
+    b = phantom((33, 50, 4), [2.0, 2.0, 11.5], 22)
+    e_img, e_m = phantom((20, 16, 3), [2.0, 2.0, 11.5], 23)
+    one = np.zeros_like(e_m)
+    one[3, 4, 1] = 1
+    c2 = phantom(CONFIGS["C2"][0], CONFIGS["C2"][1], 3)
+    c1 = [phantom(CONFIGS["C1"][0], CONFIGS["C1"][1], 40 + i) for i in range(30)]
+    sms = 148
+    helpers.check_n4_cluster(ctx, [[c2], [a, (e_img, np.zeros_like(e_m)), (e_img, one), b], c1[:16], c1], sms=sms)
+    helpers.check_n4_cluster(ctx, [[phantom((208, 256, 18), [1.5, 1.5, 10.0], 9)]], ks=(8,), sms=sms)
+    monkeypatch.setenv("VB_N4_SMEM_CAP", "0")
+    helpers.check_n4_cluster(ctx, [[c2], [a, b]], ks=(2, 8), sms=sms)
+
+
 def test_n4_stage_level_parity(ctx):
     shape = (40, 36, 6)
     img, mask = phantom(shape, [1.5, 1.5, 10.0], 5)

@@ -96,7 +96,8 @@ EXPORTS = ["vb_version", "vb_last_error", "vb_device_count", "vb_create", "vb_de
            "vb_n4_default_params", "vb_ci_table_create", "vb_ci_table_radii", "vb_snr_batch_dev", "vb_n4_batch_dev",
            "vb_vdp_batch_dev", "vb_border_batch_dev", "vb_ci_batch_dev", "vb_pipeline_batch_dev",
            "vb_pipeline_batch_host", "vb_pipeline_batch_host_packed", "vb_host_alloc", "vb_host_free", "vb_overlay_rgb_batch_dev", "vb_overlay_rgb_batch_host", "vb_crop_boxes_batch_host",
-           "vb_montage_batch_host", "vb_recon_batch_dev", "vb_recon_batch_host", "vb_pack6_batch_dev", "vb_pack6_batch_host", "vb_set_profiling", "vb_profile_fetch", "vb_set_debug", "vb_n4_debug_fetch"]
+           "vb_montage_batch_host", "vb_recon_batch_dev", "vb_recon_batch_host", "vb_pack6_batch_dev", "vb_pack6_batch_host", "vb_set_profiling", "vb_profile_fetch", "vb_set_debug", "vb_n4_debug_fetch",
+           "vb_set_n4_cluster", "vb_n4_cluster_size"]
 N_STAGES = 5
 STAGE_NAMES = ("snr", "n4", "vdp", "mask_border", "ci")
 
@@ -138,6 +139,9 @@ def bind(path):
     lib.vb_set_profiling.argtypes = [vp, i32]
     lib.vb_profile_fetch.argtypes = [vp, vp, C.POINTER(i32)]
     lib.vb_set_debug.argtypes = [vp, i32]
+    lib.vb_set_n4_cluster.argtypes = [vp, i32]
+    lib.vb_n4_cluster_size.argtypes = [vp]
+    lib.vb_n4_cluster_size.restype = i32
     lib.vb_n4_debug_fetch.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i32]
     return lib
 
@@ -556,6 +560,14 @@ class Context:
         n = C.c_int32(0)
         self.check(self.lib.vb_profile_fetch(self.h, _ptr(ms), C.byref(n)))
         return dict(zip(STAGE_NAMES, (float(x) for x in ms))), n.value
+
+    def set_n4_cluster(self, max_k=0):
+        """CTAs (SMs) per subject for N4 on small batches: 0 automatic, 1 off, 2 / 4 / 8 upper bound."""
+        self.check(self.lib.vb_set_n4_cluster(self.h, int(max_k)))
+
+    def n4_cluster_size(self):
+        """CTAs per subject of the most recent N4 launch."""
+        return int(self.lib.vb_n4_cluster_size(self.h))
 
     def set_debug(self, on=True):
         self.check(self.lib.vb_set_debug(self.h, 1 if on else 0))

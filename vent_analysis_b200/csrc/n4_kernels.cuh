@@ -128,6 +128,16 @@ struct N4Args {
     int union_bytes;         // size of the shared-memory union region
     int logI_cap;            // floats of compact log image that fit shared memory (0 = none)
     int rowtab_rows;         // rows whose row-axis tables fit shared memory (0 = keep them in global)
+    // cluster mode (K > 1): a thread-block cluster of K CTAs works on ONE subject -- small batches, single
+    // subjects (the reference's GUI use).  The compact arrays then live in global memory (L2) and are
+    // shared by the CTAs; per-CTA partial results meet in the scratch below.
+    int K;                   // CTAs per subject; 1: one persistent CTA per subject pulls subjects from the counter
+    unsigned long long* cl_hist;   // [clusters][4][K][n_bins]    partial histograms (fixed point); per team (all threads / phase team) two sets used in turn
+    unsigned* cl_q;          // [clusters][4][K][2 * q_max]  partial Q accumulators of the fit (low, high words); sets as cl_hist
+    double* cl_red;          // [clusters][2][K][4]          partial (min, max, s1, s2) of the update / range passes
+    unsigned* cl_bar;        // [clusters][4]             arrival counters of the cross-CTA barriers (zeroed before the launch)
+    int* cl_bcast;           // [clusters][16]            scalars of the setup, written by CTA 0 of the cluster
+    int q_max;
     int no_overlap;          // 1: run the convergence chain and the next iteration's phases one after the other
                              // (same results; A/B timing of the overlap)
 };
@@ -250,6 +260,18 @@ struct N4Ctx {
     uint32_t* acol;       // [nact]
     uint32_t* iorder;     // [nblk * nseg] work items sorted by voxel count, largest first
     int* ctr;             // shared-memory work counters, one per team barrier id
+    // cluster mode (see N4Args): K CTAs per subject, this CTA's rank; walk items j -> j * istep + ioff
+    int K, crank, istep, ioff, q_max;
+    unsigned long long* cl_hist;
+    unsigned* cl_q;
+    double* cl_red;
+    unsigned* cl_bar;
+    int* cl_bcast;
+    unsigned gen[3];      // cross-CTA barriers passed so far, per team barrier id
+    // which of the two sets of exchange slots is used next.  Histogram and fit run on all threads or on the
+    // phase team only: the threads of the chain team then miss exchanges, so each of the two teams has sets
+    // (and a count) of its own -- [0]: all threads, [1]: the phase team
+    int par_hist0, par_hist1, par_q0, par_q1, par_red;
     int nact, nseg, wps;  // active columns; row segments per block; 32-row words per segment
     int M;                // mask voxels (length of the compact arrays)
     int union_bytes;      // size of the shared-memory union region
@@ -303,6 +325,27 @@ VB_DEV void n4_sync(const N4Team& T) {
 VB_DEV int n4_sync_or(const N4Team& T, int pred) {
     return (T.bar == 0) ? __syncthreads_or(pred) : vb_bar_or(T.bar, T.nt, pred);
 }
+// Barrier over team T of EVERY CTA of the cluster (cluster mode; K == 1: the team barrier).  The CTAs
+// of a cluster are co-scheduled, so thread 0 of the team may spin on a counter in global memory:
+// arrive (release), wait until all K teams have arrived for this generation (acquire).  Everything
+// the teams wrote to global memory before the barrier is visible to all of them after it -- through
+// L2: such data must be read with vb_ld_cg (a line may sit in this SM's L1 from an earlier pass).
+VB_DEV void n4_csync(N4Ctx& c, const N4Team& T) {
+    n4_sync(T);
+    if (c.K == 1) return;
+    const unsigned target = (++c.gen[T.bar]) * (unsigned)c.K;
+    if (T.tid == 0) {
+        __threadfence();
+        atomicAdd(c.cl_bar + T.bar, 1u);
+        while (vb_ld_acquire(c.cl_bar + T.bar) < target) { }
+        __threadfence();
+    }
+    n4_sync(T);
+}
+
+// Loads of arrays that other CTAs of the cluster write between barriers (U, the convergence sequence):
+// through L2 in cluster mode; one CTA per subject: the plain load.
+template <class V> VB_DEV V n4_ld_x(const N4Ctx& c, const V* p) { return (c.K > 1) ? vb_ld_cg(p) : VB_N4_LDS(p); }
 
 // ---------------------------------------------------------------------------------------------
 // block-wide exclusive scan of one int per thread; every thread gets its prefix and the total
@@ -479,7 +522,8 @@ VB_DEV int n4_items_next(const N4Ctx& c, const N4Team& T) {
     return __shfl_sync(VB_FULL, i, 0);
 }
 #define VB_N4_FOR_ITEMS(c, T, it) \
-    for (int i_ = n4_items_next(c, T), it = 0; i_ < (c).nblk * (c).nseg && ((it = (int)(c).iorder[i_]), true); i_ = n4_items_next(c, T))
+    for (int i_ = n4_items_next(c, T) * (c).istep + (c).ioff, it = 0; i_ < (c).nblk * (c).nseg && ((it = (int)(c).iorder[i_]), true); \
+         i_ = n4_items_next(c, T) * (c).istep + (c).ioff)
 
 // What the row walks need from the context, as opaque local copies: otherwise the compiler
 // re-derives every pointer from the kernel parameters (blockIdx * stride + base, or shared-memory
@@ -648,12 +692,36 @@ VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float&
     bmax = vb_block_reduce(tmax, VbMaxF(), -FLT_MAX, (float*)c.red);
 }
 
+// cluster mode: combine this CTA's (min, max, s1, s2) with those of the other CTAs, in rank order (every
+// CTA ends up with the same four numbers, bit for bit)
+VB_DEV void n4_cluster_reduce4(N4Ctx& c, const N4Team& T, float& mn, float& mx, double& s1, double& s2) {
+    if (c.K == 1) return;
+    // (two sets of slots used in turn: a set is rewritten two exchanges later, i.e. after another cluster
+    // barrier that every CTA reaches only when it has read this one -- no second barrier per exchange)
+    double* slots = c.cl_red + (size_t)c.par_red * 4 * c.K;
+    c.par_red ^= 1;
+    if (T.tid == 0) {
+        double* mine = slots + 4 * c.crank;
+        mine[0] = (double)mn; mine[1] = (double)mx; mine[2] = s1; mine[3] = s2;
+    }
+    n4_csync(c, T);
+    float a = FLT_MAX, b = -FLT_MAX;
+    double p = 0.0, q = 0.0;
+    for (int r = 0; r < c.K; ++r) {
+        a = fminf(a, (float)vb_ld_cg(slots + 4 * r));
+        b = fmaxf(b, (float)vb_ld_cg(slots + 4 * r + 1));
+        p += vb_ld_cg(slots + 4 * r + 2);
+        q += vb_ld_cg(slots + 4 * r + 3);
+    }
+    mn = a; mx = b; s1 = p; s2 = q;
+}
+
 // range of U = logI - bias(L) over the mask (after a lattice refinement)
 VB_DEV void n4_range(N4Ctx& c, float& bmin, float& bmax) {
     const int nt = (int)blockDim.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
     const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     float tmin = FLT_MAX, tmax = -FLT_MAX;
-    for (int it = w; it < c.nblk * c.nseg; it += nw) {
+    for (int it = w + nw * c.crank; it < c.nblk * c.nseg; it += nw * c.K) {      // (cluster mode: the items are dealt over the CTAs)
         const N4Item I = n4_item(c, it);
         if (I.empty) continue;
         const N4Col col = n4_col(c, ac, as, I.q);
@@ -671,6 +739,12 @@ VB_DEV void n4_range(N4Ctx& c, float& bmin, float& bmax) {
     }
     bmin = vb_block_reduce(tmin, VbMinF(), FLT_MAX, (float*)c.red);
     bmax = vb_block_reduce(tmax, VbMaxF(), -FLT_MAX, (float*)c.red);
+    if (c.K > 1) {
+        N4Team full;
+        full.tid = (int)threadIdx.x; full.nt = nt; full.bar = 0;
+        double z1 = 0.0, z2 = 0.0;
+        n4_cluster_reduce4(c, full, bmin, bmax, z1, z2);
+    }
 }
 
 // one voxel of the Parzen histogram: its unit weight split between two neighbouring bins of this lane's copy
@@ -709,7 +783,9 @@ VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     // the compact array (the fixed-point sums do not depend on the order)
     const float* U = c.U;
     VB_OPAQUE_PTR(U);
-    const int M = c.M, nbins = c.nbins;
+    const int nbins = c.nbins;
+    // cluster mode: this CTA's slice of the compact array (U is in global memory then; read through L2)
+    const int M0 = (int)((long long)c.M * c.crank / c.K), M = (int)((long long)c.M * (c.crank + 1) / c.K);
     if (VB_N4_HIST4 && c.u_smem) {                       // U in shared memory: four voxels per 16-byte LDS
         const vb_saddr sU = vb_saddr_of(c.U);
         const int M4 = M & ~3;
@@ -725,9 +801,28 @@ VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
             n4_hist_add(sh, vb_lds_f32(sU + 4u * (unsigned)i), bmin, slope, rslope, nbins, one, fone);
     } else {
 #pragma unroll 4
-        for (int i = tid; i < M; i += nt) n4_hist_add(sh, U[i], bmin, slope, rslope, nbins, one, fone);
+        for (int i = M0 + tid; i < M; i += nt) n4_hist_add(sh, n4_ld_x(c, U + i), bmin, slope, rslope, nbins, one, fone);
     }
     n4_sync(T);
+    if (c.K > 1) {                                       // partial sums of the CTAs meet in global memory (two sets used in turn, see n4_cluster_reduce4)
+        const int ts = (T.bar != 0) ? 1 : 0;
+        unsigned long long* part = c.cl_hist + (size_t)(2 * ts + (ts ? c.par_hist1 : c.par_hist0)) * c.K * c.nbins;
+        if (ts) c.par_hist1 ^= 1; else c.par_hist0 ^= 1;
+        for (int bin = tid; bin < c.nbins; bin += nt) {
+            unsigned long long s = 0;
+#pragma unroll
+            for (int k = 0; k < VB_N4_HCOPIES; ++k) s += hc[(size_t)k * hstride + bin];
+            part[(size_t)c.crank * c.nbins + bin] = s;
+        }
+        n4_csync(c, T);
+        for (int bin = tid; bin < c.nbins; bin += nt) {
+            unsigned long long s = 0;
+            for (int r = 0; r < c.K; ++r) s += vb_ld_cg(part + (size_t)r * c.nbins + bin);
+            c.H[bin] = (float)((double)s / (double)one);
+        }
+        n4_sync(T);
+        return;
+    }
     for (int bin = tid; bin < c.nbins; bin += nt) {
         unsigned long long s = 0;
 #pragma unroll
@@ -931,6 +1026,9 @@ VB_DEV void n4_contract_t(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     const vb_saddr sU = SM ? vb_saddr_of(c.U) : 0, sW = SM ? vb_saddr_of(c.r_fit3) : 0, sB = SM ? vb_saddr_of(c.r_bfit) : 0;
     const int Qn = ncp0 * ncp1 * n2;
     for (int e = tid; e < 2 * Qn; e += nt) Q[e] = 0u;
+    // cluster mode: the fit's items are dealt over the CTAs (item j of this CTA = j * K + rank); omega is
+    // computed by every CTA for itself (once per level)
+    c.istep = OMEGA ? 1 : c.K; c.ioff = OMEGA ? 0 : c.crank;
     n4_items_begin(c, T);
     n4_sync(T);
 
@@ -957,7 +1055,7 @@ VB_DEV void n4_contract_t(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
                     val = 1.0f;
                     wt = ar.fit2[r];
                 } else {
-                    const float u = SM ? vb_lds_f32(sU + 4u * idx) : U[idx];
+                    const float u = SM ? vb_lds_f32(sU + 4u * idx) : n4_ld_x(c, U + idx);
                     const float cidx = n4_div(u - bmin, slope, rslope);
                     const float fl = floorf(cidx);
                     const int bi = (int)fl;
@@ -982,6 +1080,24 @@ VB_DEV void n4_contract_t(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
         }
     }
     n4_sync(T);
+    c.istep = 1; c.ioff = 0;
+    if (!OMEGA && c.K > 1) {                             // partial sums of the CTAs meet in global memory (integers: exact)
+        const int ts = (T.bar != 0) ? 1 : 0;
+        unsigned* part = c.cl_q + (size_t)(2 * ts + (ts ? c.par_q1 : c.par_q0)) * c.K * 2 * c.q_max;     // (two sets used in turn, see n4_cluster_reduce4)
+        if (ts) c.par_q1 ^= 1; else c.par_q0 ^= 1;
+        unsigned* mine = part + (size_t)c.crank * 2 * c.q_max;
+        for (int e = tid; e < 2 * Qn; e += nt) mine[e] = Q[e];
+        n4_csync(c, T);
+        for (int e = tid; e < Qn; e += nt) {
+            unsigned long long sum = 0;
+            for (int r = 0; r < c.K; ++r) {
+                const unsigned* qr = part + (size_t)r * 2 * c.q_max + 2 * e;
+                sum += ((unsigned long long)vb_ld_cg(qr + 1) << 32) | (unsigned long long)vb_ld_cg(qr);
+            }
+            Q[2 * e] = (unsigned)sum; Q[2 * e + 1] = (unsigned)(sum >> 32);
+        }
+        n4_sync(T);
+    }
 
     // slices -> lattice
     const int Ln = ncp0 * ncp1 * ncp2;
@@ -1140,11 +1256,11 @@ VB_DEV void n4_chain_chunk(N4Ctx& c, const N4Team& T, const float* epx, int star
     float px[VB_N4_EPT];
     N4Step st[VB_N4_EPT];
     if (cnt == VB_N4_EPT && VB_N4_EPT == 8) {                  // lo is a multiple of 8 here: 16-byte loads
-        const float4 p0 = VB_N4_LDS((const float4*)(epx + lo)), p1 = VB_N4_LDS((const float4*)(epx + lo + 4));
+        const float4 p0 = n4_ld_x(c, (const float4*)(epx + lo)), p1 = n4_ld_x(c, (const float4*)(epx + lo + 4));   // (cluster mode: other CTAs wrote parts of it)
         px[0] = p0.x; px[1] = p0.y; px[2] = p0.z; px[3] = p0.w; px[4] = p1.x; px[5] = p1.y; px[6] = p1.z; px[7] = p1.w;
     } else {
 #pragma unroll
-        for (int i = 0; i < VB_N4_EPT; ++i) px[i] = (i < cnt) ? epx[lo + i] : 1.0f;
+        for (int i = 0; i < VB_N4_EPT; ++i) px[i] = (i < cnt) ? n4_ld_x(c, epx + lo + i) : 1.0f;
     }
 #pragma unroll
     for (int i = 0; i < VB_N4_EPT; ++i) st[i] = n4_step_consts(px[i], lo + i + 1);
@@ -1249,7 +1365,7 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
     const int S0 = min(M, VB_N4_SERIAL);
     VB_SHARED float s_px[VB_N4_SERIAL];
     long long tq = vb_clock();
-    if (tid < S0) s_px[tid] = epx[tid];
+    if (tid < S0) s_px[tid] = n4_ld_x(c, epx + tid);
     n4_sync(T);
     // phase 1: the first elements, one thread, sequentially.  Phase 2 (optional, VB_N4_WARP_END >
     // VB_N4_SERIAL): up to VB_N4_WARP_END on one warp, chunks of <= 32 * VB_N4_EPT elements, no barrier.
@@ -1343,12 +1459,13 @@ VB_DEV void n4_update_flat(N4Ctx& c, const N4Team& T, const float* Gn, float& tm
     if (!SM) { VB_OPAQUE_PTR(U); VB_OPAQUE_PTR(revw); VB_OPAQUE_PTR(rbev); }
     const vb_saddr sU = SM ? vb_saddr_of(c.U) : 0, sW = SM ? vb_saddr_of(c.r_evw) : 0, sB = SM ? vb_saddr_of(c.r_bev) : 0;
     const vb_saddr sGo = vb_saddr_of(c.G), sGn = vb_saddr_of(Gn);
-    const int M = c.M, nt = T.nt;
+    // (cluster mode: this CTA's slice [M0, M) of the compact arrays)
+    const int M0 = (int)((long long)c.M * c.crank / c.K), M = (int)((long long)c.M * (c.crank + 1) / c.K), nt = T.nt;
     const unsigned gs4 = 4u * (unsigned)c.gstride;
     // VB_N4_UB voxels per trip: their codes and log-image values (L2) are requested together, before
     // the first of them is evaluated -- the stores of the loop body would otherwise keep the compiler
     // from moving the next loads up, and a thread would wait one L2 round trip per voxel
-    for (int i0 = T.tid; i0 < M; i0 += 64 * nt) {
+    for (int i0 = M0 + T.tid; i0 < M; i0 += 64 * nt) {
         float f1 = 0.0f, f2 = 0.0f;
         const int iend = min(M, i0 + 64 * nt);
         for (int ib = i0; ib < iend; ib += VB_N4_UB * nt) {
@@ -1437,6 +1554,7 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
     float* Gn = c.G ? (c.G2 ? c.G2 : c.un_f) : nullptr;  // table of the new lattice (spare table, else the union region: free here)
     N4Team T;
     T.tid = (int)threadIdx.x; T.nt = nt; T.bar = 0;
+    c.istep = c.K; c.ioff = c.crank;                     // (cluster mode: the column walk's items are dealt over the CTAs)
     n4_items_begin(c, T);
     if (Gn) n4_build_G(c, c.L, Gn); else __syncthreads();
     if (Gn) {
@@ -1478,6 +1596,8 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
         bmin = tmin; bmax = tmax;
     }
 #endif
+    c.istep = 1; c.ioff = 0;
+    n4_cluster_reduce4(c, T, bmin, bmax, s1, s2);        // (cluster mode; also orders the U / sequence writes of all CTAs)
     __syncthreads();
     if (c.G2) {                                          // the new lattice's table becomes the current one
         c.G2 = c.G; c.G = Gn;
@@ -1516,7 +1636,7 @@ VB_DEV void n4_finalize(N4Ctx& c, float* logbias) {
     const int ncols = c.ncols;
     const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     const int nblk_all = (ncols + 31) >> 5;              // every column, not only the active ones
-    for (int blk = w; blk < nblk_all; blk += nw) {
+    for (int blk = w + nw * c.crank; blk < nblk_all; blk += nw * c.K) {     // (cluster mode: column blocks dealt over the CTAs)
         const int q = blk * 32 + lane;
         if (q >= ncols) continue;
         const N4Col col = n4_col(c, ac, as, q);
@@ -1600,7 +1720,10 @@ VB_DEV void n4_build_tables(N4Ctx& c) {
     __syncthreads();
 }
 
-VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
+// CL = false: one persistent CTA per subject (c.K is the literal 1: the cluster-mode code and state
+// fold away); CL = true: a cluster of a.K CTAs per subject.
+template <bool CL>
+VB_DEV void n4_subject_body(const N4Args& a) {
     VB_DYN_SMEM(smem);
     VB_SHARED int s_next;
     VB_SHARED float s_conv;
@@ -1628,26 +1751,41 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
     c.nbins = a.p.n_bins; c.fftN = a.fftN; c.union_bytes = a.union_bytes;
     n4_twiddles(c);
 
-    for (;;) {
+    // cluster mode: cluster `cid` = CTAs [cid * K, (cid + 1) * K) of the grid works on subject cid; its CTAs
+    // share workspace slot cid (the per-axis tables are per CTA: every CTA builds its own)
+    c.K = CL ? max(a.K, 1) : 1; c.crank = (c.K > 1) ? (int)(blockIdx.x % (unsigned)c.K) : 0; c.istep = 1; c.ioff = 0;
+    const int cid = (c.K > 1) ? (int)(blockIdx.x / (unsigned)c.K) : (int)blockIdx.x;
+    c.q_max = a.q_max;
+    c.cl_hist = a.cl_hist ? a.cl_hist + (size_t)cid * 4 * c.K * a.p.n_bins : nullptr;
+    c.cl_q = a.cl_q ? a.cl_q + (size_t)cid * 4 * c.K * 2 * a.q_max : nullptr;
+    c.cl_red = a.cl_red ? a.cl_red + (size_t)cid * 2 * c.K * 4 : nullptr;
+    c.cl_bar = a.cl_bar ? a.cl_bar + (size_t)cid * 4 : nullptr;
+    c.cl_bcast = a.cl_bcast ? a.cl_bcast + (size_t)cid * 16 : nullptr;
+    c.gen[0] = c.gen[1] = c.gen[2] = 0u; c.par_hist0 = c.par_hist1 = c.par_q0 = c.par_q1 = c.par_red = 0;
+    const size_t slotx = (size_t)cid;
+
+    for (int round = 0;; ++round) {
         __syncthreads();
-        if (tid == 0) s_next = atomicAdd(a.work_counter, 1);
-        __syncthreads();
-        const int si = s_next;
-        if (si >= a.n) break;
+        if (c.K == 1) {
+            if (tid == 0) s_next = atomicAdd(a.work_counter, 1);
+            __syncthreads();
+        }
+        const int si = (c.K == 1) ? s_next : cid;
+        if (si >= a.n || (c.K > 1 && round > 0)) break;
         const VbSubject S = a.subj[si];
         c.n0 = S.n0; c.n1 = S.n1; c.n2 = S.n2; c.ncols = S.n1 * S.n2; c.W = (S.n0 + 31) >> 5;
         c.nblk = 0; c.nact = 0; c.nseg = 1; c.wps = c.W;
         c.V = S.V;
         c.img = a.image + S.off; c.msk = a.mask + S.off; c.out = a.out + S.off;
-        c.colmask = a.ws_colmask + (size_t)blockIdx.x * a.cmw_max;
-        c.rbb = a.ws_rbb + (size_t)blockIdx.x * a.rbb_max;
-        c.wbase = a.ws_wbase + (size_t)blockIdx.x * a.wb_max;
-        c.acol = a.ws_acol + (size_t)blockIdx.x * a.ncols_max;
-        c.iorder = a.ws_order + (size_t)blockIdx.x * a.wb_max;
+        c.colmask = a.ws_colmask + slotx * a.cmw_max;
+        c.rbb = a.ws_rbb + slotx * a.rbb_max;
+        c.wbase = a.ws_wbase + slotx * a.wb_max;
+        c.acol = a.ws_acol + slotx * a.ncols_max;
+        c.iorder = a.ws_order + slotx * a.wb_max;
         c.ctr = s_ctr;
         c.axis_base = a.ws_axis + (size_t)blockIdx.x * a.axis_stride;
-        c.ec = a.ws_ec + (size_t)blockIdx.x * (size_t)((a.Vmax + 3) & ~3LL);
-        c.code = (S.n0 <= 65536 && S.n1 * S.n2 <= 65536) ? a.ws_code + (size_t)blockIdx.x * a.Vmax : nullptr;
+        c.ec = a.ws_ec + slotx * (size_t)((a.Vmax + 3) & ~3LL);
+        c.code = (S.n0 <= 65536 && S.n1 * S.n2 <= 65536) ? a.ws_code + slotx * a.Vmax : nullptr;
         c.ncp[0] = a.p.ncp[0]; c.ncp[1] = a.p.ncp[1]; c.ncp[2] = a.p.ncp[2];
         {
             const int nn[3] = {S.n0, S.n1, S.n2};
@@ -1657,8 +1795,8 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                 c.slot[ax] = max(nn[ax], f);
             }
         }
-        c.logI = a.ws_logI + (size_t)blockIdx.x * a.Vmax;
-        c.U = a.ws_u + (size_t)blockIdx.x * a.Vmax;         // n4_setup moves it to shared memory if it fits
+        c.logI = a.ws_logI + slotx * a.Vmax;
+        c.U = a.ws_u + slotx * a.Vmax;                       // n4_setup moves it to shared memory if it fits
         c.rowtab = (a.rowtab_rows > 0 && S.n0 <= a.rowtab_rows) ? smem_rowtab : nullptr;
 
         float bmin, bmax;
@@ -1666,7 +1804,25 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         long long tq = vb_clock();
         c.t_chain = 0; c.n_sweeps = 0; c.t_sub[0] = c.t_sub[1] = c.t_sub[2] = c.t_sub[3] = 0;
-        n4_setup(c, a.p.mask_label, smem_logI, a.logI_cap, bmin, bmax, M);
+        if (c.K == 1) {
+            n4_setup(c, a.p.mask_label, smem_logI, a.logI_cap, bmin, bmax, M);
+        } else {
+            // CTA 0 of the cluster compacts the volume (in-place scans of the shared tables: one CTA) and
+            // hands the scalars to the others
+            if (c.crank == 0) {
+                n4_setup(c, a.p.mask_label, smem_logI, 0, bmin, bmax, M);
+                if (tid == 0) {
+                    int* b = c.cl_bcast;
+                    b[0] = M; b[1] = c.nact; b[2] = c.nblk; b[3] = c.nseg; b[4] = c.wps; b[5] = c.hshift;
+                    b[6] = __float_as_int(bmin); b[7] = __float_as_int(bmax);
+                }
+            }
+            n4_csync(c, full);
+            M = vb_ld_cg(c.cl_bcast + 0); c.nact = vb_ld_cg(c.cl_bcast + 1); c.nblk = vb_ld_cg(c.cl_bcast + 2);
+            c.nseg = vb_ld_cg(c.cl_bcast + 3); c.wps = vb_ld_cg(c.cl_bcast + 4); c.hshift = vb_ld_cg(c.cl_bcast + 5);
+            bmin = __int_as_float(vb_ld_cg(c.cl_bcast + 6)); bmax = __int_as_float(vb_ld_cg(c.cl_bcast + 7));
+            c.u_smem = false; c.U = a.ws_u + slotx * a.Vmax;
+        }
         c.M = M;
         for (int e = tid; e < a.Lmax; e += (int)blockDim.x) { c.L[e] = 0.0f; c.Lold[e] = 0.0f; }
         {
@@ -1721,7 +1877,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                             n4_sharpen(c, TP, bmin, bmax, a.p.fwhm, a.p.wiener_noise);
                             n4_contract<false>(c, TP, bmin, bmax);
                         }
-                        __syncthreads();
+                        n4_csync(c, full);               // (cluster mode: every CTA's chain has read the sequence before the next update rewrites it)
                         conv = s_conv;
                         __syncthreads();
                         fitted = !serial && room && !cap;
@@ -1750,7 +1906,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
                     ++ntrace;
                 }
             }
-            if (a.stats && tid == 0) a.stats[si].n4_iters[level] = it;
+            if (a.stats && tid == 0 && c.crank == 0) a.stats[si].n4_iters[level] = it;
             if (level != a.p.n_levels - 1 && M >= 2 && !capped) n4_refine(c);
         }
         if (M < 2 || capped) n4_build_tables(c);   // tables of the final lattice (M < 2: zero lattice => out = in)
@@ -1767,7 +1923,7 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
             }
         }
         tq = vb_clock();
-        if (a.stats && tid == 0) {
+        if (a.stats && tid == 0 && c.crank == 0) {
             for (int l = a.p.n_levels; l < VB_MAX_LEVELS; ++l) a.stats[si].n4_iters[l] = 0;
             a.stats[si].n4_last_conv = conv;
             a.stats[si].n4_n_mask = M;
@@ -1781,3 +1937,6 @@ VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) {
         }
     }
 }
+
+VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_subject_kernel(N4Args a) { n4_subject_body<false>(a); }
+VB_KERNEL void VB_LAUNCH_BOUNDS(VB_N4_THREADS, 1) n4_cluster_kernel(N4Args a) { n4_subject_body<true>(a); }

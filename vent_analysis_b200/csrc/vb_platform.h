@@ -26,6 +26,23 @@
 #define VB_LAUNCH(kernel, grid, block, smem, stream, ...) \
     kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #define VB_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+// launch with thread-block clusters of `k` CTAs along x (the CTAs of a cluster are co-scheduled); false when
+// the device cannot co-schedule one such cluster or the launch is refused (nothing was launched then)
+template <class KernelT, class... Args>
+inline bool vb_launch_cluster(KernelT kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int k, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)k; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int fit = 0;
+    if (cudaOccupancyMaxActiveClusters(&fit, kernel, &cfg) != cudaSuccess || fit < 1) { cudaGetLastError(); return false; }
+    if (cudaLaunchKernelEx(&cfg, kernel, args...) != cudaSuccess) { cudaGetLastError(); return false; }
+    return true;
+}
+#define VB_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, k, ...) \
+    vb_launch_cluster(kernel, (grid), (block), (smem), (cudaStream_t)(stream), (k), __VA_ARGS__)
 VB_DEV void vb_sincospi(double x, double* s, double* c) { sincospi(x, s, c); }
 VB_DEV float vb_ldg(const float* p) { return __ldg(p); }
 VB_DEV uint32_t vb_ldg(const uint32_t* p) { return __ldg(p); }
@@ -33,6 +50,18 @@ VB_DEV uint8_t vb_ldg(const uint8_t* p) { return __ldg(p); }
 VB_DEV int vb_ldg(const int* p) { return __ldg(p); }
 VB_DEV int2 vb_ldg(const int2* p) { return __ldg(p); }
 VB_DEV float4 vb_ldg(const float4* p) { return __ldg(p); }
+// loads that bypass L1 (served by L2): data another CTA of the same kernel may have written
+VB_DEV float vb_ld_cg(const float* p) { return __ldcg(p); }
+VB_DEV float4 vb_ld_cg(const float4* p) { return __ldcg(p); }
+VB_DEV unsigned vb_ld_cg(const unsigned* p) { return __ldcg(p); }
+VB_DEV int vb_ld_cg(const int* p) { return __ldcg(p); }
+VB_DEV unsigned long long vb_ld_cg(const unsigned long long* p) { return __ldcg(p); }
+VB_DEV double vb_ld_cg(const double* p) { return __ldcg(p); }
+VB_DEV unsigned vb_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 // streaming (read-once) loads: keep them out of L1
 VB_DEV float vb_ld_stream(const float* p) { return __ldcs(p); }
 VB_DEV uint8_t vb_ld_stream(const uint8_t* p) { return __ldcs(p); }
@@ -114,7 +143,11 @@ VB_DEV void vb_mbar_wait(vb_mbar_t* bar, unsigned parity) {
 #else
 // ------------------------------------------------------------------------------- emulation
 #include <math.h>
+#include <sched.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
 #include <algorithm>
 #include <barrier>
 #include <functional>
@@ -189,28 +222,58 @@ template <class T, class F> inline auto collective(T v, F reader) {
     return r;
 }
 
+// one CTA: one OS thread per CUDA thread
+template <class Body> void run_block(unsigned bx, unsigned by, unsigned bz, dim3 block, size_t smem, Body& body) {
+    const int nthreads = (int)(block.x * block.y * block.z);
+    Block blk(nthreads, smem);
+    g_block = &blk;
+    std::vector<std::thread> th;
+    th.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([&, t] {
+            t_threadIdx = Idx{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y,
+                              (unsigned)t / (block.x * block.y)};
+            t_blockIdx = Idx{bx, by, bz};
+            body();
+        });
+    for (auto& x : th) x.join();
+    g_block = nullptr;
+}
 template <class Body> void launch(dim3 grid, dim3 block, size_t smem, Body body) {
     ++g_launches;
     g_gridDim = Idx{grid.x, grid.y, grid.z};
     g_blockDim = Idx{block.x, block.y, block.z};
-    const int nthreads = (int)(block.x * block.y * block.z);
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
-                Block blk(nthreads, smem);
-                g_block = &blk;
-                std::vector<std::thread> th;
-                th.reserve(nthreads);
-                for (int t = 0; t < nthreads; ++t)
-                    th.emplace_back([&, t] {
-                        t_threadIdx = Idx{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y,
-                                          (unsigned)t / (block.x * block.y)};
-                        t_blockIdx = Idx{bx, by, bz};
-                        body();
-                    });
-                for (auto& x : th) x.join();
-                g_block = nullptr;
+            for (unsigned bx = 0; bx < grid.x; ++bx) run_block(bx, by, bz, block, smem, body);
+}
+// Thread-block clusters: the k CTAs of a cluster run CONCURRENTLY (they synchronise with each other
+// through global memory), one forked process per CTA -- the function-local `static` arrays that stand
+// for __shared__ memory are then private to a CTA, while device memory (vbrt::dev_malloc: shared
+// anonymous mappings) is common to all of them.  Clusters run one after the other.
+inline bool g_cluster_failed = false;
+template <class Body> bool launch_cluster(dim3 grid, dim3 block, size_t smem, int k, Body body) {
+    ++g_launches;
+    g_gridDim = Idx{grid.x, grid.y, grid.z};
+    g_blockDim = Idx{block.x, block.y, block.z};
+    for (unsigned c0 = 0; c0 < grid.x; c0 += (unsigned)k) {
+        std::vector<pid_t> kids;
+        for (unsigned r = 0; r < (unsigned)k && c0 + r < grid.x; ++r) {
+            const pid_t pid = fork();
+            if (pid == 0) {
+                alarm(900);                                // a deadlocked cluster must not hang the test run
+                run_block(c0 + r, 0, 0, block, smem, body);
+                _exit(0);
             }
+            if (pid < 0) { g_cluster_failed = true; break; }
+            kids.push_back(pid);
+        }
+        for (pid_t pid : kids) {
+            int st = 0;
+            if (waitpid(pid, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) g_cluster_failed = true;
+        }
+    }
+    return true;                                           // (a CTA that died is reported by vbrt::last_launch_ok)
 }
 }  // namespace vbemu
 
@@ -220,6 +283,8 @@ template <class Body> void launch(dim3 grid, dim3 block, size_t smem, Body body)
 #define gridDim vbemu::g_gridDim
 #define VB_LAUNCH(kernel, grid, block, smem, stream, ...) \
     vbemu::launch((grid), (block), (smem), [=] { kernel(__VA_ARGS__); })
+#define VB_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, k, ...) \
+    vbemu::launch_cluster((grid), (block), (smem), (k), [=] { kernel(__VA_ARGS__); })
 
 static inline void __syncthreads() { vbemu::g_block->bar.arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {
@@ -401,6 +466,8 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline void vb_sincospi(double x, double* s, double* c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }
 template <class T> static inline T vb_ldg(const T* p) { return *p; }
+template <class T> static inline T vb_ld_cg(const T* p) { return *p; }
+static inline unsigned vb_ld_acquire(const unsigned* p) { usleep(20); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 template <class T> static inline T vb_ld_stream(const T* p) { return *p; }
 static inline void vb_st_stream(float* p, float v) { *p = v; }
 static inline long long vb_clock() { return 0; }

@@ -68,8 +68,17 @@ inline bool event_elapsed(float* ms, event_t a, event_t b) { return ok(cudaEvent
 inline bool stream_wait(stream_t s, event_t e) { return ok(cudaStreamWaitEvent(s, e, 0), "cudaStreamWaitEvent"); }
 #else
 typedef void* stream_t;
-inline bool dev_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); memset(*p, 0xAB, n); return *p != nullptr; }
-inline void dev_free(void* p) { free(p); }
+// "device memory" = shared anonymous mappings: the forked CTAs of an emulated cluster launch see one copy
+inline bool dev_malloc(void** p, size_t n) {
+    const size_t total = n + 256;
+    void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    if (m == MAP_FAILED) { *p = nullptr; return false; }
+    *(size_t*)m = total;
+    *p = (char*)m + 256;
+    memset(*p, 0xAB, n);
+    return true;
+}
+inline void dev_free(void* p) { if (p) { void* m = (char*)p - 256; munmap(m, *(size_t*)m); } }
 inline bool host_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p != nullptr; }
 inline void host_free(void* p) { free(p); }
 inline bool h2d(void* d, const void* h, size_t n, stream_t) { memcpy(d, h, n); return true; }
@@ -77,7 +86,12 @@ inline bool d2h(void* h, const void* d, size_t n, stream_t) { memcpy(h, d, n); r
 inline bool dev_memset(void* d, int v, size_t n, stream_t) { memset(d, v, n); return true; }
 inline bool stream_sync(stream_t) { return true; }
 inline bool device_sync() { return true; }
-inline bool last_launch_ok(const char*) { return true; }
+inline bool last_launch_ok(const char* what) {
+    if (!vbemu::g_cluster_failed) return true;
+    vbemu::g_cluster_failed = false;
+    set_error(std::string(what) + ": a CTA of an emulated cluster launch died");
+    return false;
+}
 inline void clear_stale_error() {}
 inline bool set_device(int) { return true; }
 inline int device_count() { return 1; }

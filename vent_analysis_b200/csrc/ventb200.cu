@@ -26,7 +26,7 @@ struct Buf {
 // of the host pipeline (two compute streams) can overlap
 #define VB_MAX_CSTREAMS 4
 struct N4Ws {
-    Buf logI, u, colmask, rbb, wbase, acol, order, ec, code, axis, counter;
+    Buf logI, u, colmask, rbb, wbase, acol, order, ec, code, axis, counter, cl_hist, cl_q, cl_red, cl_bar, cl_bcast;
 };
 
 struct TableHost {
@@ -48,6 +48,8 @@ struct vb_ctx {
     int r0 = 0;                          // first subject of the range the stage runners work on
     uint64_t launches = 0;
     bool debug = false;
+    int n4_cluster_max = 0;   // vb_set_n4_cluster (0: automatic)
+    int n4_cluster = 1;       // CTAs per subject of the last N4 launch
     // subject descriptors
     std::vector<VbSubject> last_subj;
     std::vector<long long> last_wordoff;
@@ -258,16 +260,35 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     const long long static_smem = vbrt::static_smem(n4_subject_kernel);    // s_next, chain state
     if (ub + fixed + static_smem > c->max_smem)
         return fail(VB_ERR_UNSUPPORTED, "N4: working set does not fit the 227 KB of shared memory");
-    const long long cap = ((long long)c->max_smem - ub - fixed - static_smem) / 4;
-    const int grid = std::min(n, c->sms);
+    long long cap = ((long long)c->max_smem - ub - fixed - static_smem) / 4;
+    if (const char* e = getenv("VB_N4_SMEM_CAP")) cap = std::min<long long>(cap, std::max(0, atoi(e)));   // tests: U in global memory / the column-walk update
+    // A batch that leaves most SMs idle runs in CLUSTER MODE: a thread-block cluster of K CTAs per subject
+    // (n4_kernels.cuh; latency of single subjects and small batches).  Not with the debug capture.
+    int K = 1;
+    {
+        int want = (c->n4_cluster_max > 0) ? c->n4_cluster_max : 8;
+        if (const char* e = getenv("VB_N4_CLUSTER")) want = std::max(1, std::min(8, atoi(e)));    // tuning / tests
+        while (want & (want - 1)) want &= want - 1;          // a power of two
+        while (want > 1 && (long long)n * want > c->sms) want >>= 1;
+        if (!c->debug) K = want;
+    }
+    const int grid = (K > 1) ? n * K : std::min(n, c->sms);
+    const int slots = (K > 1) ? n : grid;                 // workspace slots shared by the CTAs of a cluster
     N4Ws& W = c->n4ws[c->wsi % VB_MAX_CSTREAMS];
-    if (!ensure(W.logI, sizeof(float) * (size_t)grid * (size_t)vmax) || !ensure(W.u, sizeof(float) * (size_t)grid * (size_t)vmax) ||
-        !ensure(W.colmask, 4 * (size_t)grid * (size_t)cmw) || !ensure(W.rbb, 4 * (size_t)grid * (size_t)rbb) ||
-        !ensure(W.wbase, 4 * (size_t)grid * (size_t)wb) || !ensure(W.acol, 4 * (size_t)grid * (size_t)ncmax) ||
-        !ensure(W.order, 4 * (size_t)grid * (size_t)wb) || !ensure(W.ec, 4 * (size_t)grid * (size_t)((vmax + 3) & ~3LL)) ||
-        !ensure(W.code, 4 * (size_t)grid * (size_t)vmax) ||
+    if (!ensure(W.logI, sizeof(float) * (size_t)slots * (size_t)vmax) || !ensure(W.u, sizeof(float) * (size_t)slots * (size_t)vmax) ||
+        !ensure(W.colmask, 4 * (size_t)slots * (size_t)cmw) || !ensure(W.rbb, 4 * (size_t)slots * (size_t)rbb) ||
+        !ensure(W.wbase, 4 * (size_t)slots * (size_t)wb) || !ensure(W.acol, 4 * (size_t)slots * (size_t)ncmax) ||
+        !ensure(W.order, 4 * (size_t)slots * (size_t)wb) || !ensure(W.ec, 4 * (size_t)slots * (size_t)((vmax + 3) & ~3LL)) ||
+        !ensure(W.code, 4 * (size_t)slots * (size_t)vmax) ||
         !ensure(W.axis, 4 * (size_t)grid * (size_t)axis) || !ensure(W.counter, 64))
         return VB_ERR_CUDA;
+    const long long q_max = (long long)ncpf[0] * ncpf[1] * n2max;          // Q[a][b][s] entries at the last level
+    if (K > 1) {
+        if (!ensure(W.cl_hist, 4 * 8 * (size_t)slots * K * (size_t)p.n_bins) || !ensure(W.cl_q, 4 * 8 * (size_t)slots * K * (size_t)q_max) ||
+            !ensure(W.cl_red, 2 * 32 * (size_t)slots * K) || !ensure(W.cl_bar, 16 * (size_t)slots) || !ensure(W.cl_bcast, 64 * (size_t)slots))
+            return VB_ERR_CUDA;
+        if (!vbrt::dev_memset(W.cl_bar.p, 0, 16 * (size_t)slots, s)) return VB_ERR_CUDA;
+    }
     int trace = 0;
     for (int l = 0; l < p.n_levels; ++l) trace += p.max_iter[l];
     float* dbg = nullptr;
@@ -290,6 +311,10 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     a.ws_ec = (float*)W.ec.p; a.ws_code = (uint32_t*)W.code.p; a.rowtab_rows = (int)rowtab_rows;
     { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] == '1') ? 1 : 0; }
     a.work_counter = (int*)W.counter.p; a.debug = dbg;
+    a.K = K; a.q_max = (int)q_max;
+    a.cl_hist = (K > 1) ? (unsigned long long*)W.cl_hist.p : nullptr; a.cl_q = (K > 1) ? (unsigned*)W.cl_q.p : nullptr;
+    a.cl_red = (K > 1) ? (double*)W.cl_red.p : nullptr; a.cl_bar = (K > 1) ? (unsigned*)W.cl_bar.p : nullptr;
+    a.cl_bcast = (K > 1) ? (int*)W.cl_bcast.p : nullptr;
     a.Vmax = vmax; a.cmw_max = cmw; a.rbb_max = rbb; a.wb_max = wb; a.ncols_max = ncmax;
     a.axis_stride = (int)axis; a.debug_stride = dbg_stride;
     a.Lmax = (int)Lmax; a.fftN = fftN; a.union_bytes = (int)ub;
@@ -297,7 +322,14 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     a.logI_cap = (int)std::min<long long>(std::max<long long>(cap, 0), vmax);
     const int smem = (int)(ub + fixed + 4LL * a.logI_cap);
     if (!vbrt::allow_smem(n4_subject_kernel, smem)) return VB_ERR_CUDA;
-    VB_LAUNCH(n4_subject_kernel, dim3(grid), dim3(VB_N4_THREADS), (size_t)smem, s, a);
+    bool launched = false;
+    if (K > 1) {
+        launched = vbrt::allow_smem(n4_cluster_kernel, smem) &&
+                   VB_LAUNCH_CLUSTER(n4_cluster_kernel, dim3(grid), dim3(VB_N4_THREADS), (size_t)smem, s, K, a);
+        if (!launched) { vbrt::clear_stale_error(); a.K = 1; }          // no room for such a cluster: one CTA per subject
+    }
+    if (!launched) { VB_LAUNCH(n4_subject_kernel, dim3(std::min(n, c->sms)), dim3(VB_N4_THREADS), (size_t)smem, s, a); }
+    c->n4_cluster = launched ? K : 1;
     ++c->launches;
     return vbrt::last_launch_ok("n4_subject_kernel") ? VB_OK : VB_ERR_CUDA;
 }
@@ -457,7 +489,7 @@ void vb_destroy(vb_ctx* c) {
         for (vbrt::stream_t st : all) vbrt::stream_sync(st);
     }
     for (N4Ws& W : c->n4ws) {
-        Buf* wb[] = {&W.logI, &W.u, &W.colmask, &W.rbb, &W.wbase, &W.acol, &W.order, &W.ec, &W.code, &W.axis, &W.counter};
+        Buf* wb[] = {&W.logI, &W.u, &W.colmask, &W.rbb, &W.wbase, &W.acol, &W.order, &W.ec, &W.code, &W.axis, &W.counter, &W.cl_hist, &W.cl_q, &W.cl_red, &W.cl_bar, &W.cl_bcast};
         for (Buf* b : wb) vbrt::dev_free(b->p);
     }
     vbrt::stream_destroy(c->stream2);
@@ -1355,6 +1387,15 @@ int vb_profile_fetch(vb_ctx* c, double* stage_ms, int32_t* n_calls) {
     c->ev_used = 0;
     return VB_OK;
 }
+
+int vb_set_n4_cluster(vb_ctx* c, int32_t max_k) {
+    if (!c) return fail(VB_ERR_ARG, "null ctx");
+    if (max_k < 0 || max_k > 8) return fail(VB_ERR_ARG, "N4 cluster size: 0 (automatic) or 1..8");
+    c->n4_cluster_max = max_k;
+    return VB_OK;
+}
+
+int32_t vb_n4_cluster_size(const vb_ctx* c) { return c ? c->n4_cluster : 1; }
 
 int vb_set_debug(vb_ctx* c, int32_t on) {
     if (!c) return fail(VB_ERR_ARG, "null ctx");
