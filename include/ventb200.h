@@ -255,8 +255,12 @@ int vb_profile_fetch(vb_ctx* ctx, double* stage_ms, int32_t* n_calls);
 /* N4 on small batches (the reference's use: ONE subject per Vent_Analysis object,
  * Vent_Analysis.py:316-334).  A batch that would leave most SMs idle runs with a thread-block
  * cluster of K CTAs (K SMs) per subject; results are bit-identical to one CTA per subject.
- * vb_set_n4_cluster: max_k = 0 automatic (largest K in {8, 4, 2, 1} with n * K <= SM count),
- * 1 = always one CTA per subject, 2 / 4 / 8 = upper bound for the automatic choice.
+ * vb_set_n4_cluster(max_k):
+ *   0  automatic (default): the largest K in {8, 4, 2, 1} with n * K <= 7/8 of the SM count, for
+ *      volumes of >= 200 000 voxels that are not a chunk of a multi-stream schedule (the measured
+ *      break-even points: profiles/r02_n4_cluster_timings.jsonl);
+ *   1  always one CTA per subject;
+ *   2 / 4 / 8  use up to that many CTAs per subject whenever n * K <= SM count (any volume size).
  * vb_n4_cluster_size: K of the most recent N4 launch of this context (1 before any launch). */
 int vb_set_n4_cluster(vb_ctx* ctx, int32_t max_k);
 int32_t vb_n4_cluster_size(const vb_ctx* ctx);

@@ -102,6 +102,27 @@ def test_n4_cluster_with_the_column_walk_update_and_u_in_global_memory(ctx8, mon
     helpers.check_n4_cluster(ctx8, _cluster_cases()[:2], ks=(2, 8), max_iter=(5, 3), sms=8)
 
 
+def test_n4_cluster_automatic_choice(ctx8, monkeypatch):
+    """vb_set_n4_cluster(0): small volumes keep one CTA per subject; above the size threshold the
+    largest K with n * K <= 7/8 of the SMs (8 emulated SMs: 1 subject -> 4 CTAs, 2 or 3 -> 2, 4 -> 1);
+    a forced K ignores the threshold and fills the SMs (n * K <= 8)."""
+    a = phantom((24, 20, 5), [1.5, 1.5, 10.0], 21)
+    p = ctx8.default_n4_params(max_iter=(1,))
+
+    def k_used(n, max_k):
+        ctx8.set_n4_cluster(max_k)
+        ctx8.pipeline_host([a[0].shape] * n, _lib.DO_N4, image=np.tile(a[0].ravel(), n), mask=np.tile(a[1].ravel(), n), params=p)
+        return ctx8.n4_cluster_size()
+
+    try:
+        assert k_used(1, 0) == 1                     # 2400 voxels: below the threshold
+        assert k_used(1, 8) == 8 and k_used(2, 8) == 4 and k_used(1, 1) == 1
+        monkeypatch.setenv("VB_N4_CLUSTER_MIN_V", "0")
+        assert [k_used(n, 0) for n in (1, 2, 3, 4)] == [4, 2, 2, 1]
+    finally:
+        ctx8.set_n4_cluster(0)
+
+
 def test_n4_ragged_batch_and_label_semantics(ctx):
     """Two subjects of different shapes in one launch; mask label 2 is ignored (MaskLabel=1)."""
     a_img, a_m = phantom((24, 20, 5), [1.5, 1.5, 10.0], 21)

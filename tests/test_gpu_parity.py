@@ -71,6 +71,27 @@ def test_n4_cluster_of_ctas_per_subject_is_bit_identical(ctx, monkeypatch):
     helpers.check_n4_cluster(ctx, [[c2], [a, b]], ks=(2, 8), sms=sms)
 
 
+def test_n4_cluster_automatic_choice_on_the_device(ctx, monkeypatch):
+    """vb_set_n4_cluster(0) on the 148-SM device: a C2 subject alone gets 8 CTAs; 16 subjects 8 each,
+    18 -> 4, 40 -> 2, 74 -> 1 (n * K <= 7/8 of the SMs); a small volume keeps one CTA; the chunks of a
+    multi-stream host schedule keep one CTA per subject -- and that run equals the unchunked one."""
+    c2 = phantom(CONFIGS["C2"][0], CONFIGS["C2"][1], 3)
+    tiny = phantom((48, 40, 6), [1.5, 1.5, 10.0], 21)
+    p = ctx.default_n4_params(max_iter=(2, 1))
+
+    def run(sub, n):
+        out = ctx.pipeline_host([sub[0].shape] * n, _lib.DO_N4, image=np.tile(sub[0].ravel(), n), mask=np.tile(sub[1].ravel(), n), params=p)
+        return ctx.n4_cluster_size(), out["n4"].copy()
+
+    ctx.set_n4_cluster(0)
+    assert [run(c2, n)[0] for n in (1, 16, 18, 40, 74)] == [8, 8, 4, 2, 1]
+    assert run(tiny, 1)[0] == 1
+    k_one, whole = run(c2, 4)
+    monkeypatch.setenv("VB_CHUNK_PER", "2")
+    k_chunked, chunked = run(c2, 4)
+    assert (k_one, k_chunked) == (8, 1) and chunked.tobytes() == whole.tobytes()
+
+
 def test_n4_stage_level_parity(ctx):
     shape = (40, 36, 6)
     img, mask = phantom(shape, [1.5, 1.5, 10.0], 5)

@@ -12,4 +12,4 @@ for shape, vox, nb in [((208, 256, 18), [1.5, 1.5, 10.0], 1), ((208, 256, 18), [
         t = time.perf_counter()
         m, out, st = cohort.run_cohort_host(imgs, masks, [vox] * nb, ctx=ctx, flags=_lib.DO_SNR | _lib.DO_N4 | _lib.DO_VDP)
         dt = time.perf_counter() - t
-    print(shape, "batch", nb, "mask voxels", int((masks[0] == 1).sum()), "iters", st["n4_iters"][0][:4].tolist(), f"wall {dt*1e3:.1f} ms", "VDP", round(float(m[0, 0]), 3))
+    print(shape, "batch", nb, "mask voxels", int((masks[0] == 1).sum()), "iters", st["n4_iters"][0][:4].tolist(), f"wall {dt*1e3:.1f} ms", "VDP", round(float(m[0, 0]), 3), "CTAs per subject", ctx.n4_cluster_size())

@@ -19,6 +19,11 @@ CASES = [((128, 128, 14), [2.0, 2.0, 11.5], (1, 4, 16, 18, 32, 37, 64, 74)),
 if "--quick" in sys.argv:        # a first sanity pass: one small and one C2 subject
     CASES = [((48, 40, 6), [1.5, 1.5, 10.0], (1, 3)), ((128, 128, 14), [2.0, 2.0, 11.5], (1,))]
 reps = int(os.environ.get("REPS", "3"))
+KS = (1, 2, 4, 8)
+if "--ncu" in sys.argv:          # one launch of the cluster kernel on a C4 subject (for a capture under ncu)
+    CASES, KS, reps = [((256, 256, 64), [1.5, 1.5, 3.0], (1,))], (1, 8), 0
+if "--auto" in sys.argv:         # what vb_set_n4_cluster(0) picks, and its time against one CTA per subject
+    KS = (1, 0)
 ctx = _lib.context(0)
 cache = {}
 for shape, vox, batches in CASES:
@@ -33,7 +38,7 @@ for shape, vox, batches in CASES:
         dc = cohort.DeviceCohort(imgs, masks, [vox] * nb, flags=_lib.DO_N4, want_logbias=True)
         rec = {"shape": list(shape), "batch": nb, "mask_voxels": int((masks[0] == 1).sum()), "ms": {}, "k_used": {}, "identical": {}}
         ref = None
-        for k in (1, 2, 4, 8):
+        for k in KS:
             ctx.set_n4_cluster(k)
             best = 1e30
             for r in range(reps + 1):
@@ -43,7 +48,7 @@ for shape, vox, batches in CASES:
                 dc.step()
                 e1.record()
                 torch.cuda.synchronize()
-                if r > 0:
+                if r > 0 or reps == 0:
                     best = min(best, e0.elapsed_time(e1))
             used = ctx.n4_cluster_size()
             st = dc.stats()

@@ -562,7 +562,8 @@ class Context:
         return dict(zip(STAGE_NAMES, (float(x) for x in ms))), n.value
 
     def set_n4_cluster(self, max_k=0):
-        """CTAs (SMs) per subject for N4 on small batches: 0 automatic, 1 off, 2 / 4 / 8 upper bound."""
+        """CTAs (SMs) per subject for N4 on small batches: 0 automatic (volumes of >= 200 k voxels,
+        n * K <= 7/8 of the SMs), 1 off, 2 / 4 / 8 forced upper bound (n * K <= SM count)."""
         self.check(self.lib.vb_set_n4_cluster(self.h, int(max_k)))
 
     def n4_cluster_size(self):

@@ -138,6 +138,7 @@ struct N4Args {
     unsigned* cl_bar;        // [clusters][4]             arrival counters of the cross-CTA barriers (zeroed before the launch)
     int* cl_bcast;           // [clusters][16]            scalars of the setup, written by CTA 0 of the cluster
     int q_max;
+    int cl_chain_warps;      // warps of the chain team in cluster mode (the phase team has 1 / K of the work there); 0: VB_N4_CHAIN_WARPS
     int no_overlap;          // 1: run the convergence chain and the next iteration's phases one after the other
                              // (same results; A/B timing of the overlap)
 };
@@ -1731,7 +1732,8 @@ VB_DEV void n4_subject_body(const N4Args& a) {
     const int tid = (int)threadIdx.x;
     N4Team full, TC, TP;
     full.tid = tid; full.nt = (int)blockDim.x; full.bar = 0;
-    TC.tid = tid; TC.nt = min(VB_N4_CHAIN_WARPS * 32, (int)blockDim.x - 32); TC.bar = 1;
+    const int chain_warps = (CL && a.cl_chain_warps > 0) ? a.cl_chain_warps : VB_N4_CHAIN_WARPS;
+    TC.tid = tid; TC.nt = min(chain_warps * 32, (int)blockDim.x - 32); TC.bar = 1;
     TP.tid = tid - TC.nt; TP.nt = (int)blockDim.x - TC.nt; TP.bar = 2;
     N4Ctx c;
     c.un_f = (float*)smem;

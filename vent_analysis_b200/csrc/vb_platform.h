@@ -261,7 +261,7 @@ template <class Body> bool launch_cluster(dim3 grid, dim3 block, size_t smem, in
         for (unsigned r = 0; r < (unsigned)k && c0 + r < grid.x; ++r) {
             const pid_t pid = fork();
             if (pid == 0) {
-                alarm(900);                                // a deadlocked cluster must not hang the test run
+                alarm(240);                                // a deadlocked cluster must not hang the test run
                 run_block(c0 + r, 0, 0, block, smem, body);
                 _exit(0);
             }
@@ -303,24 +303,27 @@ static inline int __syncthreads_or(int pred) {
     vbemu::g_block->bar.arrive_and_wait();
     return r;
 }
-// named barriers: one std::barrier per id, created by the first thread that needs it
+// named barriers: one std::barrier per id, created by the first thread that needs it (and again when a
+// later use of the id has another thread count, e.g. the next launch splits its teams differently)
 namespace vbemu {
 struct Named {
     std::mutex mu;
-    std::unique_ptr<std::barrier<>> bar[16];
+    std::shared_ptr<std::barrier<>> bar[16];
+    int count[16];
     int flag[16][2];
     int phase[16];
 };
 inline Named g_named;
-inline std::barrier<>& named(int id, int n) {
+inline std::shared_ptr<std::barrier<>> named_ptr(int id, int n) {
     std::lock_guard<std::mutex> g(g_named.mu);
-    if (!g_named.bar[id]) g_named.bar[id].reset(new std::barrier<>(n));
-    return *g_named.bar[id];
+    if (!g_named.bar[id] || g_named.count[id] != n) { g_named.bar[id].reset(new std::barrier<>(n)); g_named.count[id] = n; }
+    return g_named.bar[id];
 }
 }  // namespace vbemu
-static inline void vb_bar_sync(int id, int nthreads) { vbemu::named(id, nthreads).arrive_and_wait(); }
+static inline void vb_bar_sync(int id, int nthreads) { vbemu::named_ptr(id, nthreads)->arrive_and_wait(); }
 static inline int vb_bar_or(int id, int nthreads, int pred) {
-    std::barrier<>& b = vbemu::named(id, nthreads);
+    const std::shared_ptr<std::barrier<>> bp = vbemu::named_ptr(id, nthreads);
+    std::barrier<>& b = *bp;
     b.arrive_and_wait();                                   // the flag is clear
     if (pred) __atomic_store_n(&vbemu::g_named.flag[id][0], 1, __ATOMIC_SEQ_CST);
     b.arrive_and_wait();

@@ -50,6 +50,7 @@ struct vb_ctx {
     bool debug = false;
     int n4_cluster_max = 0;   // vb_set_n4_cluster (0: automatic)
     int n4_cluster = 1;       // CTAs per subject of the last N4 launch
+    int n4_parts = 1;         // chunks / parts of the schedule the next N4 launch belongs to (> 1: several N4 kernels in flight)
     // subject descriptors
     std::vector<VbSubject> last_subj;
     std::vector<long long> last_wordoff;
@@ -264,12 +265,22 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     if (const char* e = getenv("VB_N4_SMEM_CAP")) cap = std::min<long long>(cap, std::max(0, atoi(e)));   // tests: U in global memory / the column-walk update
     // A batch that leaves most SMs idle runs in CLUSTER MODE: a thread-block cluster of K CTAs per subject
     // (n4_kernels.cuh; latency of single subjects and small batches).  Not with the debug capture.
+    // The automatic choice follows the B200 timings in profiles/r02_n4_cluster_timings.jsonl: volumes below
+    // ~200 k voxels lose (2.0 -> 2.8 ms at 48x40x6: the cross-CTA barriers cost more than the split saves); a
+    // grid that fills the last SM loses too (18 subjects x 8 CTAs: 7.6 ms against 6.1 with 4) because clusters
+    // are placed within a GPC, so one eighth of the SMs stays free; chunks of a multi-stream schedule keep one
+    // CTA per subject (their kernels share the SMs).  vb_set_n4_cluster(2 / 4 / 8) overrides the first two.
     int K = 1;
     {
+        const bool forced = c->n4_cluster_max > 1;
         int want = (c->n4_cluster_max > 0) ? c->n4_cluster_max : 8;
-        if (const char* e = getenv("VB_N4_CLUSTER")) want = std::max(1, std::min(8, atoi(e)));    // tuning / tests
+        long long min_v = 200000, limit = forced ? c->sms : (long long)c->sms * 7 / 8;
+        if (const char* e = getenv("VB_N4_CLUSTER_MIN_V")) min_v = atoll(e);                      // tests
+        if (!forced && vmax < min_v) want = 1;
+        if (c->n4_parts > 1) want = 1;
+        if (const char* e = getenv("VB_N4_CLUSTER")) { want = std::max(1, std::min(8, atoi(e))); limit = c->sms; }   // tuning
         while (want & (want - 1)) want &= want - 1;          // a power of two
-        while (want > 1 && (long long)n * want > c->sms) want >>= 1;
+        while (want > 1 && (long long)n * want > limit) want >>= 1;
         if (!c->debug) K = want;
     }
     const int grid = (K > 1) ? n * K : std::min(n, c->sms);
@@ -312,6 +323,8 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] == '1') ? 1 : 0; }
     a.work_counter = (int*)W.counter.p; a.debug = dbg;
     a.K = K; a.q_max = (int)q_max;
+    a.cl_chain_warps = 0;
+    if (const char* e = getenv("VB_N4_CL_CHAIN_WARPS")) a.cl_chain_warps = std::max(4, std::min(VB_N4_THREADS / 32 - 1, atoi(e)));   // tuning (the chain needs a team of >= 4 warps)
     a.cl_hist = (K > 1) ? (unsigned long long*)W.cl_hist.p : nullptr; a.cl_q = (K > 1) ? (unsigned*)W.cl_q.p : nullptr;
     a.cl_red = (K > 1) ? (double*)W.cl_red.p : nullptr; a.cl_bar = (K > 1) ? (unsigned*)W.cl_bar.p : nullptr;
     a.cl_bcast = (K > 1) ? (int*)W.cl_bcast.p : nullptr;
@@ -759,6 +772,13 @@ static int chunk_stages(vb_ctx* c, int k, int r0, int cnt, const vb_n4_params* p
     return rc;
 }
 
+// marks the N4 launches of a schedule of `parts` chunks (run_n4 keeps one CTA per subject when several N4 kernels share the SMs)
+struct PartsScope {
+    vb_ctx* c;
+    PartsScope(vb_ctx* ctx, int parts) : c(ctx) { c->n4_parts = parts; }
+    ~PartsScope() { c->n4_parts = 1; }
+};
+
 static int pipeline_check(uint32_t flags, const int32_t* handles, const vb_n4_params* params, const vb_buffers* d) {
     if ((flags & VB_DO_CI) && !handles) return fail(VB_ERR_ARG, "pipeline: CI needs table handles");
     if ((flags & VB_DO_SNR) && !d->image) return fail(VB_ERR_ARG, "pipeline: SNR needs image");
@@ -797,6 +817,7 @@ int vb_pipeline_batch_dev(vb_ctx* c, int32_t n, const int32_t* shapes, const int
     if (const char* e = getenv("VB_PARTS")) nparts = std::max(1, std::min(8, atoi(e)));
     if (!(flags & VB_DO_N4) || c->debug) nparts = 1;
     if (nparts == 1) return pipeline_range(c, 0, n, params, thresh, flags, d, s, ev);
+    const PartsScope parts_scope(c, nparts);
     if (!c->ev_fork) {
         if (!vbrt::event_create(&c->ev_fork)) return VB_ERR_CUDA;
     }
@@ -932,6 +953,7 @@ int vb_pipeline_batch_host(vb_ctx* c, int32_t n, const int32_t* shapes, const in
     if (rc) return rc;
     const std::vector<int> bounds = chunk_bounds(c, n);        // first subject of every chunk, then n
     const int nchunks = (int)bounds.size() - 1;
+    const PartsScope parts_scope(c, nchunks);
     while (c->ev_copy.size() < 2 * (size_t)nchunks) {
         vbrt::event_t e;
         if (!vbrt::event_create(&e)) return VB_ERR_CUDA;
@@ -1046,6 +1068,7 @@ int vb_pipeline_batch_host_packed(vb_ctx* c, int32_t n, const int32_t* shapes, c
     }
     const std::vector<int> bounds = chunk_bounds(c, n);
     const int nchunks = (int)bounds.size() - 1;
+    const PartsScope parts_scope(c, nchunks);
     while (c->ev_copy.size() < 3 * (size_t)nchunks) {
         vbrt::event_t e;
         if (!vbrt::event_create(&e)) return VB_ERR_CUDA;
