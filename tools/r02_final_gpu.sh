@@ -9,6 +9,7 @@ timeout 80 python tools/time_cluster.py --auto > $O/cluster_auto.jsonl 2> $O/clu
 timeout 60 python tools/time_big.py > $O/single_subject.txt 2> $O/single_subject.err; echo "time_big rc=$?"; cat $O/single_subject.txt
 timeout 120 ncu --set full --clock-control none --import-source on -k regex:n4_cluster_kernel -c 1 -f -o $O/r02_n4_cluster_c4 \
   python tools/time_cluster.py --ncu > $O/ncu_cluster.log 2>&1; echo "ncu rc=$?"; tail -2 $O/ncu_cluster.log
+CW=14,18,22 timeout 60 python tools/sweep_cluster_chain.py > $O/sweep_fine.jsonl 2> $O/sweep_fine.err; echo "fine sweep rc=$?"; cat $O/sweep_fine.jsonl
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/r02f/bench.json").read().strip().splitlines()[-1])

@@ -14,7 +14,7 @@ from vent_analysis_b200.phantom import phantom
 
 CASES = [((128, 128, 14), [2.0, 2.0, 11.5], 1, (8, 4, 2)), ((128, 128, 14), [2.0, 2.0, 11.5], 16, (8, 4)),
          ((208, 256, 18), [1.5, 1.5, 10.0], 1, (8, 4, 2)), ((256, 256, 64), [1.5, 1.5, 3.0], 1, (8, 4, 2))]
-CW = (8, 12, 16, 20, 24)
+CW = tuple(int(x) for x in os.environ.get("CW", "8,12,16,20,24").split(","))
 ctx = _lib.context(0)
 
 

@@ -323,7 +323,10 @@ int run_n4(vb_ctx* c, const float* image, const uint8_t* mask, int n, const vb_n
     { const char* e = getenv("VB_N4_NO_OVERLAP"); a.no_overlap = (e && e[0] == '1') ? 1 : 0; }
     a.work_counter = (int*)W.counter.p; a.debug = dbg;
     a.K = K; a.q_max = (int)q_max;
-    a.cl_chain_warps = 0;
+    // chain team of the cluster kernel: the phase team of a CTA has 1 / K of the one-CTA work while every CTA runs the
+    // whole chain, so the chain gets more of the 28 warps as K grows (profiles/r02_n4_cluster_chain_sweep.jsonl:
+    // C4 subject, K = 8: 12 warps 58.7 ms, 16: 51.1, 20: 47.1, 24: 60.6; K = 4: 16 warps best; K = 2: 12)
+    a.cl_chain_warps = (K >= 8) ? 20 : (K >= 4) ? 16 : 12;
     if (const char* e = getenv("VB_N4_CL_CHAIN_WARPS")) a.cl_chain_warps = std::max(4, std::min(VB_N4_THREADS / 32 - 1, atoi(e)));   // tuning (the chain needs a team of >= 4 warps)
     a.cl_hist = (K > 1) ? (unsigned long long*)W.cl_hist.p : nullptr; a.cl_q = (K > 1) ? (unsigned*)W.cl_q.p : nullptr;
     a.cl_red = (K > 1) ? (double*)W.cl_red.p : nullptr; a.cl_bar = (K > 1) ? (unsigned*)W.cl_bar.p : nullptr;
