@@ -92,14 +92,21 @@ def test_n4_cluster_of_ctas_per_subject_is_bit_identical(ctx8):
     process each): outputs, log bias, iteration counts and the last convergence value equal the
     one-CTA run bit for bit -- single subject, two ragged subjects, a batch with an empty and a
     one-voxel mask."""
-    helpers.check_n4_cluster(ctx8, _cluster_cases(), max_iter=(6, 4, 3), sms=8)
-    helpers.check_n4_cluster(ctx8, [[phantom((40, 36, 6), [1.5, 1.5, 10.0], 5)]], ks=(4,), max_iter=(50, 50, 6, 4), sms=8)   # the first two levels run to convergence
+    one, two, four = _cluster_cases()
+    helpers.check_n4_cluster(ctx8, [one], max_iter=(6, 4, 3), sms=8)
+    helpers.check_n4_cluster(ctx8, [two], ks=(4,), max_iter=(6, 4, 3), sms=8)
+    helpers.check_n4_cluster(ctx8, [four], ks=(2,), max_iter=(6, 4, 3), sms=8)
+    # the first two levels run to convergence (the phase team's speculative fit is discarded there, after an odd
+    # and an even number of its exchanges: its slot sets must not depend on the chain team's count)
+    helpers.check_n4_cluster(ctx8, [[phantom((40, 36, 6), [1.5, 1.5, 10.0], 5)]], ks=(2,), max_iter=(50, 50, 1), sms=8)
 
 
 def test_n4_cluster_with_the_column_walk_update_and_u_in_global_memory(ctx8, monkeypatch):
     """Same with no shared-memory room for the compact arrays / coefficient tables (the path of large volumes)."""
     monkeypatch.setenv("VB_N4_SMEM_CAP", "0")
-    helpers.check_n4_cluster(ctx8, _cluster_cases()[:2], ks=(2, 8), max_iter=(5, 3), sms=8)
+    one, two, _ = _cluster_cases()
+    helpers.check_n4_cluster(ctx8, [one], ks=(8,), max_iter=(5, 3), sms=8)
+    helpers.check_n4_cluster(ctx8, [two], ks=(2,), max_iter=(5, 3), sms=8)
 
 
 def test_n4_cluster_automatic_choice(ctx8, monkeypatch):

@@ -245,7 +245,10 @@ VB_DEV void n4_build_support(float* base, int slot, int n, int ncp) {
     }
 }
 
-struct N4Ctx {
+// CL = false (one CTA per subject): the cluster accessors below are the literals 1 / 0, so the cluster-mode code
+// and state of every function fold away at instantiation.
+template <bool CL>
+struct N4CtxT {
     // subject
     int n0, n1, n2, ncols, W, nblk;   // nblk: blocks of 32 ACTIVE columns
     long long V;
@@ -263,6 +266,11 @@ struct N4Ctx {
     int* ctr;             // shared-memory work counters, one per team barrier id
     // cluster mode (see N4Args): K CTAs per subject, this CTA's rank; walk items j -> j * istep + ioff
     int K, crank, istep, ioff, q_max;
+    VB_DEV_MEMBER int k() const { return CL ? K : 1; }
+    VB_DEV_MEMBER int rank() const { return CL ? crank : 0; }
+    VB_DEV_MEMBER int step() const { return CL ? istep : 1; }
+    VB_DEV_MEMBER int off() const { return CL ? ioff : 0; }
+    VB_DEV_MEMBER void deal(int s, int o) { if (CL) { istep = s; ioff = o; } }
     unsigned long long* cl_hist;
     unsigned* cl_q;
     double* cl_red;
@@ -308,7 +316,7 @@ struct N4Ctx {
     long long t_sub[4];   // debug: chain time in prefix / chunk setup / mu sweeps / sigma sweeps
 };
 
-VB_DEV N4Axis n4_ax(const N4Ctx& c, int a) {
+template <class CTX> VB_DEV N4Axis n4_ax(const CTX& c, int a) {
     size_t off = 0;
     for (int i = 0; i < a; ++i) off += 16 * (size_t)c.slot[i];
     return n4_axis(c.axis_base + off, c.slot[a]);
@@ -331,10 +339,10 @@ VB_DEV int n4_sync_or(const N4Team& T, int pred) {
 // arrive (release), wait until all K teams have arrived for this generation (acquire).  Everything
 // the teams wrote to global memory before the barrier is visible to all of them after it -- through
 // L2: such data must be read with vb_ld_cg (a line may sit in this SM's L1 from an earlier pass).
-VB_DEV void n4_csync(N4Ctx& c, const N4Team& T) {
+template <class CTX> VB_DEV void n4_csync(CTX& c, const N4Team& T) {
     n4_sync(T);
-    if (c.K == 1) return;
-    const unsigned target = (++c.gen[T.bar]) * (unsigned)c.K;
+    if (c.k() == 1) return;
+    const unsigned target = (++c.gen[T.bar]) * (unsigned)c.k();
     if (T.tid == 0) {
         __threadfence();
         atomicAdd(c.cl_bar + T.bar, 1u);
@@ -346,7 +354,7 @@ VB_DEV void n4_csync(N4Ctx& c, const N4Team& T) {
 
 // Loads of arrays that other CTAs of the cluster write between barriers (U, the convergence sequence):
 // through L2 in cluster mode; one CTA per subject: the plain load.
-template <class V> VB_DEV V n4_ld_x(const N4Ctx& c, const V* p) { return (c.K > 1) ? vb_ld_cg(p) : VB_N4_LDS(p); }
+template <class V, class CTX> VB_DEV V n4_ld_x(const CTX& c, const V* p) { return (c.k() > 1) ? vb_ld_cg(p) : VB_N4_LDS(p); }
 
 // ---------------------------------------------------------------------------------------------
 // block-wide exclusive scan of one int per thread; every thread gets its prefix and the total
@@ -399,7 +407,7 @@ struct N4Col {
     float wc0, wc1, wc2, wc3;
     float4 ws;
 };
-VB_DEV N4Col n4_col(const N4Ctx& c, const N4Axis& ac, const N4Axis& as, int q) {
+template <class CTX> VB_DEV N4Col n4_col(const CTX& c, const N4Axis& ac, const N4Axis& as, int q) {
     N4Col k;
     const int cc = q / c.n2, ss = q - cc * c.n2;
     k.bc = ac.bev[cc]; k.bs = as.bev[ss];
@@ -408,7 +416,7 @@ VB_DEV N4Col n4_col(const N4Ctx& c, const N4Axis& ac, const N4Axis& as, int q) {
     k.ws = as.evw[ss];
     return k;
 }
-VB_DEV float n4_coef(const float* L, const N4Ctx& c, const N4Col& k, int a) {
+template <class CTX> VB_DEV float n4_coef(const float* L, const CTX& c, const N4Col& k, int a) {
     const float* lp = L + ((size_t)a * c.ncp[1] + k.bc) * c.ncp[2] + k.bs;
     const int st = c.ncp[2];
     float g = 0.0f;
@@ -426,10 +434,10 @@ struct N4Win {
     int cur;
 };
 // `G` (optional): this lane's column of a precomputed coefficient table, G[a * gs]
-VB_DEV float n4_coef_t(const float* L, const N4Ctx& c, const N4Col& k, const float* G, int gs, int a) {
+template <class CTX> VB_DEV float n4_coef_t(const float* L, const CTX& c, const N4Col& k, const float* G, int gs, int a) {
     return G ? G[(size_t)a * gs] : n4_coef(L, c, k, a);
 }
-VB_DEV void n4_win_advance(N4Win& w, const float* L, const N4Ctx& c, const N4Col& k, int base, const float* G = nullptr, int gs = 0) {
+template <class CTX> VB_DEV void n4_win_advance(N4Win& w, const float* L, const CTX& c, const N4Col& k, int base, const float* G = nullptr, int gs = 0) {
     if (base == w.cur) return;
     if (w.cur < 0 || base - w.cur >= 4 || base < w.cur) {
         w.g0 = n4_coef_t(L, c, k, G, gs, base); w.g1 = n4_coef_t(L, c, k, G, gs, base + 1);
@@ -469,7 +477,7 @@ VB_DEV float n4_div(float x, float d, float rd) {
 }
 
 // column-coefficient table of lattice L for every active column: dst[a][k]
-VB_DEV void n4_build_G(const N4Ctx& c, const float* L, float* dst) {
+template <class CTX> VB_DEV void n4_build_G(const CTX& c, const float* L, float* dst) {
     const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     const int total = c.ncp[0] * c.nact;
     for (int e = (int)threadIdx.x; e < total; e += (int)blockDim.x) {
@@ -500,7 +508,7 @@ struct N4Item {
     int blk, seg, wi0, wi1, q, k;        // k: index of this lane's column among the active columns
     bool valid, empty;
 };
-VB_DEV N4Item n4_item(const N4Ctx& c, int it) {
+template <class CTX> VB_DEV N4Item n4_item(const CTX& c, int it) {
     N4Item I;
     I.blk = it % c.nblk; I.seg = it / c.nblk;
     I.wi0 = I.seg * c.wps; I.wi1 = min(c.W, I.wi0 + c.wps);
@@ -514,17 +522,17 @@ VB_DEV N4Item n4_item(const N4Ctx& c, int it) {
 
 // Dynamic scheduler: the warps of a team draw the next (largest remaining) item from a shared
 // counter.  The counter is reset by n4_items_begin (followed by a team barrier in the caller).
-VB_DEV void n4_items_begin(const N4Ctx& c, const N4Team& T) {
+template <class CTX> VB_DEV void n4_items_begin(const CTX& c, const N4Team& T) {
     if (T.tid == 0) c.ctr[T.bar] = 0;
 }
-VB_DEV int n4_items_next(const N4Ctx& c, const N4Team& T) {
+template <class CTX> VB_DEV int n4_items_next(const CTX& c, const N4Team& T) {
     int i = 0;
     if ((T.tid & 31) == 0) i = atomicAdd(&c.ctr[T.bar], 1);
     return __shfl_sync(VB_FULL, i, 0);
 }
 #define VB_N4_FOR_ITEMS(c, T, it) \
-    for (int i_ = n4_items_next(c, T) * (c).istep + (c).ioff, it = 0; i_ < (c).nblk * (c).nseg && ((it = (int)(c).iorder[i_]), true); \
-         i_ = n4_items_next(c, T) * (c).istep + (c).ioff)
+    for (int i_ = n4_items_next(c, T) * (c).step() + (c).off(), it = 0; i_ < (c).nblk * (c).nseg && ((it = (int)(c).iorder[i_]), true); \
+         i_ = n4_items_next(c, T) * (c).step() + (c).off())
 
 // What the row walks need from the context, as opaque local copies: otherwise the compiler
 // re-derives every pointer from the kernel parameters (blockIdx * stride + base, or shared-memory
@@ -534,7 +542,7 @@ struct N4Walk {
     const uint32_t* rbb;
     int ncols, nblk, n0;
 };
-VB_DEV N4Walk n4_walk(const N4Ctx& c) {
+template <class CTX> VB_DEV N4Walk n4_walk(const CTX& c) {
     N4Walk w;
     w.colmask = c.colmask; w.rbb = c.rbb; w.ncols = c.ncols; w.nblk = c.nblk; w.n0 = c.n0;
     VB_OPAQUE_PTR(w.colmask);
@@ -572,7 +580,7 @@ VB_DEV N4Walk n4_walk(const N4Ctx& c) {
 
 // ---------------------------------------------------------------------------------------------
 // setup: column bitmasks, compaction tables, compact log image, range and count of the mask
-VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float& bmin, float& bmax, int& M) {
+template <class CTX> VB_DEV void n4_setup(CTX& c, int label, float* smem_logI, int smem_cap, float& bmin, float& bmax, int& M) {
     const int nt = (int)blockDim.x, tid = (int)threadIdx.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
     // column bitmasks (coalesced over columns) and the list of active columns
     uint32_t* flag = c.rbb;                               // scratch: [ncols + 1]
@@ -695,20 +703,20 @@ VB_DEV void n4_setup(N4Ctx& c, int label, float* smem_logI, int smem_cap, float&
 
 // cluster mode: combine this CTA's (min, max, s1, s2) with those of the other CTAs, in rank order (every
 // CTA ends up with the same four numbers, bit for bit)
-VB_DEV void n4_cluster_reduce4(N4Ctx& c, const N4Team& T, float& mn, float& mx, double& s1, double& s2) {
-    if (c.K == 1) return;
+template <class CTX> VB_DEV void n4_cluster_reduce4(CTX& c, const N4Team& T, float& mn, float& mx, double& s1, double& s2) {
+    if (c.k() == 1) return;
     // (two sets of slots used in turn: a set is rewritten two exchanges later, i.e. after another cluster
     // barrier that every CTA reaches only when it has read this one -- no second barrier per exchange)
-    double* slots = c.cl_red + (size_t)c.par_red * 4 * c.K;
+    double* slots = c.cl_red + (size_t)c.par_red * 4 * c.k();
     c.par_red ^= 1;
     if (T.tid == 0) {
-        double* mine = slots + 4 * c.crank;
+        double* mine = slots + 4 * c.rank();
         mine[0] = (double)mn; mine[1] = (double)mx; mine[2] = s1; mine[3] = s2;
     }
     n4_csync(c, T);
     float a = FLT_MAX, b = -FLT_MAX;
     double p = 0.0, q = 0.0;
-    for (int r = 0; r < c.K; ++r) {
+    for (int r = 0; r < c.k(); ++r) {
         a = fminf(a, (float)vb_ld_cg(slots + 4 * r));
         b = fmaxf(b, (float)vb_ld_cg(slots + 4 * r + 1));
         p += vb_ld_cg(slots + 4 * r + 2);
@@ -718,11 +726,11 @@ VB_DEV void n4_cluster_reduce4(N4Ctx& c, const N4Team& T, float& mn, float& mx, 
 }
 
 // range of U = logI - bias(L) over the mask (after a lattice refinement)
-VB_DEV void n4_range(N4Ctx& c, float& bmin, float& bmax) {
+template <class CTX> VB_DEV void n4_range(CTX& c, float& bmin, float& bmax) {
     const int nt = (int)blockDim.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
     const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     float tmin = FLT_MAX, tmax = -FLT_MAX;
-    for (int it = w + nw * c.crank; it < c.nblk * c.nseg; it += nw * c.K) {      // (cluster mode: the items are dealt over the CTAs)
+    for (int it = w + nw * c.rank(); it < c.nblk * c.nseg; it += nw * c.k()) {      // (cluster mode: the items are dealt over the CTAs)
         const N4Item I = n4_item(c, it);
         if (I.empty) continue;
         const N4Col col = n4_col(c, ac, as, I.q);
@@ -740,7 +748,7 @@ VB_DEV void n4_range(N4Ctx& c, float& bmin, float& bmax) {
     }
     bmin = vb_block_reduce(tmin, VbMinF(), FLT_MAX, (float*)c.red);
     bmax = vb_block_reduce(tmax, VbMaxF(), -FLT_MAX, (float*)c.red);
-    if (c.K > 1) {
+    if (c.k() > 1) {
         N4Team full;
         full.tid = (int)threadIdx.x; full.nt = nt; full.bar = 0;
         double z1 = 0.0, z2 = 0.0;
@@ -765,7 +773,7 @@ VB_DEV void n4_hist_add(vb_saddr sh, float u, float bmin, float slope, float rsl
 
 // ---------------------------------------------------------------------------------------------
 // P1: triangular Parzen histogram of U over the mask (SharpenImage, first half)
-VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
+template <class CTX> VB_DEV void n4_histogram(CTX& c, const N4Team& T, float bmin, float bmax) {
     const int nt = T.nt, tid = T.tid;
     // One copy per LANE with an odd stride: lanes of a warp never share an address, and lanes that
     // hit the same bin fall into 32 different banks (the U values cluster in a few bins, so copies
@@ -786,7 +794,7 @@ VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     VB_OPAQUE_PTR(U);
     const int nbins = c.nbins;
     // cluster mode: this CTA's slice of the compact array (U is in global memory then; read through L2)
-    const int M0 = (int)((long long)c.M * c.crank / c.K), M = (int)((long long)c.M * (c.crank + 1) / c.K);
+    const int M0 = (int)((long long)c.M * c.rank() / c.k()), M = (int)((long long)c.M * (c.rank() + 1) / c.k());
     if (VB_N4_HIST4 && c.u_smem) {                       // U in shared memory: four voxels per 16-byte LDS
         const vb_saddr sU = vb_saddr_of(c.U);
         const int M4 = M & ~3;
@@ -805,20 +813,20 @@ VB_DEV void n4_histogram(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
         for (int i = M0 + tid; i < M; i += nt) n4_hist_add(sh, n4_ld_x(c, U + i), bmin, slope, rslope, nbins, one, fone);
     }
     n4_sync(T);
-    if (c.K > 1) {                                       // partial sums of the CTAs meet in global memory (two sets used in turn, see n4_cluster_reduce4)
+    if (c.k() > 1) {                                       // partial sums of the CTAs meet in global memory (two sets used in turn, see n4_cluster_reduce4)
         const int ts = (T.bar != 0) ? 1 : 0;
-        unsigned long long* part = c.cl_hist + (size_t)(2 * ts + (ts ? c.par_hist1 : c.par_hist0)) * c.K * c.nbins;
+        unsigned long long* part = c.cl_hist + (size_t)(2 * ts + (ts ? c.par_hist1 : c.par_hist0)) * c.k() * c.nbins;
         if (ts) c.par_hist1 ^= 1; else c.par_hist0 ^= 1;
         for (int bin = tid; bin < c.nbins; bin += nt) {
             unsigned long long s = 0;
 #pragma unroll
             for (int k = 0; k < VB_N4_HCOPIES; ++k) s += hc[(size_t)k * hstride + bin];
-            part[(size_t)c.crank * c.nbins + bin] = s;
+            part[(size_t)c.rank() * c.nbins + bin] = s;
         }
         n4_csync(c, T);
         for (int bin = tid; bin < c.nbins; bin += nt) {
             unsigned long long s = 0;
-            for (int r = 0; r < c.K; ++r) s += vb_ld_cg(part + (size_t)r * c.nbins + bin);
+            for (int r = 0; r < c.k(); ++r) s += vb_ld_cg(part + (size_t)r * c.nbins + bin);
             c.H[bin] = (float)((double)s / (double)one);
         }
         n4_sync(T);
@@ -896,7 +904,7 @@ VB_DEV void n4_fft(const N4Team& T, double* re, double* im, int N, int logN, int
 // SharpenImage, second half: Wiener-deconvolve the histogram with the Gaussian bias model and
 // build E(u|v).  Two real sequences share one complex FFT (4 FFTs instead of ITK's 7).
 // The twiddles depend only on the (launch-constant) padded histogram size: c.tw, computed once per CTA.
-VB_DEV void n4_twiddles(N4Ctx& c) {
+template <class CTX> VB_DEV void n4_twiddles(CTX& c) {
     const int N = c.fftN;
     for (int n = (int)threadIdx.x; n < (N >> 1); n += (int)blockDim.x) {
         double sn, co;
@@ -905,7 +913,7 @@ VB_DEV void n4_twiddles(N4Ctx& c) {
     }
     __syncthreads();
 }
-VB_DEV void n4_sharpen(N4Ctx& c, const N4Team& T, float bmin, float bmax, float fwhm, float wiener) {
+template <class CTX> VB_DEV void n4_sharpen(CTX& c, const N4Team& T, float bmin, float bmax, float fwhm, float wiener) {
     const int nt = T.nt, tid = T.tid;
     const int N = c.fftN;
     int logN = 0;
@@ -1007,8 +1015,8 @@ VB_DEV void n4_qflush(vb_saddr Q, int a, int ncp1, int n2, int bc, int s, const 
 }
 
 // SM: U and the row tables live in shared memory (LDS through 32-bit shared addresses in the walk).
-template <bool OMEGA, bool SM>
-VB_DEV void n4_contract_t(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
+template <bool OMEGA, bool SM, class CTX>
+VB_DEV void n4_contract_t(CTX& c, const N4Team& T, float bmin, float bmax) {
     const int nt = T.nt, tid = T.tid;
     const int ncp0 = c.ncp[0], ncp1 = c.ncp[1], ncp2 = c.ncp[2];
     const int n2 = c.n2;
@@ -1029,7 +1037,7 @@ VB_DEV void n4_contract_t(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     for (int e = tid; e < 2 * Qn; e += nt) Q[e] = 0u;
     // cluster mode: the fit's items are dealt over the CTAs (item j of this CTA = j * K + rank); omega is
     // computed by every CTA for itself (once per level)
-    c.istep = OMEGA ? 1 : c.K; c.ioff = OMEGA ? 0 : c.crank;
+    c.deal(OMEGA ? 1 : c.k(), OMEGA ? 0 : c.rank());
     n4_items_begin(c, T);
     n4_sync(T);
 
@@ -1081,17 +1089,17 @@ VB_DEV void n4_contract_t(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
         }
     }
     n4_sync(T);
-    c.istep = 1; c.ioff = 0;
-    if (!OMEGA && c.K > 1) {                             // partial sums of the CTAs meet in global memory (integers: exact)
+    c.deal(1, 0);
+    if (!OMEGA && c.k() > 1) {                             // partial sums of the CTAs meet in global memory (integers: exact)
         const int ts = (T.bar != 0) ? 1 : 0;
-        unsigned* part = c.cl_q + (size_t)(2 * ts + (ts ? c.par_q1 : c.par_q0)) * c.K * 2 * c.q_max;     // (two sets used in turn, see n4_cluster_reduce4)
+        unsigned* part = c.cl_q + (size_t)(2 * ts + (ts ? c.par_q1 : c.par_q0)) * c.k() * 2 * c.q_max;     // (two sets used in turn, see n4_cluster_reduce4)
         if (ts) c.par_q1 ^= 1; else c.par_q0 ^= 1;
-        unsigned* mine = part + (size_t)c.crank * 2 * c.q_max;
+        unsigned* mine = part + (size_t)c.rank() * 2 * c.q_max;
         for (int e = tid; e < 2 * Qn; e += nt) mine[e] = Q[e];
         n4_csync(c, T);
         for (int e = tid; e < Qn; e += nt) {
             unsigned long long sum = 0;
-            for (int r = 0; r < c.K; ++r) {
+            for (int r = 0; r < c.k(); ++r) {
                 const unsigned* qr = part + (size_t)r * 2 * c.q_max + 2 * e;
                 sum += ((unsigned long long)vb_ld_cg(qr + 1) << 32) | (unsigned long long)vb_ld_cg(qr);
             }
@@ -1127,8 +1135,8 @@ VB_DEV void n4_contract_t(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
     n4_sync(T);
 }
 
-template <bool OMEGA>
-VB_DEV void n4_contract(N4Ctx& c, const N4Team& T, float bmin, float bmax) {
+template <bool OMEGA, class CTX>
+VB_DEV void n4_contract(CTX& c, const N4Team& T, float bmin, float bmax) {
     if (!OMEGA && c.u_smem && c.rowtab) n4_contract_t<OMEGA, true>(c, T, bmin, bmax);
     else n4_contract_t<OMEGA, false>(c, T, bmin, bmax);
 }
@@ -1246,8 +1254,8 @@ VB_DEV int n4_binade(int bits) { return bits >> 23; }
 // mu(lo) = mu0 + sum_{start <= i < lo} (px_i - mu0) / lo (one extra float scan) instead of mu0.
 // In the first few thousand elements the mean still moves by many ulps per element, and with
 // this guess a chunk there may be much longer than the number of elements before it.
-template <bool WARP, bool PREDICT>
-VB_DEV void n4_chain_chunk(N4Ctx& c, const N4Team& T, const float* epx, int start, int len, int& mu_b, int& sg_b,
+template <bool WARP, bool PREDICT, class CTX>
+VB_DEV void n4_chain_chunk(CTX& c, const N4Team& T, const float* epx, int start, int len, int& mu_b, int& sg_b,
                            int (*s_tot)[32], int& buf, float* s_guess) {
     const int nt = WARP ? 32 : T.nt, tid = WARP ? (T.tid & 31) : T.tid;
     const int ept = (len + nt - 1) / nt;                      // <= VB_N4_EPT
@@ -1357,7 +1365,7 @@ VB_DEV void n4_chain_chunk(N4Ctx& c, const N4Team& T, const float* epx, int star
     sg_b = sg0 + total;
 }
 
-VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
+template <class CTX> VB_DEV float n4_convergence(CTX& c, const N4Team& T, int M) {
     const int tid = T.tid;
     VB_SHARED int s_state[2];                 // float bit patterns of (mu, sigma) handed between the phases
     VB_SHARED int s_tot[2][32];               // warp totals, double buffered
@@ -1448,8 +1456,8 @@ VB_DEV float n4_convergence(N4Ctx& c, const N4Team& T, int M) {
 // accounted for in the bound).
 // SM: U and the row tables live in shared memory too (the benchmark volumes): every table access of
 // the loop is an LDS / STS through a 32-bit shared address.
-template <bool SM>
-VB_DEV void n4_update_flat(N4Ctx& c, const N4Team& T, const float* Gn, float& tmin, float& tmax, double& s1, double& s2) {
+template <bool SM, class CTX>
+VB_DEV void n4_update_flat(CTX& c, const N4Team& T, const float* Gn, float& tmin, float& tmax, double& s1, double& s2) {
     const float* logI = c.logI;
     float* ec = c.ec;
     const uint32_t* code = c.code;
@@ -1461,7 +1469,7 @@ VB_DEV void n4_update_flat(N4Ctx& c, const N4Team& T, const float* Gn, float& tm
     const vb_saddr sU = SM ? vb_saddr_of(c.U) : 0, sW = SM ? vb_saddr_of(c.r_evw) : 0, sB = SM ? vb_saddr_of(c.r_bev) : 0;
     const vb_saddr sGo = vb_saddr_of(c.G), sGn = vb_saddr_of(Gn);
     // (cluster mode: this CTA's slice [M0, M) of the compact arrays)
-    const int M0 = (int)((long long)c.M * c.crank / c.K), M = (int)((long long)c.M * (c.crank + 1) / c.K), nt = T.nt;
+    const int M0 = (int)((long long)c.M * c.rank() / c.k()), M = (int)((long long)c.M * (c.rank() + 1) / c.k()), nt = T.nt;
     const unsigned gs4 = 4u * (unsigned)c.gstride;
     // VB_N4_UB voxels per trip: their codes and log-image values (L2) are requested together, before
     // the first of them is evaluated -- the stores of the loop body would otherwise keep the compiler
@@ -1506,7 +1514,7 @@ VB_DEV void n4_update_flat(N4Ctx& c, const N4Team& T, const float* Gn, float& tm
     }
 }
 
-VB_DEV void n4_update_walk(N4Ctx& c, const N4Team& T, float& tmin, float& tmax, double& s1, double& s2) {
+template <class CTX> VB_DEV void n4_update_walk(CTX& c, const N4Team& T, float& tmin, float& tmax, double& s1, double& s2) {
     const float* logI = c.logI;
     float* ec = c.ec;
     float* U = c.U;
@@ -1548,14 +1556,14 @@ VB_DEV void n4_update_walk(N4Ctx& c, const N4Team& T, float& tmin, float& tmax, 
     }
 }
 
-VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool exact_needed, float& conv) {
+template <class CTX> VB_DEV bool n4_update(CTX& c, int M, float& bmin, float& bmax, float thr, bool exact_needed, float& conv) {
     const int nt = (int)blockDim.x;
     float tmin = FLT_MAX, tmax = -FLT_MAX;
     double s1 = 0.0, s2 = 0.0;
     float* Gn = c.G ? (c.G2 ? c.G2 : c.un_f) : nullptr;  // table of the new lattice (spare table, else the union region: free here)
     N4Team T;
     T.tid = (int)threadIdx.x; T.nt = nt; T.bar = 0;
-    c.istep = c.K; c.ioff = c.crank;                     // (cluster mode: the column walk's items are dealt over the CTAs)
+    c.deal(c.k(), c.rank());                     // (cluster mode: the column walk's items are dealt over the CTAs)
     n4_items_begin(c, T);
     if (Gn) n4_build_G(c, c.L, Gn); else __syncthreads();
     if (Gn) {
@@ -1597,7 +1605,7 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
         bmin = tmin; bmax = tmax;
     }
 #endif
-    c.istep = 1; c.ioff = 0;
+    c.deal(1, 0);
     n4_cluster_reduce4(c, T, bmin, bmax, s1, s2);        // (cluster mode; also orders the U / sequence writes of all CTAs)
     __syncthreads();
     if (c.G2) {                                          // the new lattice's table becomes the current one
@@ -1621,7 +1629,7 @@ VB_DEV bool n4_update(N4Ctx& c, int M, float& bmin, float& bmax, float thr, bool
 }
 
 // L <- L + Phi, keeping the previous lattice for the next update pass
-VB_DEV void n4_commit(N4Ctx& c) {
+template <class CTX> VB_DEV void n4_commit(CTX& c) {
     const int Ln = c.ncp[0] * c.ncp[1] * c.ncp[2];
     for (int e = (int)threadIdx.x; e < Ln; e += (int)blockDim.x) {
         const float l = c.L[e];
@@ -1632,12 +1640,12 @@ VB_DEV void n4_commit(N4Ctx& c) {
 }
 
 // final dense pass: bias at EVERY voxel, out = in / exp(bias)   (N4 GenerateData tail)
-VB_DEV void n4_finalize(N4Ctx& c, float* logbias) {
+template <class CTX> VB_DEV void n4_finalize(CTX& c, float* logbias) {
     const int nt = (int)blockDim.x, lane = vb_lane(), w = vb_warp(), nw = nt >> 5;
     const int ncols = c.ncols;
     const N4Axis ac = n4_ax(c, 1), as = n4_ax(c, 2);
     const int nblk_all = (ncols + 31) >> 5;              // every column, not only the active ones
-    for (int blk = w + nw * c.crank; blk < nblk_all; blk += nw * c.K) {     // (cluster mode: column blocks dealt over the CTAs)
+    for (int blk = w + nw * c.rank(); blk < nblk_all; blk += nw * c.k()) {     // (cluster mode: column blocks dealt over the CTAs)
         const int q = blk * 32 + lane;
         if (q >= ncols) continue;
         const N4Col col = n4_col(c, ac, as, q);
@@ -1664,7 +1672,7 @@ VB_DEV void n4_finalize(N4Ctx& c, float* logbias) {
 }
 
 // BSplineControlPointImageFilter::RefineControlPointLattice (every axis n -> 2n-3)
-VB_DEV void n4_refine(N4Ctx& c) {
+template <class CTX> VB_DEV void n4_refine(CTX& c) {
     const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
     const float C[2][4] = {{0.5f, 0.5f, 0.0f, 0.0f}, {0.125f, 0.75f, 0.125f, 0.0f}};
     const int o0 = c.ncp[0], o1 = c.ncp[1], o2 = c.ncp[2];
@@ -1692,7 +1700,7 @@ VB_DEV void n4_refine(N4Ctx& c) {
     __syncthreads();
 }
 
-VB_DEV void n4_build_tables(N4Ctx& c) {
+template <class CTX> VB_DEV void n4_build_tables(CTX& c) {
     const int n[3] = {c.n0, c.n1, c.n2};
     size_t off = 0;
     for (int a = 0; a < 3; ++a) {
@@ -1721,7 +1729,7 @@ VB_DEV void n4_build_tables(N4Ctx& c) {
     __syncthreads();
 }
 
-// CL = false: one persistent CTA per subject (c.K is the literal 1: the cluster-mode code and state
+// CL = false: one persistent CTA per subject (c.k() is the literal 1: the cluster-mode code and state
 // fold away); CL = true: a cluster of a.K CTAs per subject.
 template <bool CL>
 VB_DEV void n4_subject_body(const N4Args& a) {
@@ -1735,7 +1743,7 @@ VB_DEV void n4_subject_body(const N4Args& a) {
     const int chain_warps = (CL && a.cl_chain_warps > 0) ? a.cl_chain_warps : VB_N4_CHAIN_WARPS;
     TC.tid = tid; TC.nt = min(chain_warps * 32, (int)blockDim.x - 32); TC.bar = 1;
     TP.tid = tid - TC.nt; TP.nt = (int)blockDim.x - TC.nt; TP.bar = 2;
-    N4Ctx c;
+    N4CtxT<CL> c;
     c.un_f = (float*)smem;
     c.un_d = (double*)smem;
     unsigned char* p = smem + a.union_bytes;
@@ -1756,24 +1764,26 @@ VB_DEV void n4_subject_body(const N4Args& a) {
     // cluster mode: cluster `cid` = CTAs [cid * K, (cid + 1) * K) of the grid works on subject cid; its CTAs
     // share workspace slot cid (the per-axis tables are per CTA: every CTA builds its own)
     c.K = CL ? max(a.K, 1) : 1; c.crank = (c.K > 1) ? (int)(blockIdx.x % (unsigned)c.K) : 0; c.istep = 1; c.ioff = 0;
-    const int cid = (c.K > 1) ? (int)(blockIdx.x / (unsigned)c.K) : (int)blockIdx.x;
-    c.q_max = a.q_max;
-    c.cl_hist = a.cl_hist ? a.cl_hist + (size_t)cid * 4 * c.K * a.p.n_bins : nullptr;
-    c.cl_q = a.cl_q ? a.cl_q + (size_t)cid * 4 * c.K * 2 * a.q_max : nullptr;
-    c.cl_red = a.cl_red ? a.cl_red + (size_t)cid * 2 * c.K * 4 : nullptr;
-    c.cl_bar = a.cl_bar ? a.cl_bar + (size_t)cid * 4 : nullptr;
-    c.cl_bcast = a.cl_bcast ? a.cl_bcast + (size_t)cid * 16 : nullptr;
-    c.gen[0] = c.gen[1] = c.gen[2] = 0u; c.par_hist0 = c.par_hist1 = c.par_q0 = c.par_q1 = c.par_red = 0;
+    const int cid = (c.k() > 1) ? (int)(blockIdx.x / (unsigned)c.k()) : (int)blockIdx.x;
+    if (CL) {
+        c.q_max = a.q_max;
+        c.cl_hist = a.cl_hist ? a.cl_hist + (size_t)cid * 4 * c.k() * a.p.n_bins : nullptr;
+        c.cl_q = a.cl_q ? a.cl_q + (size_t)cid * 4 * c.k() * 2 * a.q_max : nullptr;
+        c.cl_red = a.cl_red ? a.cl_red + (size_t)cid * 2 * c.k() * 4 : nullptr;
+        c.cl_bar = a.cl_bar ? a.cl_bar + (size_t)cid * 4 : nullptr;
+        c.cl_bcast = a.cl_bcast ? a.cl_bcast + (size_t)cid * 16 : nullptr;
+        c.gen[0] = c.gen[1] = c.gen[2] = 0u; c.par_hist0 = c.par_hist1 = c.par_q0 = c.par_q1 = c.par_red = 0;
+    }
     const size_t slotx = (size_t)cid;
 
     for (int round = 0;; ++round) {
         __syncthreads();
-        if (c.K == 1) {
+        if (c.k() == 1) {
             if (tid == 0) s_next = atomicAdd(a.work_counter, 1);
             __syncthreads();
         }
-        const int si = (c.K == 1) ? s_next : cid;
-        if (si >= a.n || (c.K > 1 && round > 0)) break;
+        const int si = (c.k() == 1) ? s_next : cid;
+        if (si >= a.n || (c.k() > 1 && round > 0)) break;
         const VbSubject S = a.subj[si];
         c.n0 = S.n0; c.n1 = S.n1; c.n2 = S.n2; c.ncols = S.n1 * S.n2; c.W = (S.n0 + 31) >> 5;
         c.nblk = 0; c.nact = 0; c.nseg = 1; c.wps = c.W;
@@ -1806,12 +1816,12 @@ VB_DEV void n4_subject_body(const N4Args& a) {
         long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         long long tq = vb_clock();
         c.t_chain = 0; c.n_sweeps = 0; c.t_sub[0] = c.t_sub[1] = c.t_sub[2] = c.t_sub[3] = 0;
-        if (c.K == 1) {
+        if (c.k() == 1) {
             n4_setup(c, a.p.mask_label, smem_logI, a.logI_cap, bmin, bmax, M);
         } else {
             // CTA 0 of the cluster compacts the volume (in-place scans of the shared tables: one CTA) and
             // hands the scalars to the others
-            if (c.crank == 0) {
+            if (c.rank() == 0) {
                 n4_setup(c, a.p.mask_label, smem_logI, 0, bmin, bmax, M);
                 if (tid == 0) {
                     int* b = c.cl_bcast;
@@ -1908,7 +1918,7 @@ VB_DEV void n4_subject_body(const N4Args& a) {
                     ++ntrace;
                 }
             }
-            if (a.stats && tid == 0 && c.crank == 0) a.stats[si].n4_iters[level] = it;
+            if (a.stats && tid == 0 && c.rank() == 0) a.stats[si].n4_iters[level] = it;
             if (level != a.p.n_levels - 1 && M >= 2 && !capped) n4_refine(c);
         }
         if (M < 2 || capped) n4_build_tables(c);   // tables of the final lattice (M < 2: zero lattice => out = in)
@@ -1925,7 +1935,7 @@ VB_DEV void n4_subject_body(const N4Args& a) {
             }
         }
         tq = vb_clock();
-        if (a.stats && tid == 0 && c.crank == 0) {
+        if (a.stats && tid == 0 && c.rank() == 0) {
             for (int l = a.p.n_levels; l < VB_MAX_LEVELS; ++l) a.stats[si].n4_iters[l] = 0;
             a.stats[si].n4_last_conv = conv;
             a.stats[si].n4_n_mask = M;

@@ -149,6 +149,7 @@ VB_DEV void vb_mbar_wait(vb_mbar_t* bar, unsigned parity) {
 #include <sys/wait.h>
 #include <unistd.h>
 #include <algorithm>
+#include <atomic>
 #include <barrier>
 #include <functional>
 #include <memory>
@@ -304,26 +305,38 @@ static inline int __syncthreads_or(int pred) {
     return r;
 }
 // named barriers: one std::barrier per id, created by the first thread that needs it (and again when a
-// later use of the id has another thread count, e.g. the next launch splits its teams differently)
+// later use of the id has another thread count, e.g. the next launch splits its teams differently; the
+// replaced barrier is kept alive: a thread may still be on its way out of it)
 namespace vbemu {
+struct NamedBar {
+    std::barrier<> bar;
+    int count;
+    NamedBar(int n) : bar(n), count(n) {}
+};
 struct Named {
     std::mutex mu;
-    std::shared_ptr<std::barrier<>> bar[16];
-    int count[16];
+    std::atomic<NamedBar*> cur[16];
+    std::vector<std::unique_ptr<NamedBar>> all;
     int flag[16][2];
     int phase[16];
 };
 inline Named g_named;
-inline std::shared_ptr<std::barrier<>> named_ptr(int id, int n) {
+inline std::barrier<>& named(int id, int n) {
+    NamedBar* q = g_named.cur[id].load(std::memory_order_acquire);
+    if (q && q->count == n) return q->bar;
     std::lock_guard<std::mutex> g(g_named.mu);
-    if (!g_named.bar[id] || g_named.count[id] != n) { g_named.bar[id].reset(new std::barrier<>(n)); g_named.count[id] = n; }
-    return g_named.bar[id];
+    q = g_named.cur[id].load(std::memory_order_acquire);
+    if (!q || q->count != n) {
+        g_named.all.emplace_back(new NamedBar(n));
+        q = g_named.all.back().get();
+        g_named.cur[id].store(q, std::memory_order_release);
+    }
+    return q->bar;
 }
 }  // namespace vbemu
-static inline void vb_bar_sync(int id, int nthreads) { vbemu::named_ptr(id, nthreads)->arrive_and_wait(); }
+static inline void vb_bar_sync(int id, int nthreads) { vbemu::named(id, nthreads).arrive_and_wait(); }
 static inline int vb_bar_or(int id, int nthreads, int pred) {
-    const std::shared_ptr<std::barrier<>> bp = vbemu::named_ptr(id, nthreads);
-    std::barrier<>& b = *bp;
+    std::barrier<>& b = vbemu::named(id, nthreads);
     b.arrive_and_wait();                                   // the flag is clear
     if (pred) __atomic_store_n(&vbemu::g_named.flag[id][0], 1, __ATOMIC_SEQ_CST);
     b.arrive_and_wait();
