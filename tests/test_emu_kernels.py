@@ -90,12 +90,11 @@ def _cluster_cases():
 def test_n4_cluster_of_ctas_per_subject_is_bit_identical(ctx8):
     """K = 2, 4, 8 CTAs per subject (the CTAs of an emulated cluster run concurrently, one forked
     process each): outputs, log bias, iteration counts and the last convergence value equal the
-    one-CTA run bit for bit -- single subject, two ragged subjects, a batch with an empty and a
-    one-voxel mask."""
-    one, two, four = _cluster_cases()
-    helpers.check_n4_cluster(ctx8, [one], max_iter=(6, 4, 3), sms=8)
-    helpers.check_n4_cluster(ctx8, [two], ks=(4,), max_iter=(6, 4, 3), sms=8)
-    helpers.check_n4_cluster(ctx8, [four], ks=(2,), max_iter=(6, 4, 3), sms=8)
+    one-CTA run bit for bit -- single subject, a ragged batch with an empty and a one-voxel mask
+    (two ragged subjects: the column-walk test below)."""
+    one, _, four = _cluster_cases()
+    helpers.check_n4_cluster(ctx8, [one], ks=(4, 8), max_iter=(6, 4, 3), sms=8)
+    helpers.check_n4_cluster(ctx8, [four], ks=(2,), max_iter=(4, 3, 2), sms=8)
     # the first two levels run to convergence (the phase team's speculative fit is discarded there, after an odd
     # and an even number of its exchanges: its slot sets must not depend on the chain team's count)
     helpers.check_n4_cluster(ctx8, [[phantom((40, 36, 6), [1.5, 1.5, 10.0], 5)]], ks=(2,), max_iter=(50, 50, 1), sms=8)
