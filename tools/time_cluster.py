@@ -18,6 +18,8 @@ CASES = [((128, 128, 14), [2.0, 2.0, 11.5], (1, 4, 16, 18, 32, 37, 64, 74)),
          ((256, 256, 64), [1.5, 1.5, 3.0], (1, 2))]
 if "--quick" in sys.argv:        # a first sanity pass: one small and one C2 subject
     CASES = [((48, 40, 6), [1.5, 1.5, 10.0], (1, 3)), ((128, 128, 14), [2.0, 2.0, 11.5], (1,))]
+if "--small" in sys.argv:        # where the break-even volume lies (the automatic choice's size threshold)
+    CASES = [((64, 64, 10), [3.0, 3.0, 12.0], (1, 8)), ((96, 96, 12), [2.5, 2.5, 11.5], (1, 8)), ((112, 112, 14), [2.0, 2.0, 11.5], (1, 8))]
 reps = int(os.environ.get("REPS", "3"))
 KS = (1, 2, 4, 8)
 if "--ncu" in sys.argv:          # one launch of the cluster kernel on a C4 subject (for a capture under ncu)
