@@ -20,6 +20,13 @@ ctx = _lib.Context(0, lib=_lib.bind(sys.argv[2]))
 helpers.check_edge_cases(ctx)
 helpers.check_vdp_ci_against_golden(ctx, "small_b", True)
 helpers.check_vdp_ci_against_golden(ctx, "ragged_c", False)
+# a cluster launch is refused in this build (device memory on the instrumented heap): one CTA per subject runs instead
+from vent_analysis_b200.phantom import phantom
+img, mask = phantom((24, 20, 5), [1.5, 1.5, 10.0], 21)
+ctx.set_n4_cluster(2)
+out = ctx.pipeline_host([img.shape], _lib.DO_N4, image=img.ravel(), mask=mask.ravel(), params=ctx.default_n4_params(max_iter=(2, 1)))
+assert out["rc"] == 0 and ctx.n4_cluster_size() == 1
+ctx.set_n4_cluster(0)
 ctx.close()
 print("asan-ok")
 '''

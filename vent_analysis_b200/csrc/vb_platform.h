@@ -252,8 +252,16 @@ template <class Body> void launch(dim3 grid, dim3 block, size_t smem, Body body)
 // through global memory), one forked process per CTA -- the function-local `static` arrays that stand
 // for __shared__ memory are then private to a CTA, while device memory (vbrt::dev_malloc: shared
 // anonymous mappings) is common to all of them.  Clusters run one after the other.
+// Under AddressSanitizer device memory stays on the instrumented heap (out-of-bounds accesses of every kernel are
+// caught there), which forked CTAs cannot share: a cluster launch is refused and the caller falls back.
+#if defined(__SANITIZE_ADDRESS__)
+#define VB_EMU_SHARED_DEVMEM 0
+#else
+#define VB_EMU_SHARED_DEVMEM 1
+#endif
 inline bool g_cluster_failed = false;
 template <class Body> bool launch_cluster(dim3 grid, dim3 block, size_t smem, int k, Body body) {
+    if (!VB_EMU_SHARED_DEVMEM) return false;
     ++g_launches;
     g_gridDim = Idx{grid.x, grid.y, grid.z};
     g_blockDim = Idx{block.x, block.y, block.z};

@@ -69,7 +69,9 @@ inline bool stream_wait(stream_t s, event_t e) { return ok(cudaStreamWaitEvent(s
 #else
 typedef void* stream_t;
 // "device memory" = shared anonymous mappings: the forked CTAs of an emulated cluster launch see one copy
+// (AddressSanitizer builds: the instrumented heap, see vbemu::launch_cluster)
 inline bool dev_malloc(void** p, size_t n) {
+    if (!VB_EMU_SHARED_DEVMEM) { *p = malloc(n ? n : 1); if (*p) memset(*p, 0xAB, n); return *p != nullptr; }
     const size_t total = n + 256;
     void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     if (m == MAP_FAILED) { *p = nullptr; return false; }
@@ -78,7 +80,10 @@ inline bool dev_malloc(void** p, size_t n) {
     memset(*p, 0xAB, n);
     return true;
 }
-inline void dev_free(void* p) { if (p) { void* m = (char*)p - 256; munmap(m, *(size_t*)m); } }
+inline void dev_free(void* p) {
+    if (!VB_EMU_SHARED_DEVMEM) { free(p); return; }
+    if (p) { void* m = (char*)p - 256; munmap(m, *(size_t*)m); }
+}
 inline bool host_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p != nullptr; }
 inline void host_free(void* p) { free(p); }
 inline bool h2d(void* d, const void* h, size_t n, stream_t) { memcpy(d, h, n); return true; }
